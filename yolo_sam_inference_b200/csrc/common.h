@@ -1,0 +1,65 @@
+// Host-side helpers shared by every translation unit of libysi.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace ysi {
+
+typedef __nv_bfloat16 bf16;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define YSI_CUDA(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw ::ysi::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +    \
+                             __FILE__ + ":" + std::to_string(__LINE__));                             \
+  } while (0)
+
+#define YSI_CHECK(cond, msg)                                                                         \
+  do {                                                                                               \
+    if (!(cond))                                                                                     \
+      throw ::ysi::CudaError(std::string("check failed: ") + #cond + ": " + (msg) + " at " +         \
+                             __FILE__ + ":" + std::to_string(__LINE__));                             \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Row-major bf16 matrix [rows, cols] (row pitch ld elements) -> 2-D TMA map with a {box_cols, box_rows}
+// box and 128-byte swizzle. box_cols must be 64 (=128 B). Out-of-bounds reads return zero.
+CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                              uint32_t box_cols = 64);
+
+// Epilogue description for the tcgen05 GEMM (see gemm.cu).
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+struct GemmEpilogue {
+  const float* bias = nullptr;   // [N] added to the accumulator
+  int act = ACT_NONE;            // applied after bias
+  const float* add_src = nullptr;  // optional fp32 [add_mod, ld_add] added after the activation
+  int add_mod = 1;
+  int ld_add = 0;
+  const int* row_map = nullptr;  // optional destination row per GEMM row (<0: drop the row)
+  float* out_f32 = nullptr;      // optional fp32 destination [*, ld_out]
+  int accumulate = 0;            // out_f32 += value instead of =
+  bf16* out_bf16 = nullptr;      // optional bf16 destination [*, ld_out_bf16]
+  int ld_out = 0;
+  int ld_out_bf16 = 0;
+};
+
+// C[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation in TMEM. A: row pitch lda, W: row pitch ldw.
+void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+               cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace ysi

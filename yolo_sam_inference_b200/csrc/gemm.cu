@@ -1,0 +1,86 @@
+// Host side of the tcgen05 GEMM: tensor-map construction and tile-shape dispatch.
+#include "gemm.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace ysi {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    YSI_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    YSI_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                              uint32_t box_cols) {
+  // cached: the context's buffers are fixed, so the same few dozen maps are requested every step
+  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(base, rows, cols, ld, box_rows, box_cols);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  YSI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  YSI_CHECK((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  YSI_CHECK(box_cols * 2 == 128, "128B swizzle needs a 64-element inner box");
+  YSI_CHECK(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YSI_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+  std::lock_guard<std::mutex> g(mu);
+  cache[key] = m;
+  return m;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    YSI_CUDA(cudaGetDevice(&dev));
+    YSI_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+               cudaStream_t stream) {
+  YSI_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  YSI_CHECK(N % 32 == 0, "GEMM N must be a multiple of 32");
+  YSI_CHECK(K % 8 == 0, "GEMM K must be a multiple of 8");
+  EpiGeneric epi{ep};
+  const CUtensorMap tmA = make_tmap_bf16_2d(A, M, K, lda, GEMM_BM);
+  // widest tile that does not waste more than a quarter of its columns
+  if (N % 256 == 0 || N > 512) {
+    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 256);
+    launch_gemm<256>(tmA, tmB, M, N, K, epi, stream);
+  } else if (N % 128 == 0) {
+    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 128);
+    launch_gemm<128>(tmA, tmB, M, N, K, epi, stream);
+  } else {
+    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 64);
+    launch_gemm<64>(tmA, tmB, M, N, K, epi, stream);
+  }
+}
+
+}  // namespace ysi

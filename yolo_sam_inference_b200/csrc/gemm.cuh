@@ -1,0 +1,229 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T
+//   bf16 operands (K-major, TMA-loaded into 128B-swizzled shared memory), fp32 accumulators in TMEM.
+//   warp 0   : TMA producer (one elected lane)          -- STAGES-deep smem ring, full/empty mbarriers
+//   warp 1   : TMEM allocator + MMA issuer (one lane)    -- tcgen05.mma 128 x BN x 16, commit -> mbarriers
+//   warps 2-5: epilogue (TMEM -> registers -> global)    -- double-buffered accumulator (2 x BN columns)
+// The epilogue is a functor so the same mainloop serves the ViT linears (bias / GELU / residual add),
+// the decoder projections and the fused ConvTranspose upscaler epilogues.
+#pragma once
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ysi {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_bf16.
+struct EpiGeneric {
+  GemmEpilogue p;
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int BN) const {
+    // every lane must execute the warp-collective tcgen05.ld convergently: predicate only the stores
+    int drow = -1;
+    if (row < M) drow = p.row_map ? p.row_map[row] : row;
+    const bool active = drow >= 0;
+    const float* addp = (active && p.add_src) ? p.add_src + static_cast<size_t>(row % p.add_mod) * p.ld_add : nullptr;
+    for (int c = 0; c < BN; c += 32) {
+      const int col0 = n0 + c;
+      if (col0 >= N) break;          // uniform; N is a multiple of 32 (checked on the host)
+      uint32_t r[32];
+      tmem_ld_x32(taddr_row + c, r);
+      tmem_ld_wait();
+      if (!active) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 b = __ldg(b4 + i);
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      }
+      if (p.act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      } else if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+      }
+      if (addp) {
+        const float4* a4 = reinterpret_cast<const float4*>(addp + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 a = __ldg(a4 + i);
+          v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
+        }
+      }
+      if (p.out_f32) {
+        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(drow) * p.ld_out + col0);
+        if (p.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 o = o4[i];
+            v[4 * i] += o.x; v[4 * i + 1] += o.y; v[4 * i + 2] += o.z; v[4 * i + 3] += o.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      if (p.out_bf16) {
+        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(drow) * p.ld_out_bf16 + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+          o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+          o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          o4[i] = o;
+        }
+      }
+    }
+  }
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 Epi epi) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * GEMM_BM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 B per 16-element K step inside the 128 B swizzle atom (encoded >> 4 => +2)
+            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * GEMM_BM;
+      const int n0 = (tile % num_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
+      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, class Epi>
+void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi,
+                 cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  YSI_CUDA(cudaGetLastError());
+}
+
+}  // namespace ysi

@@ -1,0 +1,676 @@
+// a6 + a7 of SURVEY.md section 8: bilinear upsample x2 + threshold fused with the per-mask morphometrics.
+//
+//  K1 upsample_stats   logits[256,256] -> mask bytes + {area, centroid sums, bbox, perimeter code
+//                      histogram, intensity histogram, first mixed 2x2 cell}      (HBM-bound part)
+//  K2 contour_hull_disk one CTA per mask: trace contours[0] from the first mixed cell, convex hull
+//                      (exact integer arithmetic on doubled coordinates), inclusive hull raster
+//                      -> hull area + hull perimeter histogram; centre-disk brightness sums.
+//
+// Arithmetic contracts (all verified bit-for-bit against the CPU oracle in tests/):
+//  * bilinear taps are evaluated exactly like ATen's CPU kernel as built in torch 2.11
+//    (UpSampleKernel.cpp, HelperInterpLinear):  src = max(fma(scale, dst+0.5, -0.5), 0),
+//    out = fma(w0, p0, rn(w1*p1)) along W, then the same along H   (image_processing_sam.py:423-427)
+//  * perimeter codes follow skimage.measure.perimeter(neighborhood=4): border = mask & ~erode4(mask),
+//    code = 1 + 2*#border 4-neighbours + 10*#border diagonal neighbours (utils/metrics.py:65,69)
+//  * contour / hull / raster follow find_contours(level 0.5, 'low') -> ConvexHull -> polygon2mask
+//    (utils/metrics.py:31-48), see oracle/metrics_oracle.py for the restated library algorithms.
+#include <limits.h>
+
+#include "kernels.h"
+
+namespace ysi {
+
+PostGeom make_post_geom(int H, int W) {
+  // image_processing_sam.py:113-122 (_get_preprocess_shape), python float == C double
+  PostGeom g;
+  g.H = H;
+  g.W = W;
+  const int longest = H > W ? H : W;
+  const double scale = 1024 * 1.0 / longest;
+  g.rh = static_cast<int>(H * scale + 0.5);
+  g.rw = static_cast<int>(W * scale + 0.5);
+  return g;
+}
+
+// bin of a perimeter code, -1 if the code has zero weight
+__constant__ signed char c_code_bin[50] = {
+    -1, -1, -1, -1, -1, 0,  -1, 1,  -1, -1, -1, -1, -1, 2,  -1, 3,  -1, 4,  -1, -1, -1, 5,  -1, 6,  -1,
+    7,  -1, 8,  -1, -1, -1, -1, -1, 9,  -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+
+struct Lin {
+  int i0, i1;
+  float l0, l1;
+};
+
+__device__ __forceinline__ Lin lin_index(int dst, int in_size, int out_size, float scale) {
+  Lin r;
+  if (in_size == out_size) {
+    r.i0 = dst; r.i1 = dst; r.l0 = 1.0f; r.l1 = 0.0f;
+    return r;
+  }
+  float src = fmaxf(__fmaf_rn(scale, static_cast<float>(dst) + 0.5f, -0.5f), 0.0f);
+  int i0 = static_cast<int>(floorf(src));
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  r.i0 = i0;
+  r.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  r.l1 = fminf(fmaxf(__fsub_rn(src, static_cast<float>(i0)), 0.0f), 1.0f);
+  r.l0 = __fsub_rn(1.0f, r.l1);
+  return r;
+}
+
+__device__ __forceinline__ float lerp_torch(float w0, float p0, float w1, float p1) {
+  return __fmaf_rn(w0, p0, __fmul_rn(w1, p1));
+}
+
+// value at (i,k) of the 256->1024 interpolated plane
+__device__ __forceinline__ float stage1(const float* __restrict__ low, int i, int k) {
+  const Lin a = lin_index(i, 256, 1024, 0.25f);
+  const Lin b = lin_index(k, 256, 1024, 0.25f);
+  const float* r0 = low + a.i0 * 256;
+  const float* r1 = low + a.i1 * 256;
+  const float top = lerp_torch(b.l0, __ldg(r0 + b.i0), b.l1, __ldg(r0 + b.i1));
+  const float bot = lerp_torch(b.l0, __ldg(r1 + b.i0), b.l1, __ldg(r1 + b.i1));
+  return lerp_torch(a.l0, top, a.l1, bot);
+}
+
+struct PostParams {
+  PostGeom g;
+  float sh, sw;   // stage-2 scales: float(rh)/float(H), float(rw)/float(W)
+};
+
+__device__ __forceinline__ float logit_at(const float* __restrict__ low, const PostParams& p, int r, int c) {
+  if (p.g.rh == p.g.H && p.g.rw == p.g.W) return stage1(low, r, c);
+  const Lin a = lin_index(r, p.g.rh, p.g.H, p.sh);
+  const Lin b = lin_index(c, p.g.rw, p.g.W, p.sw);
+  const float top = lerp_torch(b.l0, stage1(low, a.i0, b.i0), b.l1, stage1(low, a.i0, b.i1));
+  const float bot = lerp_torch(b.l0, stage1(low, a.i1, b.i0), b.l1, stage1(low, a.i1, b.i1));
+  return lerp_torch(a.l0, top, a.l1, bot);
+}
+
+constexpr int TR = 32;    // tile rows
+constexpr int TC = 128;   // tile cols (one warp row = 32 lanes x 4 pixels)
+constexpr int MP = TC + 8;  // smem pitch
+
+__global__ void init_stats_kernel(MaskStatsDev* stats, int nmask) {
+  const int m = blockIdx.x;
+  if (m >= nmask) return;
+  MaskStatsDev* s = stats + m;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s->mask_hist[i] = 0;
+  if (threadIdx.x < YSI_PERIM_BINS) s->perim_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s->area = 0; s->sum_r = 0; s->sum_c = 0;
+    s->min_r = INT_MAX; s->min_c = INT_MAX; s->max_r = -1; s->max_c = -1;
+    s->first_cell = 0xFFFFFFFFu;
+  }
+}
+
+void launch_init_stats(MaskStatsDev* stats, int nmask, cudaStream_t s) {
+  if (nmask <= 0) return;
+  init_stats_kernel<<<nmask, 256, 0, s>>>(stats, nmask);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// MODE 0: mask = upsampled logit > 0 (and write it); MODE 1: mask read from masks_in
+template <int MODE>
+__global__ void __launch_bounds__(256)
+upsample_stats_kernel(const float* __restrict__ low_all, const uint8_t* __restrict__ masks_in, PostParams p,
+                      const uint16_t* __restrict__ sum3_all, const int* __restrict__ mask_image,
+                      uint8_t* __restrict__ masks_out, float* __restrict__ up_logits, MaskStatsDev* __restrict__ stats) {
+  __shared__ uint8_t sm[TR + 4][MP];   // mask with halo 2, origin (R0-2, C0-2)
+  __shared__ uint8_t sb[TR + 2][MP];   // border with halo 1, origin (R0-1, C0-1)
+  __shared__ unsigned int s_hist[8][256];
+  __shared__ unsigned long long s_acc[3];
+  __shared__ int s_mm[4];
+  __shared__ unsigned int s_first;
+  __shared__ unsigned int s_perim[YSI_PERIM_BINS];
+
+  const int H = p.g.H, W = p.g.W;
+  const int m = blockIdx.z;
+  const int R0 = blockIdx.y * TR, C0 = blockIdx.x * TC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const float* low = MODE == 0 ? low_all + static_cast<size_t>(m) * 65536 : nullptr;
+  const uint8_t* min_ = MODE == 1 ? masks_in + m * plane : nullptr;
+  const bool want_hist = sum3_all != nullptr;
+  const uint16_t* sum3 = want_hist ? sum3_all + static_cast<size_t>(mask_image ? mask_image[m] : 0) * plane : nullptr;
+
+  if (want_hist)
+    for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+  if (tid < 3) s_acc[tid] = 0;
+  if (tid == 0) { s_mm[0] = INT_MAX; s_mm[1] = INT_MAX; s_mm[2] = -1; s_mm[3] = -1; s_first = 0xFFFFFFFFu; }
+  if (tid < YSI_PERIM_BINS) s_perim[tid] = 0;
+
+  // ---- A: mask values on the halo'd tile
+  for (int i = tid; i < (TR + 4) * (TC + 4); i += 256) {
+    const int lr = i / (TC + 4), lc = i - lr * (TC + 4);
+    const int r = R0 - 2 + lr, c = C0 - 2 + lc;
+    uint8_t v = 0;
+    if (r >= 0 && r < H && c >= 0 && c < W) {
+      if (MODE == 0) {
+        const float x = logit_at(low, p, r, c);
+        v = x > 0.0f ? 1 : 0;
+        if (up_logits && lr >= 2 && lr < TR + 2 && lc >= 2 && lc < TC + 2) up_logits[m * plane + static_cast<size_t>(r) * W + c] = x;
+      } else {
+        v = min_[static_cast<size_t>(r) * W + c] ? 1 : 0;
+      }
+    }
+    sm[lr][lc] = v;
+  }
+  __syncthreads();
+  // ---- B: border = mask & ~erosion(cross); outside the image counts as background
+  for (int i = tid; i < (TR + 2) * (TC + 2); i += 256) {
+    const int lr = i / (TC + 2), lc = i - lr * (TC + 2);   // border-tile coords; mask-tile coords are +1
+    const int mr = lr + 1, mc = lc + 1;
+    const uint8_t v = sm[mr][mc];
+    sb[lr][lc] = v & (1 ^ (sm[mr - 1][mc] & sm[mr + 1][mc] & sm[mr][mc - 1] & sm[mr][mc + 1]));
+  }
+  __syncthreads();
+  // ---- C: interior pixels. warp -> rows warp, warp+8, ...; lane -> 4 consecutive columns
+  unsigned long long area = 0, sum_r = 0, sum_c = 0;
+  int mnr = INT_MAX, mnc = INT_MAX, mxr = -1, mxc = -1;
+  unsigned int first = 0xFFFFFFFFu;
+  unsigned int pc[YSI_PERIM_BINS];
+#pragma unroll
+  for (int b = 0; b < YSI_PERIM_BINS; ++b) pc[b] = 0;
+  for (int lr = warp; lr < TR; lr += 8) {
+    const int r = R0 + lr;
+    if (r >= H) break;
+    uint8_t outv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int lc = lane * 4 + k;
+      const int c = C0 + lc;
+      const bool inimg = c < W;
+      const int mr = lr + 2, mc = lc + 2;      // mask-tile coords
+      const uint8_t v = inimg ? sm[mr][mc] : 0;
+      outv[k] = v;
+      if (v) {
+        area += 1; sum_r += r; sum_c += c;
+        mnr = min(mnr, r); mxr = max(mxr, r); mnc = min(mnc, c); mxc = max(mxc, c);
+        if (want_hist) atomicAdd(&s_hist[warp][__ldg(sum3 + static_cast<size_t>(r) * W + c) / 3], 1u);
+      }
+      // mixed 2x2 cell with this pixel as upper-left (find_contours visits cells in raster order)
+      if (inimg && r < H - 1 && c < W - 1) {
+        const int sum4 = v + sm[mr][mc + 1] + sm[mr + 1][mc] + sm[mr + 1][mc + 1];
+        if (sum4 != 0 && sum4 != 4) first = min(first, static_cast<unsigned int>(r) * W + c);
+      }
+      int bin = -1;
+      const int br = lr + 1, bc = lc + 1;      // border-tile coords
+      if (inimg && sb[br][bc]) {
+        const int n4 = sb[br - 1][bc] + sb[br + 1][bc] + sb[br][bc - 1] + sb[br][bc + 1];
+        const int nd = sb[br - 1][bc - 1] + sb[br - 1][bc + 1] + sb[br + 1][bc - 1] + sb[br + 1][bc + 1];
+        bin = c_code_bin[1 + 2 * n4 + 10 * nd];
+      }
+#pragma unroll
+      for (int b = 0; b < YSI_PERIM_BINS; ++b) pc[b] += __popc(__ballot_sync(0xFFFFFFFFu, bin == b));
+    }
+    if (MODE == 0 && masks_out) {
+      const int c = C0 + lane * 4;
+      uint8_t* dst = masks_out + m * plane + static_cast<size_t>(r) * W + c;
+      if (c + 3 < W && (W & 3) == 0) {
+        *reinterpret_cast<uchar4*>(dst) = make_uchar4(outv[0], outv[1], outv[2], outv[3]);
+      } else {
+        for (int k = 0; k < 4; ++k)
+          if (c + k < W) dst[k] = outv[k];
+      }
+    }
+  }
+  // ---- reduce: warp -> block -> global
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    area += __shfl_xor_sync(0xFFFFFFFFu, area, o);
+    sum_r += __shfl_xor_sync(0xFFFFFFFFu, sum_r, o);
+    sum_c += __shfl_xor_sync(0xFFFFFFFFu, sum_c, o);
+    mnr = min(mnr, __shfl_xor_sync(0xFFFFFFFFu, mnr, o));
+    mnc = min(mnc, __shfl_xor_sync(0xFFFFFFFFu, mnc, o));
+    mxr = max(mxr, __shfl_xor_sync(0xFFFFFFFFu, mxr, o));
+    mxc = max(mxc, __shfl_xor_sync(0xFFFFFFFFu, mxc, o));
+    first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+  }
+  if (lane == 0) {
+    atomicAdd(&s_acc[0], area); atomicAdd(&s_acc[1], sum_r); atomicAdd(&s_acc[2], sum_c);
+    atomicMin(&s_mm[0], mnr); atomicMin(&s_mm[1], mnc); atomicMax(&s_mm[2], mxr); atomicMax(&s_mm[3], mxc);
+    atomicMin(&s_first, first);
+#pragma unroll
+    for (int b = 0; b < YSI_PERIM_BINS; ++b)
+      if (pc[b]) atomicAdd(&s_perim[b], pc[b]);
+  }
+  __syncthreads();
+  MaskStatsDev* st = stats + m;
+  if (tid == 0) {
+    if (s_acc[0]) {
+      atomicAdd(&st->area, s_acc[0]); atomicAdd(&st->sum_r, s_acc[1]); atomicAdd(&st->sum_c, s_acc[2]);
+      atomicMin(&st->min_r, s_mm[0]); atomicMin(&st->min_c, s_mm[1]);
+      atomicMax(&st->max_r, s_mm[2]); atomicMax(&st->max_c, s_mm[3]);
+    }
+    if (s_first != 0xFFFFFFFFu) atomicMin(&st->first_cell, s_first);
+  }
+  if (tid < YSI_PERIM_BINS && s_perim[tid]) atomicAdd(&st->perim_hist[tid], s_perim[tid]);
+  if (want_hist) {
+    unsigned int h = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) h += s_hist[w][tid];
+    if (h) atomicAdd(&st->mask_hist[tid], h);
+  }
+}
+
+void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const int* mask_image,
+                           uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s) {
+  if (nmask <= 0) return;
+  PostParams p;
+  p.g = g;
+  p.sh = static_cast<float>(g.rh) / static_cast<float>(g.H);
+  p.sw = static_cast<float>(g.rw) / static_cast<float>(g.W);
+  dim3 grid(ceil_div(g.W, TC), ceil_div(g.H, TR), nmask);
+  upsample_stats_kernel<0><<<grid, 256, 0, s>>>(low, nullptr, p, sum3, mask_image, masks, up_logits, stats);
+  YSI_CUDA(cudaGetLastError());
+}
+
+void launch_mask_stats(const uint8_t* masks_in, int nmask, int H, int W, const uint16_t* sum3, const int* mask_image,
+                       MaskStatsDev* stats, cudaStream_t s) {
+  if (nmask <= 0) return;
+  PostParams p;
+  p.g.H = H; p.g.W = W; p.g.rh = H; p.g.rw = W;
+  p.sh = p.sw = 1.0f;
+  dim3 grid(ceil_div(W, TC), ceil_div(H, TR), nmask);
+  upsample_stats_kernel<1><<<grid, 256, 0, s>>>(nullptr, masks_in, p, sum3, mask_image, nullptr, nullptr, stats);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: contour 0 -> hull -> hull raster; centre disk
+// ---------------------------------------------------------------------------------------------------
+// Contour vertices live on doubled coordinates: pixel (r,c) -> (2r,2c); the crossing between two
+// 4-adjacent pixels is their midpoint.  A 2x2 cell (r0,c0) has edges T=(2r0,2c0+1) B=(2r0+2,2c0+1)
+// L=(2r0+1,2c0) R=(2r0+1,2c0+2).
+enum { E_T = 0, E_B = 1, E_L = 2, E_R = 3, E_NONE = 4 };
+
+struct CellWalk {
+  const uint8_t* mk;
+  int H, W;
+  __device__ __forceinline__ int px(int r, int c) const { return mk[static_cast<size_t>(r) * W + c] ? 1 : 0; }
+  // marching-squares case of cell (r0,c0): 1*ul + 2*ur + 4*ll + 8*lr   (_find_contours_cy.pyx)
+  __device__ __forceinline__ int cell_case(int r0, int c0) const {
+    return px(r0, c0) + 2 * px(r0, c0 + 1) + 4 * px(r0 + 1, c0) + 8 * px(r0 + 1, c0 + 1);
+  }
+};
+
+// the edge paired with `e` by the segment(s) of a cell with marching-squares case `cs` (low connectivity)
+__device__ __forceinline__ int paired_edge(int cs, int e) {
+  const int ul = cs & 1, ur = (cs >> 1) & 1, ll = (cs >> 2) & 1, lr = (cs >> 3) & 1;
+  if (cs == 6) {          // segments (right,top) and (left,bottom)
+    return e == E_T ? E_R : e == E_R ? E_T : e == E_L ? E_B : E_L;
+  }
+  if (cs == 9) {          // segments (top,left) and (bottom,right)
+    return e == E_T ? E_L : e == E_L ? E_T : e == E_B ? E_R : E_B;
+  }
+  const bool ct = ul != ur, cb = ll != lr, cl = ul != ll, cr = ur != lr;
+  if (ct && e != E_T) return E_T;
+  if (cb && e != E_B) return E_B;
+  if (cl && e != E_L) return E_L;
+  if (cr && e != E_R) return E_R;
+  return E_NONE;
+}
+
+// first segment emitted by a mixed cell, as (from_edge, to_edge), per the case table of _find_contours_cy.pyx
+__device__ __forceinline__ void first_segment(int cs, int& e_from, int& e_to) {
+  switch (cs) {
+    case 1: e_from = E_T; e_to = E_L; break;
+    case 2: e_from = E_R; e_to = E_T; break;
+    case 3: e_from = E_R; e_to = E_L; break;
+    case 4: e_from = E_L; e_to = E_B; break;
+    case 5: e_from = E_T; e_to = E_B; break;
+    case 6: e_from = E_R; e_to = E_T; break;
+    case 7: e_from = E_R; e_to = E_B; break;
+    case 8: e_from = E_B; e_to = E_R; break;
+    case 9: e_from = E_T; e_to = E_L; break;
+    case 10: e_from = E_B; e_to = E_T; break;
+    case 11: e_from = E_B; e_to = E_L; break;
+    case 12: e_from = E_L; e_to = E_R; break;
+    case 13: e_from = E_T; e_to = E_R; break;
+    default: e_from = E_L; e_to = E_T; break;   // 14
+  }
+}
+
+__device__ __forceinline__ void edge_point(int r0, int c0, int e, int& y2, int& x2) {
+  y2 = 2 * r0 + (e == E_T ? 0 : e == E_B ? 2 : 1);
+  x2 = 2 * c0 + (e == E_L ? 0 : e == E_R ? 2 : 1);
+}
+
+struct RowSpan {   // per doubled row: min / max doubled column among contour vertices
+  int2* span;      // [2H+1]
+  int ymin, ymax, npts;
+  __device__ __forceinline__ void add(int y2, int x2) {
+    int2 s = span[y2];
+    if (x2 < s.x) s.x = x2;
+    if (x2 > s.y) s.y = x2;
+    span[y2] = s;
+    ymin = min(ymin, y2);
+    ymax = max(ymax, y2);
+    ++npts;
+  }
+};
+
+// walk from the vertex on edge `e` of cell (r0,c0) away from that cell until the contour closes at
+// (stop_y, stop_x) or leaves the cell grid.  Returns true if it closed.
+__device__ bool walk_contour(const CellWalk& cw, int r0, int c0, int e, int stop_y, int stop_x, RowSpan& rs,
+                             long long budget, bool& truncated) {
+  while (budget-- > 0) {
+    // cross the edge into the neighbouring cell
+    int nr = r0, nc = c0, ne;
+    if (e == E_T) { nr = r0 - 1; ne = E_B; }
+    else if (e == E_B) { nr = r0 + 1; ne = E_T; }
+    else if (e == E_L) { nc = c0 - 1; ne = E_R; }
+    else { nc = c0 + 1; ne = E_L; }
+    if (nr < 0 || nc < 0 || nr > cw.H - 2 || nc > cw.W - 2) return false;   // open end at the image border
+    const int cs = cw.cell_case(nr, nc);
+    const int ex = paired_edge(cs, ne);
+    int y2, x2;
+    edge_point(nr, nc, ex, y2, x2);
+    if (y2 == stop_y && x2 == stop_x) return true;
+    rs.add(y2, x2);
+    r0 = nr; c0 = nc; e = ex;
+  }
+  truncated = true;
+  return false;
+}
+
+constexpr int K2_THREADS = 256;
+
+__global__ void __launch_bounds__(K2_THREADS)
+contour_hull_disk_kernel(const uint8_t* __restrict__ masks, int nmask, int H, int W,
+                         const uint16_t* __restrict__ sum3_all, const int* __restrict__ mask_image,
+                         const MaskStatsDev* __restrict__ stats, ysi_mask_metrics* __restrict__ out) {
+  const int m = blockIdx.x;
+  const int tid = threadIdx.x;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const MaskStatsDev* stp = stats + m;
+  struct { unsigned long long area, sum_r, sum_c; int min_r, min_c, max_r, max_c; unsigned int first_cell; } st;
+  st.area = stp->area; st.sum_r = stp->sum_r; st.sum_c = stp->sum_c;
+  st.min_r = stp->min_r; st.min_c = stp->min_c; st.max_r = stp->max_r; st.max_c = stp->max_c;
+  st.first_cell = stp->first_cell;
+  ysi_mask_metrics* o = out + m;
+  // dynamic smem: row spans int2[2H+1] | left chain (y,x)[cap] | right chain (y,x)[cap] | lo/hi per pixel row
+  extern __shared__ int smem_all[];
+  int2* span = reinterpret_cast<int2*>(smem_all);
+  int* smem_dyn = smem_all + 2 * (2 * H + 1);
+  __shared__ int s_info[8];       // ymin, ymax, npts, closed, truncated, nleft, nright, degenerate
+  __shared__ unsigned long long s_disk[3];
+  __shared__ unsigned long long s_harea;
+  __shared__ unsigned int s_hperim[YSI_PERIM_BINS];
+
+  if (tid < 3) s_disk[tid] = 0;
+  if (tid == 0) s_harea = 0;
+  if (tid < YSI_PERIM_BINS) s_hperim[tid] = 0;
+  for (int i = tid; i < 2 * H + 1; i += K2_THREADS) span[i] = make_int2(INT_MAX, INT_MIN);
+  __syncthreads();
+
+  const bool empty = st.area == 0;
+  // ---- phase 1a (thread 0): trace contours[0]
+  if (tid == 0) {
+    RowSpan rs;
+    rs.span = span; rs.ymin = INT_MAX; rs.ymax = INT_MIN; rs.npts = 0;
+    bool truncated = false;
+    if (st.first_cell != 0xFFFFFFFFu) {
+      CellWalk cw; cw.mk = masks + m * plane; cw.H = H; cw.W = W;
+      const int r0 = st.first_cell / W, c0 = st.first_cell % W;
+      const int cs = cw.cell_case(r0, c0);
+      int ef, et;
+      first_segment(cs, ef, et);
+      int fy, fx, ty, tx;
+      edge_point(r0, c0, ef, fy, fx);
+      edge_point(r0, c0, et, ty, tx);
+      rs.add(fy, fx);
+      rs.add(ty, tx);
+      const long long budget = 4ll * H * W;
+      const bool closed = walk_contour(cw, r0, c0, et, fy, fx, rs, budget, truncated);
+      if (!closed) walk_contour(cw, r0, c0, ef, ty, tx, rs, budget, truncated);
+    }
+    s_info[0] = rs.ymin; s_info[1] = rs.ymax; s_info[2] = rs.npts; s_info[4] = truncated ? 1 : 0;
+  }
+  // ---- phase 1b (other warps): centre-disk sums, utils/metrics.py:81-94
+  if (tid >= 32 && !empty) {
+    const uint16_t* sum3 = sum3_all + static_cast<size_t>(mask_image ? mask_image[m] : 0) * plane;
+    const double cx = static_cast<double>(st.sum_r) / static_cast<double>(st.area);   // centroid row
+    const double cy = static_cast<double>(st.sum_c) / static_cast<double>(st.area);   // centroid col
+    const int radius = static_cast<int>((H < W ? H : W) * 0.1);
+    const double r2 = static_cast<double>(radius) * radius;
+    int rlo = static_cast<int>(floor(cx)) - radius - 1, rhi = static_cast<int>(ceil(cx)) + radius + 1;
+    int clo = static_cast<int>(floor(cy)) - radius - 1, chi = static_cast<int>(ceil(cy)) + radius + 1;
+    rlo = max(rlo, 0); clo = max(clo, 0); rhi = min(rhi, H - 1); chi = min(chi, W - 1);
+    const int bw = chi - clo + 1, bh = rhi - rlo + 1;
+    unsigned long long n = 0, s1 = 0, s2 = 0;
+    for (int i = tid - 32; i < bw * bh; i += K2_THREADS - 32) {
+      const int r = rlo + i / bw, c = clo + i % bw;
+      const double dr = __dsub_rn(static_cast<double>(r), cx), dc = __dsub_rn(static_cast<double>(c), cy);
+      const double d2 = __dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc));
+      if (d2 <= r2) {
+        const unsigned long long v = sum3[static_cast<size_t>(r) * W + c];
+        n += 1; s1 += v; s2 += v * v;
+      }
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      n += __shfl_xor_sync(0xFFFFFFFFu, n, ofs);
+      s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, ofs);
+      s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, ofs);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_disk[0], n); atomicAdd(&s_disk[1], s1); atomicAdd(&s_disk[2], s2); }
+  }
+  __syncthreads();
+
+  // ---- phase 2 (thread 0): monotone-chain hull over (row, min col) / (row, max col)
+  const int ymin = s_info[0], ymax = s_info[1], npts = s_info[2];
+  const int cap = (ymax >= ymin) ? (ymax - ymin + 1) : 0;
+  int* lch = smem_dyn;                 // left chain  : y at [2i], x at [2i+1]
+  int* rch = smem_dyn + 2 * cap;       // right chain
+  if (tid == 0) {
+    int nl = 0, nr = 0;
+    for (int y = ymin; y <= ymax && npts > 0; ++y) {
+      const int2 sp = span[y];
+      if (sp.x > sp.y) continue;       // no vertex on this doubled row
+      // left chain keeps vertices strictly left of the chord; pop while the middle one is on/right of it
+      while (nl >= 2) {
+        const long long ay = lch[2 * (nl - 2)], ax = lch[2 * (nl - 2) + 1];
+        const long long by = lch[2 * (nl - 1)], bx = lch[2 * (nl - 1) + 1];
+        if ((bx - ax) * (y - ay) - (sp.x - ax) * (by - ay) >= 0) --nl; else break;
+      }
+      lch[2 * nl] = y; lch[2 * nl + 1] = sp.x; ++nl;
+      while (nr >= 2) {
+        const long long ay = rch[2 * (nr - 2)], ax = rch[2 * (nr - 2) + 1];
+        const long long by = rch[2 * (nr - 1)], bx = rch[2 * (nr - 1) + 1];
+        if ((bx - ax) * (y - ay) - (sp.y - ax) * (by - ay) <= 0) --nr; else break;
+      }
+      rch[2 * nr] = y; rch[2 * nr + 1] = sp.y; ++nr;
+    }
+    // twice the polygon area (shoelace) decides degeneracy (< 3 non-collinear points => QhullError)
+    long long area2 = 0;
+    for (int i = 0; i + 1 < nl; ++i) {   // down the left chain
+      area2 += static_cast<long long>(lch[2 * i + 1]) * lch[2 * (i + 1)] - static_cast<long long>(lch[2 * (i + 1) + 1]) * lch[2 * i];
+    }
+    if (nl > 0 && nr > 0)                // bottom: left end -> right end
+      area2 += static_cast<long long>(lch[2 * (nl - 1) + 1]) * rch[2 * (nr - 1)] - static_cast<long long>(rch[2 * (nr - 1) + 1]) * lch[2 * (nl - 1)];
+    for (int i = nr - 1; i > 0; --i) {   // up the right chain
+      area2 += static_cast<long long>(rch[2 * i + 1]) * rch[2 * (i - 1)] - static_cast<long long>(rch[2 * (i - 1) + 1]) * rch[2 * i];
+    }
+    if (nl > 0 && nr > 0)                // top: right start -> left start
+      area2 += static_cast<long long>(rch[1]) * lch[0] - static_cast<long long>(lch[1]) * rch[0];
+    s_info[5] = nl; s_info[6] = nr;
+    s_info[7] = (npts < 3 || area2 == 0) ? 1 : 0;
+  }
+  __syncthreads();
+  const int nl = s_info[5], nr = s_info[6];
+  const bool degenerate = s_info[7] != 0;
+
+  // ---- phase 3: inclusive raster of the hull: per pixel row r the column interval [lo, hi]
+  // pixel rows covered: ceil(ymin/2) .. floor(ymax/2); intervals padded by 2 empty rows on both sides
+  const int pr0 = (ymin + 1) >> 1, pr1 = ymax >> 1;
+  const int nrows = (!degenerate && pr1 >= pr0) ? (pr1 - pr0 + 1) : 0;
+  int* lo = smem_dyn + 4 * cap;                 // [nrows + 4]
+  int* hi = lo + (nrows + 4);
+  for (int i = tid; i < nrows + 4; i += K2_THREADS) {
+    int l = 1, h = 0;   // empty
+    const int r = pr0 - 2 + i;
+    if (i >= 2 && i < nrows + 2) {
+      const int y = 2 * r;
+      // left boundary: segment of the left chain containing y
+      int k = 0;
+      while (k + 1 < nl && lch[2 * (k + 1)] < y) ++k;
+      {
+        const long long ay = lch[2 * k], ax = lch[2 * k + 1];
+        if (k + 1 < nl && ay != y) {
+          const long long by = lch[2 * (k + 1)], bx = lch[2 * (k + 1) + 1];
+          // x(y) = ax + (bx-ax)(y-ay)/(by-ay);  need 2c >= x  =>  c >= num / (2 den), ceil
+          const long long den = 2 * (by - ay), num = ax * (by - ay) + (bx - ax) * (y - ay);
+          l = static_cast<int>(num >= 0 ? (num + den - 1) / den : -((-num) / den));
+        } else {
+          l = static_cast<int>((ax + 1) >> 1);   // ceil(ax / 2), ax >= 0
+        }
+      }
+      k = 0;
+      while (k + 1 < nr && rch[2 * (k + 1)] < y) ++k;
+      {
+        const long long ay = rch[2 * k], ax = rch[2 * k + 1];
+        if (k + 1 < nr && ay != y) {
+          const long long by = rch[2 * (k + 1)], bx = rch[2 * (k + 1) + 1];
+          const long long den = 2 * (by - ay), num = ax * (by - ay) + (bx - ax) * (y - ay);
+          h = static_cast<int>(num >= 0 ? num / den : -((-num + den - 1) / den));   // floor
+        } else {
+          h = static_cast<int>(ax >> 1);         // floor(ax / 2)
+        }
+      }
+      if (l < 0) l = 0;
+      if (h > W - 1) h = W - 1;
+    }
+    lo[i] = l; hi[i] = h;
+  }
+  __syncthreads();
+  if (nrows > 0) {
+    // hull area + perimeter histogram (border pixels only are classified)
+    auto in_hull = [&](int i, int c) -> int { return (c >= lo[i] && c <= hi[i]) ? 1 : 0; };   // i = row index + 2
+    auto is_border = [&](int i, int c) -> int {
+      if (!in_hull(i, c)) return 0;
+      return (in_hull(i - 1, c) & in_hull(i + 1, c) & in_hull(i, c - 1) & in_hull(i, c + 1)) ? 0 : 1;
+    };
+    unsigned long long harea = 0;
+    unsigned int pc[YSI_PERIM_BINS];
+#pragma unroll
+    for (int b = 0; b < YSI_PERIM_BINS; ++b) pc[b] = 0;
+    // work items: (row, column run). Interior pixels of a row are skipped with an interval test.
+    for (int i = 2 + (tid >> 5); i < nrows + 2; i += K2_THREADS / 32) {
+      const int l = lo[i], h = hi[i];
+      if (tid % 32 == 0 && h >= l) harea += static_cast<unsigned long long>(h - l + 1);
+      // interior columns: strictly inside this row's interval and inside both neighbour rows' intervals
+      const int il = max(l + 1, max(lo[i - 1], lo[i + 1])), ih = min(h - 1, min(hi[i - 1], hi[i + 1]));
+      for (int c = l + (tid & 31); c <= h; c += 32) {
+        if (c >= il && c <= ih) {           // jump over the interior run
+          continue;
+        }
+        if (!is_border(i, c)) continue;
+        const int n4 = is_border(i - 1, c) + is_border(i + 1, c) + is_border(i, c - 1) + is_border(i, c + 1);
+        const int nd = is_border(i - 1, c - 1) + is_border(i - 1, c + 1) + is_border(i + 1, c - 1) + is_border(i + 1, c + 1);
+        const int bin = c_code_bin[1 + 2 * n4 + 10 * nd];
+        if (bin >= 0) pc[bin] += 1;
+      }
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      harea += __shfl_xor_sync(0xFFFFFFFFu, harea, ofs);
+#pragma unroll
+      for (int b = 0; b < YSI_PERIM_BINS; ++b) pc[b] += __shfl_xor_sync(0xFFFFFFFFu, pc[b], ofs);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_harea, harea);
+#pragma unroll
+      for (int b = 0; b < YSI_PERIM_BINS; ++b)
+        if (pc[b]) atomicAdd(&s_hperim[b], pc[b]);
+    }
+  }
+  __syncthreads();
+  // ---- final row
+  if (tid == 0) {
+    o->area = static_cast<int64_t>(st.area);
+    o->sum_r = static_cast<int64_t>(st.sum_r);
+    o->sum_c = static_cast<int64_t>(st.sum_c);
+    o->min_r = empty ? 0 : st.min_r; o->min_c = empty ? 0 : st.min_c;
+    o->max_r = empty ? 0 : st.max_r + 1; o->max_c = empty ? 0 : st.max_c + 1;
+    o->hull_area = static_cast<int64_t>(s_harea);
+    o->disk_n = static_cast<int64_t>(s_disk[0]);
+    o->disk_sum = s_disk[1];
+    o->disk_sumsq = s_disk[2];
+    // an empty hull raster also lands in the reference's except branch (regionprops(...)[0] raises)
+    o->flags = (empty ? YSI_FLAG_EMPTY_MASK : 0u) | ((degenerate || s_harea == 0) ? YSI_FLAG_HULL_DEGENERATE : 0u) |
+               (s_info[4] ? YSI_FLAG_CONTOUR_TRUNCATED : 0u);
+    o->contour_points = npts;
+    o->hull_vertices = degenerate ? 0 : nl + nr;
+    o->reserved = 0;
+  }
+  if (tid < YSI_PERIM_BINS) {
+    o->perim_hist[tid] = stp->perim_hist[tid];
+    o->hull_perim_hist[tid] = s_hperim[tid];
+  }
+  o->mask_hist[tid] = stp->mask_hist[tid];
+}
+
+void launch_contour_hull_disk(const uint8_t* masks, int nmask, int H, int W, const uint16_t* sum3,
+                              const int* mask_image, const MaskStatsDev* stats, ysi_mask_metrics* out,
+                              cudaStream_t s) {
+  if (nmask <= 0) return;
+  // dynamic smem: row spans + two chains of (2H+1) (y,x) pairs + lo/hi for (H+4) rows
+  const size_t smem = sizeof(int) * (6 * static_cast<size_t>(2 * H + 1) + 2 * static_cast<size_t>(H + 4));
+  YSI_CHECK(smem <= 200 * 1024, "image too tall for the hull kernel's shared memory");
+  static size_t attr = 0;
+  if (smem > attr) {
+    YSI_CUDA(cudaFuncSetAttribute(contour_hull_disk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    attr = smem;
+  }
+  contour_hull_disk_kernel<<<nmask, K2_THREADS, smem, s>>>(masks, nmask, H, W, sum3, mask_image, stats, out);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void packbits_kernel(const uint8_t* __restrict__ masks, uint8_t* __restrict__ packed, long long npix,
+                                long long nbytes) {
+  const int m = blockIdx.y;
+  const uint8_t* src = masks + m * npix;
+  uint8_t* dst = packed + m * nbytes;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nbytes;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p0 = i * 8;
+    unsigned int v = 0;
+    if (p0 + 8 <= npix && ((reinterpret_cast<uintptr_t>(src + p0) & 7) == 0)) {
+      const unsigned long long w = *reinterpret_cast<const unsigned long long*>(src + p0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v |= (((w >> (8 * k)) & 0xFF) ? 1u : 0u) << (7 - k);
+    } else {
+      for (int k = 0; k < 8 && p0 + k < npix; ++k) v |= (src[p0 + k] ? 1u : 0u) << (7 - k);
+    }
+    dst[i] = static_cast<uint8_t>(v);
+  }
+}
+
+void launch_packbits(const uint8_t* masks, uint8_t* packed, int nmask, long long npix, cudaStream_t s) {
+  if (nmask <= 0) return;
+  const long long nbytes = (npix + 7) / 8;
+  dim3 grid(static_cast<unsigned>(std::min<long long>((nbytes + 255) / 256, 1184)), nmask);
+  packbits_kernel<<<grid, 256, 0, s>>>(masks, packed, npix, nbytes);
+  YSI_CUDA(cudaGetLastError());
+}
+
+__global__ void sum3_kernel(const uint8_t* __restrict__ rgb, int H, int W, int row_stride, uint16_t* __restrict__ out) {
+  const int n = blockIdx.z;
+  const int r = blockIdx.y;
+  const uint8_t* row = rgb + (static_cast<size_t>(n) * H + r) * row_stride;
+  uint16_t* orow = out + (static_cast<size_t>(n) * H + r) * W;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < W; c += gridDim.x * blockDim.x)
+    orow[c] = static_cast<uint16_t>(row[3 * c] + row[3 * c + 1] + row[3 * c + 2]);
+}
+
+void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, cudaStream_t s) {
+  dim3 grid(ceil_div(W, 256), H, n);
+  sum3_kernel<<<grid, 256, 0, s>>>(rgb, H, W, row_stride, sum3);
+  YSI_CUDA(cudaGetLastError());
+}
+
+}  // namespace ysi
