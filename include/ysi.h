@@ -14,6 +14,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define YSI_API __attribute__((visibility("default")))
+#else
+#define YSI_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -76,10 +82,10 @@ typedef struct {
 
 /* ---- lifecycle -------------------------------------------------------------------------------- */
 /* replaces SamModel.from_pretrained(...).to(device), pipeline.py:69-77 */
-int ysi_create(int device, const ysi_config* cfg, ysi_ctx** out);
-int ysi_load_weights(ysi_ctx* ctx, const ysi_tensor_desc* tensors, size_t n);
-void ysi_destroy(ysi_ctx* ctx);
-const char* ysi_last_error(const ysi_ctx* ctx); /* ctx may be NULL: error of the failed ysi_create */
+YSI_API int ysi_create(int device, const ysi_config* cfg, ysi_ctx** out);
+YSI_API int ysi_load_weights(ysi_ctx* ctx, const ysi_tensor_desc* tensors, size_t n);
+YSI_API void ysi_destroy(ysi_ctx* ctx);
+YSI_API const char* ysi_last_error(const ysi_ctx* ctx); /* ctx may be NULL: error of the failed ysi_create */
 
 /* ---- the hot path ----------------------------------------------------------------------------- */
 /* One image: replaces the body of `if len(boxes) > 0:` in process_single_image, pipeline.py:161-175
@@ -90,58 +96,58 @@ const char* ysi_last_error(const ysi_ctx* ctx); /* ctx may be NULL: error of the
  *   packed_out uint8 [nb, ceil(H*W/8)] np.packbits order (utils/mask_encoding.py:24), or NULL
  *   metrics_out[nb]
  * nb == 0 returns immediately (pipeline.py:176-179). */
-int ysi_run(ysi_ctx* ctx, const uint8_t* rgb, int H, int W, int row_stride, const float* boxes_xyxy, int nb,
+YSI_API int ysi_run(ysi_ctx* ctx, const uint8_t* rgb, int H, int W, int row_stride, const float* boxes_xyxy, int nb,
             uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out, ysi_timing* timing);
 
 /* Several same-sized images per launch (the unit of work the folder partition of pipeline.py:537-577
  * hands to one GPU). box_counts[i] boxes belong to image i; boxes / masks / metrics are concatenated. */
-int ysi_run_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
+YSI_API int ysi_run_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
                   const float* boxes_xyxy, const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out,
                   ysi_mask_metrics* metrics_out, ysi_timing* timing);
 
 /* Split form of ysi_run_batch used by bench.py to time the device-resident leg separately:
  * stage = host->device copy of images+boxes, compute = all kernels, fetch = device->host of results. */
-int ysi_stage_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
+YSI_API int ysi_stage_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
                     const float* boxes_xyxy, const int32_t* box_counts);
-int ysi_compute_staged(ysi_ctx* ctx, ysi_timing* timing);
-int ysi_fetch_staged(ysi_ctx* ctx, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out);
+YSI_API int ysi_compute_staged(ysi_ctx* ctx, ysi_timing* timing);
+YSI_API int ysi_fetch_staged(ysi_ctx* ctx, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out);
 
 /* ---- stage-level entry points (parity tests; each is one row of SURVEY.md section 8a) --------------- */
 /* a1: sam_processor(image) -> pixel_values fp32 [n,3,1024,1024] (image_processing_sam.py:205-250) */
-int ysi_preprocess(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
+YSI_API int ysi_preprocess(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
                    float* pixel_values_out);
 /* a3: SamVisionEncoder.forward (modeling_sam.py:1058-1072). pixel_values fp32 [n,3,1024,1024] ->
  * image_embeddings fp32 [n,256,64,64]; hidden_out (optional) fp32 [num_layers+1, n, 64,64,D]:
  * slot 0 = patch embed + pos, slot i+1 = after layer i. */
-int ysi_encode(ysi_ctx* ctx, int n_images, const float* pixel_values, float* image_embeddings_out, float* hidden_out);
+YSI_API int ysi_encode(ysi_ctx* ctx, int n_images, const float* pixel_values, float* image_embeddings_out, float* hidden_out);
 /* a4+a5: prompt encoder + mask decoder (modeling_sam.py:658-698, 461-543) for one image.
  * boxes_1024 float64 [nb,4] already in the 1024-frame (processing_sam.py:215-234) -> low-res logits
  * fp32 [nb,256,256]; sparse_out (optional) fp32 [nb,2,256]. */
-int ysi_decode(ysi_ctx* ctx, const float* image_embeddings, const double* boxes_1024, int nb, float* low_res_out,
+YSI_API int ysi_decode(ysi_ctx* ctx, const float* image_embeddings, const double* boxes_1024, int nb, float* low_res_out,
                float* sparse_out);
 /* a6: post_process_masks (image_processing_sam.py:379-430) + `> 0` : low-res logits fp32 [nb,256,256]
  * -> masks uint8 [nb,H,W]; upsampled_out (optional) fp32 [nb,H,W]. */
-int ysi_postprocess(ysi_ctx* ctx, const float* low_res, int nb, int H, int W, uint8_t* masks_out,
+YSI_API int ysi_postprocess(ysi_ctx* ctx, const float* low_res, int nb, int H, int W, uint8_t* masks_out,
                     float* upsampled_out);
 /* a7: calculate_metrics (utils/metrics.py:9-119) on given masks uint8 [nb,H,W] of one image. */
-int ysi_metrics(ysi_ctx* ctx, const uint8_t* rgb, int H, int W, int row_stride, const uint8_t* masks, int nb,
+YSI_API int ysi_metrics(ysi_ctx* ctx, const uint8_t* rgb, int H, int W, int row_stride, const uint8_t* masks, int nb,
                 ysi_mask_metrics* metrics_out);
 /* the GEMM core on its own: C[M,N] fp32 = A[M,K] * W[N,K]^T (+bias[N]) with bf16-rounded operands;
  * act: 0 none, 1 erf-GELU, 2 ReLU. */
-int ysi_gemm(ysi_ctx* ctx, const float* A, const float* W, const float* bias, int M, int N, int K, int act,
+YSI_API int ysi_gemm(ysi_ctx* ctx, const float* A, const float* W, const float* bias, int M, int N, int K, int act,
              float* C_out);
 /* windowed / global attention of one encoder layer on its own (modeling_sam.py:843-882):
  * qkv fp32 [n_seq, T, 3*heads*64] (T = 196 windowed, 4096 global), rel_pos_h/w fp32 [2S-1, 64]
  * -> out fp32 [n_seq, T, heads*64]. */
-int ysi_attention(ysi_ctx* ctx, const float* qkv, const float* rel_pos_h, const float* rel_pos_w, int n_seq,
+YSI_API int ysi_attention(ysi_ctx* ctx, const float* qkv, const float* rel_pos_h, const float* rel_pos_w, int n_seq,
                   int heads, int is_global, float* out);
 
 /* image-wide positional embedding fp32 [256,64,64] (modeling_sam.py:1128-1139), computed at weight load */
-int ysi_get_image_pe(ysi_ctx* ctx, float* out);
+YSI_API int ysi_get_image_pe(ysi_ctx* ctx, float* out);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
-int64_t ysi_launch_count(const ysi_ctx* ctx);
+YSI_API int64_t ysi_launch_count(const ysi_ctx* ctx);
 /* last completed timing of the run entry points */
-int ysi_version(void);
+YSI_API int ysi_version(void);
 
 #ifdef __cplusplus
 }

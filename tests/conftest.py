@@ -1,0 +1,59 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def _have_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def tiny_weights():
+    from yolo_sam_inference_b200.weights import seeded_state_dict
+    return seeded_state_dict("vit_t", 1234)
+
+
+@pytest.fixture(scope="session")
+def tiny_oracle(tiny_weights):
+    from oracle import sam_oracle
+    return sam_oracle.build_model("vit_t", state_dict=tiny_weights)
+
+
+@pytest.fixture(scope="session")
+def tiny_stage(tiny_weights):
+    """vit_t context sized for every GPU parity test (up to 2048x2048 images, 40 masks)."""
+    from yolo_sam_inference_b200.sam_stage import SamStage
+    st = SamStage("vit_t", device="cuda:0", state_dict=tiny_weights, max_batch=2, max_boxes=40,
+                  max_image_hw=(2048, 2048))
+    yield st
+    st.close()
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

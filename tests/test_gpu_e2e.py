@@ -1,0 +1,64 @@
+"""End-to-end SAM stage (image + boxes -> masks + metrics) through ysi_run_batch vs the oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_zero_boxes_short_circuit(tiny_stage):
+    img = np.zeros((1024, 1024, 3), np.uint8)
+    before = tiny_stage.launch_count
+    masks, mets, crops = tiny_stage.run(img, np.zeros((0, 4), np.float32))
+    assert masks.shape == (0, 1024, 1024) and mets == [] and crops == []
+    assert tiny_stage.launch_count == before       # pipeline.py:176-179: SAM skipped, nothing launched
+
+
+def test_stage_end_to_end(tiny_stage, tiny_oracle):
+    from oracle import metrics_oracle as mo
+    from oracle import sam_oracle
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    imgs, boxes, ref_masks, ref_up = [], [], [], []
+    for idx, nb in ((10, 1), (11, 3)):
+        g, b = synth_image(idx, 1024, nb)
+        im = gray_to_rgb_u8(g)
+        m, d = sam_oracle.run_stage(tiny_oracle, im, b, dump=True)
+        imgs.append(im); boxes.append(b); ref_masks.append(m); ref_up.append(d["upsampled_logits"])
+    tiny_stage.on_empty = "zeros"
+    out = tiny_stage.run_batch(imgs, boxes)
+    ious = []
+    for (masks, mets, crops), rm, im, b in zip(out, ref_masks, imgs, boxes):
+        assert masks.shape == rm.shape and len(mets) == len(rm) == len(crops)
+        for k in range(len(rm)):
+            inter = np.logical_and(masks[k], rm[k]).sum()
+            union = np.logical_or(masks[k], rm[k]).sum()
+            ious.append(inter / max(union, 1))
+            # metrics of OUR mask must equal the oracle's metrics of OUR mask exactly (a7 on identical masks)
+            if masks[k].any():
+                ref = mo.calculate_metrics(im, masks[k])
+                for key, val in ref.items():
+                    if isinstance(val, int):
+                        assert mets[k][key] == val, (key, mets[k][key], val)
+                    else:
+                        assert mets[k][key] == pytest.approx(val, rel=1e-9, abs=1e-12), key
+            x1, y1, x2, y2 = b[k].astype(int)
+            assert np.array_equal(crops[k], im[y1:y2, x1:x2])
+    print("end-to-end mask IoU vs fp32 oracle (random-init noise-field logits):", ["%.4f" % i for i in ious])
+    # random-init logits are a zero-mean noise field: bf16 operands cannot reach 0.999 on
+    # them; the gate here is the documented bf16 floor, the 0.999 gate is checked on identical logits (a6).
+    assert min(ious) > 0.97
+
+
+def test_batch_equals_single(tiny_stage):
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    imgs, boxes = [], []
+    for idx in (20, 21):
+        g, b = synth_image(idx, 1024, 2)
+        imgs.append(gray_to_rgb_u8(g)); boxes.append(b)
+    tiny_stage.on_empty = "zeros"
+    both = tiny_stage.run_batch(imgs, boxes)
+    for i in range(2):
+        single = tiny_stage.run(imgs[i], boxes[i])
+        assert np.array_equal(both[i][0], single[0])
+        assert both[i][1] == single[1]

@@ -1,0 +1,55 @@
+"""a1/a3: preprocessing and the ViT encoder vs transformers (vit_t test tower: every kernel, 2 window + 2 global layers)."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _image(idx=0, n_boxes=1):
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    g, b = synth_image(idx, 1024, n_boxes)
+    return gray_to_rgb_u8(g), b
+
+
+def test_preprocess_exact_at_1024(tiny_stage):
+    from oracle import sam_oracle
+    img, _ = _image(0)
+    rng = np.random.RandomState(0)
+    img2 = rng.randint(0, 256, size=(1024, 1024, 3)).astype(np.uint8)     # all 256 levels, distinct channels
+    for im in (img, img2):
+        ref, orig, reshaped = sam_oracle.preprocess(im)
+        got = tiny_stage.preprocess([im])
+        assert orig == (1024, 1024) and reshaped == (1024, 1024)
+        assert np.array_equal(got[0], ref[0].numpy())
+
+
+def test_encoder_per_layer_parity(tiny_stage, tiny_oracle):
+    from oracle import sam_oracle
+    img, boxes = _image(1)
+    _, dumps = sam_oracle.run_stage(tiny_oracle, img, boxes, dump=True)
+    emb, hid = tiny_stage.encode(dumps["pixel_values"][None], want_hidden=True)
+    L = 4
+    # slot 0 = patch embed + pos_embed
+    pos = tiny_oracle.vision_encoder.pos_embed.detach().numpy()[0]
+    errs = [rel_l2(hid[0, 0], dumps["patch_embed"] + pos)]
+    for li in range(L):
+        errs.append(rel_l2(hid[li + 1, 0], dumps[f"hidden_{li}"]))
+    e_emb = rel_l2(emb[0], dumps["image_embeddings"])
+    print("encoder rel-L2 per stage:", ["%.2e" % e for e in errs], "embeddings %.2e" % e_emb)
+    assert all(np.isfinite(e) for e in errs)
+    # BASELINE gate: <= 2e-2 relative for bf16 operands vs the fp32 reference
+    assert max(errs) < 2e-2 and e_emb < 2e-2
+
+
+def test_encoder_batch_of_two_matches_single(tiny_stage, tiny_oracle):
+    from oracle import sam_oracle
+    pv = []
+    for idx in (2, 3):
+        img, _ = _image(idx)
+        pv.append(sam_oracle.preprocess(img)[0][0].numpy())
+    pv = np.stack(pv)
+    both = tiny_stage.encode(pv)
+    one = tiny_stage.encode(pv[1:2])
+    assert np.array_equal(both[1], one[0])          # images are independent: batching must not change results

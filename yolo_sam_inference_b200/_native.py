@@ -1,0 +1,125 @@
+"""ctypes binding of libysi.so (include/ysi.h).  No torch types cross this boundary.
+
+The library is the product path: if it cannot be loaded or a call fails, we raise -- there is no CPU
+or PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+YSI_MAX_GLOBAL_LAYERS = 8
+YSI_PERIM_BINS = 10
+PERIM_CODES = (5, 7, 13, 15, 17, 21, 23, 25, 27, 33)
+FLAG_EMPTY_MASK = 1
+FLAG_HULL_DEGENERATE = 2
+FLAG_CONTOUR_TRUNCATED = 4
+
+
+class YsiConfig(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
+                ("mlp_dim", C.c_int32), ("num_global", C.c_int32),
+                ("global_attn_indexes", C.c_int32 * YSI_MAX_GLOBAL_LAYERS),
+                ("max_batch", C.c_int32), ("max_boxes", C.c_int32),
+                ("max_image_h", C.c_int32), ("max_image_w", C.c_int32)]
+
+
+class YsiTensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * 4)]
+
+
+class YsiTiming(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "preprocess_ms", "encoder_ms", "decoder_ms",
+                                         "postprocess_ms", "metrics_ms", "d2h_ms", "total_ms")]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+
+
+# numpy mirror of ysi_mask_metrics (same field order / sizes; no padding needed: all naturally aligned)
+METRICS_DTYPE = np.dtype([
+    ("area", "<i8"), ("sum_r", "<i8"), ("sum_c", "<i8"),
+    ("min_r", "<i4"), ("min_c", "<i4"), ("max_r", "<i4"), ("max_c", "<i4"),
+    ("perim_hist", "<u4", (YSI_PERIM_BINS,)),
+    ("hull_area", "<i8"),
+    ("hull_perim_hist", "<u4", (YSI_PERIM_BINS,)),
+    ("disk_n", "<i8"), ("disk_sum", "<u8"), ("disk_sumsq", "<u8"),
+    ("flags", "<u4"), ("contour_points", "<i4"), ("hull_vertices", "<i4"), ("reserved", "<i4"),
+    ("mask_hist", "<u4", (256,)),
+], align=True)
+
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_ctx = C.c_void_p
+
+EXPORTS = {
+    "ysi_version": (C.c_int, []),
+    "ysi_create": (C.c_int, [C.c_int, C.POINTER(YsiConfig), C.POINTER(_ctx)]),
+    "ysi_load_weights": (C.c_int, [_ctx, C.POINTER(YsiTensorDesc), C.c_size_t]),
+    "ysi_destroy": (None, [_ctx]),
+    "ysi_last_error": (C.c_char_p, [_ctx]),
+    "ysi_run": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _u8p, _u8p, C.c_void_p,
+                          C.POINTER(YsiTiming)]),
+    "ysi_run_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p, _u8p, _u8p,
+                                C.c_void_p, C.POINTER(YsiTiming)]),
+    "ysi_stage_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
+    "ysi_compute_staged": (C.c_int, [_ctx, C.POINTER(YsiTiming)]),
+    "ysi_fetch_staged": (C.c_int, [_ctx, _u8p, _u8p, C.c_void_p]),
+    "ysi_preprocess": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p]),
+    "ysi_encode": (C.c_int, [_ctx, C.c_int, _f32p, _f32p, _f32p]),
+    "ysi_decode": (C.c_int, [_ctx, _f32p, _f64p, C.c_int, _f32p, _f32p]),
+    "ysi_postprocess": (C.c_int, [_ctx, _f32p, C.c_int, C.c_int, C.c_int, _u8p, _f32p]),
+    "ysi_metrics": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_void_p]),
+    "ysi_gemm": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
+    "ysi_attention": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p]),
+    "ysi_get_image_pe": (C.c_int, [_ctx, _f32p]),
+    "ysi_launch_count": (C.c_int64, [_ctx]),
+}
+
+_LIB: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libysi.so")
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load libysi.so and bind every symbol of include/ysi.h (raises if any is missing)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: run `python -m yolo_sam_inference_b200.build`")
+        from .build import build
+        build()
+    lib = C.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def as_u8p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_u8p)
+
+
+def as_f32p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_f32p)
+
+
+def as_f64p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_f64p)
+
+
+def as_i32p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_i32p)

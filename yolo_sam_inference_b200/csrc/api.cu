@@ -1,0 +1,680 @@
+// C ABI of libysi.so (include/ysi.h): context, weight upload, workspaces and the run entry points.
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace ysi;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostTensor {
+  const float* data;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto d : shape) n *= static_cast<size_t>(d);
+    return n;
+  }
+};
+
+}  // namespace
+
+struct ysi_ctx {
+  int device = 0;
+  ysi_config cfg{};
+  std::string error;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  std::vector<void*> host_allocs;
+  bool weights_loaded = false;
+  int64_t launches = 0;
+
+  // weights
+  std::vector<EncoderLayerW> enc_layers;
+  EncoderW enc{};
+  DecoderW dec{};
+  float mean255[3], std255[3];
+
+  // workspaces
+  EncoderWork ew{};
+  DecoderWork dw{};
+  uint8_t* d_rgb = nullptr;        // [max_batch, H, W, 3]
+  uint16_t* d_sum3 = nullptr;      // [max_batch, H, W]
+  float* d_pix = nullptr;          // [max_batch, 3, 1024, 1024] (stage API only, lazily allocated)
+  float* d_emb = nullptr;          // [max_batch*4096, 256] token-major image embeddings
+  float* d_low = nullptr;          // [max_boxes, 256, 256]
+  uint8_t* d_masks = nullptr;      // [max_boxes, H, W]
+  uint8_t* d_packed = nullptr;     // [max_boxes, ceil(H*W/8)]
+  MaskStatsDev* d_stats = nullptr;
+  ysi_mask_metrics* d_metrics = nullptr;
+  int* d_mask_img = nullptr;
+  float* d_hidden = nullptr;       // stage API dump
+  size_t hidden_cap = 0;
+
+  // staged batch (ysi_stage_batch)
+  int st_n = 0, st_H = 0, st_W = 0, st_nb = 0;
+  std::vector<int> st_box_img;
+  cudaEvent_t ev[8]{};
+
+  template <class T>
+  T* dalloc(size_t n) {
+    void* p = nullptr;
+    YSI_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    allocs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  float* upload_f32(const float* h, size_t n) {
+    float* d = dalloc<float>(n);
+    YSI_CUDA(cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+  }
+  bf16* upload_bf16(const std::vector<bf16>& h) {
+    bf16* d = dalloc<bf16>(h.size());
+    YSI_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    return d;
+  }
+};
+
+namespace {
+
+std::vector<bf16> to_bf16(const float* p, size_t n) {
+  std::vector<bf16> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = __float2bfloat16(p[i]);
+  return v;
+}
+
+template <class F>
+int guarded(ysi_ctx* ctx, F&& f) {
+  if (!ctx) return -1;
+  try {
+    YSI_CUDA(cudaSetDevice(ctx->device));
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    ctx->error = e.what();
+    cudaGetLastError();
+    return -2;
+  }
+}
+
+struct WeightMap {
+  std::map<std::string, HostTensor> m;
+  const HostTensor& get(const std::string& name) const {
+    auto it = m.find(name);
+    if (it == m.end()) throw CudaError("missing weight tensor: " + name);
+    return it->second;
+  }
+  const HostTensor& get(const std::string& name, std::initializer_list<int64_t> shape) const {
+    const HostTensor& t = get(name);
+    if (t.shape != std::vector<int64_t>(shape)) throw CudaError("unexpected shape for weight tensor: " + name);
+    return t;
+  }
+};
+
+void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
+  WeightMap wm;
+  for (size_t i = 0; i < n; ++i) {
+    HostTensor t;
+    t.data = tensors[i].data;
+    t.shape.assign(tensors[i].shape, tensors[i].shape + tensors[i].ndim);
+    wm.m[tensors[i].name] = t;
+  }
+  const int D = c->cfg.hidden_size, L = c->cfg.num_layers, heads = c->cfg.num_heads, mlp = c->cfg.mlp_dim;
+  auto f32 = [&](const std::string& name, std::initializer_list<int64_t> shape) {
+    const HostTensor& t = wm.get(name, shape);
+    return c->upload_f32(t.data, t.numel());
+  };
+  auto b16 = [&](const std::string& name, std::initializer_list<int64_t> shape) {
+    const HostTensor& t = wm.get(name, shape);
+    return c->upload_bf16(to_bf16(t.data, t.numel()));
+  };
+  // ---------------- encoder
+  EncoderW& e = c->enc;
+  e.D = D; e.L = L; e.heads = heads; e.mlp = mlp;
+  e.w_patch = b16("vision_encoder.patch_embed.projection.weight", {D, 3, 16, 16});
+  e.b_patch = f32("vision_encoder.patch_embed.projection.bias", {D});
+  e.pos_embed = f32("vision_encoder.pos_embed", {1, 64, 64, D});
+  c->enc_layers.resize(L);
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "vision_encoder.layers." + std::to_string(i) + ".";
+    bool glob = false;
+    for (int g = 0; g < c->cfg.num_global; ++g) glob |= c->cfg.global_attn_indexes[g] == i;
+    const int S = glob ? 64 : 14;
+    EncoderLayerW& lw = c->enc_layers[i];
+    lw.is_global = glob ? 1 : 0;
+    lw.ln1_g = f32(p + "layer_norm1.weight", {D}); lw.ln1_b = f32(p + "layer_norm1.bias", {D});
+    lw.ln2_g = f32(p + "layer_norm2.weight", {D}); lw.ln2_b = f32(p + "layer_norm2.bias", {D});
+    lw.w_qkv = b16(p + "attn.qkv.weight", {3 * D, D}); lw.b_qkv = f32(p + "attn.qkv.bias", {3 * D});
+    lw.w_proj = b16(p + "attn.proj.weight", {D, D}); lw.b_proj = f32(p + "attn.proj.bias", {D});
+    lw.w_fc1 = b16(p + "mlp.lin1.weight", {mlp, D}); lw.b_fc1 = f32(p + "mlp.lin1.bias", {mlp});
+    lw.w_fc2 = b16(p + "mlp.lin2.weight", {D, mlp}); lw.b_fc2 = f32(p + "mlp.lin2.bias", {D});
+    const HostTensor& rh = wm.get(p + "attn.rel_pos_h", {2 * S - 1, 64});
+    const HostTensor& rw = wm.get(p + "attn.rel_pos_w", {2 * S - 1, 64});
+    std::vector<bf16> tab(256 * 64, __float2bfloat16(0.f));
+    for (int r = 0; r < 2 * S - 1; ++r)
+      for (int k = 0; k < 64; ++k) {
+        tab[r * 64 + k] = __float2bfloat16(rh.data[r * 64 + k]);
+        tab[(128 + r) * 64 + k] = __float2bfloat16(rw.data[r * 64 + k]);
+      }
+    lw.rel_tab = c->upload_bf16(tab);
+  }
+  e.layers = c->enc_layers.data();
+  e.w_neck1 = b16("vision_encoder.neck.conv1.weight", {256, D, 1, 1});
+  e.neck_ln1_g = f32("vision_encoder.neck.layer_norm1.weight", {256});
+  e.neck_ln1_b = f32("vision_encoder.neck.layer_norm1.bias", {256});
+  {
+    const HostTensor& t = wm.get("vision_encoder.neck.conv2.weight", {256, 256, 3, 3});
+    std::vector<bf16> wv(256 * 2304);
+    for (int o = 0; o < 256; ++o)
+      for (int ci = 0; ci < 256; ++ci)
+        for (int tap = 0; tap < 9; ++tap) wv[o * 2304 + tap * 256 + ci] = __float2bfloat16(t.data[(o * 256 + ci) * 9 + tap]);
+    e.w_neck2 = c->upload_bf16(wv);
+  }
+  e.neck_ln2_g = f32("vision_encoder.neck.layer_norm2.weight", {256});
+  e.neck_ln2_b = f32("vision_encoder.neck.layer_norm2.bias", {256});
+  // ---------------- prompt encoder + decoder
+  DecoderW& d = c->dec;
+  d.gauss = f32("shared_image_embedding.positional_embedding", {2, 128});
+  {
+    std::vector<float> pe(4 * 256);
+    for (int i = 0; i < 4; ++i) {
+      const HostTensor& t = wm.get("prompt_encoder.point_embed." + std::to_string(i) + ".weight", {1, 256});
+      std::memcpy(pe.data() + i * 256, t.data, 256 * sizeof(float));
+    }
+    d.point_embed = c->upload_f32(pe.data(), pe.size());
+  }
+  d.no_mask_embed = f32("prompt_encoder.no_mask_embed.weight", {1, 256});
+  d.iou_token = f32("mask_decoder.iou_token.weight", {1, 256});
+  d.mask_tokens = f32("mask_decoder.mask_tokens.weight", {4, 256});
+  auto attn = [&](const std::string& p, int internal) {
+    DecAttnW a;
+    a.wq = f32(p + ".q_proj.weight", {internal, 256}); a.bq = f32(p + ".q_proj.bias", {internal});
+    a.wk = f32(p + ".k_proj.weight", {internal, 256}); a.bk = f32(p + ".k_proj.bias", {internal});
+    a.wv = f32(p + ".v_proj.weight", {internal, 256}); a.bv = f32(p + ".v_proj.bias", {internal});
+    a.wo = f32(p + ".out_proj.weight", {256, internal}); a.bo = f32(p + ".out_proj.bias", {256});
+    return a;
+  };
+  for (int i = 0; i < 2; ++i) {
+    const std::string p = "mask_decoder.transformer.layers." + std::to_string(i);
+    DecLayerW& lw = d.layers[i];
+    lw.self_attn = attn(p + ".self_attn", 256);
+    lw.t2i = attn(p + ".cross_attn_token_to_image", 128);
+    lw.i2t = attn(p + ".cross_attn_image_to_token", 128);
+    lw.ln1_g = f32(p + ".layer_norm1.weight", {256}); lw.ln1_b = f32(p + ".layer_norm1.bias", {256});
+    lw.ln2_g = f32(p + ".layer_norm2.weight", {256}); lw.ln2_b = f32(p + ".layer_norm2.bias", {256});
+    lw.ln3_g = f32(p + ".layer_norm3.weight", {256}); lw.ln3_b = f32(p + ".layer_norm3.bias", {256});
+    lw.ln4_g = f32(p + ".layer_norm4.weight", {256}); lw.ln4_b = f32(p + ".layer_norm4.bias", {256});
+    lw.w_fc1 = f32(p + ".mlp.lin1.weight", {2048, 256}); lw.b_fc1 = f32(p + ".mlp.lin1.bias", {2048});
+    lw.w_fc2 = f32(p + ".mlp.lin2.weight", {256, 2048}); lw.b_fc2 = f32(p + ".mlp.lin2.bias", {256});
+    const HostTensor& wk = wm.get(p + ".cross_attn_token_to_image.k_proj.weight", {128, 256});
+    const HostTensor& wq = wm.get(p + ".cross_attn_image_to_token.q_proj.weight", {128, 256});
+    std::vector<bf16> kq(256 * 256);
+    for (int k = 0; k < 128 * 256; ++k) { kq[k] = __float2bfloat16(wk.data[k]); kq[128 * 256 + k] = __float2bfloat16(wq.data[k]); }
+    lw.w_kq_img = c->upload_bf16(kq);
+    std::vector<float> bkq(256);
+    std::memcpy(bkq.data(), wm.get(p + ".cross_attn_token_to_image.k_proj.bias", {128}).data, 128 * sizeof(float));
+    std::memcpy(bkq.data() + 128, wm.get(p + ".cross_attn_image_to_token.q_proj.bias", {128}).data, 128 * sizeof(float));
+    lw.b_kq_img = c->upload_f32(bkq.data(), 256);
+    lw.w_v_img = b16(p + ".cross_attn_token_to_image.v_proj.weight", {128, 256});
+    lw.w_i2t_out = b16(p + ".cross_attn_image_to_token.out_proj.weight", {256, 128});
+  }
+  d.final_attn = attn("mask_decoder.transformer.final_attn_token_to_image", 128);
+  d.w_k_final = b16("mask_decoder.transformer.final_attn_token_to_image.k_proj.weight", {128, 256});
+  d.w_v_final = b16("mask_decoder.transformer.final_attn_token_to_image.v_proj.weight", {128, 256});
+  d.lnf_g = f32("mask_decoder.transformer.layer_norm_final_attn.weight", {256});
+  d.lnf_b = f32("mask_decoder.transformer.layer_norm_final_attn.bias", {256});
+  {
+    // ConvTranspose2d weight [in, out, kh, kw] -> GEMM weight [(dy*2+dx)*out + o][in]
+    const HostTensor& t1 = wm.get("mask_decoder.upscale_conv1.weight", {256, 64, 2, 2});
+    std::vector<bf16> w1(256 * 256);
+    for (int i = 0; i < 256; ++i)
+      for (int o = 0; o < 64; ++o)
+        for (int sp = 0; sp < 4; ++sp) w1[(sp * 64 + o) * 256 + i] = __float2bfloat16(t1.data[(i * 64 + o) * 4 + sp]);
+    d.w_ct1 = c->upload_bf16(w1);
+    const HostTensor& t2 = wm.get("mask_decoder.upscale_conv2.weight", {64, 32, 2, 2});
+    std::vector<bf16> w2(128 * 64);
+    for (int i = 0; i < 64; ++i)
+      for (int o = 0; o < 32; ++o)
+        for (int sp = 0; sp < 4; ++sp) w2[(sp * 32 + o) * 64 + i] = __float2bfloat16(t2.data[(i * 32 + o) * 4 + sp]);
+    d.w_ct2 = c->upload_bf16(w2);
+  }
+  d.b_ct1 = f32("mask_decoder.upscale_conv1.bias", {64});
+  d.b_ct2 = f32("mask_decoder.upscale_conv2.bias", {32});
+  d.lnu_g = f32("mask_decoder.upscale_layer_norm.weight", {64});
+  d.lnu_b = f32("mask_decoder.upscale_layer_norm.bias", {64});
+  d.hy_w0 = f32("mask_decoder.output_hypernetworks_mlps.0.proj_in.weight", {256, 256});
+  d.hy_b0 = f32("mask_decoder.output_hypernetworks_mlps.0.proj_in.bias", {256});
+  d.hy_w1 = f32("mask_decoder.output_hypernetworks_mlps.0.layers.0.weight", {256, 256});
+  d.hy_b1 = f32("mask_decoder.output_hypernetworks_mlps.0.layers.0.bias", {256});
+  d.hy_w2 = f32("mask_decoder.output_hypernetworks_mlps.0.proj_out.weight", {32, 256});
+  d.hy_b2 = f32("mask_decoder.output_hypernetworks_mlps.0.proj_out.bias", {32});
+  float* pe = c->dalloc<float>(4096 * 256);
+  launch_image_pe(d.gauss, pe, c->stream);
+  d.image_pe = pe;
+  YSI_CUDA(cudaStreamSynchronize(c->stream));
+  c->weights_loaded = true;
+}
+
+void create_impl(ysi_ctx* c) {
+  const ysi_config& cfg = c->cfg;
+  YSI_CHECK(cfg.hidden_size == cfg.num_heads * 64, "this build supports head_dim 64 only (ViT-B/L)");
+  YSI_CHECK(cfg.hidden_size % 64 == 0 && cfg.hidden_size <= 1280, "hidden_size must be a multiple of 64, <= 1280");
+  YSI_CHECK(cfg.mlp_dim % 64 == 0, "mlp_dim must be a multiple of 64");
+  YSI_CHECK(cfg.num_global >= 0 && cfg.num_global <= YSI_MAX_GLOBAL_LAYERS, "too many global layers");
+  YSI_CHECK(cfg.max_batch >= 1 && cfg.max_boxes >= 1, "max_batch and max_boxes must be positive");
+  YSI_CHECK(cfg.max_image_h >= 16 && cfg.max_image_w >= 16 && cfg.max_image_h <= 4096 && cfg.max_image_w <= 4096,
+            "max image size out of range");
+  int cc_major = 0;
+  YSI_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, c->device));
+  YSI_CHECK(cc_major == 10, "libysi.so is built for sm_100a only (needs a B200-class GPU)");
+  YSI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) YSI_CUDA(cudaEventCreate(&e));
+  // (x - mean*255) / (std*255) with the fp32 products tvF.normalize sees
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+  const float inv_rescale = static_cast<float>(1.0 / (1.0 / 255.0));
+  for (int i = 0; i < 3; ++i) { c->mean255[i] = mean[i] * inv_rescale; c->std255[i] = sd[i] * inv_rescale; }
+
+  const size_t B = cfg.max_batch, NB = cfg.max_boxes, D = cfg.hidden_size;
+  const size_t HW = static_cast<size_t>(cfg.max_image_h) * cfg.max_image_w;
+  EncoderWork& ew = c->ew;
+  ew.cap = cfg.max_batch;
+  ew.a_patch = c->dalloc<bf16>(B * 4096 * 768);
+  ew.x = c->dalloc<float>(B * 4096 * D);
+  ew.h = c->dalloc<bf16>(B * 4900 * D);
+  ew.qkv = c->dalloc<bf16>(B * 4900 * 3 * D);
+  ew.attn = c->dalloc<bf16>(B * 4900 * D);
+  ew.u = c->dalloc<bf16>(B * 4096 * cfg.mlp_dim);
+  ew.n1 = c->dalloc<float>(B * 4096 * 256);
+  ew.n1b = c->dalloc<bf16>(B * 4096 * 256);
+  ew.a_neck = c->dalloc<bf16>(B * 4096 * 2304);
+  ew.n2 = c->dalloc<float>(B * 4096 * 256);
+  int* map = c->dalloc<int>(B * 4900);
+  launch_build_win_row_map(map, cfg.max_batch, c->stream);
+  ew.win_row_map = map;
+  DecoderWork& dw = c->dw;
+  dw.cap_img = cfg.max_batch; dw.cap_box = cfg.max_boxes;
+  dw.keys0 = c->dalloc<float>(B * 4096 * 256);
+  dw.keys0_bf = c->dalloc<bf16>(B * 4096 * 256);
+  dw.keyspos0_bf = c->dalloc<bf16>(B * 4096 * 256);
+  dw.kq0 = c->dalloc<float>(B * 4096 * 256);
+  dw.v0 = c->dalloc<float>(B * 4096 * 128);
+  dw.keys = c->dalloc<float>(NB * 4096 * 256);
+  dw.keys_bf = c->dalloc<bf16>(NB * 4096 * 256);
+  dw.keyspos_bf = c->dalloc<bf16>(NB * 4096 * 256);
+  dw.kq = c->dalloc<float>(NB * 4096 * 256);
+  dw.v = c->dalloc<float>(NB * 4096 * 128);
+  dw.attn_i2t = c->dalloc<bf16>(NB * 4096 * 128);
+  dw.up1 = c->dalloc<bf16>(NB * 16384 * 64);
+  dw.tok0 = c->dalloc<float>(NB * 7 * 256);
+  dw.queries = c->dalloc<float>(NB * 7 * 256);
+  dw.q_t2i = c->dalloc<float>(NB * 7 * 128);
+  dw.attn_t2i = c->dalloc<float>(NB * 7 * 128);
+  dw.k_tok = c->dalloc<float>(NB * 7 * 128);
+  dw.v_tok = c->dalloc<float>(NB * 7 * 128);
+  dw.hyper = c->dalloc<float>(NB * 32);
+  dw.boxes1024 = c->dalloc<double>(NB * 4);
+  dw.box_img = c->dalloc<int>(NB);
+  c->d_rgb = c->dalloc<uint8_t>(B * HW * 3);
+  c->d_sum3 = c->dalloc<uint16_t>(B * HW);
+  c->d_emb = c->dalloc<float>(B * 4096 * 256);
+  c->d_low = c->dalloc<float>(NB * 65536);
+  c->d_masks = c->dalloc<uint8_t>(NB * HW);
+  c->d_packed = c->dalloc<uint8_t>(NB * ((HW + 7) / 8));
+  c->d_stats = c->dalloc<MaskStatsDev>(NB);
+  c->d_metrics = c->dalloc<ysi_mask_metrics>(NB);
+  c->d_mask_img = c->dalloc<int>(NB);
+  YSI_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// processing_sam.py:215-234: boxes (float32, original pixels) -> float64 in the resized frame
+void rescale_boxes(const float* boxes, int nb, int H, int W, std::vector<double>& out) {
+  const PostGeom g = make_post_geom(H, W);
+  out.resize(static_cast<size_t>(nb) * 4);
+  const double sx = static_cast<double>(g.rw) / W, sy = static_cast<double>(g.rh) / H;
+  for (int i = 0; i < nb; ++i) {
+    out[4 * i + 0] = static_cast<double>(boxes[4 * i + 0]) * sx;
+    out[4 * i + 1] = static_cast<double>(boxes[4 * i + 1]) * sy;
+    out[4 * i + 2] = static_cast<double>(boxes[4 * i + 2]) * sx;
+    out[4 * i + 3] = static_cast<double>(boxes[4 * i + 3]) * sy;
+  }
+}
+
+void check_batch(ysi_ctx* c, int n, int H, int W, int nb) {
+  YSI_CHECK(c->weights_loaded, "ysi_load_weights has not been called");
+  YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
+  YSI_CHECK(nb >= 0 && nb <= c->cfg.max_boxes, "box count exceeds max_boxes");
+  YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+  YSI_CHECK(H == 1024 && W == 1024, "this build runs the fused preprocess for 1024x1024 inputs only");
+}
+
+void stage_impl(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
+                const int32_t* box_counts) {
+  int nb = 0;
+  for (int i = 0; i < n; ++i) nb += box_counts[i];
+  check_batch(c, n, H, W, nb);
+  YSI_CHECK(row_stride >= 3 * W, "row_stride smaller than 3*W");
+  c->st_n = n; c->st_H = H; c->st_W = W; c->st_nb = nb;
+  const size_t img_bytes = static_cast<size_t>(H) * W * 3;
+  for (int i = 0; i < n; ++i)
+    YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
+                               static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->stream));
+  c->st_box_img.clear();
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < box_counts[i]; ++k) c->st_box_img.push_back(i);
+  if (nb > 0) {
+    std::vector<double> b1024;
+    rescale_boxes(boxes, nb, H, W, b1024);
+    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, b1024.data(), sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, c->st_box_img.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, c->st_box_img.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+  }
+  YSI_CUDA(cudaStreamSynchronize(c->stream));   // the host vectors above go out of scope
+}
+
+void compute_impl(ysi_ctx* c, ysi_timing* tm) {
+  const int n = c->st_n, H = c->st_H, W = c->st_W, nb = c->st_nb;
+  YSI_CHECK(n > 0, "no staged batch");
+  cudaStream_t s = c->stream;
+  YSI_CUDA(cudaEventRecord(c->ev[0], s));
+  if (nb > 0) {
+    launch_sum3(c->d_rgb, n, H, W, W * 3, c->d_sum3, s);
+    launch_preprocess_1024(c->d_rgb, n, W * 3, c->mean255, c->std255, nullptr, c->ew.a_patch, s);
+    c->launches += 2;
+  }
+  YSI_CUDA(cudaEventRecord(c->ev[1], s));
+  if (nb > 0) encoder_forward(c->enc, c->ew, n, c->d_emb, nullptr, s, &c->launches);
+  YSI_CUDA(cudaEventRecord(c->ev[2], s));
+  if (nb > 0) decoder_forward(c->dec, c->dw, c->d_emb, n, nb, c->d_low, nullptr, s, &c->launches);
+  YSI_CUDA(cudaEventRecord(c->ev[3], s));
+  if (nb > 0) {
+    launch_init_stats(c->d_stats, nb, s);
+    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), c->d_sum3, c->d_mask_img, c->d_masks, nullptr, c->d_stats, s);
+    c->launches += 2;
+  }
+  YSI_CUDA(cudaEventRecord(c->ev[4], s));
+  if (nb > 0) {
+    launch_contour_hull_disk(c->d_masks, nb, H, W, c->d_sum3, c->d_mask_img, c->d_stats, c->d_metrics, s);
+    c->launches += 1;
+  }
+  YSI_CUDA(cudaEventRecord(c->ev[5], s));
+  YSI_CUDA(cudaStreamSynchronize(s));
+  if (tm) {
+    std::memset(tm, 0, sizeof(*tm));
+    YSI_CUDA(cudaEventElapsedTime(&tm->preprocess_ms, c->ev[0], c->ev[1]));
+    YSI_CUDA(cudaEventElapsedTime(&tm->encoder_ms, c->ev[1], c->ev[2]));
+    YSI_CUDA(cudaEventElapsedTime(&tm->decoder_ms, c->ev[2], c->ev[3]));
+    YSI_CUDA(cudaEventElapsedTime(&tm->postprocess_ms, c->ev[3], c->ev[4]));
+    YSI_CUDA(cudaEventElapsedTime(&tm->metrics_ms, c->ev[4], c->ev[5]));
+    YSI_CUDA(cudaEventElapsedTime(&tm->total_ms, c->ev[0], c->ev[5]));
+  }
+}
+
+void fetch_impl(ysi_ctx* c, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
+  const int nb = c->st_nb;
+  if (nb <= 0) return;
+  const size_t HW = static_cast<size_t>(c->st_H) * c->st_W;
+  cudaStream_t s = c->stream;
+  if (packed_out) {
+    launch_packbits(c->d_masks, c->d_packed, nb, static_cast<long long>(HW), s);
+    c->launches += 1;
+    YSI_CUDA(cudaMemcpyAsync(packed_out, c->d_packed, static_cast<size_t>(nb) * ((HW + 7) / 8), cudaMemcpyDeviceToHost, s));
+  }
+  if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, c->d_masks, nb * HW, cudaMemcpyDeviceToHost, s));
+  if (metrics_out)
+    YSI_CUDA(cudaMemcpyAsync(metrics_out, c->d_metrics, sizeof(ysi_mask_metrics) * nb, cudaMemcpyDeviceToHost, s));
+  YSI_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ysi_version(void) { return 1; }
+
+int ysi_create(int device, const ysi_config* cfg, ysi_ctx** out) {
+  if (!cfg || !out) return -1;
+  ysi_ctx* c = new ysi_ctx();
+  c->device = device;
+  c->cfg = *cfg;
+  try {
+    YSI_CUDA(cudaSetDevice(device));
+    create_impl(c);
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+    *out = nullptr;
+    return -2;
+  }
+  *out = c;
+  return 0;
+}
+
+void ysi_destroy(ysi_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->allocs) cudaFree(p);
+  for (void* p : c->host_allocs) cudaFreeHost(p);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* ysi_last_error(const ysi_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+int64_t ysi_launch_count(const ysi_ctx* c) { return c ? c->launches : 0; }
+
+int ysi_load_weights(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
+  return guarded(c, [&] { load_weights_impl(c, tensors, n); });
+}
+
+int ysi_stage_batch(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
+                    const int32_t* box_counts) {
+  return guarded(c, [&] { stage_impl(c, n, rgb, H, W, row_stride, boxes, box_counts); });
+}
+
+int ysi_compute_staged(ysi_ctx* c, ysi_timing* tm) {
+  return guarded(c, [&] { compute_impl(c, tm); });
+}
+
+int ysi_fetch_staged(ysi_ctx* c, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
+  return guarded(c, [&] { fetch_impl(c, masks_out, packed_out, metrics_out); });
+}
+
+int ysi_run_batch(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
+                  const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out,
+                  ysi_timing* tm) {
+  return guarded(c, [&] {
+    cudaEvent_t e0 = c->ev[6], e1 = c->ev[7];
+    YSI_CUDA(cudaEventRecord(e0, c->stream));
+    stage_impl(c, n, rgb, H, W, row_stride, boxes, box_counts);
+    YSI_CUDA(cudaEventRecord(e1, c->stream));
+    ysi_timing t{};
+    compute_impl(c, &t);
+    YSI_CUDA(cudaEventElapsedTime(&t.h2d_ms, e0, e1));
+    YSI_CUDA(cudaEventRecord(e0, c->stream));
+    fetch_impl(c, masks_out, packed_out, metrics_out);
+    YSI_CUDA(cudaEventRecord(e1, c->stream));
+    YSI_CUDA(cudaEventSynchronize(e1));
+    YSI_CUDA(cudaEventElapsedTime(&t.d2h_ms, e0, e1));
+    t.total_ms += t.h2d_ms + t.d2h_ms;
+    if (tm) *tm = t;
+  });
+}
+
+int ysi_run(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, const float* boxes, int nb,
+            uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out, ysi_timing* tm) {
+  if (nb == 0) {                       // pipeline.py:176-179: SAM is skipped entirely
+    if (tm) std::memset(tm, 0, sizeof(*tm));
+    return c ? 0 : -1;
+  }
+  const uint8_t* imgs[1] = {rgb};
+  const int32_t counts[1] = {nb};
+  return ysi_run_batch(c, 1, imgs, H, W, row_stride, boxes, counts, masks_out, packed_out, metrics_out, tm);
+}
+
+// ------------------------------------------------------------------------------------------- stage API
+int ysi_preprocess(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, float* pixel_values_out) {
+  return guarded(c, [&] {
+    YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
+    YSI_CHECK(H == 1024 && W == 1024, "this build runs the fused preprocess for 1024x1024 inputs only");
+    if (!c->d_pix) c->d_pix = c->dalloc<float>(static_cast<size_t>(c->cfg.max_batch) * 3 * 1024 * 1024);
+    const size_t img_bytes = static_cast<size_t>(H) * W * 3;
+    for (int i = 0; i < n; ++i)
+      YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
+                                 static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->stream));
+    launch_preprocess_1024(c->d_rgb, n, W * 3, c->mean255, c->std255, c->d_pix, nullptr, c->stream);
+    c->launches += 1;
+    YSI_CUDA(cudaMemcpyAsync(pixel_values_out, c->d_pix, sizeof(float) * n * 3 * 1024 * 1024, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ysi_encode(ysi_ctx* c, int n, const float* pixel_values, float* emb_out, float* hidden_out) {
+  return guarded(c, [&] {
+    YSI_CHECK(c->weights_loaded, "ysi_load_weights has not been called");
+    YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
+    if (!c->d_pix) c->d_pix = c->dalloc<float>(static_cast<size_t>(c->cfg.max_batch) * 3 * 1024 * 1024);
+    const size_t T = static_cast<size_t>(n) * 4096, D = c->cfg.hidden_size;
+    YSI_CUDA(cudaMemcpyAsync(c->d_pix, pixel_values, sizeof(float) * n * 3 * 1024 * 1024, cudaMemcpyHostToDevice, c->stream));
+    launch_im2col_patch_f32(c->d_pix, n, c->ew.a_patch, c->stream);
+    c->launches += 1;
+    float* hid = nullptr;
+    if (hidden_out) {
+      const size_t need = (c->cfg.num_layers + 1) * T * D;
+      if (need > c->hidden_cap) { c->d_hidden = c->dalloc<float>(need); c->hidden_cap = need; }
+      hid = c->d_hidden;
+    }
+    encoder_forward(c->enc, c->ew, n, c->d_emb, hid, c->stream, &c->launches);
+    // token-major [n,4096,256] -> NCHW [n,256,64,64] on the host side of the copy (small)
+    std::vector<float> tm(T * 256);
+    YSI_CUDA(cudaMemcpyAsync(tm.data(), c->d_emb, sizeof(float) * T * 256, cudaMemcpyDeviceToHost, c->stream));
+    if (hidden_out)
+      YSI_CUDA(cudaMemcpyAsync(hidden_out, hid, sizeof(float) * (c->cfg.num_layers + 1) * T * D, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < n; ++b)
+      for (int t = 0; t < 4096; ++t)
+        for (int ch = 0; ch < 256; ++ch) emb_out[(static_cast<size_t>(b) * 256 + ch) * 4096 + t] = tm[(static_cast<size_t>(b) * 4096 + t) * 256 + ch];
+  });
+}
+
+int ysi_decode(ysi_ctx* c, const float* emb_nchw, const double* boxes_1024, int nb, float* low_res_out, float* sparse_out) {
+  return guarded(c, [&] {
+    YSI_CHECK(c->weights_loaded, "ysi_load_weights has not been called");
+    YSI_CHECK(nb >= 1 && nb <= c->cfg.max_boxes, "box count exceeds max_boxes");
+    std::vector<float> tm(4096 * 256);
+    for (int ch = 0; ch < 256; ++ch)
+      for (int t = 0; t < 4096; ++t) tm[static_cast<size_t>(t) * 256 + ch] = emb_nchw[static_cast<size_t>(ch) * 4096 + t];
+    std::vector<int> img(nb, 0);
+    YSI_CUDA(cudaMemcpyAsync(c->d_emb, tm.data(), sizeof(float) * 4096 * 256, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, boxes_1024, sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, img.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+    float* d_sparse = sparse_out ? c->dalloc<float>(static_cast<size_t>(nb) * 2 * 256) : nullptr;   // test API: freed with the ctx
+    decoder_forward(c->dec, c->dw, c->d_emb, 1, nb, c->d_low, d_sparse, c->stream, &c->launches);
+    YSI_CUDA(cudaMemcpyAsync(low_res_out, c->d_low, sizeof(float) * 65536 * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (sparse_out) YSI_CUDA(cudaMemcpyAsync(sparse_out, d_sparse, sizeof(float) * nb * 512, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ysi_postprocess(ysi_ctx* c, const float* low_res, int nb, int H, int W, uint8_t* masks_out, float* upsampled_out) {
+  return guarded(c, [&] {
+    YSI_CHECK(nb >= 1 && nb <= c->cfg.max_boxes, "box count exceeds max_boxes");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+    const size_t HW = static_cast<size_t>(H) * W;
+    YSI_CUDA(cudaMemcpyAsync(c->d_low, low_res, sizeof(float) * 65536 * nb, cudaMemcpyHostToDevice, c->stream));
+    float* d_up = nullptr;
+    if (upsampled_out) { YSI_CUDA(cudaMalloc(&d_up, sizeof(float) * nb * HW)); }
+    launch_init_stats(c->d_stats, nb, c->stream);
+    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), nullptr, nullptr, c->d_masks, d_up, c->d_stats, c->stream);
+    c->launches += 2;
+    if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, c->d_masks, nb * HW, cudaMemcpyDeviceToHost, c->stream));
+    if (upsampled_out) YSI_CUDA(cudaMemcpyAsync(upsampled_out, d_up, sizeof(float) * nb * HW, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    if (d_up) cudaFree(d_up);
+  });
+}
+
+int ysi_metrics(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, const uint8_t* masks, int nb,
+                ysi_mask_metrics* metrics_out) {
+  return guarded(c, [&] {
+    YSI_CHECK(nb >= 1 && nb <= c->cfg.max_boxes, "mask count exceeds max_boxes");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+    const size_t HW = static_cast<size_t>(H) * W;
+    YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb, static_cast<size_t>(W) * 3, rgb, row_stride, static_cast<size_t>(W) * 3, H,
+                               cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->d_masks, masks, nb * HW, cudaMemcpyHostToDevice, c->stream));
+    launch_sum3(c->d_rgb, 1, H, W, W * 3, c->d_sum3, c->stream);
+    launch_init_stats(c->d_stats, nb, c->stream);
+    launch_mask_stats(c->d_masks, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->stream);
+    launch_contour_hull_disk(c->d_masks, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->d_metrics, c->stream);
+    c->launches += 4;
+    YSI_CUDA(cudaMemcpyAsync(metrics_out, c->d_metrics, sizeof(ysi_mask_metrics) * nb, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ysi_gemm(ysi_ctx* c, const float* A, const float* W, const float* bias, int M, int N, int K, int act, float* C_out) {
+  return guarded(c, [&] {
+    std::vector<bf16> a = to_bf16(A, static_cast<size_t>(M) * K), w = to_bf16(W, static_cast<size_t>(N) * K);
+    bf16 *dA = nullptr, *dW = nullptr;
+    float *dC = nullptr, *dB = nullptr;
+    YSI_CUDA(cudaMalloc(&dA, a.size() * 2)); YSI_CUDA(cudaMalloc(&dW, w.size() * 2));
+    YSI_CUDA(cudaMalloc(&dC, sizeof(float) * M * N));
+    YSI_CUDA(cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    YSI_CUDA(cudaMemcpy(dW, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+    if (bias) { YSI_CUDA(cudaMalloc(&dB, sizeof(float) * N)); YSI_CUDA(cudaMemcpy(dB, bias, sizeof(float) * N, cudaMemcpyHostToDevice)); }
+    GemmEpilogue ep;
+    ep.bias = dB; ep.act = act; ep.out_f32 = dC; ep.ld_out = N;
+    gemm_bf16(dA, K, dW, K, M, N, K, ep, c->stream);
+    c->launches += 1;
+    YSI_CUDA(cudaMemcpyAsync(C_out, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(dA); cudaFree(dW); cudaFree(dC); if (dB) cudaFree(dB);
+  });
+}
+
+int ysi_attention(ysi_ctx* c, const float* qkv, const float* rel_h, const float* rel_w, int n_seq, int heads,
+                  int is_global, float* out) {
+  return guarded(c, [&] {
+    const int T = is_global ? 4096 : 196, S = is_global ? 64 : 14, D = heads * 64;
+    const size_t rows = static_cast<size_t>(n_seq) * T;
+    std::vector<bf16> q = to_bf16(qkv, rows * 3 * D);
+    std::vector<bf16> tab(256 * 64, __float2bfloat16(0.f));
+    for (int r = 0; r < 2 * S - 1; ++r)
+      for (int k = 0; k < 64; ++k) {
+        tab[r * 64 + k] = __float2bfloat16(rel_h[r * 64 + k]);
+        tab[(128 + r) * 64 + k] = __float2bfloat16(rel_w[r * 64 + k]);
+      }
+    bf16 *dq = nullptr, *dt = nullptr, *dout = nullptr;
+    YSI_CUDA(cudaMalloc(&dq, q.size() * 2)); YSI_CUDA(cudaMalloc(&dt, tab.size() * 2)); YSI_CUDA(cudaMalloc(&dout, rows * D * 2));
+    YSI_CUDA(cudaMemcpy(dq, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
+    YSI_CUDA(cudaMemcpy(dt, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
+    launch_encoder_attention(dq, dt, dout, n_seq, T, heads, is_global != 0, c->stream);
+    c->launches += 1;
+    std::vector<bf16> o(rows * D);
+    YSI_CUDA(cudaMemcpyAsync(o.data(), dout, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < o.size(); ++i) out[i] = __bfloat162float(o[i]);
+    cudaFree(dq); cudaFree(dt); cudaFree(dout);
+  });
+}
+
+int ysi_get_image_pe(ysi_ctx* c, float* out) {
+  return guarded(c, [&] {
+    YSI_CHECK(c->weights_loaded, "ysi_load_weights has not been called");
+    std::vector<float> tm(4096 * 256);
+    YSI_CUDA(cudaMemcpy(tm.data(), c->dec.image_pe, sizeof(float) * tm.size(), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < 4096; ++t)
+      for (int ch = 0; ch < 256; ++ch) out[static_cast<size_t>(ch) * 4096 + t] = tm[static_cast<size_t>(t) * 256 + ch];
+  });
+}
+
+}  // extern "C"

@@ -48,6 +48,7 @@ struct GemmEpilogue {
   const float* add_src = nullptr;  // optional fp32 [add_mod, ld_add] added after the activation
   int add_mod = 1;
   int ld_add = 0;
+  const int* add_group = nullptr;  // optional: add row = add_group[row / add_mod] * add_mod + row % add_mod
   const int* row_map = nullptr;  // optional destination row per GEMM row (<0: drop the row)
   float* out_f32 = nullptr;      // optional fp32 destination [*, ld_out]
   int accumulate = 0;            // out_f32 += value instead of =

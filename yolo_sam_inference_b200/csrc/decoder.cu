@@ -1,0 +1,613 @@
+// Prompt encoder + two-way-transformer mask decoder + ConvTranspose upscaler, batched over all boxes
+// (modeling_sam.py:546-566, 647-698, 273-405, 461-543).
+//
+// Image-side work (4096 tokens x 256 channels per box) runs on the tcgen05 GEMM:
+//   k/v/q projections of the cross attentions, the image->token out-projection (+ residual), and the
+//   two stride-2 transposed convolutions as GEMMs with fused LayerNorm/GELU/pixel-shuffle and
+//   GELU + hypernetwork-dot epilogues (the [32,256,256] upscaled embedding is never materialised).
+// Token-side work (7 tokens per box) runs in small fp32 CUDA-core kernels, one CTA per box.
+// Block-0 image-side projections are box independent (keys = image_emb + no_mask_embed for every box)
+// and are computed once per image.
+#include "gemm.cuh"
+#include "kernels.h"
+
+namespace ysi {
+
+constexpr int NT = 7;       // tokens per box: iou, 4 mask tokens, 2 box corners
+constexpr int C = 256;
+constexpr float TWO_PI = 6.283185307179586f;
+
+// ---------------------------------------------------------------------------------------------------
+// positional encoding (SamPositionalEmbedding.forward :552-566): c in [0,1]^2 -> [sin(2pi (2c-1)G), cos(...)]
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pe_encode(float cx, float cy, const float* __restrict__ gauss, int j, float& s, float& c) {
+  // coordinates @ positional_embedding ([..,2] x [2,128]) then * 2*pi, fp32
+  float v = __fadd_rn(__fmul_rn(cx, gauss[j]), __fmul_rn(cy, gauss[128 + j]));
+  v = __fmul_rn(TWO_PI, v);
+  s = sinf(v);
+  c = cosf(v);
+}
+
+// image-wide PE (:1128-1139): grid ((j+0.5)/64, (i+0.5)/64) -> token-major [4096,256]
+__global__ void image_pe_kernel(const float* __restrict__ gauss, float* __restrict__ pe) {
+  const int tok = blockIdx.x, j = threadIdx.x;   // 128 threads
+  const int i = tok >> 6, jj = tok & 63;
+  const float y = (static_cast<float>(i + 1) - 0.5f) / 64.0f, x = (static_cast<float>(jj + 1) - 0.5f) / 64.0f;
+  float s, c;
+  pe_encode(2.0f * x - 1.0f, 2.0f * y - 1.0f, gauss, j, s, c);
+  pe[tok * 256 + j] = s;
+  pe[tok * 256 + 128 + j] = c;
+}
+
+void launch_image_pe(const float* gauss, float* image_pe, cudaStream_t s) {
+  image_pe_kernel<<<4096, 128, 0, s>>>(gauss, image_pe);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// tokens [nb,7,256] = [iou_token; mask_tokens(4); corner1; corner2]  (:489-496, :647-656)
+__global__ void prompt_tokens_kernel(const double* __restrict__ boxes1024, DecoderW w, float* __restrict__ tok0,
+                                     float* __restrict__ sparse_out) {
+  const int b = blockIdx.x, t = threadIdx.x;   // 256 threads
+  float* out = tok0 + static_cast<size_t>(b) * NT * C;
+  out[t] = w.iou_token[t];
+  for (int m = 0; m < 4; ++m) out[(1 + m) * C + t] = w.mask_tokens[m * C + t];
+  const int j = t & 127;
+  for (int corner = 0; corner < 2; ++corner) {
+    // fp64: (box + 0.5) / 1024, 2c - 1; then cast to fp32 (:649-651, :556-562)
+    const double bx = (boxes1024[b * 4 + 2 * corner] + 0.5) / 1024.0;
+    const double by = (boxes1024[b * 4 + 2 * corner + 1] + 0.5) / 1024.0;
+    const float cx = static_cast<float>(2.0 * bx - 1.0), cy = static_cast<float>(2.0 * by - 1.0);
+    float s, c;
+    pe_encode(cx, cy, w.gauss, j, s, c);
+    const float v = (t < 128 ? s : c) + w.point_embed[(2 + corner) * C + t];
+    out[(5 + corner) * C + t] = v;
+    if (sparse_out) sparse_out[(static_cast<size_t>(b) * 2 + corner) * C + t] = v;
+  }
+}
+
+// keys0 = emb + no_mask_embed ; bf16 copies of keys0 and keys0 + pe   (:499, :320-321)
+__global__ void prep_keys_kernel(const float* __restrict__ emb, const float* __restrict__ no_mask,
+                                 const float* __restrict__ pe, long long n4, float* __restrict__ keys,
+                                 bf16* __restrict__ keys_bf, bf16* __restrict__ keyspos_bf) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i & 63);
+    const long long row = i >> 6;
+    float4 e = reinterpret_cast<const float4*>(emb)[i];
+    const float4 nm = reinterpret_cast<const float4*>(no_mask)[c4];
+    const float4 p = reinterpret_cast<const float4*>(pe)[(row & 4095) * 64 + c4];
+    e.x += nm.x; e.y += nm.y; e.z += nm.z; e.w += nm.w;
+    reinterpret_cast<float4*>(keys)[i] = e;
+    uint2 o;
+    o.x = pack_bf16x2(e.x, e.y); o.y = pack_bf16x2(e.z, e.w);
+    reinterpret_cast<uint2*>(keys_bf)[i] = o;
+    o.x = pack_bf16x2(e.x + p.x, e.y + p.y); o.y = pack_bf16x2(e.z + p.z, e.w + p.w);
+    reinterpret_cast<uint2*>(keyspos_bf)[i] = o;
+  }
+}
+
+// LayerNorm4 over per-box keys (warp per row) -> fp32 keys + bf16(keys) + bf16(keys + pe)   (:343-347)
+__global__ void __launch_bounds__(256)
+keys_ln_kernel(const float* __restrict__ in, long long rows, const float* __restrict__ g, const float* __restrict__ bta,
+               const float* __restrict__ pe, float* __restrict__ keys, bf16* __restrict__ keys_bf,
+               bf16* __restrict__ keyspos_bf) {
+  const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(in + row * C);
+  float4 v[2] = {xr[lane], xr[lane + 32]};
+  float sum = (v[0].x + v[0].y) + (v[0].z + v[0].w) + (v[1].x + v[1].y) + (v[1].z + v[1].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+  const float rstd = rsqrtf(sq / C + 1e-6f);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = lane + 32 * k;
+    const float4 gg = reinterpret_cast<const float4*>(g)[i], bb = reinterpret_cast<const float4*>(bta)[i];
+    const float4 p = reinterpret_cast<const float4*>(pe)[(row & 4095) * 64 + i];
+    float4 y;
+    y.x = (v[k].x - mean) * rstd * gg.x + bb.x; y.y = (v[k].y - mean) * rstd * gg.y + bb.y;
+    y.z = (v[k].z - mean) * rstd * gg.z + bb.z; y.w = (v[k].w - mean) * rstd * gg.w + bb.w;
+    reinterpret_cast<float4*>(keys + row * C)[i] = y;
+    uint2 o;
+    o.x = pack_bf16x2(y.x, y.y); o.y = pack_bf16x2(y.z, y.w);
+    reinterpret_cast<uint2*>(keys_bf + row * C)[i] = o;
+    o.x = pack_bf16x2(y.x + p.x, y.y + p.y); o.y = pack_bf16x2(y.z + p.z, y.w + p.w);
+    reinterpret_cast<uint2*>(keyspos_bf + row * C)[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// token-side building blocks (one CTA of 256 threads per box; activations in shared memory)
+// ---------------------------------------------------------------------------------------------------
+// y[r][n] = act(sum_k x[r][k] W[n][k] + b[n]) for r < 7. Warp per output column, lanes over K.
+__device__ void cta_linear(const float* x_s, int K, const float* __restrict__ W, const float* __restrict__ bias, int N,
+                           float* y_s, int ldy, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < N; n += 8) {
+    float acc[NT];
+#pragma unroll
+    for (int r = 0; r < NT; ++r) acc[r] = 0.f;
+    const float4* wr = reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K);
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      const float4 wv = __ldg(wr + k4);
+#pragma unroll
+      for (int r = 0; r < NT; ++r) {
+        const float4 xv = reinterpret_cast<const float4*>(x_s + r * K)[k4];
+        acc[r] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[r]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xFFFFFFFFu, acc[r], o);
+    }
+    if (lane == 0) {
+      const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+      for (int r = 0; r < NT; ++r) {
+        float v = acc[r] + b;
+        if (relu) v = fmaxf(v, 0.f);
+        y_s[r * ldy + n] = v;
+      }
+    }
+  }
+}
+
+// in-place LayerNorm of 7 rows of 256 in shared memory (warp r handles row r)
+__device__ void cta_layernorm(float* x_s, const float* __restrict__ g, const float* __restrict__ b, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < NT) {
+    float* row = x_s + warp * C;
+    float v[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = row[lane + 32 * k]; sum += v[k]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; sq += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+    const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) row[lane + 32 * k] = (v[k] - mean) * rstd * g[lane + 32 * k] + b[lane + 32 * k];
+  }
+}
+
+// TK1: self attention (+LN1) of the 7 tokens, then the token->image query projection   (:316-327)
+__global__ void __launch_bounds__(256)
+token_self_attn_kernel(DecLayerW lw, int first_layer, const float* __restrict__ tok0, float* __restrict__ queries,
+                       float* __restrict__ q_t2i) {
+  __shared__ __align__(16) float s_q[NT * C], s_in[NT * C], s_a[NT * C], s_b[NT * C], s_c[NT * C];
+  __shared__ float s_p[8 * NT * NT];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* pe = tok0 + static_cast<size_t>(b) * NT * C;
+  const float* qin = (first_layer ? tok0 : queries) + static_cast<size_t>(b) * NT * C;
+  for (int i = t; i < NT * C; i += 256) {
+    s_q[i] = qin[i];
+    s_in[i] = first_layer ? qin[i] : qin[i] + pe[i];    // q = k = queries (+ pe unless skip_first_layer_pe)
+  }
+  __syncthreads();
+  cta_linear(s_in, C, lw.self_attn.wq, lw.self_attn.bq, C, s_a, C, false);
+  cta_linear(s_in, C, lw.self_attn.wk, lw.self_attn.bk, C, s_b, C, false);
+  cta_linear(s_q, C, lw.self_attn.wv, lw.self_attn.bv, C, s_c, C, false);
+  __syncthreads();
+  // 8 heads x 32 dims, scale 32^-0.5
+  for (int i = t; i < 8 * NT * NT; i += 256) {
+    const int h = i / (NT * NT), r = (i / NT) % NT, c = i % NT;
+    float acc = 0.f;
+    for (int d = 0; d < 32; ++d) acc = fmaf(s_a[r * C + h * 32 + d], s_b[c * C + h * 32 + d], acc);
+    s_p[i] = acc * 0.17677669529663687f;
+  }
+  __syncthreads();
+  if (t < 8 * NT) {
+    float* row = s_p + t * NT;
+    float m = row[0];
+    for (int c = 1; c < NT; ++c) m = fmaxf(m, row[c]);
+    float sum = 0.f;
+    for (int c = 0; c < NT; ++c) { row[c] = expf(row[c] - m); sum += row[c]; }
+    for (int c = 0; c < NT; ++c) row[c] /= sum;
+  }
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) {
+    const int r = i / C, ch = i % C, h = ch / 32;
+    float acc = 0.f;
+    for (int c = 0; c < NT; ++c) acc = fmaf(s_p[(h * NT + r) * NT + c], s_c[c * C + ch], acc);
+    s_in[i] = acc;
+  }
+  __syncthreads();
+  cta_linear(s_in, C, lw.self_attn.wo, lw.self_attn.bo, C, s_a, C, false);
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) s_a[i] = first_layer ? s_a[i] : s_q[i] + s_a[i];
+  __syncthreads();
+  cta_layernorm(s_a, lw.ln1_g, lw.ln1_b, 1e-6f);
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) {
+    queries[static_cast<size_t>(b) * NT * C + i] = s_a[i];
+    s_in[i] = s_a[i] + pe[i];
+  }
+  __syncthreads();
+  cta_linear(s_in, C, lw.t2i.wq, lw.t2i.bq, 128, s_b, 128, false);
+  __syncthreads();
+  for (int i = t; i < NT * 128; i += 256) q_t2i[static_cast<size_t>(b) * NT * 128 + i] = s_b[i];
+}
+
+// token -> image attention core: 7 queries x 4096 keys, 8 heads x 16, scale 0.25; grid (8, nb)   (:324-327, :398-401)
+// K: fp32 rows of pitch ldk (head h at columns h*16..), V: pitch ldv. group: box -> source sequence (or null = box)
+__global__ void __launch_bounds__(256)
+t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ K, int ldk, const float* __restrict__ V,
+                     int ldv, const int* __restrict__ group, float* __restrict__ attn_out) {
+  extern __shared__ float s_sc[];              // [7][4096]
+  __shared__ float s_qh[NT * 16];
+  __shared__ float s_red[8 * NT];
+  __shared__ float s_max[NT], s_sum[NT];
+  __shared__ float s_part[2 * NT * 16];
+  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const size_t seq = group ? group[b] : b;
+  const float* Kb = K + seq * 4096 * ldk + h * 16;
+  const float* Vb = V + seq * 4096 * ldv + h * 16;
+  if (t < NT * 16) s_qh[t] = q_t2i[(static_cast<size_t>(b) * NT + t / 16) * 128 + h * 16 + (t % 16)];
+  __syncthreads();
+  float lmax[NT];
+#pragma unroll
+  for (int r = 0; r < NT; ++r) lmax[r] = -INFINITY;
+  for (int key = t; key < 4096; key += 256) {
+    const float4* kp = reinterpret_cast<const float4*>(Kb + static_cast<size_t>(key) * ldk);
+    const float4 k0 = __ldg(kp), k1 = __ldg(kp + 1), k2 = __ldg(kp + 2), k3 = __ldg(kp + 3);
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      const float* q = s_qh + r * 16;
+      float a = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w;
+      a += q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
+      a += q[8] * k2.x + q[9] * k2.y + q[10] * k2.z + q[11] * k2.w;
+      a += q[12] * k3.x + q[13] * k3.y + q[14] * k3.z + q[15] * k3.w;
+      a *= 0.25f;
+      s_sc[r * 4096 + key] = a;
+      lmax[r] = fmaxf(lmax[r], a);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax[r] = fmaxf(lmax[r], __shfl_xor_sync(0xFFFFFFFFu, lmax[r], o));
+    if (lane == 0) s_red[warp * NT + r] = lmax[r];
+  }
+  __syncthreads();
+  if (t < NT) {
+    float m = s_red[t];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w * NT + t]);
+    s_max[t] = m;
+  }
+  __syncthreads();
+  float lsum[NT];
+#pragma unroll
+  for (int r = 0; r < NT; ++r) lsum[r] = 0.f;
+  for (int key = t; key < 4096; key += 256) {
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      const float p = expf(s_sc[r * 4096 + key] - s_max[r]);
+      s_sc[r * 4096 + key] = p;
+      lsum[r] += p;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum[r] += __shfl_xor_sync(0xFFFFFFFFu, lsum[r], o);
+    if (lane == 0) s_red[warp * NT + r] = lsum[r];
+  }
+  __syncthreads();
+  if (t < NT) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_red[w * NT + t];
+    s_sum[t] = s;
+  }
+  __syncthreads();
+  // out[r][d] = sum_key p[r][key] V[key][d]; 224 threads = 2 key halves x 7 x 16
+  if (t < 2 * NT * 16) {
+    const int half = t / (NT * 16), idx = t % (NT * 16), r = idx / 16, d = idx % 16;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const float* pr = s_sc + r * 4096 + half * 2048;
+    const float* vp = Vb + static_cast<size_t>(half) * 2048 * ldv + d;
+    for (int key = 0; key < 2048; key += 4) {
+      acc0 = fmaf(pr[key], __ldg(vp + static_cast<size_t>(key) * ldv), acc0);
+      acc1 = fmaf(pr[key + 1], __ldg(vp + static_cast<size_t>(key + 1) * ldv), acc1);
+      acc2 = fmaf(pr[key + 2], __ldg(vp + static_cast<size_t>(key + 2) * ldv), acc2);
+      acc3 = fmaf(pr[key + 3], __ldg(vp + static_cast<size_t>(key + 3) * ldv), acc3);
+    }
+    s_part[t] = (acc0 + acc1) + (acc2 + acc3);
+  }
+  __syncthreads();
+  if (t < NT * 16) {
+    const int r = t / 16, d = t % 16;
+    attn_out[(static_cast<size_t>(b) * NT + r) * 128 + h * 16 + d] = (s_part[t] + s_part[NT * 16 + t]) / s_sum[r];
+  }
+}
+
+// TK2: queries += out_proj(attn) ; LN2 ; MLP ; LN3 ; image->token key/value projections   (:328-341)
+__global__ void __launch_bounds__(256)
+token_mlp_kernel(DecLayerW lw, const float* __restrict__ tok0, const float* __restrict__ attn_t2i,
+                 float* __restrict__ queries, float* __restrict__ k_tok, float* __restrict__ v_tok) {
+  extern __shared__ __align__(16) float s_dyn[];      // [7][2048] MLP hidden
+  __shared__ __align__(16) float s_q[NT * C], s_a[NT * C], s_at[NT * 128];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* pe = tok0 + static_cast<size_t>(b) * NT * C;
+  for (int i = t; i < NT * C; i += 256) s_q[i] = queries[static_cast<size_t>(b) * NT * C + i];
+  for (int i = t; i < NT * 128; i += 256) s_at[i] = attn_t2i[static_cast<size_t>(b) * NT * 128 + i];
+  __syncthreads();
+  cta_linear(s_at, 128, lw.t2i.wo, lw.t2i.bo, C, s_a, C, false);
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) s_q[i] += s_a[i];
+  __syncthreads();
+  cta_layernorm(s_q, lw.ln2_g, lw.ln2_b, 1e-6f);
+  __syncthreads();
+  cta_linear(s_q, C, lw.w_fc1, lw.b_fc1, 2048, s_dyn, 2048, true);
+  __syncthreads();
+  cta_linear(s_dyn, 2048, lw.w_fc2, lw.b_fc2, C, s_a, C, false);
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) s_q[i] += s_a[i];
+  __syncthreads();
+  cta_layernorm(s_q, lw.ln3_g, lw.ln3_b, 1e-6f);
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) {
+    queries[static_cast<size_t>(b) * NT * C + i] = s_q[i];
+    s_a[i] = s_q[i] + pe[i];
+  }
+  __syncthreads();
+  float* s_k = s_dyn;            // [7][128]
+  float* s_v = s_dyn + NT * 128;
+  cta_linear(s_a, C, lw.i2t.wk, lw.i2t.bk, 128, s_k, 128, false);
+  cta_linear(s_q, C, lw.i2t.wv, lw.i2t.bv, 128, s_v, 128, false);
+  __syncthreads();
+  for (int i = t; i < NT * 128; i += 256) {
+    k_tok[static_cast<size_t>(b) * NT * 128 + i] = s_k[i];
+    v_tok[static_cast<size_t>(b) * NT * 128 + i] = s_v[i];
+  }
+}
+
+// image -> token attention (:337-341): every image token attends over the 7 tokens of its box.
+// Q: fp32 [*,ldq] (columns 128..255 of the fused k|q projection). One thread = (token, head).
+__global__ void __launch_bounds__(256)
+i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict__ group, const float* __restrict__ k_tok,
+                     const float* __restrict__ v_tok, bf16* __restrict__ out) {
+  __shared__ float s_k[NT * 128], s_v[NT * 128];
+  const int b = blockIdx.y, t = threadIdx.x;
+  for (int i = t; i < NT * 128; i += 256) {
+    s_k[i] = k_tok[static_cast<size_t>(b) * NT * 128 + i];
+    s_v[i] = v_tok[static_cast<size_t>(b) * NT * 128 + i];
+  }
+  __syncthreads();
+  const int tok = blockIdx.x * 32 + (t >> 3), h = t & 7;
+  const size_t seq = group ? group[b] : b;
+  const float4* qp = reinterpret_cast<const float4*>(Q + (seq * 4096 + tok) * ldq + h * 16);
+  float q[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float4 v = __ldg(qp + i); q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w; }
+  float sc[NT], m = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) a = fmaf(q[d], s_k[r * 128 + h * 16 + d], a);
+    sc[r] = a * 0.25f;
+    m = fmaxf(m, sc[r]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < NT; ++r) { sc[r] = expf(sc[r] - m); sum += sc[r]; }
+  const float inv = 1.0f / sum;
+  float o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < NT; ++r) a = fmaf(sc[r], s_v[r * 128 + h * 16 + d], a);
+    o[d] = a * inv;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * 4096 + tok) * 128 + h * 16);
+  uint4 v0, v1;
+  v0.x = pack_bf16x2(o[0], o[1]); v0.y = pack_bf16x2(o[2], o[3]); v0.z = pack_bf16x2(o[4], o[5]); v0.w = pack_bf16x2(o[6], o[7]);
+  v1.x = pack_bf16x2(o[8], o[9]); v1.y = pack_bf16x2(o[10], o[11]); v1.z = pack_bf16x2(o[12], o[13]); v1.w = pack_bf16x2(o[14], o[15]);
+  dst[0] = v0;
+  dst[1] = v1;
+}
+
+// final token->image query projection (:394-398)
+__global__ void __launch_bounds__(256)
+token_final_q_kernel(DecAttnW aw, const float* __restrict__ tok0, const float* __restrict__ queries, float* __restrict__ q_t2i) {
+  __shared__ __align__(16) float s_in[NT * C], s_o[NT * 128];
+  const int b = blockIdx.x, t = threadIdx.x;
+  for (int i = t; i < NT * C; i += 256) s_in[i] = queries[static_cast<size_t>(b) * NT * C + i] + tok0[static_cast<size_t>(b) * NT * C + i];
+  __syncthreads();
+  cta_linear(s_in, C, aw.wq, aw.bq, 128, s_o, 128, false);
+  __syncthreads();
+  for (int i = t; i < NT * 128; i += 256) q_t2i[static_cast<size_t>(b) * NT * 128 + i] = s_o[i];
+}
+
+// queries += out_proj(attn); layer_norm_final_attn (eps 1e-5); hypernetwork MLP of mask token 0   (:401-404, :523-527)
+__global__ void __launch_bounds__(256)
+token_final_kernel(DecoderW w, const float* __restrict__ attn_t2i, const float* __restrict__ queries, float* __restrict__ hyper) {
+  __shared__ __align__(16) float s_q[NT * C], s_a[NT * C], s_at[NT * 128];
+  const int b = blockIdx.x, t = threadIdx.x;
+  for (int i = t; i < NT * C; i += 256) s_q[i] = queries[static_cast<size_t>(b) * NT * C + i];
+  for (int i = t; i < NT * 128; i += 256) s_at[i] = attn_t2i[static_cast<size_t>(b) * NT * 128 + i];
+  __syncthreads();
+  cta_linear(s_at, 128, w.final_attn.wo, w.final_attn.bo, C, s_a, C, false);
+  __syncthreads();
+  for (int i = t; i < NT * C; i += 256) s_q[i] += s_a[i];
+  __syncthreads();
+  cta_layernorm(s_q, w.lnf_g, w.lnf_b, 1e-5f);
+  __syncthreads();
+  // hypernetwork 0 on mask token 0 (= token index 1). cta_linear works on 7 rows; rows other than 1 are ignored.
+  cta_linear(s_q, C, w.hy_w0, w.hy_b0, C, s_a, C, true);
+  __syncthreads();
+  cta_linear(s_a, C, w.hy_w1, w.hy_b1, C, s_q, C, true);
+  __syncthreads();
+  cta_linear(s_q, C, w.hy_w2, w.hy_b2, 32, s_a, 32, false);
+  __syncthreads();
+  if (t < 32) hyper[b * 32 + t] = s_a[1 * 32 + t];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// upscaler epilogues
+// ---------------------------------------------------------------------------------------------------
+// ConvTranspose2d(256->64,k2,s2) as a GEMM with N = 4 sub-positions x 64 channels; per sub-position:
+// + bias, LayerNorm over the 64 channels (eps 1e-6), GELU, bf16, stored pixel-shuffled   (:515-520)
+struct EpiConvT1 {
+  const float *bias, *g, *b;
+  bf16* out;   // [nb*16384, 64]
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int BN) const {
+    const bool active = row < M;
+    const int box = row >> 12, tok = row & 4095, y = tok >> 6, x = tok & 63;
+    for (int sp = 0; sp < 4; ++sp) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_x32(taddr_row + sp * 64, r0);
+      tmem_ld_x32(taddr_row + sp * 64 + 32, r1);
+      tmem_ld_wait();
+      if (!active) continue;
+      float v[64];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        v[i] = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) + __ldg(bias + i);
+        sum += v[i];
+      }
+      const float mean = sum * (1.0f / 64.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; sq += d * d; }
+      const float rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-6f);
+      const int dy = sp >> 1, dx = sp & 1;
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(box) * 16384 + (2 * y + dy) * 128 + (2 * x + dx)) * 64);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = 8 * c + k;
+          u[k] = gelu_erf((v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i));
+        }
+        uint4 o;
+        o.x = pack_bf16x2(u[0], u[1]); o.y = pack_bf16x2(u[2], u[3]); o.z = pack_bf16x2(u[4], u[5]); o.w = pack_bf16x2(u[6], u[7]);
+        dst[c] = o;
+      }
+    }
+  }
+};
+
+// ConvTranspose2d(64->32,k2,s2) as a GEMM with N = 4 x 32; per sub-position: + bias, GELU, dot with the
+// box's hypernetwork vector -> one low-res logit   (:521, :531)
+struct EpiConvT2 {
+  const float* bias;    // [32]
+  const float* hyper;   // [nb,32]
+  float* low;           // [nb,256,256]
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int BN) const {
+    const bool active = row < M;
+    const int box = row >> 14, pos = row & 16383, Y = pos >> 7, X = pos & 127;
+    for (int sp = 0; sp < 4; ++sp) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr_row + sp * 32, r);
+      tmem_ld_wait();
+      if (!active) continue;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc = fmaf(gelu_erf(__uint_as_float(r[i]) + __ldg(bias + i)), __ldg(hyper + box * 32 + i), acc);
+      low[static_cast<size_t>(box) * 65536 + (2 * Y + (sp >> 1)) * 256 + 2 * X + (sp & 1)] = acc;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb, int n_img, int nb, float* low_res_out,
+                     float* sparse_out, cudaStream_t s, int64_t* launches) {
+  YSI_CHECK(n_img >= 1 && n_img <= wk.cap_img && nb >= 1 && nb <= wk.cap_box, "decoder batch exceeds the workspace");
+  int64_t nl = 0;
+  static bool attr = false;
+  if (!attr) {
+    YSI_CUDA(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT * 4096 * 4));
+    YSI_CUDA(cudaFuncSetAttribute(token_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT * 2048 * 4));
+    attr = true;
+  }
+  const int TI = n_img * 4096, TB = nb * 4096;
+  prompt_tokens_kernel<<<nb, 256, 0, s>>>(wk.boxes1024, w, wk.tok0, sparse_out); ++nl;
+  {
+    const long long n4 = static_cast<long long>(TI) * 64;
+    prep_keys_kernel<<<static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, s>>>(
+        emb, w.no_mask_embed, w.image_pe, n4, wk.keys0, wk.keys0_bf, wk.keyspos0_bf); ++nl;
+  }
+  YSI_CUDA(cudaGetLastError());
+  for (int li = 0; li < 2; ++li) {
+    const DecLayerW& lw = w.layers[li];
+    const bool per_img = li == 0;                       // block 0: keys are shared by all boxes of an image
+    const int rows = per_img ? TI : TB;
+    const bf16* a_keys = per_img ? wk.keys0_bf : wk.keys_bf;
+    const bf16* a_keyspos = per_img ? wk.keyspos0_bf : wk.keyspos_bf;
+    float* kq = per_img ? wk.kq0 : wk.kq;
+    float* v = per_img ? wk.v0 : wk.v;
+    const int* group = per_img ? wk.box_img : nullptr;
+    token_self_attn_kernel<<<nb, 256, 0, s>>>(lw, li == 0 ? 1 : 0, wk.tok0, wk.queries, wk.q_t2i); ++nl;
+    {
+      GemmEpilogue ep;
+      ep.bias = lw.b_kq_img; ep.out_f32 = kq; ep.ld_out = 256;
+      gemm_bf16(a_keyspos, C, lw.w_kq_img, C, rows, 256, C, ep, s); ++nl;
+      GemmEpilogue ev;
+      ev.bias = lw.t2i.bv; ev.out_f32 = v; ev.ld_out = 128;
+      gemm_bf16(a_keys, C, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
+    }
+    t2i_attention_kernel<<<dim3(8, nb), 256, NT * 4096 * 4, s>>>(wk.q_t2i, kq, 256, v, 128, group, wk.attn_t2i); ++nl;
+    token_mlp_kernel<<<nb, 256, NT * 2048 * 4, s>>>(lw, wk.tok0, wk.attn_t2i, wk.queries, wk.k_tok, wk.v_tok); ++nl;
+    i2t_attention_kernel<<<dim3(128, nb), 256, 0, s>>>(kq + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t); ++nl;
+    YSI_CUDA(cudaGetLastError());
+    {
+      // keys = keys_prev + out_proj(attn) ; then LN4
+      GemmEpilogue ep;
+      ep.bias = lw.i2t.bo; ep.out_f32 = wk.kq; ep.ld_out = 256;      // kq (per-box) is free now: reuse as pre-LN buffer
+      ep.add_src = per_img ? wk.keys0 : wk.keys; ep.ld_add = 256;
+      if (per_img) { ep.add_mod = 4096; ep.add_group = wk.box_img; } else { ep.add_mod = TB; }
+      // block 1 reads kq (q columns) in i2t above, which is complete before this GEMM starts (same stream)
+      gemm_bf16(wk.attn_i2t, 128, lw.w_i2t_out, 128, TB, 256, 128, ep, s); ++nl;
+      keys_ln_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(wk.kq, TB, lw.ln4_g, lw.ln4_b, w.image_pe, wk.keys, wk.keys_bf, wk.keyspos_bf); ++nl;
+      YSI_CUDA(cudaGetLastError());
+    }
+  }
+  // final token -> image attention (:394-404)
+  token_final_q_kernel<<<nb, 256, 0, s>>>(w.final_attn, wk.tok0, wk.queries, wk.q_t2i); ++nl;
+  {
+    GemmEpilogue ek;
+    ek.bias = w.final_attn.bk; ek.out_f32 = wk.kq; ek.ld_out = 256;    // K in columns 0..127 of kq
+    gemm_bf16(wk.keyspos_bf, C, w.w_k_final, C, TB, 128, C, ek, s); ++nl;
+    GemmEpilogue ev;
+    ev.bias = w.final_attn.bv; ev.out_f32 = wk.v; ev.ld_out = 128;
+    gemm_bf16(wk.keys_bf, C, w.w_v_final, C, TB, 128, C, ev, s); ++nl;
+  }
+  t2i_attention_kernel<<<dim3(8, nb), 256, NT * 4096 * 4, s>>>(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, wk.attn_t2i); ++nl;
+  token_final_kernel<<<nb, 256, 0, s>>>(w, wk.attn_t2i, wk.queries, wk.hyper); ++nl;
+  YSI_CUDA(cudaGetLastError());
+  // upscaler (:515-531)
+  {
+    const CUtensorMap tmA = make_tmap_bf16_2d(wk.keys_bf, TB, C, C, GEMM_BM);
+    const CUtensorMap tmB = make_tmap_bf16_2d(w.w_ct1, 256, C, C, 256);
+    EpiConvT1 e1{w.b_ct1, w.lnu_g, w.lnu_b, wk.up1};
+    launch_gemm<256>(tmA, tmB, TB, 256, C, e1, s); ++nl;
+    const int M2 = nb * 16384;
+    const CUtensorMap tmA2 = make_tmap_bf16_2d(wk.up1, M2, 64, 64, GEMM_BM);
+    const CUtensorMap tmB2 = make_tmap_bf16_2d(w.w_ct2, 128, 64, 64, 128);
+    EpiConvT2 e2{w.b_ct2, wk.hyper, low_res_out};
+    launch_gemm<128>(tmA2, tmB2, M2, 128, 64, e2, s); ++nl;
+  }
+  *launches += nl;
+}
+
+}  // namespace ysi

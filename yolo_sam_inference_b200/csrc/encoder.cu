@@ -1,0 +1,281 @@
+// SAM ViT image encoder assembly (modeling_sam.py:1058-1072): preprocessing, patch-embed im2col,
+// LayerNorm (+ window partition), neck; the contractions run on the tcgen05 GEMM / attention kernels.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ysi {
+
+// ------------------------------------------------------------------------------------------------
+// a1 at 1024x1024 (identity resize): (x - 255*mean) / (255*std) in fp32, exactly as tvF.normalize
+// (image_processing_backends.py rescale_and_normalize: mean,std pre-multiplied by 1/rescale_factor).
+// One thread = 8 horizontally adjacent pixels of one channel of one patch row.
+// A row (token) = patch (py,px); column = c*256 + ky*16 + kx   (Conv2d weight [D,3,16,16] flattened)
+// ------------------------------------------------------------------------------------------------
+__global__ void preprocess_1024_kernel(const uint8_t* __restrict__ rgb, int n, int row_stride,
+                                       float m0, float m1, float m2, float s0, float s1, float s2,
+                                       float* __restrict__ pix, bf16* __restrict__ a_patch) {
+  const long long total = static_cast<long long>(n) * 3 * 1024 * 128;   // 8-pixel groups
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(i & 127);
+    const int y = static_cast<int>((i >> 7) & 1023);
+    const int c = static_cast<int>((i >> 17) % 3);
+    const int b = static_cast<int>(i / (3ll << 17));
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const uint8_t* src = rgb + (static_cast<size_t>(b) * 1024 + y) * row_stride + static_cast<size_t>(xg) * 8 * 3 + c;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __fdiv_rn(__fsub_rn(static_cast<float>(src[3 * k]), mean), sd);
+    if (pix) {
+      float4* d = reinterpret_cast<float4*>(pix + ((static_cast<size_t>(b) * 3 + c) * 1024 + y) * 1024 + xg * 8);
+      d[0] = make_float4(v[0], v[1], v[2], v[3]);
+      d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (a_patch) {
+      const int py = y >> 4, ky = y & 15, px = xg >> 1, kx0 = (xg & 1) * 8;
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(a_patch + (static_cast<size_t>(b) * 4096 + py * 64 + px) * 768 + c * 256 + ky * 16 + kx0) = o;
+    }
+  }
+}
+
+void launch_preprocess_1024(const uint8_t* rgb, int n, int row_stride, const float* mean255, const float* std255,
+                            float* pixel_values, bf16* a_patch, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  preprocess_1024_kernel<<<grid, 256, 0, s>>>(rgb, n, row_stride, mean255[0], mean255[1], mean255[2], std255[0],
+                                              std255[1], std255[2], pixel_values, a_patch);
+  YSI_CUDA(cudaGetLastError());
+}
+
+__global__ void im2col_patch_f32_kernel(const float* __restrict__ pix, int n, bf16* __restrict__ a_patch) {
+  const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(i & 127);
+    const int y = static_cast<int>((i >> 7) & 1023);
+    const int c = static_cast<int>((i >> 17) % 3);
+    const int b = static_cast<int>(i / (3ll << 17));
+    const float4* sp = reinterpret_cast<const float4*>(pix + ((static_cast<size_t>(b) * 3 + c) * 1024 + y) * 1024 + xg * 8);
+    const float4 a = sp[0], d = sp[1];
+    const int py = y >> 4, ky = y & 15, px = xg >> 1, kx0 = (xg & 1) * 8;
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(d.x, d.y); o.w = pack_bf16x2(d.z, d.w);
+    *reinterpret_cast<uint4*>(a_patch + (static_cast<size_t>(b) * 4096 + py * 64 + px) * 768 + c * 256 + ky * 16 + kx0) = o;
+  }
+}
+
+void launch_im2col_patch_f32(const float* pixel_values, int n, bf16* a_patch, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  im2col_patch_f32_kernel<<<grid, 256, 0, s>>>(pixel_values, n, a_patch);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim of fp32 rows, one warp per OUTPUT row.
+//   WINDOWED: output rows are in window-partition order (25 windows x 196 per image, 64->70 zero pad,
+//             modeling_sam.py:900-922); pad rows are written as zeros (they become q=k=v=bias).
+// Output bf16 (GEMM operand) and/or fp32.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int window_row_to_token(int wrow) {   // row within one image's 4900 -> token or -1
+  const int w = wrow / 196, l = wrow - w * 196;
+  const int wy = w / 5, wx = w - wy * 5, ly = l / 14, lx = l - ly * 14;
+  const int y = wy * 14 + ly, x = wx * 14 + lx;
+  return (y < 64 && x < 64) ? y * 64 + x : -1;
+}
+
+template <bool WINDOWED>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, bf16* __restrict__ out_bf, float* __restrict__ out_f) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= rows_out) return;
+  int src_row = warp_global;
+  if (WINDOWED) {
+    const int img = warp_global / 4900;
+    const int tok = window_row_to_token(warp_global - img * 4900);
+    if (tok < 0) {
+      if (out_bf) {
+        uint4* o = reinterpret_cast<uint4*>(out_bf + static_cast<size_t>(warp_global) * D);
+        for (int i = lane; i < D / 8; i += 32) o[i] = make_uint4(0, 0, 0, 0);
+      }
+      return;
+    }
+    src_row = img * 4096 + tok;
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(src_row) * D);
+  constexpr int MAXV = 10;               // D <= 1280
+  float4 v[MAXV];
+  const int nv = D / 4;                  // float4 per row
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) { v[k] = xr[i]; sum += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  const float mean = sum / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+  const float rstd = rsqrtf(sq / D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const float4 g = __ldg(g4 + i), bb = __ldg(b4 + i);
+      float4 y;
+      y.x = (v[k].x - mean) * rstd * g.x + bb.x;
+      y.y = (v[k].y - mean) * rstd * g.y + bb.y;
+      y.z = (v[k].z - mean) * rstd * g.z + bb.z;
+      y.w = (v[k].w - mean) * rstd * g.w + bb.w;
+      if (out_f) reinterpret_cast<float4*>(out_f + static_cast<size_t>(warp_global) * D)[i] = y;
+      if (out_bf) {
+        uint2 o;
+        o.x = pack_bf16x2(y.x, y.y);
+        o.y = pack_bf16x2(y.z, y.w);
+        reinterpret_cast<uint2*>(out_bf + static_cast<size_t>(warp_global) * D)[i] = o;
+      }
+    }
+  }
+}
+
+void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
+                      bf16* out_bf, float* out_f, bool windowed, cudaStream_t s) {
+  YSI_CHECK(D % 8 == 0 && D <= 1280, "LayerNorm width must be a multiple of 8 and <= 1280");
+  const int blocks = ceil_div(rows_out, 8);
+  if (windowed)
+    layernorm_kernel<true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
+  else
+    layernorm_kernel<false><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
+  YSI_CUDA(cudaGetLastError());
+}
+
+__global__ void build_win_row_map_kernel(int* map, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = i / 4900;
+  const int tok = window_row_to_token(i - img * 4900);
+  map[i] = tok < 0 ? -1 : img * 4096 + tok;
+}
+
+void launch_build_win_row_map(int* map, int n_images, cudaStream_t s) {
+  const int total = n_images * 4900;
+  build_win_row_map_kernel<<<ceil_div(total, 256), 256, 0, s>>>(map, total);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// 3x3 / pad 1 im2col over the 64x64 token grid, 256 channels, tap-major columns:
+//   A[t, (ky*3+kx)*256 + c] = in[(y+ky-1, x+kx-1), c]  (zero outside the grid)
+__global__ void im2col_3x3_kernel(const bf16* __restrict__ in, int n, bf16* __restrict__ out) {
+  const long long total = static_cast<long long>(n) * 4096 * 9 * 32;   // uint4 (8 channel) groups
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i & 31);
+    const int tap = static_cast<int>((i >> 5) % 9);
+    const long long t = i / (9 * 32);
+    const int tok = static_cast<int>(t & 4095);
+    const int b = static_cast<int>(t >> 12);
+    const int y = (tok >> 6) + tap / 3 - 1, x = (tok & 63) + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < 64 && x >= 0 && x < 64)
+      v = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(b) * 4096 + y * 64 + x) * 256 + cg * 8);
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * 2304 + tap * 256 + cg * 8) = v;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* emb_out, float* hidden_dump,
+                     cudaStream_t s, int64_t* launches) {
+  YSI_CHECK(n >= 1 && n <= work.cap, "encoder batch exceeds the workspace");
+  const int D = w.D, T = n * 4096, TW = n * 4900;
+  int64_t nl = 0;
+  // patch embed: x = A * Wp^T + b + pos_embed   (modeling_sam.py:128, 1065-1066)
+  {
+    GemmEpilogue ep;
+    ep.bias = w.b_patch; ep.add_src = w.pos_embed; ep.add_mod = 4096; ep.ld_add = D;
+    ep.out_f32 = work.x; ep.ld_out = D;
+    gemm_bf16(work.a_patch, 768, w.w_patch, 768, T, D, 768, ep, s); ++nl;
+  }
+  if (hidden_dump) YSI_CUDA(cudaMemcpyAsync(hidden_dump, work.x, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, s));
+  for (int li = 0; li < w.L; ++li) {
+    const EncoderLayerW& lw = w.layers[li];
+    const bool glob = lw.is_global != 0;
+    const int rows = glob ? T : TW;
+    launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s); ++nl;
+    {
+      GemmEpilogue ep;
+      ep.bias = lw.b_qkv; ep.out_bf16 = work.qkv; ep.ld_out_bf16 = 3 * D;
+      gemm_bf16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
+    }
+    launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, glob, s); ++nl;
+    {
+      GemmEpilogue ep;   // x += attn * Wproj^T + b ; windowed rows scatter back through the partition map
+      ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
+      ep.row_map = glob ? nullptr : work.win_row_map;
+      gemm_bf16(work.attn, D, lw.w_proj, D, rows, D, D, ep, s); ++nl;
+    }
+    launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s); ++nl;
+    {
+      GemmEpilogue ep;
+      ep.bias = lw.b_fc1; ep.act = ACT_GELU; ep.out_bf16 = work.u; ep.ld_out_bf16 = w.mlp;
+      gemm_bf16(work.h, D, lw.w_fc1, D, T, w.mlp, D, ep, s); ++nl;
+    }
+    {
+      GemmEpilogue ep;
+      ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
+      gemm_bf16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
+    }
+    if (hidden_dump)
+      YSI_CUDA(cudaMemcpyAsync(hidden_dump + static_cast<size_t>(li + 1) * T * D, work.x, sizeof(float) * T * D,
+                               cudaMemcpyDeviceToDevice, s));
+  }
+  // neck (modeling_sam.py:985-992): 1x1 conv -> LN2d -> 3x3 conv -> LN2d, all in token-major (NHWC) layout
+  {
+    const long long n8 = static_cast<long long>(T) * D / 8;
+    cast_bf16_kernel<<<static_cast<int>(std::min<long long>((n8 + 255) / 256, 148 * 16)), 256, 0, s>>>(work.x, work.h, n8);
+    YSI_CUDA(cudaGetLastError()); ++nl;
+    GemmEpilogue ep;
+    ep.out_f32 = work.n1; ep.ld_out = 256;
+    gemm_bf16(work.h, D, w.w_neck1, D, T, 256, D, ep, s); ++nl;
+    launch_layernorm(work.n1, T, 256, w.neck_ln1_g, w.neck_ln1_b, 1e-6f, work.n1b, nullptr, false, s); ++nl;
+    const long long tot = static_cast<long long>(T) * 9 * 32;
+    im2col_3x3_kernel<<<static_cast<int>(std::min<long long>((tot + 255) / 256, 148 * 16)), 256, 0, s>>>(work.n1b, n, work.a_neck);
+    YSI_CUDA(cudaGetLastError()); ++nl;
+    GemmEpilogue ep2;
+    ep2.out_f32 = work.n2; ep2.ld_out = 256;
+    gemm_bf16(work.a_neck, 2304, w.w_neck2, 2304, T, 256, 2304, ep2, s); ++nl;
+    launch_layernorm(work.n2, T, 256, w.neck_ln2_g, w.neck_ln2_b, 1e-6f, nullptr, emb_out, false, s); ++nl;
+  }
+  *launches += nl;
+}
+
+}  // namespace ysi

@@ -35,7 +35,11 @@ struct EpiGeneric {
     int drow = -1;
     if (row < M) drow = p.row_map ? p.row_map[row] : row;
     const bool active = drow >= 0;
-    const float* addp = (active && p.add_src) ? p.add_src + static_cast<size_t>(row % p.add_mod) * p.ld_add : nullptr;
+    const float* addp = nullptr;
+    if (active && p.add_src) {
+      const int arow = p.add_group ? p.add_group[row / p.add_mod] * p.add_mod + row % p.add_mod : row % p.add_mod;
+      addp = p.add_src + static_cast<size_t>(arow) * p.ld_add;
+    }
     for (int c = 0; c < BN; c += 32) {
       const int col0 = n0 + c;
       if (col0 >= N) break;          // uniform; N is a multiple of 32 (checked on the host)

@@ -39,4 +39,104 @@ void launch_packbits(const uint8_t* masks, uint8_t* packed, int nmask, long long
 // uint8 RGB [n,H,W,3] (pitch row_stride) -> R+G+B uint16 planes
 void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, cudaStream_t s);
 
+// ------------------------------------------------------------------ encoder
+// fused flash-style attention with decomposed rel-pos bias (attn.cu)
+void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads,
+                              bool is_global, cudaStream_t stream);
+
+struct EncoderLayerW {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const bf16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
+  const float *b_qkv, *b_proj, *b_fc1, *b_fc2;
+  const bf16* rel_tab;   // [256,64]: rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
+  int is_global;
+};
+
+struct EncoderW {
+  int D, L, heads, mlp;
+  const bf16* w_patch;    // [D, 768]
+  const float* b_patch;   // [D]
+  const float* pos_embed; // [4096, D]
+  const EncoderLayerW* layers;   // host array, L entries
+  const bf16* w_neck1;    // [256, D]
+  const float *neck_ln1_g, *neck_ln1_b;
+  const bf16* w_neck2;    // [256, 9*256]  (tap-major: [(ky*3+kx)*256 + cin])
+  const float *neck_ln2_g, *neck_ln2_b;
+};
+
+struct EncoderWork {      // activation workspace for `cap` images
+  int cap;
+  bf16* a_patch;          // [cap*4096, 768]
+  float* x;               // [cap*4096, D]   fp32 residual stream
+  bf16* h;                // [cap*4900, D]
+  bf16* qkv;              // [cap*4900, 3D]
+  bf16* attn;             // [cap*4900, D]
+  bf16* u;                // [cap*4096, mlp]
+  float* n1;              // [cap*4096, 256]
+  bf16* n1b;              // [cap*4096, 256]
+  bf16* a_neck;           // [cap*4096, 2304]
+  float* n2;              // [cap*4096, 256]
+  const int* win_row_map; // [cap*4900] window row -> token row (or -1)
+};
+
+// uint8 RGB [n,1024,1024,3] (pitch row_stride bytes) -> normalised pixel_values fp32 [n,3,1024,1024] (optional)
+// and/or the patch-embed A matrix bf16 [n*4096, 768]
+void launch_preprocess_1024(const uint8_t* rgb, int n, int row_stride, const float* mean255, const float* std255,
+                            float* pixel_values, bf16* a_patch, cudaStream_t s);
+void launch_im2col_patch_f32(const float* pixel_values, int n, bf16* a_patch, cudaStream_t s);
+void launch_build_win_row_map(int* map, int n_images, cudaStream_t s);
+void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
+                      bf16* out_bf, float* out_f, bool windowed, cudaStream_t s);
+// runs the whole encoder on work.a_patch (n images); result: image embeddings fp32 token-major [n*4096, 256].
+// hidden_dump (optional, device) fp32 [(L+1), n*4096, D]
+void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* emb_out, float* hidden_dump,
+                     cudaStream_t s, int64_t* launches);
+
+// ------------------------------------------------------------------ prompt encoder + mask decoder
+struct DecAttnW {          // SamAttention weights, fp32 (token-side use)
+  const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+};
+struct DecLayerW {
+  DecAttnW self_attn, t2i, i2t;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b, *ln4_g, *ln4_b;
+  const float *w_fc1, *b_fc1, *w_fc2, *b_fc2;       // 256 -> 2048 -> 256 (ReLU)
+  const bf16* w_kq_img;    // [256,256]: rows 0..127 t2i.k_proj, rows 128..255 i2t.q_proj  (input keys + pos)
+  const float* b_kq_img;   // [256]
+  const bf16* w_v_img;     // [128,256] t2i.v_proj (input keys)
+  const bf16* w_i2t_out;   // [256,128] i2t.out_proj
+};
+struct DecoderW {
+  const float* gauss;          // [2,128] shared_image_embedding.positional_embedding
+  const float* point_embed;    // [4,256]
+  const float* no_mask_embed;  // [256]
+  const float* iou_token;      // [256]
+  const float* mask_tokens;    // [4,256]
+  DecLayerW layers[2];
+  DecAttnW final_attn;
+  const bf16 *w_k_final, *w_v_final;     // [128,256]
+  const float *lnf_g, *lnf_b;
+  const bf16* w_ct1;           // [256 = (dy,dx,o64), 256]
+  const float *b_ct1, *lnu_g, *lnu_b;    // [64]
+  const bf16* w_ct2;           // [128 = (dy,dx,o32), 64]
+  const float* b_ct2;          // [32]
+  const float *hy_w0, *hy_b0, *hy_w1, *hy_b1, *hy_w2, *hy_b2;   // hypernetwork MLP of mask token 0
+  const float* image_pe;       // [4096,256] token-major, built at weight load
+};
+struct DecoderWork {           // workspace for cap_img images and cap_box boxes
+  int cap_img, cap_box;
+  float* keys0;  bf16* keys0_bf;  bf16* keyspos0_bf;    // [cap_img*4096, 256]
+  float* kq0;    float* v0;                              // [cap_img*4096, 256] / [cap_img*4096,128]
+  float* keys;   bf16* keys_bf;   bf16* keyspos_bf;      // [cap_box*4096, 256] per-box keys
+  float* kq;     float* v;                               // [cap_box*4096, 256] / [.,128]
+  bf16* attn_i2t;                                        // [cap_box*4096, 128]
+  bf16* up1;                                             // [cap_box*16384, 64]
+  float *tok0, *queries, *q_t2i, *attn_t2i, *k_tok, *v_tok, *hyper;   // token-side [cap_box, 7, *]
+  double* boxes1024;  int* box_img;                      // [cap_box,4] / [cap_box]
+};
+void launch_image_pe(const float* gauss, float* image_pe, cudaStream_t s);
+// emb: image embeddings fp32 token-major [n_img*4096,256]; boxes1024 (device, fp64 [nb,4]) and box_img
+// (device int [nb]) live in work.  low_res_out: device fp32 [nb,256,256]; sparse_out optional [nb,2,256]
+void decoder_forward(const DecoderW& w, const DecoderWork& work, const float* emb, int n_img, int nb,
+                     float* low_res_out, float* sparse_out, cudaStream_t s, int64_t* launches);
+
 }  // namespace ysi

@@ -1,0 +1,311 @@
+"""SamStage: host-side mirror of the reference's SAM stage, executing on libysi.so (sm_100a CUDA).
+
+Replaces, for one image, the loop body of CellSegmentationPipeline.process_single_image
+(/root/reference/src/yolo_sam_inference/pipeline.py:161-175): SamProcessor preprocessing, per-box
+SamModel forward (:89-124), post_process_masks + threshold, and calculate_metrics
+(utils/metrics.py:9-119).  Inputs and outputs keep the reference's types:
+
+    run(image uint8[H,W,3] RGB, boxes float32[N,4] xyxy)
+        -> masks bool[N,H,W], metrics list[dict] (the 16 keys / python types of metrics.py:102-119),
+           crops list[uint8[h,w,3]] (image[y1:y2, x1:x2] with box.astype(int), pipeline.py:379)
+
+There is no CPU or PyTorch fallback: construction fails if the CUDA library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from fractions import Fraction
+from math import sqrt
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from .weights import SamVariant, variant_of
+
+
+def _perimeter_weights() -> np.ndarray:
+    # skimage.measure.perimeter weights (see oracle/metrics_oracle.py for the derivation)
+    w = np.zeros(50, dtype=np.float64)
+    w[[5, 7, 15, 17, 25, 27]] = 1
+    w[[21, 33]] = sqrt(2)
+    w[[13, 23]] = (1 + sqrt(2)) / 2
+    return w
+
+
+_PERIM_W = _perimeter_weights()
+
+
+def _perimeter_from_bins(bins: np.ndarray) -> float:
+    hist = np.zeros(50, dtype=np.int64)
+    hist[list(nat.PERIM_CODES)] = bins.astype(np.int64)
+    return float(hist @ _PERIM_W)          # the very reduction skimage performs
+
+
+def metrics_from_raw(raw: np.void, on_empty: str = "raise") -> Dict[str, Any]:
+    """ysi_mask_metrics row -> the dict of utils/metrics.py:102-119 (same keys, order and python types).
+
+    Every integer comes straight from the CUDA kernels; the float64 scalars are formed here with the
+    reference's own formulas (:62-100).  An empty mask raises IndexError like metrics.py:28 does
+    (``on_empty="raise"``, parity) or yields an all-zero row (``on_empty="zeros"``).
+    """
+    area = int(raw["area"])
+    if area == 0:
+        if on_empty == "raise":
+            raise IndexError("list index out of range")     # regionprops(mask)[0] on an empty mask
+        return {"deformability": 1.0, "area": 0, "area_ratio": 0.0, "circularity": 0.0, "convex_hull_area": 0,
+                "mask_x_length": 0, "mask_y_length": 0, "min_x": 0, "min_y": 0, "max_x": 0, "max_y": 0,
+                "mean_brightness": 0.0, "brightness_std": 0.0, "perimeter": 0.0, "aspect_ratio": 0.0,
+                "convex_hull_perimeter": 0.0}
+    degenerate = bool(int(raw["flags"]) & nat.FLAG_HULL_DEGENERATE)
+    perimeter = _perimeter_from_bins(raw["perim_hist"])                                   # :65
+    convex_hull_area = 0 if degenerate else int(raw["hull_area"])                           # :68
+    convex_hull_perimeter = 0 if degenerate else _perimeter_from_bins(raw["hull_perim_hist"])   # :69
+    area_ratio = convex_hull_area / area if area > 0 else 0                                 # :72
+    circularity = (2 * np.sqrt(np.pi * convex_hull_area)) / convex_hull_perimeter \
+        if convex_hull_perimeter > 0 else 0                                                 # :75
+    deformability = 1 - circularity                                                         # :78
+    n, s1, s2 = int(raw["disk_n"]), int(raw["disk_sum"]), int(raw["disk_sumsq"])
+    if n > 0:                                                                               # :92-94
+        mean_brightness = float(Fraction(s1, 3 * n))
+        brightness_std = sqrt(float(Fraction(n * s2 - s1 * s1, 9 * n * n)))
+    else:
+        mean_brightness = 0
+        brightness_std = 0
+    min_x, min_y, max_x, max_y = (int(raw["min_r"]), int(raw["min_c"]), int(raw["max_r"]), int(raw["max_c"]))  # :97
+    aspect_ratio = (max_x - min_x) / (max_y - min_y) if (max_x - min_x) > 0 and (max_y - min_y) > 0 else 0
+    return {
+        "deformability": float(deformability),
+        "area": int(area),
+        "area_ratio": float(area_ratio),
+        "circularity": float(circularity),
+        "convex_hull_area": int(convex_hull_area),
+        "mask_x_length": int(max_x - min_x),
+        "mask_y_length": int(max_y - min_y),
+        "min_x": int(min_x),
+        "min_y": int(min_y),
+        "max_x": int(max_x),
+        "max_y": int(max_y),
+        "mean_brightness": float(mean_brightness),
+        "brightness_std": float(brightness_std),
+        "perimeter": float(perimeter),
+        "aspect_ratio": float(aspect_ratio),
+        "convex_hull_perimeter": float(convex_hull_perimeter),
+    }
+
+
+def parse_device(device: str) -> int:
+    """'cuda' / 'cuda:3' -> CUDA device index. 'cpu' is refused: this path has no CPU fallback."""
+    d = str(device)
+    if d == "cuda":
+        return 0
+    if d.startswith("cuda:"):
+        return int(d.split(":", 1)[1])
+    raise ValueError(f"SamStage runs on a B200 only (device={device!r}); the CPU path is the reference's")
+
+
+class SamStage:
+    """One context per (GPU, worker); not thread-safe; distinct instances are independent."""
+
+    def __init__(self, sam_model_type: str = "facebook/sam-vit-huge", device: str = "cuda",
+                 state_dict: Optional[Dict[str, Any]] = None, max_batch: int = 8, max_boxes: int = 64,
+                 max_image_hw: Tuple[int, int] = (1024, 1024), on_empty: str = "raise"):
+        self.variant: SamVariant = variant_of(sam_model_type)
+        self.device_index = parse_device(device)
+        self.on_empty = on_empty
+        self.max_batch, self.max_boxes = int(max_batch), int(max_boxes)
+        self._lib = nat.load()
+        cfg = nat.YsiConfig()
+        v = self.variant
+        cfg.hidden_size, cfg.num_layers, cfg.num_heads, cfg.mlp_dim = v.hidden_size, v.num_layers, v.num_heads, v.mlp_dim
+        cfg.num_global = len(v.global_attn_indexes)
+        for i, g in enumerate(v.global_attn_indexes):
+            cfg.global_attn_indexes[i] = g
+        cfg.max_batch, cfg.max_boxes = self.max_batch, self.max_boxes
+        cfg.max_image_h, cfg.max_image_w = int(max_image_hw[0]), int(max_image_hw[1])
+        self._ctx = nat._ctx()
+        rc = self._lib.ysi_create(self.device_index, C.byref(cfg), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.ysi_last_error(None)
+            self._ctx = None
+            raise RuntimeError(f"ysi_create failed ({rc}): {msg.decode() if msg else '?'}")
+        self.last_timing: Dict[str, float] = {}
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------ lifecycle
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self._lib.ysi_last_error(self._ctx)
+            raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+    def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
+        """Upload SamModel.state_dict() (torch tensors or numpy arrays, any float dtype)."""
+        keep: List[np.ndarray] = []
+        descs = (nat.YsiTensorDesc * len(state_dict))()
+        for i, (name, t) in enumerate(state_dict.items()):
+            if hasattr(t, "detach"):
+                t = t.detach().float().cpu().numpy()
+            a = np.ascontiguousarray(t, dtype=np.float32)
+            keep.append(a)
+            descs[i].name = name.encode()
+            descs[i].data = nat.as_f32p(a)
+            descs[i].ndim = a.ndim
+            for k in range(a.ndim):
+                descs[i].shape[k] = a.shape[k]
+        self._check(self._lib.ysi_load_weights(self._ctx, descs, len(state_dict)), "ysi_load_weights")
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.ysi_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ysi_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ the hot path
+    def run(self, image: np.ndarray, boxes: np.ndarray, want_masks: bool = True
+            ) -> Tuple[np.ndarray, List[Dict[str, Any]], List[np.ndarray]]:
+        out = self.run_batch([image], [boxes], want_masks=want_masks)
+        return out[0]
+
+    def run_batch(self, images: Sequence[np.ndarray], boxes: Sequence[np.ndarray], want_masks: bool = True,
+                  raw: bool = False):
+        """Process several same-sized images in one call. Returns a list of (masks, metrics, crops)."""
+        n = len(images)
+        assert n == len(boxes) and n >= 1
+        H, W = images[0].shape[:2]
+        imgs = []
+        for im in images:
+            assert im.dtype == np.uint8 and im.ndim == 3 and im.shape == (H, W, 3), "images must be uint8 [H,W,3], same size"
+            imgs.append(im if im.strides[2] == 1 and im.strides[1] == 3 else np.ascontiguousarray(im))
+        counts = np.array([len(b) for b in boxes], dtype=np.int32)
+        nb = int(counts.sum())
+        if nb == 0:                                   # pipeline.py:176-179
+            return [(np.zeros((0, H, W), bool), [], []) for _ in range(n)]
+        allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
+        row_stride = imgs[0].strides[0]
+        assert all(im.strides[0] == row_stride for im in imgs)
+        ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in imgs])
+        masks = np.empty((nb, H, W), np.uint8) if want_masks else None
+        rows = np.zeros(nb, dtype=nat.METRICS_DTYPE)
+        tm = nat.YsiTiming()
+        self._check(self._lib.ysi_run_batch(self._ctx, n, ptrs, H, W, row_stride, nat.as_f32p(allb), nat.as_i32p(counts),
+                                            nat.as_u8p(masks), None, rows.ctypes.data_as(C.c_void_p), C.byref(tm)),
+                    "ysi_run_batch")
+        self.last_timing = tm.as_dict()
+        out = []
+        k = 0
+        for i in range(n):
+            c = int(counts[i])
+            m = masks[k:k + c].view(bool) if want_masks else None
+            r = rows[k:k + c]
+            mets = r if raw else [metrics_from_raw(r[j], self.on_empty) for j in range(c)]
+            crops = []
+            for bx in np.asarray(boxes[i], np.float32).reshape(-1, 4):
+                x1, y1, x2, y2 = bx.astype(int)
+                crops.append(images[i][max(y1, 0):max(y2, 0), max(x1, 0):max(x2, 0)])
+            out.append((m, mets, crops))
+            k += c
+        return out
+
+    # split form (bench.py times the device-resident leg on its own)
+    def stage_batch(self, images: Sequence[np.ndarray], boxes: Sequence[np.ndarray]) -> int:
+        n = len(images)
+        H, W = images[0].shape[:2]
+        counts = np.array([len(b) for b in boxes], dtype=np.int32)
+        allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
+        ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in images])
+        self._check(self._lib.ysi_stage_batch(self._ctx, n, ptrs, H, W, images[0].strides[0], nat.as_f32p(allb),
+                                              nat.as_i32p(counts)), "ysi_stage_batch")
+        self._staged = (int(counts.sum()), H, W)
+        return int(counts.sum())
+
+    def compute_staged(self) -> Dict[str, float]:
+        tm = nat.YsiTiming()
+        self._check(self._lib.ysi_compute_staged(self._ctx, C.byref(tm)), "ysi_compute_staged")
+        self.last_timing = tm.as_dict()
+        return self.last_timing
+
+    def fetch_staged(self, want_masks: bool = True):
+        nb, H, W = self._staged
+        masks = np.empty((nb, H, W), np.uint8) if want_masks else None
+        rows = np.zeros(nb, dtype=nat.METRICS_DTYPE)
+        self._check(self._lib.ysi_fetch_staged(self._ctx, nat.as_u8p(masks), None, rows.ctypes.data_as(C.c_void_p)),
+                    "ysi_fetch_staged")
+        return masks, rows
+
+    # ------------------------------------------------------------------ stage-level API (parity tests)
+    def preprocess(self, images: Sequence[np.ndarray]) -> np.ndarray:
+        n = len(images)
+        H, W = images[0].shape[:2]
+        imgs = [np.ascontiguousarray(im) for im in images]
+        ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in imgs])
+        out = np.empty((n, 3, 1024, 1024), np.float32)
+        self._check(self._lib.ysi_preprocess(self._ctx, n, ptrs, H, W, imgs[0].strides[0], nat.as_f32p(out)), "ysi_preprocess")
+        return out
+
+    def encode(self, pixel_values: np.ndarray, want_hidden: bool = False):
+        pv = np.ascontiguousarray(pixel_values, np.float32)
+        n = pv.shape[0]
+        emb = np.empty((n, 256, 64, 64), np.float32)
+        hid = np.empty((self.variant.num_layers + 1, n, 64, 64, self.variant.hidden_size), np.float32) if want_hidden else None
+        self._check(self._lib.ysi_encode(self._ctx, n, nat.as_f32p(pv), nat.as_f32p(emb), nat.as_f32p(hid)), "ysi_encode")
+        return (emb, hid) if want_hidden else emb
+
+    def decode(self, image_embeddings: np.ndarray, boxes_1024: np.ndarray, want_sparse: bool = False):
+        emb = np.ascontiguousarray(image_embeddings, np.float32).reshape(256, 64, 64)
+        b = np.ascontiguousarray(boxes_1024, np.float64).reshape(-1, 4)
+        nb = b.shape[0]
+        low = np.empty((nb, 256, 256), np.float32)
+        sp = np.empty((nb, 2, 256), np.float32) if want_sparse else None
+        self._check(self._lib.ysi_decode(self._ctx, nat.as_f32p(emb), nat.as_f64p(b), nb, nat.as_f32p(low), nat.as_f32p(sp)), "ysi_decode")
+        return (low, sp) if want_sparse else low
+
+    def postprocess(self, low_res: np.ndarray, H: int, W: int, want_logits: bool = False):
+        low = np.ascontiguousarray(low_res, np.float32).reshape(-1, 256, 256)
+        nb = low.shape[0]
+        masks = np.empty((nb, H, W), np.uint8)
+        up = np.empty((nb, H, W), np.float32) if want_logits else None
+        self._check(self._lib.ysi_postprocess(self._ctx, nat.as_f32p(low), nb, H, W, nat.as_u8p(masks), nat.as_f32p(up)), "ysi_postprocess")
+        return (masks.view(bool), up) if want_logits else masks.view(bool)
+
+    def metrics(self, image: np.ndarray, masks: np.ndarray, raw: bool = False):
+        img = np.ascontiguousarray(image, np.uint8)
+        H, W = img.shape[:2]
+        m = np.ascontiguousarray(masks).astype(np.uint8).reshape(-1, H, W)
+        rows = np.zeros(m.shape[0], dtype=nat.METRICS_DTYPE)
+        self._check(self._lib.ysi_metrics(self._ctx, nat.as_u8p(img), H, W, img.strides[0], nat.as_u8p(m), m.shape[0],
+                                          rows.ctypes.data_as(C.c_void_p)), "ysi_metrics")
+        return rows if raw else [metrics_from_raw(rows[j], self.on_empty) for j in range(len(rows))]
+
+    def gemm(self, A: np.ndarray, W: np.ndarray, bias: Optional[np.ndarray] = None, act: int = 0) -> np.ndarray:
+        A = np.ascontiguousarray(A, np.float32)
+        W = np.ascontiguousarray(W, np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        M, K = A.shape
+        N = W.shape[0]
+        out = np.empty((M, N), np.float32)
+        self._check(self._lib.ysi_gemm(self._ctx, nat.as_f32p(A), nat.as_f32p(W), nat.as_f32p(b), M, N, K, act, nat.as_f32p(out)), "ysi_gemm")
+        return out
+
+    def attention(self, qkv: np.ndarray, rel_h: np.ndarray, rel_w: np.ndarray, heads: int, is_global: bool) -> np.ndarray:
+        q = np.ascontiguousarray(qkv, np.float32)
+        n_seq, T = q.shape[0], q.shape[1]
+        out = np.empty((n_seq, T, heads * 64), np.float32)
+        self._check(self._lib.ysi_attention(self._ctx, nat.as_f32p(q), nat.as_f32p(np.ascontiguousarray(rel_h, np.float32)),
+                                            nat.as_f32p(np.ascontiguousarray(rel_w, np.float32)), n_seq, heads,
+                                            1 if is_global else 0, nat.as_f32p(out)), "ysi_attention")
+        return out
+
+    def image_pe(self) -> np.ndarray:
+        out = np.empty((256, 64, 64), np.float32)
+        self._check(self._lib.ysi_get_image_pe(self._ctx, nat.as_f32p(out)), "ysi_get_image_pe")
+        return out
