@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- SAM box-prompt stage throughput on B200 (BASELINE.json metric), plus the reference CPU arm.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libysi.so, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle)
+
+A *step* is one pass of the hot path (preprocess -> ViT encoder -> prompt encoder/mask decoder ->
+upsample+threshold -> morphometrics) over one batch of BATCH synthetic 1024x1024 images, 1 box each
+(BASELINE.json configs[1]).  Rank r of N processes its own contiguous shard of the image list (folder
+partition, no data-path collective; per-GPU work is fixed => weak scaling).
+
+  value  images/s with the inputs resident in HBM before the timed region (K steps enqueued back to back
+         on the context's stream, CUDA events on that stream, max over ranks)
+  e2e    images/s through the public API SamStage.run_batch with pinned HOST buffers: H2D of the images
+         and D2H of masks + metric rows are inside the timed region
+  roofline  tensor-pipe roofline of the dominant kernel class (the tcgen05 GEMM behind every ViT linear),
+         from per-launch CUDA events in a separate profiled pass over the same steps
+  cpu_baseline  the reference path (transformers SamModel fp32 + restated metrics) on the host cores,
+         bounded sample, rank 0 / N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 8                    # images per step
+POOL_IMAGES = 256            # BASELINE configs[1]: 256 synthetic 1024x1024 images
+ENC_FLOPS_VIT_B = 937.6e9    # algorithmic FLOPs / image
+DEC_FLOPS_BOX = 3.61e9
+METRIC = "SAM box-prompt images/s (ViT-B, 1024x1024, 1 box/image; masks/s == images/s)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "src": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+                "src": "fallback (B200_PROFILING.md)"}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def init_dist(world: int, backend: str):
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend)
+    return dist
+
+
+def max_over_ranks(dist, value: float, device=None) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_inputs(first_index: int, count: int):
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    imgs, boxes = [], []
+    for i in range(first_index, first_index + count):
+        g, b = synth_image(i, 1024, 1)
+        imgs.append(gray_to_rgb_u8(g))
+        boxes.append(b)
+    return imgs, boxes
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (transformers fp32 + restated skimage metrics) on host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_images_per_s(n_images: int, warmup: int, threads: int, budget_s: float = 150.0):
+    """Times pipeline.py:161-175 as the reference executes it (encoder re-run per box; 1 box/image here)."""
+    import torch
+    from oracle import metrics_oracle, sam_oracle
+    torch.set_num_threads(threads)
+    model = sam_oracle.build_model("vit_b", 1234)
+    imgs, boxes = make_inputs(0, max(n_images, 1))
+
+    def one(i):
+        im, bx = imgs[i % len(imgs)], boxes[i % len(imgs)]
+        masks, _ = sam_oracle.run_stage(model, im, bx)
+        for m in masks:
+            if m.any():
+                metrics_oracle.calculate_metrics(im, m)
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n_images):
+        one(i)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:      # keep the whole run within a few minutes
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, dt, done
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ips, dt, done = cpu_reference_images_per_s(args.steps, min(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: SAM ViT-B, synthetic 1024x1024 images, 1 box/image; each step = 1 image "
+                               "(bounded sample of the 8-image batch) through transformers SamModel fp32 + restated "
+                               "skimage/scipy metrics on the host cores"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{done} images, 1 box each, seeded random-init ViT-B"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def host_dry_run(rank: int, world: int, n_images: int = 10):
+    """Host-side logic of the multi-rank bench without a GPU (used by the gloo test): shard, time, reduce."""
+    import torch.distributed as dist
+    from yolo_sam_inference_b200.sharding import shard_range
+    import torch
+    mine = shard_range(n_images * 1, rank, world)
+    t0 = time.perf_counter()
+    time.sleep(0.01 * (rank + 1))
+    dt = time.perf_counter() - t0
+    tmax = max_over_ranks(dist, dt)
+    counts = torch.zeros(world, dtype=torch.int64)
+    counts[rank] = len(mine)
+    dist.all_reduce(counts)           # bookkeeping only (not on the data path)
+    return {"n_gpus": world, "images_total": int(counts.sum()), "shards": counts.tolist(), "scaling": "weak",
+            "ms_per_step": tmax * 1e3}
+
+
+def run_ours(args):
+    import torch
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dist = init_dist(world, "nccl")
+    dev = torch.device("cuda", local)
+    from yolo_sam_inference_b200.sam_stage import SamStage
+    from yolo_sam_inference_b200.weights import seeded_state_dict
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    pool_n = min(POOL_IMAGES, BATCH * max(K, 1))
+    # folder partition: rank r owns images [r*POOL, (r+1)*POOL) of the global synthetic list
+    imgs, boxes = make_inputs(rank * POOL_IMAGES, pool_n)
+    stage = SamStage("vit_b", device=f"cuda:{local}", state_dict=seeded_state_dict("vit_b", 1234), max_batch=BATCH,
+                     max_boxes=BATCH, max_image_hw=(1024, 1024), on_empty="zeros")
+    stage.pool_upload(imgs)
+    nbat = pool_n // BATCH
+
+    def step_resident(i, sync=False):
+        b = (i % nbat) * BATCH
+        return stage.compute_pool(b, BATCH, boxes[b:b + BATCH], sync=sync)
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    for i in range(Wm):
+        step_resident(i, sync=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = stage.launch_count
+    stage.timer_record(0)
+    for i in range(K):
+        step_resident(i)
+    stage.timer_record(1)
+    stage.sync()
+    torch.cuda.synchronize()
+    ms_total = stage.timer_elapsed_ms(0, 1)
+    launches = stage.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    if dist is not None:
+        dist.barrier()
+    ms_total = max_over_ranks(dist, ms_total, dev)
+    value = world * K * BATCH / (ms_total / 1e3)
+
+    # ---- end-to-end leg: pinned host buffers, H2D + D2H inside the timed region ------------------------
+    pinned = [torch.empty((1024, 1024, 3), dtype=torch.uint8).pin_memory() for _ in range(pool_n)]
+    for t, im in zip(pinned, imgs):
+        t.numpy()[...] = im
+    host_imgs = [t.numpy() for t in pinned]
+    for i in range(2):
+        stage.run_batch(host_imgs[:BATCH], boxes[:BATCH], raw=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        b = (i % nbat) * BATCH
+        out = stage.run_batch(host_imgs[b:b + BATCH], boxes[b:b + BATCH], raw=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(dist, e2e_s, dev)
+    e2e_value = world * K * BATCH / e2e_s
+    h2d = BATCH * 1024 * 1024 * 3 + BATCH * (4 * 8 + 8)
+    d2h = BATCH * 1024 * 1024 + BATCH * 1192
+
+    # ---- profiled pass: per-launch CUDA events by kernel class (roofline + breakdown) ---------------------
+    roof, breakdown = None, None
+    if rank == 0:
+        stage.profile(True)
+        psteps = min(K, 4)
+        for i in range(psteps):
+            step_resident(i, sync=True)
+        prof = stage.profile_read()
+        stage.profile(False)
+        pk = peaks()
+        gemm_classes = ["gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2"]
+        g_ms = sum(prof[c]["ms"] for c in gemm_classes)
+        g_fl = sum(prof[c]["flops"] for c in gemm_classes)
+        g_n = sum(prof[c]["records"] for c in gemm_classes)
+        tot_ms = sum(v["ms"] for v in prof.values())
+        achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,EpiGeneric> (tcgen05 GEMM of the ViT linears)",
+                "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "frac_of_burst": achieved / pk["bf16_tflops"],
+                "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
+                "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1),
+                "share_of_step": g_ms / tot_ms if tot_ms else None, "traffic": None,
+                "how": f"CUDA events around every launch, {psteps} profiled steps after the timed region"}
+        breakdown = {k: {"ms_per_step": v["ms"] / psteps,
+                         "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
+                     for k, v in prof.items()}
+        # whole-encoder tensor utilisation from the device-resident number
+        enc_ms = sum(prof[c]["ms"] for c in gemm_classes + ["attn_window", "attn_global", "layernorm", "neck"]) / psteps
+        breakdown["_encoder_alg_tflops"] = ENC_FLOPS_VIT_B * BATCH / (enc_ms / 1e3) / 1e12 if enc_ms else None
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n = 4
+        ips, dt, n = cpu_reference_images_per_s(n, 1, threads, 60.0)
+        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{n} images (1 box each) of the same workload, {dt:.1f} s: transformers SamModel fp32 + "
+                         "restated skimage/scipy metrics"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: SAM ViT-B bf16 (fp32 accumulate/residual), 256 synthetic 1024x1024 "
+                                   "images per GPU, 1 box/image, batch 8 images per step",
+                       "batch": BATCH, "pool_images_per_gpu": pool_n, "weights": "seeded random-init (no checkpoints offline)",
+                       "l2": "inputs differ every step and the per-step working set (~0.9 GB of activations) exceeds the "
+                             "126 MB L2, so no L2 flush is needed between timed iterations",
+                       "parallelism": f"image-sharded x{world}, no collective"},
+            "masks_per_s": value,
+            "alg_tflops": (ENC_FLOPS_VIT_B + DEC_FLOPS_BOX) * value / 1e12,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roof, "cpu_baseline": cpu, "breakdown": breakdown,
+        }
+        print(json.dumps(line))
+    stage.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

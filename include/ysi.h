@@ -112,6 +112,20 @@ YSI_API int ysi_stage_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rg
 YSI_API int ysi_compute_staged(ysi_ctx* ctx, ysi_timing* timing);
 YSI_API int ysi_fetch_staged(ysi_ctx* ctx, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out);
 
+/* ---- measurement support (bench.py) ------------------------------------------------------------- */
+/* resident input pool: images uploaded once, then processed straight from HBM (device-resident leg) */
+YSI_API int ysi_pool_upload(ysi_ctx* ctx, int pool_size, int idx, const uint8_t* rgb, int H, int W, int row_stride);
+/* run images [first_idx, first_idx+n) of the pool; sync == 0 only enqueues (results stay on the device) */
+YSI_API int ysi_compute_pool(ysi_ctx* ctx, int first_idx, int n, const float* boxes_xyxy, const int32_t* box_counts, int sync,
+                     ysi_timing* timing);
+/* CUDA events on the context's own stream (torch.cuda.Event would only see torch's stream) */
+YSI_API int ysi_timer_record(ysi_ctx* ctx, int slot);
+YSI_API int ysi_timer_elapsed_ms(ysi_ctx* ctx, int slot_a, int slot_b, float* ms);
+YSI_API int ysi_sync(ysi_ctx* ctx);
+/* per-kernel-class event timing: enable, run steps, read (returns the number of classes written) */
+YSI_API int ysi_profile(ysi_ctx* ctx, int enable);
+YSI_API int ysi_profile_read(ysi_ctx* ctx, int max_classes, const char** names, double* ms, int64_t* records, double* flops);
+
 /* ---- stage-level entry points (parity tests; each is one row of SURVEY.md section 8a) --------------- */
 /* a1: sam_processor(image) -> pixel_values fp32 [n,3,1024,1024] (image_processing_sam.py:205-250) */
 YSI_API int ysi_preprocess(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,

@@ -71,6 +71,13 @@ EXPORTS = {
     "ysi_stage_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
     "ysi_compute_staged": (C.c_int, [_ctx, C.POINTER(YsiTiming)]),
     "ysi_fetch_staged": (C.c_int, [_ctx, _u8p, _u8p, C.c_void_p]),
+    "ysi_pool_upload": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]),
+    "ysi_compute_pool": (C.c_int, [_ctx, C.c_int, C.c_int, _f32p, _i32p, C.c_int, C.POINTER(YsiTiming)]),
+    "ysi_timer_record": (C.c_int, [_ctx, C.c_int]),
+    "ysi_timer_elapsed_ms": (C.c_int, [_ctx, C.c_int, C.c_int, _f32p]),
+    "ysi_sync": (C.c_int, [_ctx]),
+    "ysi_profile": (C.c_int, [_ctx, C.c_int]),
+    "ysi_profile_read": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_char_p), _f64p, C.POINTER(C.c_int64), _f64p]),
     "ysi_preprocess": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p]),
     "ysi_encode": (C.c_int, [_ctx, C.c_int, _f32p, _f32p, _f32p]),
     "ysi_decode": (C.c_int, [_ctx, _f32p, _f64p, C.c_int, _f32p, _f32p]),

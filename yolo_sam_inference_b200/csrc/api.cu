@@ -56,9 +56,20 @@ struct ysi_ctx {
   float* d_hidden = nullptr;       // stage API dump
   size_t hidden_cap = 0;
 
+  // resident image pool (bench: inputs already in HBM) and profiler
+  uint8_t* d_pool = nullptr;
+  int pool_cap = 0, pool_H = 0, pool_W = 0;
+  Profiler prof;
+  cudaEvent_t timers[8]{};
+  // pinned ring for the small per-step box arrays (lets ysi_compute_pool enqueue steps without syncing)
+  static constexpr int RING = 64;
+  double* h_boxes = nullptr;   // [RING, max_boxes, 4]
+  int* h_box_img = nullptr;    // [RING, max_boxes]
+  int ring_pos = 0;
+
   // staged batch (ysi_stage_batch)
+  const uint8_t* st_rgb = nullptr;
   int st_n = 0, st_H = 0, st_W = 0, st_nb = 0;
-  std::vector<int> st_box_img;
   cudaEvent_t ev[8]{};
 
   template <class T>
@@ -274,6 +285,8 @@ void create_impl(ysi_ctx* c) {
   YSI_CHECK(cc_major == 10, "libysi.so is built for sm_100a only (needs a B200-class GPU)");
   YSI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) YSI_CUDA(cudaEventCreate(&e));
+  for (auto& e : c->timers) YSI_CUDA(cudaEventCreate(&e));
+  c->prof.stream = c->stream;
   // (x - mean*255) / (std*255) with the fp32 products tvF.normalize sees
   const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
   const float inv_rescale = static_cast<float>(1.0 / (1.0 / 255.0));
@@ -328,6 +341,13 @@ void create_impl(ysi_ctx* c) {
   c->d_stats = c->dalloc<MaskStatsDev>(NB);
   c->d_metrics = c->dalloc<ysi_mask_metrics>(NB);
   c->d_mask_img = c->dalloc<int>(NB);
+  {
+    void* p = nullptr;
+    YSI_CUDA(cudaHostAlloc(&p, sizeof(double) * 4 * NB * ysi_ctx::RING, cudaHostAllocDefault));
+    c->host_allocs.push_back(p); c->h_boxes = static_cast<double*>(p);
+    YSI_CUDA(cudaHostAlloc(&p, sizeof(int) * NB * ysi_ctx::RING, cudaHostAllocDefault));
+    c->host_allocs.push_back(p); c->h_box_img = static_cast<int*>(p);
+  }
   YSI_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -357,51 +377,65 @@ void stage_impl(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int 
   int nb = 0;
   for (int i = 0; i < n; ++i) nb += box_counts[i];
   check_batch(c, n, H, W, nb);
-  YSI_CHECK(row_stride >= 3 * W, "row_stride smaller than 3*W");
+  YSI_CHECK(!rgb || row_stride >= 3 * W, "row_stride smaller than 3*W");
   c->st_n = n; c->st_H = H; c->st_W = W; c->st_nb = nb;
   const size_t img_bytes = static_cast<size_t>(H) * W * 3;
-  for (int i = 0; i < n; ++i)
-    YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
-                               static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->stream));
-  c->st_box_img.clear();
-  for (int i = 0; i < n; ++i)
-    for (int k = 0; k < box_counts[i]; ++k) c->st_box_img.push_back(i);
+  if (rgb) {
+    for (int i = 0; i < n; ++i)
+      YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
+                                 static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->stream));
+    c->st_rgb = c->d_rgb;
+  }
   if (nb > 0) {
+    const int slot = c->ring_pos;
+    c->ring_pos = (c->ring_pos + 1) % ysi_ctx::RING;
+    double* hb = c->h_boxes + static_cast<size_t>(slot) * 4 * c->cfg.max_boxes;
+    int* hi = c->h_box_img + static_cast<size_t>(slot) * c->cfg.max_boxes;
     std::vector<double> b1024;
     rescale_boxes(boxes, nb, H, W, b1024);
-    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, b1024.data(), sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, c->stream));
-    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, c->st_box_img.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
-    YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, c->st_box_img.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+    std::memcpy(hb, b1024.data(), sizeof(double) * 4 * nb);
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < box_counts[i]; ++j) hi[k++] = i;
+    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, hb, sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
   }
-  YSI_CUDA(cudaStreamSynchronize(c->stream));   // the host vectors above go out of scope
+  if (rgb) YSI_CUDA(cudaStreamSynchronize(c->stream));   // the caller may reuse its image buffers
 }
 
-void compute_impl(ysi_ctx* c, ysi_timing* tm) {
+void compute_impl(ysi_ctx* c, ysi_timing* tm, bool sync = true) {
   const int n = c->st_n, H = c->st_H, W = c->st_W, nb = c->st_nb;
-  YSI_CHECK(n > 0, "no staged batch");
+  YSI_CHECK(n > 0 && c->st_rgb, "no staged batch");
   cudaStream_t s = c->stream;
+  Profiler* prof = c->prof.active ? &c->prof : nullptr;
+  const uint8_t* d_rgb = c->st_rgb;
   YSI_CUDA(cudaEventRecord(c->ev[0], s));
   if (nb > 0) {
-    launch_sum3(c->d_rgb, n, H, W, W * 3, c->d_sum3, s);
-    launch_preprocess_1024(c->d_rgb, n, W * 3, c->mean255, c->std255, nullptr, c->ew.a_patch, s);
+    ProfScope ps(prof, KC_PREPROCESS);
+    launch_sum3(d_rgb, n, H, W, W * 3, c->d_sum3, s);
+    launch_preprocess_1024(d_rgb, n, W * 3, c->mean255, c->std255, nullptr, c->ew.a_patch, s);
     c->launches += 2;
   }
   YSI_CUDA(cudaEventRecord(c->ev[1], s));
-  if (nb > 0) encoder_forward(c->enc, c->ew, n, c->d_emb, nullptr, s, &c->launches);
+  if (nb > 0) encoder_forward(c->enc, c->ew, n, c->d_emb, nullptr, s, &c->launches, prof);
   YSI_CUDA(cudaEventRecord(c->ev[2], s));
-  if (nb > 0) decoder_forward(c->dec, c->dw, c->d_emb, n, nb, c->d_low, nullptr, s, &c->launches);
+  if (nb > 0) decoder_forward(c->dec, c->dw, c->d_emb, n, nb, c->d_low, nullptr, s, &c->launches, prof);
   YSI_CUDA(cudaEventRecord(c->ev[3], s));
   if (nb > 0) {
+    ProfScope ps(prof, KC_POST_UPSAMPLE);
     launch_init_stats(c->d_stats, nb, s);
     launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), c->d_sum3, c->d_mask_img, c->d_masks, nullptr, c->d_stats, s);
     c->launches += 2;
   }
   YSI_CUDA(cudaEventRecord(c->ev[4], s));
   if (nb > 0) {
+    ProfScope ps(prof, KC_POST_HULL);
     launch_contour_hull_disk(c->d_masks, nb, H, W, c->d_sum3, c->d_mask_img, c->d_stats, c->d_metrics, s);
     c->launches += 1;
   }
   YSI_CUDA(cudaEventRecord(c->ev[5], s));
+  if (!sync) return;
   YSI_CUDA(cudaStreamSynchronize(s));
   if (tm) {
     std::memset(tm, 0, sizeof(*tm));
@@ -518,6 +552,68 @@ int ysi_run(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, const 
   const uint8_t* imgs[1] = {rgb};
   const int32_t counts[1] = {nb};
   return ysi_run_batch(c, 1, imgs, H, W, row_stride, boxes, counts, masks_out, packed_out, metrics_out, tm);
+}
+
+// ------------------------------------------------------------------------------------------- bench support
+int ysi_pool_upload(ysi_ctx* c, int pool_size, int idx, const uint8_t* rgb, int H, int W, int row_stride) {
+  return guarded(c, [&] {
+    YSI_CHECK(H <= c->cfg.max_image_h && W <= c->cfg.max_image_w && pool_size >= 1 && idx >= 0 && idx < pool_size, "bad pool arguments");
+    const size_t img_bytes = static_cast<size_t>(H) * W * 3;
+    if (!c->d_pool || c->pool_cap < pool_size || c->pool_H != H || c->pool_W != W) {
+      c->d_pool = c->dalloc<uint8_t>(img_bytes * pool_size);
+      c->pool_cap = pool_size; c->pool_H = H; c->pool_W = W;
+    }
+    YSI_CUDA(cudaMemcpy2D(c->d_pool + idx * img_bytes, static_cast<size_t>(W) * 3, rgb, row_stride, static_cast<size_t>(W) * 3, H,
+                          cudaMemcpyHostToDevice));
+  });
+}
+
+int ysi_compute_pool(ysi_ctx* c, int first_idx, int n, const float* boxes, const int32_t* box_counts, int sync, ysi_timing* tm) {
+  return guarded(c, [&] {
+    YSI_CHECK(c->d_pool && first_idx >= 0 && first_idx + n <= c->pool_cap, "pool range out of bounds");
+    stage_impl(c, n, nullptr, c->pool_H, c->pool_W, 0, boxes, box_counts);
+    c->st_rgb = c->d_pool + static_cast<size_t>(first_idx) * c->pool_H * c->pool_W * 3;
+    compute_impl(c, tm, sync != 0);
+  });
+}
+
+int ysi_timer_record(ysi_ctx* c, int slot) {
+  return guarded(c, [&] {
+    YSI_CHECK(slot >= 0 && slot < 8, "timer slot out of range");
+    YSI_CUDA(cudaEventRecord(c->timers[slot], c->stream));
+  });
+}
+
+int ysi_timer_elapsed_ms(ysi_ctx* c, int slot_a, int slot_b, float* ms) {
+  return guarded(c, [&] {
+    YSI_CUDA(cudaEventSynchronize(c->timers[slot_b]));
+    YSI_CUDA(cudaEventElapsedTime(ms, c->timers[slot_a], c->timers[slot_b]));
+  });
+}
+
+int ysi_sync(ysi_ctx* c) {
+  return guarded(c, [&] { YSI_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+int ysi_profile(ysi_ctx* c, int enable) {
+  return guarded(c, [&] {
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    c->prof.reset();
+    c->prof.active = enable != 0;
+  });
+}
+
+int ysi_profile_read(ysi_ctx* c, int max_classes, const char** names, double* ms, int64_t* records, double* flops) {
+  int n = -2;
+  guarded(c, [&] {
+    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    double m[KC_COUNT], f[KC_COUNT];
+    long long l[KC_COUNT];
+    c->prof.collect(m, l, f);
+    n = KC_COUNT < max_classes ? KC_COUNT : max_classes;
+    for (int i = 0; i < n; ++i) { names[i] = kernel_class_name(i); ms[i] = m[i]; records[i] = l[i]; flops[i] = f[i]; }
+  });
+  return n;
 }
 
 // ------------------------------------------------------------------------------------------- stage API

@@ -7,6 +7,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace ysi {
 
@@ -62,5 +63,34 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int
                cudaStream_t stream);
 
 int sm_count();
+
+// Optional per-launch CUDA-event timing by kernel class (bench.py's roofline / breakdown pass).
+// Inactive (null) in the product path: zero overhead.
+enum KernelClass {
+  KC_PREPROCESS = 0, KC_LAYERNORM, KC_GEMM_PATCH, KC_GEMM_QKV, KC_ATTN_WINDOW, KC_ATTN_GLOBAL, KC_GEMM_PROJ,
+  KC_GEMM_FC1, KC_GEMM_FC2, KC_NECK, KC_DEC_TOKEN, KC_DEC_GEMM, KC_DEC_ATTN, KC_DEC_UPSCALE, KC_POST_UPSAMPLE,
+  KC_POST_HULL, KC_COUNT
+};
+const char* kernel_class_name(int kc);
+
+struct Profiler {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> pool;
+  struct Rec { int kc; int e0, e1; double flops; };
+  std::vector<Rec> recs;
+  int next = 0;
+  bool active = false;
+  int begin(int kc, double flops = 0.0);
+  void end(int rec);
+  void collect(double* ms, long long* launches, double* flops);   // arrays of KC_COUNT; call after a stream sync
+  void reset();
+  ~Profiler();
+};
+// scope helper: times everything launched between construction and destruction as one record
+struct ProfScope {
+  Profiler* p; int r;
+  ProfScope(Profiler* prof, int kc, double flops = 0.0) : p(prof && prof->active ? prof : nullptr), r(-1) { if (p) r = p->begin(kc, flops); }
+  ~ProfScope() { if (p) p->end(r); }
+};
 
 }  // namespace ysi

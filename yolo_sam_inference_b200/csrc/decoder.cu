@@ -531,7 +531,7 @@ struct EpiConvT2 {
 
 // ---------------------------------------------------------------------------------------------------
 void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb, int n_img, int nb, float* low_res_out,
-                     float* sparse_out, cudaStream_t s, int64_t* launches) {
+                     float* sparse_out, cudaStream_t s, int64_t* launches, Profiler* prof) {
   YSI_CHECK(n_img >= 1 && n_img <= wk.cap_img && nb >= 1 && nb <= wk.cap_box, "decoder batch exceeds the workspace");
   int64_t nl = 0;
   static bool attr = false;
@@ -557,8 +557,9 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     float* kq = per_img ? wk.kq0 : wk.kq;
     float* v = per_img ? wk.v0 : wk.v;
     const int* group = per_img ? wk.box_img : nullptr;
-    token_self_attn_kernel<<<nb, 256, 0, s>>>(lw, li == 0 ? 1 : 0, wk.tok0, wk.queries, wk.q_t2i); ++nl;
+    { ProfScope ps(prof, KC_DEC_TOKEN); token_self_attn_kernel<<<nb, 256, 0, s>>>(lw, li == 0 ? 1 : 0, wk.tok0, wk.queries, wk.q_t2i); ++nl; }
     {
+      ProfScope ps(prof, KC_DEC_GEMM, 2.0 * rows * 384 * 256);
       GemmEpilogue ep;
       ep.bias = lw.b_kq_img; ep.out_f32 = kq; ep.ld_out = 256;
       gemm_bf16(a_keyspos, C, lw.w_kq_img, C, rows, 256, C, ep, s); ++nl;
@@ -566,12 +567,13 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       ev.bias = lw.t2i.bv; ev.out_f32 = v; ev.ld_out = 128;
       gemm_bf16(a_keys, C, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
     }
-    t2i_attention_kernel<<<dim3(8, nb), 256, NT * 4096 * 4, s>>>(wk.q_t2i, kq, 256, v, 128, group, wk.attn_t2i); ++nl;
-    token_mlp_kernel<<<nb, 256, NT * 2048 * 4, s>>>(lw, wk.tok0, wk.attn_t2i, wk.queries, wk.k_tok, wk.v_tok); ++nl;
-    i2t_attention_kernel<<<dim3(128, nb), 256, 0, s>>>(kq + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t); ++nl;
+    { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb), 256, NT * 4096 * 4, s>>>(wk.q_t2i, kq, 256, v, 128, group, wk.attn_t2i); ++nl; }
+    { ProfScope ps(prof, KC_DEC_TOKEN); token_mlp_kernel<<<nb, 256, NT * 2048 * 4, s>>>(lw, wk.tok0, wk.attn_t2i, wk.queries, wk.k_tok, wk.v_tok); ++nl; }
+    { ProfScope ps(prof, KC_DEC_ATTN); i2t_attention_kernel<<<dim3(128, nb), 256, 0, s>>>(kq + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t); ++nl; }
     YSI_CUDA(cudaGetLastError());
     {
       // keys = keys_prev + out_proj(attn) ; then LN4
+      ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 128);
       GemmEpilogue ep;
       ep.bias = lw.i2t.bo; ep.out_f32 = wk.kq; ep.ld_out = 256;      // kq (per-box) is free now: reuse as pre-LN buffer
       ep.add_src = per_img ? wk.keys0 : wk.keys; ep.ld_add = 256;
@@ -585,6 +587,7 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   // final token -> image attention (:394-404)
   token_final_q_kernel<<<nb, 256, 0, s>>>(w.final_attn, wk.tok0, wk.queries, wk.q_t2i); ++nl;
   {
+    ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 256);
     GemmEpilogue ek;
     ek.bias = w.final_attn.bk; ek.out_f32 = wk.kq; ek.ld_out = 256;    // K in columns 0..127 of kq
     gemm_bf16(wk.keyspos_bf, C, w.w_k_final, C, TB, 128, C, ek, s); ++nl;
@@ -597,6 +600,7 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   YSI_CUDA(cudaGetLastError());
   // upscaler (:515-531)
   {
+    ProfScope ps(prof, KC_DEC_UPSCALE, 2.0 * TB * 256 * 256 + 2.0 * nb * 16384.0 * 128 * 64);
     const CUtensorMap tmA = make_tmap_bf16_2d(wk.keys_bf, TB, C, C, GEMM_BM);
     const CUtensorMap tmB = make_tmap_bf16_2d(w.w_ct1, 256, C, C, 256);
     EpiConvT1 e1{w.b_ct1, w.lnu_g, w.lnu_b, wk.up1};

@@ -214,7 +214,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict_
 
 // ------------------------------------------------------------------------------------------------
 void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* emb_out, float* hidden_dump,
-                     cudaStream_t s, int64_t* launches) {
+                     cudaStream_t s, int64_t* launches, Profiler* prof) {
   YSI_CHECK(n >= 1 && n <= work.cap, "encoder batch exceeds the workspace");
   const int D = w.D, T = n * 4096, TW = n * 4900;
   int64_t nl = 0;
@@ -223,6 +223,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     GemmEpilogue ep;
     ep.bias = w.b_patch; ep.add_src = w.pos_embed; ep.add_mod = 4096; ep.ld_add = D;
     ep.out_f32 = work.x; ep.ld_out = D;
+    ProfScope ps(prof, KC_GEMM_PATCH, 2.0 * T * D * 768);
     gemm_bf16(work.a_patch, 768, w.w_patch, 768, T, D, 768, ep, s); ++nl;
   }
   if (hidden_dump) YSI_CUDA(cudaMemcpyAsync(hidden_dump, work.x, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, s));
@@ -230,28 +231,38 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     const EncoderLayerW& lw = w.layers[li];
     const bool glob = lw.is_global != 0;
     const int rows = glob ? T : TW;
-    launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s); ++nl;
+    // algorithmic FLOPs (pad rows / pad keys excluded) are attached to every record for the roofline
+    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s); ++nl; }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_qkv; ep.out_bf16 = work.qkv; ep.ld_out_bf16 = 3 * D;
+      ProfScope ps(prof, KC_GEMM_QKV, 2.0 * T * 3 * D * D);
       gemm_bf16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
     }
-    launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, glob, s); ++nl;
+    {
+      const double S = glob ? 64.0 : 14.0, tok = glob ? 4096.0 : 196.0, nseq = glob ? n : n * 25.0;
+      // QK^T + PV (4 * T^2 * hd per head) + rel-pos terms (2 * 2 * T * S * hd per head)
+      ProfScope ps(prof, glob ? KC_ATTN_GLOBAL : KC_ATTN_WINDOW, nseq * w.heads * (4.0 * tok * tok * 64 + 4.0 * tok * S * 64));
+      launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, glob, s); ++nl;
+    }
     {
       GemmEpilogue ep;   // x += attn * Wproj^T + b ; windowed rows scatter back through the partition map
       ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
       ep.row_map = glob ? nullptr : work.win_row_map;
+      ProfScope ps(prof, KC_GEMM_PROJ, 2.0 * T * D * D);
       gemm_bf16(work.attn, D, lw.w_proj, D, rows, D, D, ep, s); ++nl;
     }
-    launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s); ++nl;
+    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s); ++nl; }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_fc1; ep.act = ACT_GELU; ep.out_bf16 = work.u; ep.ld_out_bf16 = w.mlp;
+      ProfScope ps(prof, KC_GEMM_FC1, 2.0 * T * w.mlp * D);
       gemm_bf16(work.h, D, lw.w_fc1, D, T, w.mlp, D, ep, s); ++nl;
     }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
+      ProfScope ps(prof, KC_GEMM_FC2, 2.0 * T * w.mlp * D);
       gemm_bf16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
     }
     if (hidden_dump)
@@ -260,6 +271,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
   }
   // neck (modeling_sam.py:985-992): 1x1 conv -> LN2d -> 3x3 conv -> LN2d, all in token-major (NHWC) layout
   {
+    ProfScope ps(prof, KC_NECK, 2.0 * T * 256 * (D + 2304.0));
     const long long n8 = static_cast<long long>(T) * D / 8;
     cast_bf16_kernel<<<static_cast<int>(std::min<long long>((n8 + 255) / 256, 148 * 16)), 256, 0, s>>>(work.x, work.h, n8);
     YSI_CUDA(cudaGetLastError()); ++nl;

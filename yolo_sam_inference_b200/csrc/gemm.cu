@@ -53,6 +53,37 @@ CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, ui
   return m;
 }
 
+const char* kernel_class_name(int kc) {
+  static const char* names[KC_COUNT] = {"preprocess", "layernorm", "gemm_patch", "gemm_qkv", "attn_window", "attn_global",
+                                        "gemm_proj", "gemm_fc1", "gemm_fc2", "neck", "dec_token", "dec_gemm", "dec_attn",
+                                        "dec_upscale", "post_upsample", "post_hull"};
+  return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "?";
+}
+
+int Profiler::begin(int kc, double flops) {
+  while (static_cast<int>(pool.size()) < next + 2) {
+    cudaEvent_t e;
+    YSI_CUDA(cudaEventCreate(&e));
+    pool.push_back(e);
+  }
+  Rec r{kc, next, next + 1, flops};
+  next += 2;
+  YSI_CUDA(cudaEventRecord(pool[r.e0], stream));
+  recs.push_back(r);
+  return static_cast<int>(recs.size()) - 1;
+}
+void Profiler::end(int rec) { YSI_CUDA(cudaEventRecord(pool[recs[rec].e1], stream)); }
+void Profiler::collect(double* ms, long long* launches, double* flops) {
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flops[i] = 0; }
+  for (const Rec& r : recs) {
+    float t = 0.f;
+    YSI_CUDA(cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]));
+    ms[r.kc] += t; launches[r.kc] += 1; flops[r.kc] += r.flops;
+  }
+}
+void Profiler::reset() { recs.clear(); next = 0; }
+Profiler::~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
+
 int sm_count() {
   static int n = 0;
   if (!n) {

@@ -90,7 +90,7 @@ void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, c
 // runs the whole encoder on work.a_patch (n images); result: image embeddings fp32 token-major [n*4096, 256].
 // hidden_dump (optional, device) fp32 [(L+1), n*4096, D]
 void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* emb_out, float* hidden_dump,
-                     cudaStream_t s, int64_t* launches);
+                     cudaStream_t s, int64_t* launches, Profiler* prof = nullptr);
 
 // ------------------------------------------------------------------ prompt encoder + mask decoder
 struct DecAttnW {          // SamAttention weights, fp32 (token-side use)
@@ -137,6 +137,6 @@ void launch_image_pe(const float* gauss, float* image_pe, cudaStream_t s);
 // emb: image embeddings fp32 token-major [n_img*4096,256]; boxes1024 (device, fp64 [nb,4]) and box_img
 // (device int [nb]) live in work.  low_res_out: device fp32 [nb,256,256]; sparse_out optional [nb,2,256]
 void decoder_forward(const DecoderW& w, const DecoderWork& work, const float* emb, int n_img, int nb,
-                     float* low_res_out, float* sparse_out, cudaStream_t s, int64_t* launches);
+                     float* low_res_out, float* sparse_out, cudaStream_t s, int64_t* launches, Profiler* prof = nullptr);
 
 }  // namespace ysi

@@ -242,6 +242,50 @@ class SamStage:
                     "ysi_fetch_staged")
         return masks, rows
 
+    # ------------------------------------------------------------------ measurement support (bench.py)
+    def pool_upload(self, images: Sequence[np.ndarray]) -> None:
+        """Make `images` resident in HBM (device-resident leg of the bench)."""
+        n = len(images)
+        for i, im in enumerate(images):
+            im = np.ascontiguousarray(im)
+            H, W = im.shape[:2]
+            self._check(self._lib.ysi_pool_upload(self._ctx, n, i, nat.as_u8p(im), H, W, im.strides[0]), "ysi_pool_upload")
+        self._pool_hw = (H, W)
+
+    def compute_pool(self, first: int, n: int, boxes: Sequence[np.ndarray], sync: bool = True) -> Dict[str, float]:
+        counts = np.array([len(b) for b in boxes], dtype=np.int32)
+        allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
+        tm = nat.YsiTiming()
+        self._check(self._lib.ysi_compute_pool(self._ctx, first, n, nat.as_f32p(allb), nat.as_i32p(counts), 1 if sync else 0,
+                                               C.byref(tm)), "ysi_compute_pool")
+        self._staged = (int(counts.sum()), *self._pool_hw)
+        return tm.as_dict() if sync else {}
+
+    def timer_record(self, slot: int) -> None:
+        self._check(self._lib.ysi_timer_record(self._ctx, slot), "ysi_timer_record")
+
+    def timer_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._check(self._lib.ysi_timer_elapsed_ms(self._ctx, a, b, C.byref(ms)), "ysi_timer_elapsed_ms")
+        return float(ms.value)
+
+    def sync(self) -> None:
+        self._check(self._lib.ysi_sync(self._ctx), "ysi_sync")
+
+    def profile(self, enable: bool) -> None:
+        self._check(self._lib.ysi_profile(self._ctx, 1 if enable else 0), "ysi_profile")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        n = 32
+        names = (C.c_char_p * n)()
+        ms = np.zeros(n, np.float64)
+        rec = np.zeros(n, np.int64)
+        fl = np.zeros(n, np.float64)
+        k = self._lib.ysi_profile_read(self._ctx, n, names, nat.as_f64p(ms), rec.ctypes.data_as(C.POINTER(C.c_int64)), nat.as_f64p(fl))
+        if k < 0:
+            self._check(k, "ysi_profile_read")
+        return {names[i].decode(): {"ms": float(ms[i]), "records": int(rec[i]), "flops": float(fl[i])} for i in range(k)}
+
     # ------------------------------------------------------------------ stage-level API (parity tests)
     def preprocess(self, images: Sequence[np.ndarray]) -> np.ndarray:
         n = len(images)
