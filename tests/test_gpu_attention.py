@@ -43,3 +43,27 @@ def test_attention_matches_reference(tiny_stage, is_global, n_seq, heads):
     # P and the output are rounded to bf16 (2^-9); everything else is fp32
     assert rel_l2(out, ref) < 6e-3
     assert np.abs(out - ref).max() < 0.03 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("is_global", [False, True])
+def test_attention_growing_logits_exercise_lazy_rescale(tiny_stage, is_global):
+    """Keys whose logits grow steadily along the sequence force the running maximum to move by far more
+    than the lazy-rescale threshold (2^8), tile after tile; some query rows see it shrink instead."""
+    g = torch.Generator().manual_seed(99)
+    S = 64 if is_global else 14
+    T, heads, n_seq = S * S, 2, 2
+    qkv = torch.randn(n_seq, T, 3 * heads * 64, generator=g) * 0.5
+    u = torch.randn(64, generator=g)
+    u = u / u.norm()
+    ramp = torch.linspace(0.0, 60.0, T)                      # up to ~ +60*|q.u|*0.125 in the exponent
+    for h in range(heads):
+        k0 = heads * 64 + h * 64
+        qkv[:, :, k0:k0 + 64] += ramp[None, :, None] * u[None, None, :]
+        qkv[:, :, h * 64:h * 64 + 64] += 2.0 * u[None, None, :] * torch.sign(torch.randn(n_seq, T, 1, generator=g))
+    qkv = _bf16(qkv)
+    rel_h = _bf16(torch.randn(2 * S - 1, 64, generator=g) * 0.15)
+    rel_w = _bf16(torch.randn(2 * S - 1, 64, generator=g) * 0.15)
+    ref = reference_attention(qkv, rel_h, rel_w, heads, S).numpy()
+    out = tiny_stage.attention(qkv.numpy(), rel_h.numpy(), rel_w.numpy(), heads, is_global)
+    assert np.isfinite(out).all()
+    assert rel_l2(out, ref) < 8e-3

@@ -169,8 +169,8 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
     std::vector<bf16> tab(256 * 64, __float2bfloat16(0.f));
     for (int r = 0; r < 2 * S - 1; ++r)
       for (int k = 0; k < 64; ++k) {
-        tab[r * 64 + k] = __float2bfloat16(rh.data[r * 64 + k]);
-        tab[(128 + r) * 64 + k] = __float2bfloat16(rw.data[r * 64 + k]);
+        tab[r * 64 + k] = __float2bfloat16(rh.data[r * 64 + k] * ATTN_LOG2E);
+        tab[(128 + r) * 64 + k] = __float2bfloat16(rw.data[r * 64 + k] * ATTN_LOG2E);
       }
     lw.rel_tab = c->upload_bf16(tab);
   }
@@ -300,7 +300,7 @@ void create_impl(ysi_ctx* c) {
   ew.x = c->dalloc<float>(B * 4096 * D);
   ew.h = c->dalloc<bf16>(B * 4900 * D);
   ew.qkv = c->dalloc<bf16>(B * 4900 * 3 * D);
-  ew.attn = c->dalloc<bf16>(B * 4900 * D);
+  ew.attn = c->dalloc<bf16>(B * 4096 * D);
   ew.u = c->dalloc<bf16>(B * 4096 * cfg.mlp_dim);
   ew.n1 = c->dalloc<float>(B * 4096 * 256);
   ew.n1b = c->dalloc<bf16>(B * 4096 * 256);
@@ -743,17 +743,19 @@ int ysi_attention(ysi_ctx* c, const float* qkv, const float* rel_h, const float*
     const int T = is_global ? 4096 : 196, S = is_global ? 64 : 14, D = heads * 64;
     const size_t rows = static_cast<size_t>(n_seq) * T;
     std::vector<bf16> q = to_bf16(qkv, rows * 3 * D);
+    for (size_t r = 0; r < rows; ++r)           // what the qkv GEMM epilogue does: K in log2 units
+      for (int k = D; k < 2 * D; ++k) q[r * 3 * D + k] = __float2bfloat16(qkv[r * 3 * D + k] * ATTN_K_SCALE);
     std::vector<bf16> tab(256 * 64, __float2bfloat16(0.f));
     for (int r = 0; r < 2 * S - 1; ++r)
       for (int k = 0; k < 64; ++k) {
-        tab[r * 64 + k] = __float2bfloat16(rel_h[r * 64 + k]);
-        tab[(128 + r) * 64 + k] = __float2bfloat16(rel_w[r * 64 + k]);
+        tab[r * 64 + k] = __float2bfloat16(rel_h[r * 64 + k] * ATTN_LOG2E);
+        tab[(128 + r) * 64 + k] = __float2bfloat16(rel_w[r * 64 + k] * ATTN_LOG2E);
       }
     bf16 *dq = nullptr, *dt = nullptr, *dout = nullptr;
     YSI_CUDA(cudaMalloc(&dq, q.size() * 2)); YSI_CUDA(cudaMalloc(&dt, tab.size() * 2)); YSI_CUDA(cudaMalloc(&dout, rows * D * 2));
     YSI_CUDA(cudaMemcpy(dq, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
     YSI_CUDA(cudaMemcpy(dt, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
-    launch_encoder_attention(dq, dt, dout, n_seq, T, heads, is_global != 0, c->stream);
+    launch_encoder_attention(dq, dt, dout, n_seq, T, heads, is_global != 0, false, c->stream);
     c->launches += 1;
     std::vector<bf16> o(rows * D);
     YSI_CUDA(cudaMemcpyAsync(o.data(), dout, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));

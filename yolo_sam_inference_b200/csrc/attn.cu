@@ -2,18 +2,28 @@
 //
 //   out = softmax(q k^T * hd^-0.5 + q.Rh[qh-kh] + q.Rw[qw-kw]) v      (decomposed rel-pos bias, unscaled q)
 //
+// Inputs are prepared by the qkv GEMM epilogue / weight loader so that the kernel works in the log2 domain:
+// the K columns arrive pre-multiplied by hd^-0.5 * log2(e) and the rel-pos tables by log2(e); p = 2^(x - m).
+//
 // One CTA = 128 queries of one (sequence, head); keys/values stream through in tiles of 64.
-//   warp 4 (one lane) : TMA loads (Q, rel-pos tables, K/V double buffer) + all tcgen05.mma issue
-//   warps 0-3         : one query row per thread: S from TMEM, bias, online softmax (fp32, exp2),
-//                       P -> bf16 -> 128B-swizzled smem, O accumulated in registers from TMEM partials
-// Tensor-core work per tile: S = Q K^T (128x64x64, both K-major) and PV = P V (128x64x64, V is the
-// MN-major B operand straight out of the qkv activation, no transpose pass). The rel-pos terms are
-// two extra 128x128x64 MMAs per CTA (Q . table^T) whose TMEM result is re-indexed per query:
-//   global   (S=64): rel_h stays in TMEM (column qh-kh+63 is warp-uniform), rel_w goes to smem [kw][q]
-//   windowed (S=14): both go to smem [k][q]; 64->70 zero-padded tokens are ordinary keys (they carry
-//                    the qkv bias, modeling_sam.py:913-916), keys >= 196 of the tile are masked.
-// 2 CTAs/SM (96 KB smem, 256 TMEM columns each) overlap one CTA's softmax with the other's MMAs.
+//   warp 4 (one lane) : TMA loads (Q, rel-pos tables, K and V rings) + every tcgen05.mma
+//   warps 0-3         : one query row per thread; S from TMEM, bias add (FADD2), max (FMNMX3), exp2 (MUFU),
+//                       P -> bf16 -> 128B-swizzled smem (double buffered)
+// Tensor-core work per tile: S = Q K^T (128x64x64, both K-major) and O += P V (128x64x64, V is the MN-major B
+// operand straight out of the qkv activation). O stays in TMEM for the whole CTA: it is rescaled in place
+// (tcgen05.ld / tcgen05.st) only when the running row maximum grows by more than 2^8 ("lazy rescale"), so the
+// softmax threads never wait on the PV MMA in steady state. The S buffer is released as soon as it is in
+// registers, so S_{j+1} is computed while the softmax of tile j runs.
+// The rel-pos terms are two extra MMAs per CTA (Q . table^T) whose TMEM result is re-indexed per query:
+//   global   (S=64): rel_w -> 64 registers per thread (same for every tile); rel_h stays in TMEM, one
+//                    warp-uniform column per tile, folded into the exponent offset
+//   windowed (S=14): 14+14 registers per thread; 64->70 zero-padded tokens are ordinary keys (they carry the
+//                    qkv bias, modeling_sam.py:913-916); the window's 196 keys are resident (tiles 64,64,64,16),
+//                    keys >= 196 of the last tile are masked.
+// 2 CTAs/SM overlap one CTA's softmax with the other's MMAs; the kernel is MUFU(ex2)-bound by design.
 #include "kernels.h"
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace ysi {
@@ -23,56 +33,75 @@ constexpr int BQ = 128, BKV = 64, HD = 64;
 constexpr int THREADS = 160;
 constexpr int Q_BYTES = BQ * HD * 2;        // 16 KB
 constexpr int KV_BYTES = BKV * HD * 2;      // 8 KB
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + Q_BYTES;            // 2 stages (also the rel_w table during setup)
-constexpr int OFF_V = OFF_K + 2 * KV_BYTES;       // 2 stages
-constexpr int OFF_P = OFF_V + 2 * KV_BYTES;       // 16 KB (also the rel_h table during setup)
-constexpr int OFF_REL = OFF_P + Q_BYTES;          // fp32 bias tables [k][128]
-constexpr int REL_BYTES = 64 * 128 * 4;           // 32 KB (global: rel_w; windowed: rel_h | rel_w, 14 rows each)
-constexpr int OFF_BAR = OFF_REL + REL_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;  // + alignment slack
-constexpr int TMEM_COLS = 256;
-constexpr int COL_TH = 0, COL_S = 128, COL_PV = 192, COL_TW = 128;
-}  // namespace attn
+constexpr int P_BYTES = BQ * BKV * 2;       // 16 KB
+constexpr float LAZY_LOG2 = 8.0f;           // rescale O only when the row max grows by more than 2^8
 
-__constant__ unsigned char c_div14[256];
+template <bool GLOBAL>
+struct Cfg {
+  static constexpr int NST = GLOBAL ? 3 : 4;                        // K / V ring depth (window: whole window)
+  static constexpr int KV_TOTAL = GLOBAL ? 3 * KV_BYTES : 208 * 128; // bytes of the K (and of the V) area
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;      // also rel_pos_h table during setup
+  static constexpr int OFF_V = OFF_K + KV_TOTAL;     // also rel_pos_w table during setup
+  static constexpr int OFF_P = OFF_V + KV_TOTAL;     // 2 x 16 KB; fp32 bias scratch [k][128] during setup
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+  static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
+  static constexpr int TMEM_COLS = GLOBAL ? 256 : 128;
+  static constexpr int COL_TH = 0;
+  static constexpr int COL_TW = GLOBAL ? 128 : 32;
+  static constexpr int COL_S = GLOBAL ? 128 : 0;            // aliases the tables (free after setup)
+  static constexpr int COL_O = GLOBAL ? 192 : 64;
+  static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0, "swizzle atoms need 1 KB alignment");
+};
+}  // namespace attn
 
 struct AttnParams {
   int T;          // sequence length: 196 (window) or 4096 (global)
   int D;          // heads * 64
-  float scale_log2e;   // hd^-0.5 * log2(e)
-  bf16* out;      // [n_seq * T, D]
+  int unwindow;   // windowed only: write rows in token order [img*4096 + y*64 + x] and drop the pad tokens
+  bf16* out;      // [n_seq * T, D]  (or [n_img * 4096, D] when unwindow)
 };
 
 template <bool GLOBAL>
 __global__ void __launch_bounds__(attn::THREADS, 2)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                         const __grid_constant__ CUtensorMap tmRel, AttnParams p) {
+                         const __grid_constant__ CUtensorMap tmKVtail, const __grid_constant__ CUtensorMap tmRel,
+                         AttnParams p) {
   using namespace attn;
+  using C = Cfg<GLOBAL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  float* rel_s = reinterpret_cast<float*>(sgen + OFF_REL);
-  const uint32_t bar = sbase + OFF_BAR;
-  const uint32_t bar_q = bar, bar_tab = bar + 8, bar_rel = bar + 16, bar_s = bar + 24, bar_p = bar + 32,
-                 bar_o = bar + 40, bar_kvfull0 = bar + 48, bar_kvempty0 = bar + 64;
-  const uint32_t tmem_ptr_smem = bar + 80;
+  float* rel_s = reinterpret_cast<float*>(sgen + C::OFF_P);
+  const uint32_t bar = sbase + C::OFF_BAR;
+  const uint32_t bar_q = bar, bar_tab = bar + 8, bar_rel = bar + 16, bar_s_full = bar + 24, bar_s_free = bar + 32;
+  const uint32_t bar_p_full = bar + 40;    // [2]
+  const uint32_t bar_p_free = bar + 56;    // [2]
+  const uint32_t bar_kfull = bar + 72;     // [4]
+  const uint32_t bar_kempty = bar + 104;   // [4]
+  const uint32_t bar_vfull = bar + 136;    // [4]
+  const uint32_t bar_vempty = bar + 168;   // [4]
+  const uint32_t tmem_ptr_smem = bar + 200;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int row0 = seq * p.T;                 // first row of this sequence in the qkv matrix
-  const int ntiles = (p.T + BKV - 1) / BKV;
+  const int ntiles = GLOBAL ? p.T / BKV : 4;
   const int cq = head * HD, ck = p.D + head * HD, cv = 2 * p.D + head * HD;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, 128); mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128); mbar_init(bar_o, 1);
-    mbar_init(bar_kvfull0, 1); mbar_init(bar_kvfull0 + 8, 1);
-    mbar_init(bar_kvempty0, 1); mbar_init(bar_kvempty0 + 8, 1);
+    mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, 128);
+    mbar_init(bar_s_full, 1); mbar_init(bar_s_free, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_p_full + 8 * i, 128); mbar_init(bar_p_free + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_kfull + 8 * i, 1); mbar_init(bar_kempty + 8 * i, 1);
+      mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
+    }
     fence_mbar_init();
   }
   if (warp == 4) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -83,67 +112,87 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp == 4) {
     if (lane == 0) {
-      constexpr uint32_t idesc_n128 = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, BKV, 0, 0);
+      constexpr uint32_t idesc_tab = umma_idesc_bf16(128, C::TAB_ROWS, 0, 0);
+      constexpr uint32_t idesc_s64 = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);   // B (= V) is MN-major
+      constexpr int TAB_BYTES = C::TAB_ROWS * 128;
       // ---- setup: Q tile + both rel-pos tables
-      mbar_arrive_expect_tx(bar_q, 3 * Q_BYTES);
-      tma_load_2d(sbase + OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
-      tma_load_2d(sbase + OFF_P, &tmRel, bar_q, 0, 0);      // rel_pos_h, 128 rows (zero padded)
-      tma_load_2d(sbase + OFF_K, &tmRel, bar_q, 0, 128);    // rel_pos_w
+      mbar_arrive_expect_tx(bar_q, Q_BYTES + 2 * TAB_BYTES);
+      tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
+      tma_load_2d(sbase + C::OFF_K, &tmRel, bar_q, 0, 0);      // rel_pos_h rows (zero padded)
+      tma_load_2d(sbase + C::OFF_V, &tmRel, bar_q, 0, 128);    // rel_pos_w rows
       mbar_wait(bar_q, 0);
       tc_fence_after();
-      const uint64_t qdesc = umma_desc_sw128(sbase + OFF_Q, 16, 1024);
+      const uint64_t qdesc = umma_desc_sw128(sbase + C::OFF_Q, 16, 1024);
       {
-        const uint64_t hdesc = umma_desc_sw128(sbase + OFF_P, 16, 1024);
-        const uint64_t wdesc = umma_desc_sw128(sbase + OFF_K, 16, 1024);
+        const uint64_t hdesc = umma_desc_sw128(sbase + C::OFF_K, 16, 1024);
+        const uint64_t wdesc = umma_desc_sw128(sbase + C::OFF_V, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_n128, k);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_tab, k);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + COL_TW, qdesc + 2u * k, wdesc + 2u * k, idesc_n128, k);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TW, qdesc + 2u * k, wdesc + 2u * k, idesc_tab, k);
         umma_commit(bar_tab);
       }
-      mbar_wait(bar_rel, 0);     // tables copied out of TMEM; K stages and S/PV columns are free
-      tc_fence_after();
-      // ---- K/V prologue
-      for (int j = 0; j < 2 && j < ntiles; ++j) {
-        mbar_arrive_expect_tx(bar_kvfull0 + 8 * j, 2 * KV_BYTES);
-        tma_load_2d(sbase + OFF_K + j * KV_BYTES, &tmKV, bar_kvfull0 + 8 * j, ck, row0 + j * BKV);
-        tma_load_2d(sbase + OFF_V + j * KV_BYTES, &tmKV, bar_kvfull0 + 8 * j, cv, row0 + j * BKV);
-      }
-      mbar_wait(bar_kvfull0, 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = umma_desc_sw128(sbase + OFF_K, 16, 1024);
+      mbar_wait(bar_tab, 0);     // tables consumed: the K / V areas are free
+      // ---- K / V prologue
+      auto load_k = [&](int tile, int st) {
+        const bool tail = !GLOBAL && tile == 3;
+        mbar_arrive_expect_tx(bar_kfull + 8 * st, tail ? 16 * 128 : KV_BYTES);
+        tma_load_2d(sbase + C::OFF_K + st * KV_BYTES, tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck, row0 + tile * BKV);
+      };
+      auto load_v = [&](int tile, int st) {
+        const bool tail = !GLOBAL && tile == 3;
+        mbar_arrive_expect_tx(bar_vfull + 8 * st, tail ? 16 * 128 : KV_BYTES);
+        tma_load_2d(sbase + C::OFF_V + st * KV_BYTES, tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv, row0 + tile * BKV);
+      };
+      for (int j = 0; j < C::NST && j < ntiles; ++j) load_k(j, j);
+      for (int j = 0; j < C::NST && j < ntiles; ++j) load_v(j, j);
+      auto issue_s = [&](int tile) {
+        const int st = tile % C::NST;
+        const uint64_t kdesc = umma_desc_sw128(sbase + C::OFF_K + st * KV_BYTES, 16, 1024);
+        const uint32_t idesc = (!GLOBAL && tile == 3) ? idesc_s16 : idesc_s64;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + COL_S, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k);
-        umma_commit(bar_s);
-      }
-      const uint64_t pdesc = umma_desc_sw128(sbase + OFF_P, 16, 1024);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_S, qdesc + 2u * k, kdesc + 2u * k, idesc, k);
+        umma_commit(bar_kempty + 8 * st);    // (the barrier somebody always waits on is committed last)
+        umma_commit(bar_s_full);
+      };
+      mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S / O columns are free
+      mbar_wait(bar_kfull, 0);
+      tc_fence_after();
+      issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(bar_p, j & 1);
-        tc_fence_after();
-        // PV_j : A = P (K-major, K = 64 keys), B = V_j (MN-major: 64 key rows x 64 hd); 16 keys = 2048 B
-        const uint64_t vdesc = umma_desc_sw128(sbase + OFF_V + st * KV_BYTES, 1024, 1024);
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) umma_bf16_ss(tmem_base + COL_PV, pdesc + 2u * k, vdesc + 128u * k, idesc_pv, k);
-        umma_commit(bar_o);
-        umma_commit(bar_kvempty0 + 8 * st);
         if (j + 1 < ntiles) {
-          const int sn = (j + 1) & 1;
-          mbar_wait(bar_kvfull0 + 8 * sn, ((j + 1) >> 1) & 1);
+          const int s1 = (j + 1) % C::NST;
+          mbar_wait(bar_kfull + 8 * s1, ((j + 1) / C::NST) & 1);
+          mbar_wait(bar_s_free, j & 1);           // S_j is in registers
           tc_fence_after();
-          const uint64_t kdesc = umma_desc_sw128(sbase + OFF_K + sn * KV_BYTES, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + COL_S, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k);
-          umma_commit(bar_s);
+          issue_s(j + 1);
         }
-        if (j + 2 < ntiles) {
-          mbar_wait(bar_kvempty0 + 8 * st, (j >> 1) & 1);
-          mbar_arrive_expect_tx(bar_kvfull0 + 8 * st, 2 * KV_BYTES);
-          tma_load_2d(sbase + OFF_K + st * KV_BYTES, &tmKV, bar_kvfull0 + 8 * st, ck, row0 + (j + 2) * BKV);
-          tma_load_2d(sbase + OFF_V + st * KV_BYTES, &tmKV, bar_kvfull0 + 8 * st, cv, row0 + (j + 2) * BKV);
+        const int st = j % C::NST, pb = j & 1;
+        mbar_wait(bar_vfull + 8 * st, (j / C::NST) & 1);
+        mbar_wait(bar_p_full + 8 * pb, (j >> 1) & 1);
+        tc_fence_after();
+        {
+          // O (+)= P_j V_j : A = P (K-major, K = keys), B = V_j (MN-major: key rows x 64 hd); 16 keys = 2048 B
+          const uint64_t pdesc = umma_desc_sw128(sbase + C::OFF_P + pb * P_BYTES, 16, 1024);
+          const uint64_t vdesc = umma_desc_sw128(sbase + C::OFF_V + st * KV_BYTES, 1024, 1024);
+          const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ss(tmem_base + C::COL_O, pdesc + 2u * k, vdesc + 128u * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_commit(bar_vempty + 8 * st);
+          umma_commit(bar_p_free + 8 * pb);
+        }
+        if (GLOBAL) {
+          if (j + C::NST < ntiles) {               // K stage of tile j was released by S_j long ago
+            mbar_wait(bar_kempty + 8 * st, (j / C::NST) & 1);
+            load_k(j + C::NST, st);
+          }
+          if (j >= 1 && j - 1 + C::NST < ntiles) { // V stage of tile j-1: PV_{j-1} was issued one iteration ago
+            const int sv = (j - 1) % C::NST;
+            mbar_wait(bar_vempty + 8 * sv, ((j - 1) / C::NST) & 1);
+            load_v(j - 1 + C::NST, sv);
+          }
         }
       }
     }
@@ -153,180 +202,219 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const int lq = qt * BQ + t;                      // query index inside the sequence
     const bool q_valid = lq < p.T;
+    const bool warp_active = GLOBAL || (qt * BQ + warp * 32) < p.T;   // warps with no valid query only keep the barriers moving
     int qh, qw;
-    if (GLOBAL) { qh = lq >> 6; qw = lq & 63; } else { qh = (lq < 196 ? lq : 195) / 14; qw = (lq < 196 ? lq : 195) - qh * 14; }
+    if (GLOBAL) { qh = lq >> 6; qw = lq & 63; } else { const int l = lq < 196 ? lq : 195; qh = l / 14; qw = l - qh * 14; }
     constexpr int S = GLOBAL ? 64 : 14;
+    constexpr int NB = GLOBAL ? 64 : 28;             // bias registers: rel_w[64] | rel_h[14] + rel_w[14]
+    float bias[NB];
 
     mbar_wait(bar_tab, 0);
     tc_fence_after();
-    // rel_w (and rel_h when windowed) -> smem [k][q], picking column (q_pos - k_pos + S-1) of Q.table^T
-    {
-      const int ncol = 2 * S - 1;
-      for (int c0 = 0; c0 < ncol; c0 += 32) {
+    // Q.table^T sits in TMEM as [query][table row]; thread t needs column (q_pos - k_pos + S-1) for every key
+    // position: scatter through smem scratch [k][t] (the column is thread dependent), then keep it in registers.
+    if (GLOBAL) {
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t r[32];
-        tmem_ld_x32(tlane + COL_TW + c0, r);
+        tmem_ld_x32p(tlane + C::COL_TW + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kw = qw + (S - 1) - (c0 + i);
-          if (kw >= 0 && kw < S) rel_s[(GLOBAL ? 0 : 14 * 128) + kw * 128 + t] = __uint_as_float(r[i]);
+          if (kw >= 0 && kw < S) rel_s[kw * 128 + t] = __uint_as_float(r[i]);
         }
       }
-      if (!GLOBAL) {
-        uint32_t r[32];
-        tmem_ld_x32(tlane + COL_TH, r);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kh = qh + (S - 1) - i;
-          if (kh >= 0 && kh < S) rel_s[kh * 128 + t] = __uint_as_float(r[i]);
-        }
+      for (int i = 0; i < 64; ++i) bias[i] = rel_s[i * 128 + t];
+    } else {
+      uint32_t r[32];
+      tmem_ld_x32p(tlane + C::COL_TH, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kh = qh + (S - 1) - i;
+        if (kh >= 0 && kh < S) rel_s[kh * 128 + t] = __uint_as_float(r[i]);
       }
+      tmem_ld_x32p(tlane + C::COL_TW, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kw = qw + (S - 1) - i;
+        if (kw >= 0 && kw < S) rel_s[(14 + kw) * 128 + t] = __uint_as_float(r[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 28; ++i) bias[i] = rel_s[i * 128 + t];
     }
     tc_fence_before();
     mbar_arrive(bar_rel);
 
-    const float LOG2E = 1.4426950408889634f;
-    float m_run = -1.0e30f, l_run = 0.0f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.0f;
-    const uint32_t p_row = sbase + OFF_P + static_cast<uint32_t>(t) * 128u;
+    float m_used = -INFINITY;
+    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
+    const uint32_t p_row0 = sbase + C::OFF_P + static_cast<uint32_t>(t) * 128u;
     const uint32_t swz = static_cast<uint32_t>(t & 7);
 
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(bar_s, j & 1);
+    // one KV tile: NW columns of S, the first NV of them valid keys
+    auto do_tile = [&](auto nw_c, auto nv_c, int j, const float* b /* NW bias values (log2 units) */) {
+      constexpr int NW = decltype(nw_c)::value, NV = decltype(nv_c)::value;
+      mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
-      float x[BKV];
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld_x32(tlane + COL_S, r0);
-        tmem_ld_x32(tlane + COL_S + 32, r1);
-        float bh = 0.0f;
+      uint32_t r[NW];
+      float bh = 0.f;
+      if (warp_active) {
+        if constexpr (NW == 64) { tmem_ld_x32p(tlane + C::COL_S, r); tmem_ld_x32p(tlane + C::COL_S + 32, r + 32); }
+        else tmem_ld_x16p(tlane + C::COL_S, r);
         if (GLOBAL) {
           uint32_t rb;
-          tmem_ld_x1(tlane + COL_TH + static_cast<uint32_t>(qh + 63 - j), rb);   // warp-uniform column
+          tmem_ld_x1(tlane + C::COL_TH + static_cast<uint32_t>(qh + 63 - j), rb);   // warp-uniform column
           tmem_ld_wait();
-          bh = __uint_as_float(rb) * LOG2E;
+          bh = __uint_as_float(rb);
         } else {
           tmem_ld_wait();
         }
-#pragma unroll
-        for (int i = 0; i < BKV; ++i) {
-          const float s = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-          if (GLOBAL) {
-            x[i] = fmaf(s, p.scale_log2e, fmaf(rel_s[i * 128 + t], LOG2E, bh));
-          } else {
-            const int k = j * BKV + i;
-            if (k < 196) {
-              const int kh = c_div14[k], kw = k - 14 * kh;
-              x[i] = fmaf(s, p.scale_log2e, (rel_s[kh * 128 + t] + rel_s[14 * 128 + kw * 128 + t]) * LOG2E);
-            } else {
-              x[i] = -INFINITY;
-            }
-          }
-        }
       }
-      float tmax = x[0];
-#pragma unroll
-      for (int i = 1; i < BKV; ++i) tmax = fmaxf(tmax, x[i]);
-      const float m_new = fmaxf(m_run, tmax);
-      const float alpha = ex2_approx(m_run - m_new);
-      float lsum = 0.0f;
-      uint32_t pk[BKV / 2];
-#pragma unroll
-      for (int i = 0; i < BKV; i += 2) {
-        const float p0 = ex2_approx(x[i] - m_new), p1 = ex2_approx(x[i + 1] - m_new);
-        lsum += p0 + p1;
-        pk[i / 2] = pack_bf16x2(p0, p1);
-      }
-      l_run = fmaf(l_run, alpha, lsum);
-      m_run = m_new;
-      if (j > 0) {
-        // PV_{j-1} (relative to the previous max) is complete; fold it in, then rescale to the new max
-        mbar_wait(bar_o, (j - 1) & 1);
-        tc_fence_after();
-        uint32_t r0[32], r1[32];
-        tmem_ld_x32(tlane + COL_PV, r0);
-        tmem_ld_x32(tlane + COL_PV + 32, r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          o[i] = (o[i] + __uint_as_float(r0[i])) * alpha;
-          o[i + 32] = (o[i + 32] + __uint_as_float(r1[i])) * alpha;
-        }
-      }
-      // P_j -> smem (K-major, 128B swizzle: 16-byte chunk c of row t lands at chunk c ^ (t & 7))
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = p_row + ((static_cast<uint32_t>(c) ^ swz) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
-                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                     : "memory");
-      }
-      fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
-    }
-    mbar_wait(bar_o, (ntiles - 1) & 1);
-    tc_fence_after();
-    {
-      uint32_t r0[32], r1[32];
-      tmem_ld_x32(tlane + COL_PV, r0);
-      tmem_ld_x32(tlane + COL_PV + 32, r1);
-      tmem_ld_wait();
-      const float inv = 1.0f / l_run;
+      mbar_arrive(bar_s_free);
+      const int pb = j & 1;
+      if (warp_active) {
+        float2 y[NW / 2];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o[i] = (o[i] + __uint_as_float(r0[i])) * inv;
-        o[i + 32] = (o[i + 32] + __uint_as_float(r1[i])) * inv;
+        for (int i = 0; i < NW / 2; ++i)
+          y[i] = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(b[2 * i], b[2 * i + 1]));
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
+        const float m_cand = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
+        if (__any_sync(0xFFFFFFFFu, m_cand > m_used + LAZY_LOG2)) {
+          const float m_new = fmaxf(m_used, m_cand);
+          if (j > 0) {
+            // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed, PV_j has not been issued
+            const float f = ex2_approx(m_used - m_new);
+            mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int qr = 0; qr < 4; ++qr) {
+              uint32_t o[16];
+              tmem_ld_x16p(tlane + C::COL_O + 16 * qr, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_x16p(tlane + C::COL_O + 16 * qr, o);
+            }
+            tmem_st_wait();
+            l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
+          }
+          m_used = m_new;
+        }
+        const float c = bh - m_used;
+        const float2 c2 = make_float2(c, c);
+        if (j >= 2) mbar_wait(bar_p_free + 8 * pb, ((j - 2) >> 1) & 1);    // P buffer consumed by PV_{j-2}
+        const uint32_t p_row = p_row0 + pb * P_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < NW / 8; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int i = ch * 4 + h;                 // pair index
+            float2 e = add2(y[i], c2);
+            e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
+            e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
+            if (h & 1) l2b = add2(l2b, e); else l2a = add2(l2a, e);
+            pk[h] = pack_bf16x2(e.x, e.y);
+          }
+          // K-major, 128B swizzle: 16-byte chunk ch of row t lands at chunk ch ^ (t & 7)
+          const uint32_t addr = p_row + ((static_cast<uint32_t>(ch) ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+      }
+      mbar_arrive(bar_p_full + 8 * pb);
+    };
+
+    if (GLOBAL) {
+      for (int j = 0; j < ntiles; ++j) do_tile(std::integral_constant<int, 64>{}, std::integral_constant<int, 64>{}, j, bias);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // key k = 64 j + i of the window: kh = k / 14, kw = k % 14 (compile-time after unrolling)
+        if (j < 3) {
+          float b[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) b[i] = bias[(64 * j + i) / 14] + bias[14 + (64 * j + i) % 14];
+          do_tile(std::integral_constant<int, 64>{}, std::integral_constant<int, 64>{}, j, b);
+        } else {
+          float b[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) b[i] = i < 4 ? bias[(192 + i) / 14] + bias[14 + (192 + i) % 14] : 0.f;
+          do_tile(std::integral_constant<int, 16>{}, std::integral_constant<int, 4>{}, j, b);
+        }
       }
     }
-    if (q_valid) {
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row0 + lq) * p.D + head * HD);
+    mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
+    tc_fence_after();
+    if (warp_active) {
+      uint32_t o[64];
+      tmem_ld_x32p(tlane + C::COL_O, o);
+      tmem_ld_x32p(tlane + C::COL_O + 32, o + 32);
+      tmem_ld_wait();
+      const float inv = 1.0f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
+      long long orow = -1;
+      if (q_valid) {
+        if (!GLOBAL && p.unwindow) {
+          const int img = seq / 25, win = seq - img * 25;
+          const int y = (win / 5) * 14 + qh, x = (win % 5) * 14 + qw;
+          if (y < 64 && x < 64) orow = static_cast<long long>(img) * 4096 + y * 64 + x;
+        } else {
+          orow = static_cast<long long>(row0) + lq;
+        }
+      }
+      if (orow >= 0) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(orow) * p.D + head * HD);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 v;
-        v.x = pack_bf16x2(o[8 * c], o[8 * c + 1]);
-        v.y = pack_bf16x2(o[8 * c + 2], o[8 * c + 3]);
-        v.z = pack_bf16x2(o[8 * c + 4], o[8 * c + 5]);
-        v.w = pack_bf16x2(o[8 * c + 6], o[8 * c + 7]);
-        dst[c] = v;
+        for (int c = 0; c < 8; ++c) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          dst[c] = v;
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, attn::TMEM_COLS);
+  if (warp == 4) tmem_dealloc(tmem_base, Cfg<GLOBAL>::TMEM_COLS);
 }
 
-// qkv: bf16 [n_seq*T, 3D]; rel_tab: bf16 [256, 64] (rows 0..127 rel_pos_h zero-padded, 128..255 rel_pos_w)
+// qkv: bf16 [n_seq*T, 3D] with the K columns pre-scaled by 0.125*log2(e); rel_tab: bf16 [256, 64] pre-scaled by
+// log2(e) (rows 0..127 rel_pos_h zero-padded, 128..255 rel_pos_w). unwindow: see AttnParams.
 void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads,
-                              bool is_global, cudaStream_t stream) {
+                              bool is_global, bool unwindow, cudaStream_t stream) {
   using namespace attn;
   static bool init = false;
   if (!init) {
-    unsigned char h[256];
-    for (int i = 0; i < 256; ++i) h[i] = static_cast<unsigned char>(i / 14);
-    YSI_CUDA(cudaMemcpyToSymbol(c_div14, h, sizeof(h)));
-    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
     init = true;
   }
   const int D = heads * HD;
   const long long rows = static_cast<long long>(n_seq) * T;
   YSI_CHECK(is_global ? T == 4096 : T == 196, "attention kernel supports T = 4096 (global) or 196 (window)");
+  YSI_CHECK(!unwindow || (!is_global && n_seq % 25 == 0), "unwindow needs whole images of 25 windows");
   const CUtensorMap tmQ = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BQ);
   const CUtensorMap tmKV = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BKV);
-  const CUtensorMap tmRel = make_tmap_bf16_2d(rel_tab, 256, HD, HD, 128);
+  const CUtensorMap tmKVtail = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, 16);
+  const CUtensorMap tmRel = make_tmap_bf16_2d(rel_tab, 256, HD, HD, is_global ? 128 : 32);
   AttnParams p;
-  p.T = T; p.D = D; p.out = out;
-  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  p.T = T; p.D = D; p.out = out; p.unwindow = unwindow ? 1 : 0;
   dim3 grid(ceil_div(T, BQ), heads, n_seq);
   if (is_global)
-    encoder_attention_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmRel, p);
+    encoder_attention_kernel<true><<<grid, THREADS, Cfg<true>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, p);
   else
-    encoder_attention_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmRel, p);
+    encoder_attention_kernel<false><<<grid, THREADS, Cfg<false>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, p);
   YSI_CUDA(cudaGetLastError());
 }
 

@@ -468,10 +468,10 @@ token_final_kernel(DecoderW w, const float* __restrict__ attn_t2i, const float* 
 struct EpiConvT1 {
   const float *bias, *g, *b;
   bf16* out;   // [nb*16384, 64]
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int BN) const {
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end) const {
     const bool active = row < M;
     const int box = row >> 12, tok = row & 4095, y = tok >> 6, x = tok & 63;
-    for (int sp = 0; sp < 4; ++sp) {
+    for (int sp = c_begin / 64; sp < c_end / 64; ++sp) {
       uint32_t r0[32], r1[32];
       tmem_ld_x32(taddr_row + sp * 64, r0);
       tmem_ld_x32(taddr_row + sp * 64 + 32, r1);
@@ -513,10 +513,10 @@ struct EpiConvT2 {
   const float* bias;    // [32]
   const float* hyper;   // [nb,32]
   float* low;           // [nb,256,256]
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int BN) const {
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end) const {
     const bool active = row < M;
     const int box = row >> 14, pos = row & 16383, Y = pos >> 7, X = pos & 127;
-    for (int sp = 0; sp < 4; ++sp) {
+    for (int sp = c_begin / 32; sp < c_end / 32; ++sp) {
       uint32_t r[32];
       tmem_ld_x32(taddr_row + sp * 32, r);
       tmem_ld_wait();

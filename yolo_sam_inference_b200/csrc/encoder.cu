@@ -236,6 +236,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     {
       GemmEpilogue ep;
       ep.bias = lw.b_qkv; ep.out_bf16 = work.qkv; ep.ld_out_bf16 = 3 * D;
+      ep.col_scale = ATTN_K_SCALE; ep.scale_c0 = D; ep.scale_c1 = 2 * D;     // K in log2 units for the attention kernel
       ProfScope ps(prof, KC_GEMM_QKV, 2.0 * T * 3 * D * D);
       gemm_bf16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
     }
@@ -243,14 +244,13 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
       const double S = glob ? 64.0 : 14.0, tok = glob ? 4096.0 : 196.0, nseq = glob ? n : n * 25.0;
       // QK^T + PV (4 * T^2 * hd per head) + rel-pos terms (2 * 2 * T * S * hd per head)
       ProfScope ps(prof, glob ? KC_ATTN_GLOBAL : KC_ATTN_WINDOW, nseq * w.heads * (4.0 * tok * tok * 64 + 4.0 * tok * S * 64));
-      launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, glob, s); ++nl;
+      launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, glob, !glob, s); ++nl;
     }
     {
-      GemmEpilogue ep;   // x += attn * Wproj^T + b ; windowed rows scatter back through the partition map
+      GemmEpilogue ep;   // x += attn * Wproj^T + b ; the attention kernel already un-partitioned the windows
       ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
-      ep.row_map = glob ? nullptr : work.win_row_map;
       ProfScope ps(prof, KC_GEMM_PROJ, 2.0 * T * D * D);
-      gemm_bf16(work.attn, D, lw.w_proj, D, rows, D, D, ep, s); ++nl;
+      gemm_bf16(work.attn, D, lw.w_proj, D, T, D, D, ep, s); ++nl;
     }
     { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s); ++nl; }
     {

@@ -2,7 +2,9 @@
 //   bf16 operands (K-major, TMA-loaded into 128B-swizzled shared memory), fp32 accumulators in TMEM.
 //   warp 0   : TMA producer (one elected lane)          -- STAGES-deep smem ring, full/empty mbarriers
 //   warp 1   : TMEM allocator + MMA issuer (one lane)    -- tcgen05.mma 128 x BN x 16, commit -> mbarriers
-//   warps 2-5: epilogue (TMEM -> registers -> global)    -- double-buffered accumulator (2 x BN columns)
+//   warps 2-9: epilogue (TMEM -> registers -> global)    -- double-buffered accumulator (2 x BN columns);
+//              warp w owns TMEM lane quarter w%4 and column half (w-2)/4, so two warps per SM sub-partition
+//              keep loads / MUFU / stores of the epilogue in flight while the next tile's MMAs run
 // The epilogue is a functor so the same mainloop serves the ViT linears (bias / GELU / residual add),
 // the decoder projections and the fused ConvTranspose upscaler epilogues.
 #pragma once
@@ -13,7 +15,8 @@ namespace ysi {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -27,10 +30,48 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-GELU on a pair of values (packed FFMA2 / FMUL2), erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7):
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z = |x| / sqrt(2)
+//   gelu(x) = x/2 + |x/2| * erf(z)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 d = fma2(ax, make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  float2 q = fma2(t, make_float2(-1.061405429f, -1.061405429f), make_float2(1.453152027f, 1.453152027f));
+  q = fma2(q, t, make_float2(-1.421413741f, -1.421413741f));
+  q = fma2(q, t, make_float2(0.284496736f, 0.284496736f));
+  q = fma2(q, t, make_float2(-0.254829592f, -0.254829592f));
+  q = mul2(q, t);                                             // = -(a1 t + ... + a5 t^5)
+  float2 s = mul2(x, x);
+  s = mul2(s, make_float2(-0.72134752044448170f, -0.72134752044448170f));   // -z^2 * log2(e) = -x^2/2 * log2(e)
+  const float2 e = make_float2(ex2_approx(s.x), ex2_approx(s.y));
+  const float2 erfv = fma2(q, e, make_float2(1.f, 1.f));
+  const float2 hx = mul2(x, make_float2(0.5f, 0.5f));
+  return fma2(make_float2(fabsf(hx.x), fabsf(hx.y)), erfv, hx);
+}
+
 // Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_bf16.
 struct EpiGeneric {
   GemmEpilogue p;
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int BN) const {
+  // columns [c_begin, c_end) of the BN-wide accumulator tile belong to the calling warp
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end) const {
     // every lane must execute the warp-collective tcgen05.ld convergently: predicate only the stores
     int drow = -1;
     if (row < M) drow = p.row_map ? p.row_map[row] : row;
@@ -40,7 +81,7 @@ struct EpiGeneric {
       const int arow = p.add_group ? p.add_group[row / p.add_mod] * p.add_mod + row % p.add_mod : row % p.add_mod;
       addp = p.add_src + static_cast<size_t>(arow) * p.ld_add;
     }
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       const int col0 = n0 + c;
       if (col0 >= N) break;          // uniform; N is a multiple of 32 (checked on the host)
       uint32_t r[32];
@@ -58,9 +99,16 @@ struct EpiGeneric {
           v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
       }
+      if (col0 >= p.scale_c0 && col0 < p.scale_c1) {     // uniform per 32-column chunk
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= p.col_scale;
+      }
       if (p.act == ACT_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 32; i += 2) {
+          const float2 g = gelu_erf2(make_float2(v[i], v[i + 1]));
+          v[i] = g.x; v[i + 1] = g.y;
+        }
       } else if (p.act == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
@@ -132,7 +180,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -194,6 +242,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -202,7 +252,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, BN);
+      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

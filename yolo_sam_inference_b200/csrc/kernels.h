@@ -41,14 +41,18 @@ void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16
 
 // ------------------------------------------------------------------ encoder
 // fused flash-style attention with decomposed rel-pos bias (attn.cu)
+// qkv K columns pre-scaled by hd^-0.5 * log2(e), rel_tab pre-scaled by log2(e) (see attn.cu);
+// unwindow (windowed only): rows are written in token order and the 64->70 pad tokens are dropped
+constexpr float ATTN_K_SCALE = 0.125f * 1.4426950408889634f;
+constexpr float ATTN_LOG2E = 1.4426950408889634f;
 void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads,
-                              bool is_global, cudaStream_t stream);
+                              bool is_global, bool unwindow, cudaStream_t stream);
 
 struct EncoderLayerW {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   const bf16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
   const float *b_qkv, *b_proj, *b_fc1, *b_fc2;
-  const bf16* rel_tab;   // [256,64]: rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
+  const bf16* rel_tab;   // [256,64] * log2(e): rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
   int is_global;
 };
 
@@ -70,7 +74,7 @@ struct EncoderWork {      // activation workspace for `cap` images
   float* x;               // [cap*4096, D]   fp32 residual stream
   bf16* h;                // [cap*4900, D]
   bf16* qkv;              // [cap*4900, 3D]
-  bf16* attn;             // [cap*4900, D]
+  bf16* attn;             // [cap*4096, D]  attention output in token order
   bf16* u;                // [cap*4096, mlp]
   float* n1;              // [cap*4096, 256]
   bf16* n1b;              // [cap*4096, 256]
