@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BATCH = 8                    # images per step
+BATCH = int(os.environ.get("YSI_BENCH_BATCH", "8"))   # images per step
 POOL_IMAGES = 256            # BASELINE configs[1]: 256 synthetic 1024x1024 images
 ENC_FLOPS_VIT_B = 937.6e9    # algorithmic FLOPs / image
 DEC_FLOPS_BOX = 3.61e9
@@ -324,7 +324,7 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "configs[1]: SAM ViT-B bf16 (fp32 accumulate/residual), 256 synthetic 1024x1024 "
-                                   "images per GPU, 1 box/image, batch 8 images per step",
+                                   f"images per GPU, 1 box/image, batch {BATCH} images per step",
                        "batch": BATCH, "pool_images_per_gpu": pool_n, "weights": "seeded random-init (no checkpoints offline)",
                        "l2": "inputs differ every step and the per-step working set (~0.9 GB of activations) exceeds the "
                              "126 MB L2, so no L2 flush is needed between timed iterations",

@@ -1,4 +1,5 @@
 // C ABI of libysi.so (include/ysi.h): context, weight upload, workspaces and the run entry points.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -147,6 +148,7 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   // ---------------- encoder
   EncoderW& e = c->enc;
   e.D = D; e.L = L; e.heads = heads; e.mlp = mlp;
+  if (const char* rm = getenv("YSI_RESIDUAL_MODE")) e.residual_mode = atoi(rm) == 1 ? 1 : 2;   // tuning knob (bench only)
   e.w_patch = b16("vision_encoder.patch_embed.projection.weight", {D, 3, 16, 16});
   e.b_patch = f32("vision_encoder.patch_embed.projection.bias", {D});
   e.pos_embed = f32("vision_encoder.pos_embed", {1, 64, 64, D});
@@ -330,6 +332,7 @@ void create_impl(ysi_ctx* c) {
   dw.k_tok = c->dalloc<float>(NB * 7 * 128);
   dw.v_tok = c->dalloc<float>(NB * 7 * 128);
   dw.hyper = c->dalloc<float>(NB * 32);
+  dw.tok_ws = c->dalloc<float>(NB * (7 * (6 * 256 + 2048) + 2 * 256 + 8 * 4 * 126));
   dw.boxes1024 = c->dalloc<double>(NB * 4);
   dw.box_img = c->dalloc<int>(NB);
   c->d_rgb = c->dalloc<uint8_t>(B * HW * 3);

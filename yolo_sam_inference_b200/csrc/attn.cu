@@ -44,6 +44,10 @@ struct Cfg {
   static constexpr int OFF_K = OFF_Q + Q_BYTES;      // also rel_pos_h table during setup
   static constexpr int OFF_V = OFF_K + KV_TOTAL;     // also rel_pos_w table during setup
   static constexpr int OFF_P = OFF_V + KV_TOTAL;     // 2 x 16 KB; fp32 bias scratch [k][128] during setup
+  // rel-pos tables as TMA'd for the table MMA: global -> the K / V areas (16 KB each, K/V loads wait for the MMA);
+  // windowed -> second P buffer (4 KB each), so the whole window's K / V can be requested up front with Q
+  static constexpr int OFF_TABH = GLOBAL ? OFF_K : OFF_P + P_BYTES;
+  static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_P + P_BYTES + 4096;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
   static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
@@ -120,22 +124,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       // ---- setup: Q tile + both rel-pos tables
       mbar_arrive_expect_tx(bar_q, Q_BYTES + 2 * TAB_BYTES);
       tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
-      tma_load_2d(sbase + C::OFF_K, &tmRel, bar_q, 0, 0);      // rel_pos_h rows (zero padded)
-      tma_load_2d(sbase + C::OFF_V, &tmRel, bar_q, 0, 128);    // rel_pos_w rows
-      mbar_wait(bar_q, 0);
-      tc_fence_after();
-      const uint64_t qdesc = umma_desc_sw128(sbase + C::OFF_Q, 16, 1024);
-      {
-        const uint64_t hdesc = umma_desc_sw128(sbase + C::OFF_K, 16, 1024);
-        const uint64_t wdesc = umma_desc_sw128(sbase + C::OFF_V, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_tab, k);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TW, qdesc + 2u * k, wdesc + 2u * k, idesc_tab, k);
-        umma_commit(bar_tab);
-      }
-      mbar_wait(bar_tab, 0);     // tables consumed: the K / V areas are free
-      // ---- K / V prologue
+      tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);      // rel_pos_h rows (zero padded)
+      tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);    // rel_pos_w rows
       auto load_k = [&](int tile, int st) {
         const bool tail = !GLOBAL && tile == 3;
         mbar_arrive_expect_tx(bar_kfull + 8 * st, tail ? 16 * 128 : KV_BYTES);
@@ -146,8 +136,27 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_arrive_expect_tx(bar_vfull + 8 * st, tail ? 16 * 128 : KV_BYTES);
         tma_load_2d(sbase + C::OFF_V + st * KV_BYTES, tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv, row0 + tile * BKV);
       };
-      for (int j = 0; j < C::NST && j < ntiles; ++j) load_k(j, j);
-      for (int j = 0; j < C::NST && j < ntiles; ++j) load_v(j, j);
+      if (!GLOBAL) {             // whole window: K / V do not alias the tables, request them right away
+        for (int j = 0; j < 4; ++j) load_k(j, j);
+        for (int j = 0; j < 4; ++j) load_v(j, j);
+      }
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      const uint64_t qdesc = umma_desc_sw128(sbase + C::OFF_Q, 16, 1024);
+      {
+        const uint64_t hdesc = umma_desc_sw128(sbase + C::OFF_TABH, 16, 1024);
+        const uint64_t wdesc = umma_desc_sw128(sbase + C::OFF_TABW, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_tab, k);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TW, qdesc + 2u * k, wdesc + 2u * k, idesc_tab, k);
+        umma_commit(bar_tab);
+      }
+      if (GLOBAL) {
+        mbar_wait(bar_tab, 0);     // tables consumed: the K / V areas are free
+        for (int j = 0; j < C::NST && j < ntiles; ++j) load_k(j, j);
+        for (int j = 0; j < C::NST && j < ntiles; ++j) load_v(j, j);
+      }
       auto issue_s = [&](int tile) {
         const int st = tile % C::NST;
         const uint64_t kdesc = umma_desc_sw128(sbase + C::OFF_K + st * KV_BYTES, 16, 1024);

@@ -52,7 +52,7 @@ struct GemmEpilogue {
   const int* add_group = nullptr;  // optional: add row = add_group[row / add_mod] * add_mod + row % add_mod
   const int* row_map = nullptr;  // optional destination row per GEMM row (<0: drop the row)
   float* out_f32 = nullptr;      // optional fp32 destination [*, ld_out]
-  int accumulate = 0;            // out_f32 += value instead of =
+  int accumulate = 0;            // 1: out_f32 += value (load/add/store); 2: same sum through red.global.add (L2 atomics)
   float col_scale = 1.0f;        // columns [scale_c0, scale_c1) are multiplied by col_scale after the bias
   int scale_c0 = 0, scale_c1 = 0;  //   (multiples of 32; used to hand K to the attention kernel in log2 units)
   bf16* out_bf16 = nullptr;      // optional bf16 destination [*, ld_out_bf16]

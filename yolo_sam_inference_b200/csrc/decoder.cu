@@ -127,88 +127,110 @@ keys_ln_kernel(const float* __restrict__ in, long long rows, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
-// token-side building blocks (one CTA of 256 threads per box; activations in shared memory)
+// token-side building blocks. The 7 tokens of every box are rows of one [R = 7 nb, C] fp32 matrix, and each
+// linear layer is one launch over all boxes: a warp owns one output column (its weight row lives in
+// registers) and walks the rows four at a time, so the grid is N/8 CTAs instead of one CTA per box.
 // ---------------------------------------------------------------------------------------------------
-// y[r][n] = act(sum_k x[r][k] W[n][k] + b[n]) for r < 7. Warp per output column, lanes over K.
-__device__ void cta_linear(const float* x_s, int K, const float* __restrict__ W, const float* __restrict__ bias, int N,
-                           float* y_s, int ldy, bool relu) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int n = warp; n < N; n += 8) {
-    float acc[NT];
-#pragma unroll
-    for (int r = 0; r < NT; ++r) acc[r] = 0.f;
-    const float4* wr = reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K);
-    for (int k4 = lane; k4 < K / 4; k4 += 32) {
-      const float4 wv = __ldg(wr + k4);
-#pragma unroll
-      for (int r = 0; r < NT; ++r) {
-        const float4 xv = reinterpret_cast<const float4*>(x_s + r * K)[k4];
-        acc[r] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[r]))));
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < NT; ++r) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xFFFFFFFFu, acc[r], o);
-    }
-    if (lane == 0) {
-      const float b = bias ? bias[n] : 0.f;
-#pragma unroll
-      for (int r = 0; r < NT; ++r) {
-        float v = acc[r] + b;
-        if (relu) v = fmaxf(v, 0.f);
-        y_s[r * ldy + n] = v;
-      }
-    }
-  }
-}
+struct TokLin {
+  const float* X;  const float* Xadd;  int ldx;     // input rows (optionally X + Xadd), row pitch ldx
+  const float* W;  const float* b;                   // [N, K], [N]
+  const float* res;  int ldres;                      // optional residual added to the output
+  float* Y;  int ldy;
+  int K, N, relu;                                    // K multiple of 128, <= 2048
+};
+struct TokLin3 { TokLin t[3]; };
 
-// in-place LayerNorm of 7 rows of 256 in shared memory (warp r handles row r)
-__device__ void cta_layernorm(float* x_s, const float* __restrict__ g, const float* __restrict__ b, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < NT) {
-    float* row = x_s + warp * C;
-    float v[8];
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { v[k] = row[lane + 32 * k]; sum += v[k]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-    const float mean = sum / C;
-    float sq = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; sq += d * d; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
-    const float rstd = rsqrtf(sq / C + eps);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) row[lane + 32 * k] = (v[k] - mean) * rstd * g[lane + 32 * k] + b[lane + 32 * k];
-  }
-}
+constexpr int TOK_ROWS = 8;     // rows per CTA
 
-// TK1: self attention (+LN1) of the 7 tokens, then the token->image query projection   (:316-327)
 __global__ void __launch_bounds__(256)
-token_self_attn_kernel(DecLayerW lw, int first_layer, const float* __restrict__ tok0, float* __restrict__ queries,
-                       float* __restrict__ q_t2i) {
-  __shared__ __align__(16) float s_q[NT * C], s_in[NT * C], s_a[NT * C], s_b[NT * C], s_c[NT * C];
+tok_linear_kernel(TokLin3 P, int R) {
+  const TokLin& p = P.t[blockIdx.z];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= p.N) return;
+  const int nk4 = p.K >> 7;
+  float4 w[16];
+  const float4* wr = reinterpret_cast<const float4*>(p.W + static_cast<size_t>(n) * p.K);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < nk4) w[i] = __ldg(wr + i * 32 + lane);
+  const float bias = p.b ? __ldg(p.b + n) : 0.f;
+  const int rbeg = blockIdx.y * TOK_ROWS, rend = min(R, rbeg + TOK_ROWS);
+  for (int r0 = rbeg; r0 < rend; r0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < nk4) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          if (r0 + rr < rend) {
+            float4 x = __ldg(reinterpret_cast<const float4*>(p.X + static_cast<size_t>(r0 + rr) * p.ldx) + i * 32 + lane);
+            if (p.Xadd) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.Xadd + static_cast<size_t>(r0 + rr) * p.ldx) + i * 32 + lane);
+              x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+            }
+            acc[rr] = fmaf(x.x, w[i].x, fmaf(x.y, w[i].y, fmaf(x.z, w[i].z, fmaf(x.w, w[i].w, acc[rr]))));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[rr] += __shfl_xor_sync(0xFFFFFFFFu, acc[rr], o);
+    }
+    if (lane < 4 && r0 + lane < rend) {
+      float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + bias;
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.res) v += p.res[static_cast<size_t>(r0 + lane) * p.ldres + n];
+      p.Y[static_cast<size_t>(r0 + lane) * p.ldy + n] = v;
+    }
+  }
+}
+
+// LayerNorm over rows of 256 (warp per row) -> out, and optionally out + pe
+__global__ void __launch_bounds__(256)
+tok_layernorm_kernel(const float* __restrict__ in, int R, const float* __restrict__ g, const float* __restrict__ b, float eps,
+                     const float* __restrict__ pe, float* __restrict__ out, float* __restrict__ out_pe) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* x = in + static_cast<size_t>(row) * C;
+  float v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = x[lane + 32 * k]; sum += v[k]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; sq += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = lane + 32 * k;
+    const float y = (v[k] - mean) * rstd * g[c] + b[c];
+    out[static_cast<size_t>(row) * C + c] = y;
+    if (out_pe) out_pe[static_cast<size_t>(row) * C + c] = y + pe[static_cast<size_t>(row) * C + c];
+  }
+}
+
+// self-attention core over the 7 tokens of one box: 8 heads x 32 dims, scale 32^-0.5   (:208-231)
+__global__ void __launch_bounds__(256)
+tok_self_attn_core_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                          float* __restrict__ out) {
+  __shared__ float s_q[NT * C], s_k[NT * C], s_v[NT * C];
   __shared__ float s_p[8 * NT * NT];
   const int b = blockIdx.x, t = threadIdx.x;
-  const float* pe = tok0 + static_cast<size_t>(b) * NT * C;
-  const float* qin = (first_layer ? tok0 : queries) + static_cast<size_t>(b) * NT * C;
-  for (int i = t; i < NT * C; i += 256) {
-    s_q[i] = qin[i];
-    s_in[i] = first_layer ? qin[i] : qin[i] + pe[i];    // q = k = queries (+ pe unless skip_first_layer_pe)
-  }
+  const size_t base = static_cast<size_t>(b) * NT * C;
+  for (int i = t; i < NT * C; i += 256) { s_q[i] = q[base + i]; s_k[i] = k[base + i]; s_v[i] = v[base + i]; }
   __syncthreads();
-  cta_linear(s_in, C, lw.self_attn.wq, lw.self_attn.bq, C, s_a, C, false);
-  cta_linear(s_in, C, lw.self_attn.wk, lw.self_attn.bk, C, s_b, C, false);
-  cta_linear(s_q, C, lw.self_attn.wv, lw.self_attn.bv, C, s_c, C, false);
-  __syncthreads();
-  // 8 heads x 32 dims, scale 32^-0.5
   for (int i = t; i < 8 * NT * NT; i += 256) {
     const int h = i / (NT * NT), r = (i / NT) % NT, c = i % NT;
     float acc = 0.f;
-    for (int d = 0; d < 32; ++d) acc = fmaf(s_a[r * C + h * 32 + d], s_b[c * C + h * 32 + d], acc);
+    for (int d = 0; d < 32; ++d) acc = fmaf(s_q[r * C + h * 32 + d], s_k[c * C + h * 32 + d], acc);
     s_p[i] = acc * 0.17677669529663687f;
   }
   __syncthreads();
@@ -224,46 +246,40 @@ token_self_attn_kernel(DecLayerW lw, int first_layer, const float* __restrict__ 
   for (int i = t; i < NT * C; i += 256) {
     const int r = i / C, ch = i % C, h = ch / 32;
     float acc = 0.f;
-    for (int c = 0; c < NT; ++c) acc = fmaf(s_p[(h * NT + r) * NT + c], s_c[c * C + ch], acc);
-    s_in[i] = acc;
+    for (int c = 0; c < NT; ++c) acc = fmaf(s_p[(h * NT + r) * NT + c], s_v[c * C + ch], acc);
+    out[base + i] = acc;
   }
-  __syncthreads();
-  cta_linear(s_in, C, lw.self_attn.wo, lw.self_attn.bo, C, s_a, C, false);
-  __syncthreads();
-  for (int i = t; i < NT * C; i += 256) s_a[i] = first_layer ? s_a[i] : s_q[i] + s_a[i];
-  __syncthreads();
-  cta_layernorm(s_a, lw.ln1_g, lw.ln1_b, 1e-6f);
-  __syncthreads();
-  for (int i = t; i < NT * C; i += 256) {
-    queries[static_cast<size_t>(b) * NT * C + i] = s_a[i];
-    s_in[i] = s_a[i] + pe[i];
-  }
-  __syncthreads();
-  cta_linear(s_in, C, lw.t2i.wq, lw.t2i.bq, 128, s_b, 128, false);
-  __syncthreads();
-  for (int i = t; i < NT * 128; i += 256) q_t2i[static_cast<size_t>(b) * NT * 128 + i] = s_b[i];
 }
 
-// token -> image attention core: 7 queries x 4096 keys, 8 heads x 16, scale 0.25; grid (8, nb)   (:324-327, :398-401)
-// K: fp32 rows of pitch ldk (head h at columns h*16..), V: pitch ldv. group: box -> source sequence (or null = box)
+// token -> image attention core: 7 queries x 4096 keys, 8 heads x 16, scale 0.25   (:324-327, :398-401)
+// grid (8 heads, nb, T2I_SPLIT key ranges): every CTA produces the un-normalised partial (max, sum, P.V) of its
+// 1024 keys; t2i_merge_kernel combines the ranges. K: fp32 rows of pitch ldk (head h at columns h*16..),
+// V: pitch ldv. group: box -> source sequence (or null = box).
+constexpr int T2I_SPLIT = 4;
+constexpr int T2I_KEYS = 4096 / T2I_SPLIT;
+constexpr int T2I_PART = NT * 2 + NT * 16;     // per (box, head, split): m[7], l[7], o[7][16]
+
 __global__ void __launch_bounds__(256)
 t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ K, int ldk, const float* __restrict__ V,
-                     int ldv, const int* __restrict__ group, float* __restrict__ attn_out) {
-  extern __shared__ float s_sc[];              // [7][4096]
+                     int ldv, const int* __restrict__ group, float* __restrict__ part) {
+  __shared__ float s_sc[NT * T2I_KEYS];        // 28 KB
   __shared__ float s_qh[NT * 16];
   __shared__ float s_red[8 * NT];
-  __shared__ float s_max[NT], s_sum[NT];
+  __shared__ float s_max[NT];
   __shared__ float s_part[2 * NT * 16];
-  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const size_t seq = group ? group[b] : b;
-  const float* Kb = K + seq * 4096 * ldk + h * 16;
-  const float* Vb = V + seq * 4096 * ldv + h * 16;
+  const float* Kb = K + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS) * ldk + h * 16;
+  const float* Vb = V + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS) * ldv + h * 16;
+  float* pout = part + ((static_cast<size_t>(b) * 8 + h) * T2I_SPLIT + sp) * T2I_PART;
   if (t < NT * 16) s_qh[t] = q_t2i[(static_cast<size_t>(b) * NT + t / 16) * 128 + h * 16 + (t % 16)];
   __syncthreads();
   float lmax[NT];
 #pragma unroll
   for (int r = 0; r < NT; ++r) lmax[r] = -INFINITY;
-  for (int key = t; key < 4096; key += 256) {
+#pragma unroll
+  for (int it = 0; it < T2I_KEYS / 256; ++it) {
+    const int key = t + it * 256;
     const float4* kp = reinterpret_cast<const float4*>(Kb + static_cast<size_t>(key) * ldk);
     const float4 k0 = __ldg(kp), k1 = __ldg(kp + 1), k2 = __ldg(kp + 2), k3 = __ldg(kp + 3);
 #pragma unroll
@@ -274,7 +290,7 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
       a += q[8] * k2.x + q[9] * k2.y + q[10] * k2.z + q[11] * k2.w;
       a += q[12] * k3.x + q[13] * k3.y + q[14] * k3.z + q[15] * k3.w;
       a *= 0.25f;
-      s_sc[r * 4096 + key] = a;
+      s_sc[r * T2I_KEYS + key] = a;
       lmax[r] = fmaxf(lmax[r], a);
     }
   }
@@ -289,17 +305,20 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
     float m = s_red[t];
     for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w * NT + t]);
     s_max[t] = m;
+    pout[t] = m;
   }
   __syncthreads();
   float lsum[NT];
 #pragma unroll
   for (int r = 0; r < NT; ++r) lsum[r] = 0.f;
-  for (int key = t; key < 4096; key += 256) {
+#pragma unroll
+  for (int it = 0; it < T2I_KEYS / 256; ++it) {
+    const int key = t + it * 256;
 #pragma unroll
     for (int r = 0; r < NT; ++r) {
-      const float p = expf(s_sc[r * 4096 + key] - s_max[r]);
-      s_sc[r * 4096 + key] = p;
-      lsum[r] += p;
+      const float pv = expf(s_sc[r * T2I_KEYS + key] - s_max[r]);
+      s_sc[r * T2I_KEYS + key] = pv;
+      lsum[r] += pv;
     }
   }
 #pragma unroll
@@ -310,18 +329,17 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
   }
   __syncthreads();
   if (t < NT) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += s_red[w * NT + t];
-    s_sum[t] = s;
+    float sm = 0.f;
+    for (int w = 0; w < 8; ++w) sm += s_red[w * NT + t];
+    pout[NT + t] = sm;
   }
-  __syncthreads();
-  // out[r][d] = sum_key p[r][key] V[key][d]; 224 threads = 2 key halves x 7 x 16
+  // o[r][d] = sum_key p[r][key] V[key][d]; 224 threads = 2 key halves x 7 x 16
   if (t < 2 * NT * 16) {
     const int half = t / (NT * 16), idx = t % (NT * 16), r = idx / 16, d = idx % 16;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    const float* pr = s_sc + r * 4096 + half * 2048;
-    const float* vp = Vb + static_cast<size_t>(half) * 2048 * ldv + d;
-    for (int key = 0; key < 2048; key += 4) {
+    const float* pr = s_sc + r * T2I_KEYS + half * (T2I_KEYS / 2);
+    const float* vp = Vb + static_cast<size_t>(half) * (T2I_KEYS / 2) * ldv + d;
+    for (int key = 0; key < T2I_KEYS / 2; key += 4) {
       acc0 = fmaf(pr[key], __ldg(vp + static_cast<size_t>(key) * ldv), acc0);
       acc1 = fmaf(pr[key + 1], __ldg(vp + static_cast<size_t>(key + 1) * ldv), acc1);
       acc2 = fmaf(pr[key + 2], __ldg(vp + static_cast<size_t>(key + 2) * ldv), acc2);
@@ -330,50 +348,27 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
     s_part[t] = (acc0 + acc1) + (acc2 + acc3);
   }
   __syncthreads();
-  if (t < NT * 16) {
-    const int r = t / 16, d = t % 16;
-    attn_out[(static_cast<size_t>(b) * NT + r) * 128 + h * 16 + d] = (s_part[t] + s_part[NT * 16 + t]) / s_sum[r];
-  }
+  if (t < NT * 16) pout[2 * NT + t] = s_part[t] + s_part[NT * 16 + t];
 }
 
-// TK2: queries += out_proj(attn) ; LN2 ; MLP ; LN3 ; image->token key/value projections   (:328-341)
+// combine the key ranges: out[b][r][h*16+d] = sum_s e^(m_s-m) o_s / sum_s e^(m_s-m) l_s
 __global__ void __launch_bounds__(256)
-token_mlp_kernel(DecLayerW lw, const float* __restrict__ tok0, const float* __restrict__ attn_t2i,
-                 float* __restrict__ queries, float* __restrict__ k_tok, float* __restrict__ v_tok) {
-  extern __shared__ __align__(16) float s_dyn[];      // [7][2048] MLP hidden
-  __shared__ __align__(16) float s_q[NT * C], s_a[NT * C], s_at[NT * 128];
-  const int b = blockIdx.x, t = threadIdx.x;
-  const float* pe = tok0 + static_cast<size_t>(b) * NT * C;
-  for (int i = t; i < NT * C; i += 256) s_q[i] = queries[static_cast<size_t>(b) * NT * C + i];
-  for (int i = t; i < NT * 128; i += 256) s_at[i] = attn_t2i[static_cast<size_t>(b) * NT * 128 + i];
-  __syncthreads();
-  cta_linear(s_at, 128, lw.t2i.wo, lw.t2i.bo, C, s_a, C, false);
-  __syncthreads();
-  for (int i = t; i < NT * C; i += 256) s_q[i] += s_a[i];
-  __syncthreads();
-  cta_layernorm(s_q, lw.ln2_g, lw.ln2_b, 1e-6f);
-  __syncthreads();
-  cta_linear(s_q, C, lw.w_fc1, lw.b_fc1, 2048, s_dyn, 2048, true);
-  __syncthreads();
-  cta_linear(s_dyn, 2048, lw.w_fc2, lw.b_fc2, C, s_a, C, false);
-  __syncthreads();
-  for (int i = t; i < NT * C; i += 256) s_q[i] += s_a[i];
-  __syncthreads();
-  cta_layernorm(s_q, lw.ln3_g, lw.ln3_b, 1e-6f);
-  __syncthreads();
-  for (int i = t; i < NT * C; i += 256) {
-    queries[static_cast<size_t>(b) * NT * C + i] = s_q[i];
-    s_a[i] = s_q[i] + pe[i];
-  }
-  __syncthreads();
-  float* s_k = s_dyn;            // [7][128]
-  float* s_v = s_dyn + NT * 128;
-  cta_linear(s_a, C, lw.i2t.wk, lw.i2t.bk, 128, s_k, 128, false);
-  cta_linear(s_q, C, lw.i2t.wv, lw.i2t.bv, 128, s_v, 128, false);
-  __syncthreads();
-  for (int i = t; i < NT * 128; i += 256) {
-    k_tok[static_cast<size_t>(b) * NT * 128 + i] = s_k[i];
-    v_tok[static_cast<size_t>(b) * NT * 128 + i] = s_v[i];
+t2i_merge_kernel(const float* __restrict__ part, float* __restrict__ attn_out) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < NT * 128; i += 256) {
+    const int r = i / 128, hd = i % 128, h = hd / 16, d = hd % 16;
+    const float* pp = part + (static_cast<size_t>(b) * 8 + h) * T2I_SPLIT * T2I_PART;
+    float m = -INFINITY;
+#pragma unroll
+    for (int sp = 0; sp < T2I_SPLIT; ++sp) m = fmaxf(m, pp[sp * T2I_PART + r]);
+    float l = 0.f, o = 0.f;
+#pragma unroll
+    for (int sp = 0; sp < T2I_SPLIT; ++sp) {
+      const float f = expf(pp[sp * T2I_PART + r] - m);
+      l = fmaf(f, pp[sp * T2I_PART + NT + r], l);
+      o = fmaf(f, pp[sp * T2I_PART + 2 * NT + r * 16 + d], o);
+    }
+    attn_out[(static_cast<size_t>(b) * NT + r) * 128 + hd] = o / l;
   }
 }
 
@@ -422,42 +417,6 @@ i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict
   v1.x = pack_bf16x2(o[8], o[9]); v1.y = pack_bf16x2(o[10], o[11]); v1.z = pack_bf16x2(o[12], o[13]); v1.w = pack_bf16x2(o[14], o[15]);
   dst[0] = v0;
   dst[1] = v1;
-}
-
-// final token->image query projection (:394-398)
-__global__ void __launch_bounds__(256)
-token_final_q_kernel(DecAttnW aw, const float* __restrict__ tok0, const float* __restrict__ queries, float* __restrict__ q_t2i) {
-  __shared__ __align__(16) float s_in[NT * C], s_o[NT * 128];
-  const int b = blockIdx.x, t = threadIdx.x;
-  for (int i = t; i < NT * C; i += 256) s_in[i] = queries[static_cast<size_t>(b) * NT * C + i] + tok0[static_cast<size_t>(b) * NT * C + i];
-  __syncthreads();
-  cta_linear(s_in, C, aw.wq, aw.bq, 128, s_o, 128, false);
-  __syncthreads();
-  for (int i = t; i < NT * 128; i += 256) q_t2i[static_cast<size_t>(b) * NT * 128 + i] = s_o[i];
-}
-
-// queries += out_proj(attn); layer_norm_final_attn (eps 1e-5); hypernetwork MLP of mask token 0   (:401-404, :523-527)
-__global__ void __launch_bounds__(256)
-token_final_kernel(DecoderW w, const float* __restrict__ attn_t2i, const float* __restrict__ queries, float* __restrict__ hyper) {
-  __shared__ __align__(16) float s_q[NT * C], s_a[NT * C], s_at[NT * 128];
-  const int b = blockIdx.x, t = threadIdx.x;
-  for (int i = t; i < NT * C; i += 256) s_q[i] = queries[static_cast<size_t>(b) * NT * C + i];
-  for (int i = t; i < NT * 128; i += 256) s_at[i] = attn_t2i[static_cast<size_t>(b) * NT * 128 + i];
-  __syncthreads();
-  cta_linear(s_at, 128, w.final_attn.wo, w.final_attn.bo, C, s_a, C, false);
-  __syncthreads();
-  for (int i = t; i < NT * C; i += 256) s_q[i] += s_a[i];
-  __syncthreads();
-  cta_layernorm(s_q, w.lnf_g, w.lnf_b, 1e-5f);
-  __syncthreads();
-  // hypernetwork 0 on mask token 0 (= token index 1). cta_linear works on 7 rows; rows other than 1 are ignored.
-  cta_linear(s_q, C, w.hy_w0, w.hy_b0, C, s_a, C, true);
-  __syncthreads();
-  cta_linear(s_a, C, w.hy_w1, w.hy_b1, C, s_q, C, true);
-  __syncthreads();
-  cta_linear(s_q, C, w.hy_w2, w.hy_b2, 32, s_a, 32, false);
-  __syncthreads();
-  if (t < 32) hyper[b * 32 + t] = s_a[1 * 32 + t];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -530,17 +489,46 @@ struct EpiConvT2 {
 };
 
 // ---------------------------------------------------------------------------------------------------
+static TokLin tok_lin(const float* X, const float* Xadd, int ldx, const float* W, const float* b, int K, int N, float* Y, int ldy,
+                      const float* res = nullptr, int ldres = 0, int relu = 0) {
+  TokLin t;
+  t.X = X; t.Xadd = Xadd; t.ldx = ldx; t.W = W; t.b = b; t.res = res; t.ldres = ldres; t.Y = Y; t.ldy = ldy;
+  t.K = K; t.N = N; t.relu = relu;
+  return t;
+}
+
+static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s) {
+  TokLin3 P;
+  int nmax = 0;
+  for (int i = 0; i < 3; ++i) {
+    P.t[i] = t[i < count ? i : 0];
+    if (i < count) {
+      YSI_CHECK(t[i].K % 128 == 0 && t[i].K <= 2048 && t[i].N % 8 == 0, "token linear shape");
+      nmax = t[i].N > nmax ? t[i].N : nmax;
+    }
+  }
+  tok_linear_kernel<<<dim3(nmax / 8, ceil_div(R, TOK_ROWS), count), 256, 0, s>>>(P, R);
+}
+
 void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb, int n_img, int nb, float* low_res_out,
                      float* sparse_out, cudaStream_t s, int64_t* launches, Profiler* prof) {
   YSI_CHECK(n_img >= 1 && n_img <= wk.cap_img && nb >= 1 && nb <= wk.cap_box, "decoder batch exceeds the workspace");
   int64_t nl = 0;
   static bool attr = false;
   if (!attr) {
-    YSI_CUDA(cudaFuncSetAttribute(t2i_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT * 4096 * 4));
-    YSI_CUDA(cudaFuncSetAttribute(token_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT * 2048 * 4));
     attr = true;
   }
   const int TI = n_img * 4096, TB = nb * 4096;
+  const int R = NT * nb;                                  // token rows of the whole batch
+  // token-side scratch (all [R,256] unless noted)
+  float* t_q = wk.tok_ws;            float* t_k = t_q + static_cast<size_t>(R) * C;
+  float* t_v = t_k + static_cast<size_t>(R) * C;   float* t_a = t_v + static_cast<size_t>(R) * C;
+  float* t_tmp = t_a + static_cast<size_t>(R) * C; float* t_qpe = t_tmp + static_cast<size_t>(R) * C;
+  float* t_hid = t_qpe + static_cast<size_t>(R) * C;       // [R,2048]
+  float* t_h0 = t_hid + static_cast<size_t>(R) * 2048;     // [nb,256]
+  float* t_h1 = t_h0 + static_cast<size_t>(nb) * C;        // [nb,256]
+  float* t_part = t_h1 + static_cast<size_t>(nb) * C;      // [nb,8,T2I_SPLIT,T2I_PART] partial token->image attention
+  const int ln_blocks = ceil_div(R, 8);
   prompt_tokens_kernel<<<nb, 256, 0, s>>>(wk.boxes1024, w, wk.tok0, sparse_out); ++nl;
   {
     const long long n4 = static_cast<long long>(TI) * 64;
@@ -550,6 +538,7 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   YSI_CUDA(cudaGetLastError());
   for (int li = 0; li < 2; ++li) {
     const DecLayerW& lw = w.layers[li];
+    const bool first = li == 0;
     const bool per_img = li == 0;                       // block 0: keys are shared by all boxes of an image
     const int rows = per_img ? TI : TB;
     const bf16* a_keys = per_img ? wk.keys0_bf : wk.keys_bf;
@@ -557,7 +546,23 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     float* kq = per_img ? wk.kq0 : wk.kq;
     float* v = per_img ? wk.v0 : wk.v;
     const int* group = per_img ? wk.box_img : nullptr;
-    { ProfScope ps(prof, KC_DEC_TOKEN); token_self_attn_kernel<<<nb, 256, 0, s>>>(lw, li == 0 ? 1 : 0, wk.tok0, wk.queries, wk.q_t2i); ++nl; }
+    {
+      // self attention (:316-321; block 0 has neither PE nor residual), LN1, token->image query projection
+      ProfScope ps(prof, KC_DEC_TOKEN);
+      const float* qin = first ? wk.tok0 : wk.queries;
+      const float* qadd = first ? nullptr : wk.tok0;
+      const TokLin qkv[3] = {tok_lin(qin, qadd, C, lw.self_attn.wq, lw.self_attn.bq, C, C, t_q, C),
+                             tok_lin(qin, qadd, C, lw.self_attn.wk, lw.self_attn.bk, C, C, t_k, C),
+                             tok_lin(qin, nullptr, C, lw.self_attn.wv, lw.self_attn.bv, C, C, t_v, C)};
+      launch_tok_linear(qkv, 3, R, s); ++nl;
+      tok_self_attn_core_kernel<<<nb, 256, 0, s>>>(t_q, t_k, t_v, t_a); ++nl;
+      const TokLin o = tok_lin(t_a, nullptr, C, lw.self_attn.wo, lw.self_attn.bo, C, C, t_tmp, C, first ? nullptr : wk.queries, C);
+      launch_tok_linear(&o, 1, R, s); ++nl;
+      tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, lw.ln1_g, lw.ln1_b, 1e-6f, wk.tok0, wk.queries, t_qpe); ++nl;
+      const TokLin tq = tok_lin(t_qpe, nullptr, C, lw.t2i.wq, lw.t2i.bq, C, 128, wk.q_t2i, 128);
+      launch_tok_linear(&tq, 1, R, s); ++nl;
+      YSI_CUDA(cudaGetLastError());
+    }
     {
       ProfScope ps(prof, KC_DEC_GEMM, 2.0 * rows * 384 * 256);
       GemmEpilogue ep;
@@ -567,8 +572,24 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       ev.bias = lw.t2i.bv; ev.out_f32 = v; ev.ld_out = 128;
       gemm_bf16(a_keys, C, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
     }
-    { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb), 256, NT * 4096 * 4, s>>>(wk.q_t2i, kq, 256, v, 128, group, wk.attn_t2i); ++nl; }
-    { ProfScope ps(prof, KC_DEC_TOKEN); token_mlp_kernel<<<nb, 256, NT * 2048 * 4, s>>>(lw, wk.tok0, wk.attn_t2i, wk.queries, wk.k_tok, wk.v_tok); ++nl; }
+    { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(wk.q_t2i, kq, 256, v, 128, group, t_part); ++nl;
+      t2i_merge_kernel<<<nb, 256, 0, s>>>(t_part, wk.attn_t2i); ++nl; }
+    {
+      // queries += out_proj(attn); LN2; MLP; LN3; image->token key / value projections   (:328-341)
+      ProfScope ps(prof, KC_DEC_TOKEN);
+      const TokLin o = tok_lin(wk.attn_t2i, nullptr, 128, lw.t2i.wo, lw.t2i.bo, 128, C, t_tmp, C, wk.queries, C);
+      launch_tok_linear(&o, 1, R, s); ++nl;
+      tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, lw.ln2_g, lw.ln2_b, 1e-6f, nullptr, wk.queries, nullptr); ++nl;
+      const TokLin f1 = tok_lin(wk.queries, nullptr, C, lw.w_fc1, lw.b_fc1, C, 2048, t_hid, 2048, nullptr, 0, 1);
+      launch_tok_linear(&f1, 1, R, s); ++nl;
+      const TokLin f2 = tok_lin(t_hid, nullptr, 2048, lw.w_fc2, lw.b_fc2, 2048, C, t_tmp, C, wk.queries, C);
+      launch_tok_linear(&f2, 1, R, s); ++nl;
+      tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, lw.ln3_g, lw.ln3_b, 1e-6f, wk.tok0, wk.queries, t_qpe); ++nl;
+      const TokLin kv[2] = {tok_lin(t_qpe, nullptr, C, lw.i2t.wk, lw.i2t.bk, C, 128, wk.k_tok, 128),
+                            tok_lin(wk.queries, nullptr, C, lw.i2t.wv, lw.i2t.bv, C, 128, wk.v_tok, 128)};
+      launch_tok_linear(kv, 2, R, s); ++nl;
+      YSI_CUDA(cudaGetLastError());
+    }
     { ProfScope ps(prof, KC_DEC_ATTN); i2t_attention_kernel<<<dim3(128, nb), 256, 0, s>>>(kq + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t); ++nl; }
     YSI_CUDA(cudaGetLastError());
     {
@@ -584,8 +605,12 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       YSI_CUDA(cudaGetLastError());
     }
   }
-  // final token -> image attention (:394-404)
-  token_final_q_kernel<<<nb, 256, 0, s>>>(w.final_attn, wk.tok0, wk.queries, wk.q_t2i); ++nl;
+  // final token -> image attention (:394-404); t_qpe = queries + pe from LN3 of block 1
+  {
+    ProfScope ps(prof, KC_DEC_TOKEN);
+    const TokLin fq = tok_lin(t_qpe, nullptr, C, w.final_attn.wq, w.final_attn.bq, C, 128, wk.q_t2i, 128);
+    launch_tok_linear(&fq, 1, R, s); ++nl;
+  }
   {
     ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 256);
     GemmEpilogue ek;
@@ -595,9 +620,22 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     ev.bias = w.final_attn.bv; ev.out_f32 = wk.v; ev.ld_out = 128;
     gemm_bf16(wk.keys_bf, C, w.w_v_final, C, TB, 128, C, ev, s); ++nl;
   }
-  t2i_attention_kernel<<<dim3(8, nb), 256, NT * 4096 * 4, s>>>(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, wk.attn_t2i); ++nl;
-  token_final_kernel<<<nb, 256, 0, s>>>(w, wk.attn_t2i, wk.queries, wk.hyper); ++nl;
-  YSI_CUDA(cudaGetLastError());
+  { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, t_part); ++nl;
+    t2i_merge_kernel<<<nb, 256, 0, s>>>(t_part, wk.attn_t2i); ++nl; }
+  {
+    // queries += out_proj(attn); layer_norm_final_attn (eps 1e-5); hypernetwork MLP of mask token 0 (= token row 1)
+    ProfScope ps(prof, KC_DEC_TOKEN);
+    const TokLin o = tok_lin(wk.attn_t2i, nullptr, 128, w.final_attn.wo, w.final_attn.bo, 128, C, t_tmp, C, wk.queries, C);
+    launch_tok_linear(&o, 1, R, s); ++nl;
+    tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, w.lnf_g, w.lnf_b, 1e-5f, nullptr, wk.queries, nullptr); ++nl;
+    const TokLin h0 = tok_lin(wk.queries + C, nullptr, NT * C, w.hy_w0, w.hy_b0, C, C, t_h0, C, nullptr, 0, 1);
+    launch_tok_linear(&h0, 1, nb, s); ++nl;
+    const TokLin h1 = tok_lin(t_h0, nullptr, C, w.hy_w1, w.hy_b1, C, C, t_h1, C, nullptr, 0, 1);
+    launch_tok_linear(&h1, 1, nb, s); ++nl;
+    const TokLin h2 = tok_lin(t_h1, nullptr, C, w.hy_w2, w.hy_b2, C, 32, wk.hyper, 32);
+    launch_tok_linear(&h2, 1, nb, s); ++nl;
+    YSI_CUDA(cudaGetLastError());
+  }
   // upscaler (:515-531)
   {
     ProfScope ps(prof, KC_DEC_UPSCALE, 2.0 * TB * 256 * 256 + 2.0 * nb * 16384.0 * 128 * 64);

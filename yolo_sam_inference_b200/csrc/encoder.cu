@@ -248,7 +248,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     }
     {
       GemmEpilogue ep;   // x += attn * Wproj^T + b ; the attention kernel already un-partitioned the windows
-      ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
+      ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
       ProfScope ps(prof, KC_GEMM_PROJ, 2.0 * T * D * D);
       gemm_bf16(work.attn, D, lw.w_proj, D, T, D, D, ep, s); ++nl;
     }
@@ -261,7 +261,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     }
     {
       GemmEpilogue ep;
-      ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = 1;
+      ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
       ProfScope ps(prof, KC_GEMM_FC2, 2.0 * T * w.mlp * D);
       gemm_bf16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
     }

@@ -123,6 +123,16 @@ struct EpiGeneric {
       }
       if (p.out_f32) {
         float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(drow) * p.ld_out + col0);
+        if (p.accumulate == 2) {
+          // fire-and-forget fp32 adds executed by the L2 (one add per element, so the result is the same
+          // round-to-nearest sum a load/add/store would give) -- no read latency on the epilogue's critical path
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o4 + i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                         "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                         : "memory");
+          continue;
+        }
         if (p.accumulate) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {

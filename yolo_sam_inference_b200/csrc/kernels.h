@@ -58,6 +58,7 @@ struct EncoderLayerW {
 
 struct EncoderW {
   int D, L, heads, mlp;
+  int residual_mode = 2;   // GemmEpilogue::accumulate for the two residual adds of a layer
   const bf16* w_patch;    // [D, 768]
   const float* b_patch;   // [D]
   const float* pos_embed; // [4096, D]
@@ -135,6 +136,7 @@ struct DecoderWork {           // workspace for cap_img images and cap_box boxes
   bf16* attn_i2t;                                        // [cap_box*4096, 128]
   bf16* up1;                                             // [cap_box*16384, 64]
   float *tok0, *queries, *q_t2i, *attn_t2i, *k_tok, *v_tok, *hyper;   // token-side [cap_box, 7, *]
+  float* tok_ws;                                         // token-side scratch: cap_box * (7*(6*256 + 2048) + 2*256 + 8*4*126) floats
   double* boxes1024;  int* box_img;                      // [cap_box,4] / [cap_box]
 };
 void launch_image_pe(const float* gauss, float* image_pe, cudaStream_t s);
