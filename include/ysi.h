@@ -156,6 +156,15 @@ YSI_API int ysi_gemm(ysi_ctx* ctx, const float* A, const float* W, const float* 
 YSI_API int ysi_attention(ysi_ctx* ctx, const float* qkv, const float* rel_pos_h, const float* rel_pos_w, int n_seq,
                   int heads, int is_global, float* out);
 
+/* the GEMM core through the production tile dispatcher, with the encoder's epilogue kinds:
+ * out_kind 0: C = result (fp32); 1: C = bf16-rounded result; 2: C += result (the residual add of
+ * modeling_sam.py:969-971). C_inout fp32 [M,N] is read for kind 2. */
+YSI_API int ysi_gemm_ex(ysi_ctx* ctx, const float* A, const float* W, const float* bias, int M, int N, int K, int act,
+                int out_kind, float* C_inout);
+/* measurement support: time `iters` launches of one GEMM shape on device-resident bf16 operands.
+ * mode 0 bf16-output epilogue, 1 fp32 red-add epilogue, 2 drain-only (mainloop speed); pair != 0: CTA-pair kernel. */
+YSI_API int ysi_gemm_bench(ysi_ctx* ctx, int M, int N, int K, int pair, int mode, int iters, float* ms_per_iter);
+
 /* image-wide positional embedding fp32 [256,64,64] (modeling_sam.py:1128-1139), computed at weight load */
 YSI_API int ysi_get_image_pe(ysi_ctx* ctx, float* out);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */

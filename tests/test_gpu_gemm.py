@@ -48,3 +48,30 @@ def test_gemm_activation_epilogues(tiny_stage, act):
     ref = (torch.nn.functional.gelu(pre) if act == 1 else torch.relu(pre)).numpy()
     out = tiny_stage.gemm(A, W, bias, act=act)
     assert np.abs(out - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,act,out_kind", [
+    (4900, 2304, 768, 0, 1),     # qkv: bf16 output through the staged TMA-store epilogue, ragged M tail
+    (4096, 3072, 768, 1, 1),     # fc1: GELU + bf16 output
+    (4100, 768, 3072, 0, 2),     # fc2: residual add through cp.reduce.async.bulk, ragged M tail
+    (2048, 768, 768, 0, 2),      # proj
+    (512, 768, 768, 0, 2),       # small M: single-CTA kernel, red.global.add epilogue
+    (512, 192, 192, 1, 1),       # small N: single-CTA kernel, direct bf16 stores
+])
+def test_gemm_production_epilogues(tiny_stage, M, N, K, act, out_kind):
+    rng = np.random.RandomState(M + N + K + act)
+    A = _bf16(rng.standard_normal((M, K)).astype(np.float32))
+    W = _bf16((rng.standard_normal((N, K)) * 0.05).astype(np.float32))
+    bias = rng.standard_normal(N).astype(np.float32)
+    pre = torch.from_numpy(A.astype(np.float64) @ W.astype(np.float64).T + bias)
+    ref = (torch.nn.functional.gelu(pre) if act == 1 else pre).numpy()
+    if out_kind == 2:
+        C0 = rng.standard_normal((M, N)).astype(np.float32)
+        out = tiny_stage.gemm_ex(A, W, bias, act, 2, C0)
+        assert np.abs(out - (C0.astype(np.float64) + ref)).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    else:
+        out = tiny_stage.gemm_ex(A, W, bias, act, 1)
+        ref_bf = torch.from_numpy(ref).to(torch.float32).to(torch.bfloat16).to(torch.float32).numpy()
+        # bf16 rounding of a value that is itself only fp32-accurate: allow one bf16 ulp
+        assert np.abs(out - ref_bf).max() <= 2.0 ** -7 * max(1.0, np.abs(ref).max())
+        assert rel_l2(out, ref) < 4e-3

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 
+#include "gemm.cuh"
 #include "kernels.h"
 
 using namespace ysi;
@@ -737,6 +738,72 @@ int ysi_gemm(ysi_ctx* c, const float* A, const float* W, const float* bias, int 
     YSI_CUDA(cudaMemcpyAsync(C_out, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c->stream));
     YSI_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(dA); cudaFree(dW); cudaFree(dC); if (dB) cudaFree(dB);
+  });
+}
+
+// GEMM through the production dispatcher with the epilogue kinds the encoder uses:
+// out_kind 0: C = fp32 result; 1: C = bf16-rounded result (K-scale style column scaling off); 2: C += result (residual add)
+int ysi_gemm_ex(ysi_ctx* c, const float* A, const float* W, const float* bias, int M, int N, int K, int act, int out_kind,
+                float* C_inout) {
+  return guarded(c, [&] {
+    std::vector<bf16> a = to_bf16(A, static_cast<size_t>(M) * K), w = to_bf16(W, static_cast<size_t>(N) * K);
+    bf16 *dA = nullptr, *dW = nullptr, *dO = nullptr;
+    float *dC = nullptr, *dB = nullptr;
+    YSI_CUDA(cudaMalloc(&dA, a.size() * 2)); YSI_CUDA(cudaMalloc(&dW, w.size() * 2));
+    YSI_CUDA(cudaMalloc(&dC, sizeof(float) * M * N)); YSI_CUDA(cudaMalloc(&dO, sizeof(bf16) * M * N));
+    YSI_CUDA(cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    YSI_CUDA(cudaMemcpy(dW, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+    YSI_CUDA(cudaMemcpy(dC, C_inout, sizeof(float) * M * N, cudaMemcpyHostToDevice));
+    if (bias) { YSI_CUDA(cudaMalloc(&dB, sizeof(float) * N)); YSI_CUDA(cudaMemcpy(dB, bias, sizeof(float) * N, cudaMemcpyHostToDevice)); }
+    GemmEpilogue ep;
+    ep.bias = dB; ep.act = act;
+    if (out_kind == 1) { ep.out_bf16 = dO; ep.ld_out_bf16 = N; } else { ep.out_f32 = dC; ep.ld_out = N; ep.accumulate = out_kind == 2 ? 2 : 0; }
+    gemm_bf16(dA, K, dW, K, M, N, K, ep, c->stream);
+    c->launches += 1;
+    if (out_kind == 1) {
+      std::vector<bf16> o(static_cast<size_t>(M) * N);
+      YSI_CUDA(cudaMemcpyAsync(o.data(), dO, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));
+      YSI_CUDA(cudaStreamSynchronize(c->stream));
+      for (size_t i = 0; i < o.size(); ++i) C_inout[i] = __bfloat162float(o[i]);
+    } else {
+      YSI_CUDA(cudaMemcpyAsync(C_inout, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c->stream));
+      YSI_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dC); cudaFree(dO); if (dB) cudaFree(dB);
+  });
+}
+
+// measurement support: time `iters` back-to-back launches of one GEMM shape on device-resident operands.
+// mode 0: bf16 output epilogue; 1: fp32 red-add epilogue; 2: drain-only epilogue (mainloop speed). pair: CTA-pair kernel.
+int ysi_gemm_bench(ysi_ctx* c, int M, int N, int K, int pair, int mode, int iters, float* ms_per_iter) {
+  return guarded(c, [&] {
+    bf16 *dA = nullptr, *dW = nullptr, *dO = nullptr;
+    float* dF = nullptr;
+    YSI_CUDA(cudaMalloc(&dA, static_cast<size_t>(M) * K * 2)); YSI_CUDA(cudaMalloc(&dW, static_cast<size_t>(N) * K * 2));
+    YSI_CUDA(cudaMalloc(&dO, static_cast<size_t>(M) * N * 2)); YSI_CUDA(cudaMalloc(&dF, static_cast<size_t>(M) * N * 4));
+    YSI_CUDA(cudaMemset(dA, 0x3c, static_cast<size_t>(M) * K * 2)); YSI_CUDA(cudaMemset(dW, 0x3c, static_cast<size_t>(N) * K * 2));
+    YSI_CUDA(cudaMemset(dF, 0, static_cast<size_t>(M) * N * 4));
+    const CUtensorMap tmA = make_tmap_bf16_2d(dA, M, K, K, GEMM_BM);
+    const CUtensorMap tmB = make_tmap_bf16_2d(dW, N, K, K, pair ? 128 : 256);
+    GemmEpilogue ep;
+    if (mode == 0) { ep.out_bf16 = dO; ep.ld_out_bf16 = N; } else { ep.out_f32 = dF; ep.ld_out = N; ep.accumulate = 2; }
+    EpiGeneric eg{ep};
+    EpiDrain ed{dF};
+    auto run = [&] {
+      if (mode == 2) { if (pair) launch_gemm2(tmA, tmB, M, N, K, ed, c->stream); else launch_gemm<256>(tmA, tmB, M, N, K, ed, c->stream); }
+      else if (pair == 2) gemm_bf16(dA, K, dW, K, M, N, K, ep, c->stream);      // production dispatch (staged epilogue)
+      else { if (pair) launch_gemm2(tmA, tmB, M, N, K, eg, c->stream); else launch_gemm<256>(tmA, tmB, M, N, K, eg, c->stream); }
+    };
+    for (int i = 0; i < 3; ++i) run();
+    YSI_CUDA(cudaEventRecord(c->timers[6], c->stream));
+    for (int i = 0; i < iters; ++i) run();
+    YSI_CUDA(cudaEventRecord(c->timers[7], c->stream));
+    YSI_CUDA(cudaEventSynchronize(c->timers[7]));
+    float ms = 0.f;
+    YSI_CUDA(cudaEventElapsedTime(&ms, c->timers[6], c->timers[7]));
+    *ms_per_iter = ms / iters;
+    c->launches += iters + 3;
+    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dF);
   });
 }
 

@@ -40,6 +40,10 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                               uint32_t box_cols = 64);
 
+// Row-major fp32 matrix -> 2-D TMA map with a {32 cols, box_rows} box (128 B inner extent), 128-byte swizzle;
+// used by the staged GEMM epilogue for cp.reduce.async.bulk (x += tile).
+CUtensorMap make_tmap_f32_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 // Epilogue description for the tcgen05 GEMM (see gemm.cu).
 enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 

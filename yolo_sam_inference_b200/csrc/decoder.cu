@@ -427,7 +427,8 @@ i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict
 struct EpiConvT1 {
   const float *bias, *g, *b;
   bf16* out;   // [nb*16384, 64]
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end) const {
+  __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     const bool active = row < M;
     const int box = row >> 12, tok = row & 4095, y = tok >> 6, x = tok & 63;
     for (int sp = c_begin / 64; sp < c_end / 64; ++sp) {
@@ -472,7 +473,8 @@ struct EpiConvT2 {
   const float* bias;    // [32]
   const float* hyper;   // [nb,32]
   float* low;           // [nb,256,256]
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end) const {
+  __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     const bool active = row < M;
     const int box = row >> 14, pos = row & 16383, Y = pos >> 7, X = pos & 127;
     for (int sp = c_begin / 32; sp < c_end / 32; ++sp) {

@@ -67,11 +67,20 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return fma2(make_float2(fabsf(hx.x), fabsf(hx.y)), erfv, hx);
 }
 
+// per-warp epilogue context: staging shared memory (CTA-pair kernel only) and the warp's first output row
+struct EpiCtx {
+  uint32_t smem;     // 2 x 4 KB staging buffers of this warp (0: none)
+  uint32_t nbuf;     // running buffer counter
+  int row0;          // first row of the warp's 32-row slab
+  int lane;
+};
+
 // Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_bf16.
 struct EpiGeneric {
   GemmEpilogue p;
+  __device__ __forceinline__ void finish(EpiCtx&) const {}
   // columns [c_begin, c_end) of the BN-wide accumulator tile belong to the calling warp
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end) const {
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     // every lane must execute the warp-collective tcgen05.ld convergently: predicate only the stores
     int drow = -1;
     if (row < M) drow = p.row_map ? p.row_map[row] : row;
@@ -156,6 +165,120 @@ struct EpiGeneric {
         }
       }
     }
+  }
+};
+
+// Staged epilogue (CTA-pair kernel): each warp converts a 32-row x 128-byte slab of its accumulator quarter,
+// writes it to 128B-swizzled shared memory (conflict free) and one lane hands it to the TMA:
+//   bf16 activations -> cp.async.bulk.tensor store (64 columns per slab)
+//   fp32 residual    -> cp.reduce.async.bulk.tensor .add (32 columns per slab): x += acc + bias, added in the L2
+// Global writes are full 128-byte rows instead of 32 scattered 16-byte pieces per instruction, and rows past M
+// are clipped by the tensor map.
+struct alignas(64) EpiStaged {
+  CUtensorMap tm_out;
+  const float* bias;
+  int act;
+  float col_scale;
+  int scale_c0, scale_c1;
+  int f32_add;
+  __device__ __forceinline__ void finish(EpiCtx& ctx) const {
+    if (ctx.lane == 0) bulk_wait_read<0>();
+  }
+  __device__ __forceinline__ void slab_out(EpiCtx& ctx, const uint32_t (&pk)[32], int col0) const {
+    const uint32_t buf = ctx.smem + (ctx.nbuf & 1u) * 4096u;
+    if (ctx.lane == 0) bulk_wait_read<1>();       // the slab stored from this buffer two steps ago has been read
+    __syncwarp();
+    const uint32_t rowp = buf + static_cast<uint32_t>(ctx.lane) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(ctx.lane & 7);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((static_cast<uint32_t>(j) ^ swz) << 4)), "r"(pk[4 * j]),
+                   "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                   : "memory");
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (ctx.lane == 0) {
+      if (f32_add) tma_reduce_add_2d(&tm_out, buf, col0, ctx.row0); else tma_store_2d(&tm_out, buf, col0, ctx.row0);
+      bulk_commit();
+    }
+    ++ctx.nbuf;
+  }
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx& ctx) const {
+    if (f32_add) {
+      for (int c = c_begin; c < c_end; c += 32) {
+        const int col0 = n0 + c;
+        uint32_t r[32];
+        tmem_ld_x32(taddr_row + c, r);
+        tmem_ld_wait();
+        if (bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + b.x);
+            r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b.y);
+            r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b.z);
+            r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b.w);
+          }
+        }
+        slab_out(ctx, r, col0);
+      }
+    } else {
+      for (int c = c_begin; c < c_end; c += 64) {
+        const int col0 = n0 + c;
+        uint32_t pk[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr_row + c + 32 * h, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          const int colh = col0 + 32 * h;
+          if (bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + colh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (colh >= scale_c0 && colh < scale_c1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= col_scale;
+          }
+          if (act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 g = gelu_erf2(make_float2(v[i], v[i + 1]));
+              v[i] = g.x; v[i + 1] = g.y;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[16 * h + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
+        slab_out(ctx, pk, col0);
+      }
+    }
+  }
+};
+
+// measurement-only epilogue (ysi_gemm_bench): drains the accumulator from TMEM and stores nothing unless the value
+// is an (impossible) sentinel, so the mainloop can be timed without the epilogue's global-memory traffic
+struct EpiDrain {
+  float* sink;
+  __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
+    float acc = 0.f;
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr_row + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc += __uint_as_float(r[i]);
+    }
+    if (acc == 1.2345678e33f) sink[0] = acc;
   }
 };
 
@@ -262,7 +385,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end);
+      EpiCtx ctx{0u, 0u, m0 + q * 32, lane};
+      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end, ctx);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -272,6 +396,162 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant: cluster of 2 CTAs, tcgen05.mma.cta_group::2 with M = 256 (128 rows per CTA), N = 256.
+// Each CTA stages its own 128 x 64 slice of A and HALF of the 256 x 64 B tile per k-block (32 KB / stage
+// instead of 48 KB), so the ring is 6 deep in the same shared memory -- enough bytes in flight to cover
+// HBM latency at full MMA rate -- and the tensor core reads half as much shared memory per flop.
+//   leader CTA (rank 0): arms the full barriers with the bytes of BOTH CTAs, issues every MMA, commits
+//                        (multicast) to the empty / accumulator-full barriers of both CTAs
+//   both CTAs          : TMA producer for their own slices (completion counted on the leader's barrier),
+//                        8 epilogue warps on their own 128 accumulator lanes, which release the accumulator
+//                        on the leader's barrier
+// ------------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 5;
+  static constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * 2 * 4096;   // two 32-row x 128-byte slabs per epilogue warp
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+};
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                  const __grid_constant__ Epi epi) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_smem = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = epi_smem + Cfg::EPI_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int num_n = N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);       // leader: arrive.expect_tx (bytes of both CTAs)
+      mbar_init(empty_bar(s), 1);      // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);                      // multicast commit
+      mbar_init(tempty_bar(a), 2 * GEMM_EPI_WARPS);    // leader's copy collects the epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / num_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+        const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+          tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cg2_mc(empty_bar(stage), 3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_cg2_mc(tfull_bar(acc), 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    EpiCtx ctx{epi_smem + static_cast<uint32_t>(warp - 2) * 8192u, 0u, 0, lane};
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / num_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+      const int n0 = (tile % num_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
+      ctx.row0 = m0 + q * 32;
+      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end, ctx);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    epi.finish(ctx);
+  }
+  tc_fence_before();
+  cluster_sync_all();      // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <class Epi>
+void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  auto kern = gemm2_bf16_kernel<Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, 2 * GEMM_BM) * (N / Cfg::BN);
+  const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  YSI_CUDA(cudaGetLastError());
 }
 
 template <int BN, class Epi>

@@ -349,6 +349,25 @@ class SamStage:
                                             1 if is_global else 0, nat.as_f32p(out)), "ysi_attention")
         return out
 
+    def gemm_ex(self, A: np.ndarray, W: np.ndarray, bias: Optional[np.ndarray], act: int, out_kind: int,
+                C0: Optional[np.ndarray] = None) -> np.ndarray:
+        """GEMM through the production dispatcher: out_kind 0 fp32, 1 bf16-rounded, 2 C0 += result."""
+        A = np.ascontiguousarray(A, np.float32)
+        W = np.ascontiguousarray(W, np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        M, K = A.shape
+        N = W.shape[0]
+        out = np.zeros((M, N), np.float32) if C0 is None else np.array(C0, dtype=np.float32, order="C", copy=True)
+        self._check(self._lib.ysi_gemm_ex(self._ctx, nat.as_f32p(A), nat.as_f32p(W), nat.as_f32p(b), M, N, K, act, out_kind,
+                                          nat.as_f32p(out)), "ysi_gemm_ex")
+        return out
+
+    def gemm_bench(self, M: int, N: int, K: int, pair: bool, mode: int, iters: int = 20) -> float:
+        """ms per launch of one GEMM shape on device-resident operands (measurement support)."""
+        ms = C.c_float(0)
+        self._check(self._lib.ysi_gemm_bench(self._ctx, M, N, K, int(pair), mode, iters, C.byref(ms)), "ysi_gemm_bench")
+        return float(ms.value)
+
     def image_pe(self) -> np.ndarray:
         out = np.empty((256, 64, 64), np.float32)
         self._check(self._lib.ysi_get_image_pe(self._ctx, nat.as_f32p(out)), "ysi_get_image_pe")
