@@ -12,11 +12,14 @@
 // Tensor-core work per tile: S = Q K^T (128x64x64, both K-major) and O += P V (128x64x64, V is the MN-major B
 // operand straight out of the qkv activation). O stays in TMEM for the whole CTA: it is rescaled in place
 // (tcgen05.ld / tcgen05.st) only when the running row maximum grows by more than 2^8 ("lazy rescale"), so the
-// softmax threads never wait on the PV MMA in steady state. The S buffer is released as soon as it is in
-// registers, so S_{j+1} is computed while the softmax of tile j runs.
-// The rel-pos terms are two extra MMAs per CTA (Q . table^T) whose TMEM result is re-indexed per query:
-//   global   (S=64): rel_w -> 64 registers per thread (same for every tile); rel_h stays in TMEM, one
-//                    warp-uniform column per tile, folded into the exponent offset
+// softmax threads never wait on the PV MMA in steady state. S is double buffered in TMEM and each buffer is
+// released as soon as it is in registers, so S_{j+1} is complete before the softmax of tile j ends.
+// The rel-pos terms:
+//   global   (S=64): rel_w = one extra MMA per CTA (Q . Rw^T) whose TMEM result is re-indexed per query into
+//                    64 registers per thread (same for every tile). rel_h of tile j (key row kh = j) only
+//                    depends on the query row: the two rel_pos_h rows the CTA's two query rows need are
+//                    appended to the K tile as extra "keys" (S is 128 x 80), so the bias arrives as column
+//                    64 + (qh - qh0) of S and is folded into the exponent offset
 //   windowed (S=14): 14+14 registers per thread; 64->70 zero-padded tokens are ordinary keys (they carry the
 //                    qkv bias, modeling_sam.py:913-916); the window's 196 keys are resident (tiles 64,64,64,16),
 //                    keys >= 196 of the last tile are masked.
@@ -39,24 +42,28 @@ constexpr float LAZY_LOG2 = 8.0f;           // rescale O only when the row max g
 template <bool GLOBAL>
 struct Cfg {
   static constexpr int NST = GLOBAL ? 3 : 4;                        // K / V ring depth (window: whole window)
-  static constexpr int KV_TOTAL = GLOBAL ? 3 * KV_BYTES : 208 * 128; // bytes of the K (and of the V) area
+  static constexpr int K_STAGE = GLOBAL ? 80 * 128 : KV_BYTES;      // global: 64 keys + 16 rows for the rel_pos_h "keys"
+  static constexpr int K_TOTAL = GLOBAL ? 3 * K_STAGE : 208 * 128;
+  static constexpr int V_TOTAL = GLOBAL ? 3 * KV_BYTES : 208 * 128;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;      // also rel_pos_h table during setup
-  static constexpr int OFF_V = OFF_K + KV_TOTAL;     // also rel_pos_w table during setup
-  static constexpr int OFF_P = OFF_V + KV_TOTAL;     // 2 x 16 KB; fp32 bias scratch [k][128] during setup
-  // rel-pos tables as TMA'd for the table MMA: global -> the K / V areas (16 KB each, K/V loads wait for the MMA);
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + K_TOTAL;
+  static constexpr int OFF_P = OFF_V + V_TOTAL;      // 2 x 16 KB; fp32 bias scratch [k][128] during setup
+  // rel-pos tables as TMA'd for the table MMA: global -> rel_pos_w in the V area (16 KB, the V loads wait for the MMA);
   // windowed -> second P buffer (4 KB each), so the whole window's K / V can be requested up front with Q
-  static constexpr int OFF_TABH = GLOBAL ? OFF_K : OFF_P + P_BYTES;
+  static constexpr int OFF_TABH = GLOBAL ? OFF_K : OFF_P + P_BYTES;     // (unused when GLOBAL)
   static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_P + P_BYTES + 4096;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
   static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
-  static constexpr int TMEM_COLS = GLOBAL ? 256 : 128;
-  static constexpr int COL_TH = 0;
-  static constexpr int COL_TW = GLOBAL ? 128 : 32;
-  static constexpr int COL_S = GLOBAL ? 128 : 0;            // aliases the tables (free after setup)
-  static constexpr int COL_O = GLOBAL ? 192 : 64;
-  static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0, "swizzle atoms need 1 KB alignment");
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int S_N = GLOBAL ? 80 : 64;              // columns of one S buffer
+  static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
+  static constexpr int COL_O = 2 * S_N;
+  static constexpr int COL_TH = 0;                          // windowed setup only
+  static constexpr int COL_TW = GLOBAL ? 0 : 32;
+  static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_STAGE % 1024 == 0, "swizzle atoms need 1 KB alignment");
+  static_assert(COL_O + 64 <= TMEM_COLS, "TMEM budget");
 };
 }  // namespace attn
 
@@ -71,7 +78,7 @@ template <bool GLOBAL>
 __global__ void __launch_bounds__(attn::THREADS, 2)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const __grid_constant__ CUtensorMap tmKVtail, const __grid_constant__ CUtensorMap tmRel,
-                         AttnParams p) {
+                         const __grid_constant__ CUtensorMap tmRel8, AttnParams p) {
   using namespace attn;
   using C = Cfg<GLOBAL>;
   extern __shared__ uint8_t smem_raw[];
@@ -79,14 +86,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   float* rel_s = reinterpret_cast<float*>(sgen + C::OFF_P);
   const uint32_t bar = sbase + C::OFF_BAR;
-  const uint32_t bar_q = bar, bar_tab = bar + 8, bar_rel = bar + 16, bar_s_full = bar + 24, bar_s_free = bar + 32;
-  const uint32_t bar_p_full = bar + 40;    // [2]
-  const uint32_t bar_p_free = bar + 56;    // [2]
-  const uint32_t bar_kfull = bar + 72;     // [4]
-  const uint32_t bar_kempty = bar + 104;   // [4]
-  const uint32_t bar_vfull = bar + 136;    // [4]
-  const uint32_t bar_vempty = bar + 168;   // [4]
-  const uint32_t tmem_ptr_smem = bar + 200;
+  const uint32_t bar_q = bar, bar_tab = bar + 8, bar_rel = bar + 16;
+  const uint32_t bar_s_full = bar + 24;    // [2]
+  const uint32_t bar_s_free = bar + 40;    // [2]
+  const uint32_t bar_p_full = bar + 56;    // [2]
+  const uint32_t bar_p_free = bar + 72;    // [2]
+  const uint32_t bar_kfull = bar + 88;     // [4]
+  const uint32_t bar_kempty = bar + 120;   // [4]
+  const uint32_t bar_vfull = bar + 152;    // [4]
+  const uint32_t bar_vempty = bar + 184;   // [4]
+  const uint32_t tmem_ptr_smem = bar + 216;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
@@ -96,8 +105,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, 128);
-    mbar_init(bar_s_full, 1); mbar_init(bar_s_free, 128);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_p_full + 8 * i, 128); mbar_init(bar_p_free + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_free + 8 * i, 128);
+      mbar_init(bar_p_full + 8 * i, 128); mbar_init(bar_p_free + 8 * i, 1);
+    }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_kfull + 8 * i, 1); mbar_init(bar_kempty + 8 * i, 1);
       mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
@@ -117,19 +128,22 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc_tab = umma_idesc_bf16(128, C::TAB_ROWS, 0, 0);
-      constexpr uint32_t idesc_s64 = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::S_N, 0, 0);
       constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);   // B (= V) is MN-major
       constexpr int TAB_BYTES = C::TAB_ROWS * 128;
-      // ---- setup: Q tile + both rel-pos tables
-      mbar_arrive_expect_tx(bar_q, Q_BYTES + 2 * TAB_BYTES);
+      // ---- setup: Q tile + rel-pos table(s)
+      mbar_arrive_expect_tx(bar_q, Q_BYTES + (GLOBAL ? 1 : 2) * TAB_BYTES);
       tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
-      tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);      // rel_pos_h rows (zero padded)
-      tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);    // rel_pos_w rows
+      if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);      // rel_pos_h rows (zero padded)
+      tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);                 // rel_pos_w rows
       auto load_k = [&](int tile, int st) {
         const bool tail = !GLOBAL && tile == 3;
-        mbar_arrive_expect_tx(bar_kfull + 8 * st, tail ? 16 * 128 : KV_BYTES);
-        tma_load_2d(sbase + C::OFF_K + st * KV_BYTES, tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck, row0 + tile * BKV);
+        const uint32_t dst = sbase + C::OFF_K + st * C::K_STAGE;
+        mbar_arrive_expect_tx(bar_kfull + 8 * st, GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES));
+        tma_load_2d(dst, tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck, row0 + tile * BKV);
+        // global: rows 64.. of the K tile = rel_pos_h[qh - kh + 63] for the CTA's two query rows (qh0 = 2 qt, kh = tile)
+        if (GLOBAL) tma_load_2d(dst + KV_BYTES, &tmRel8, bar_kfull + 8 * st, 0, 2 * qt - tile + 63);
       };
       auto load_v = [&](int tile, int st) {
         const bool tail = !GLOBAL && tile == 3;
@@ -139,46 +153,56 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (!GLOBAL) {             // whole window: K / V do not alias the tables, request them right away
         for (int j = 0; j < 4; ++j) load_k(j, j);
         for (int j = 0; j < 4; ++j) load_v(j, j);
+      } else {                   // the K ring does not alias the rel_pos_w table
+        for (int j = 0; j < C::NST && j < ntiles; ++j) load_k(j, j);
       }
       mbar_wait(bar_q, 0);
       tc_fence_after();
       const uint64_t qdesc = umma_desc_sw128(sbase + C::OFF_Q, 16, 1024);
       {
-        const uint64_t hdesc = umma_desc_sw128(sbase + C::OFF_TABH, 16, 1024);
-        const uint64_t wdesc = umma_desc_sw128(sbase + C::OFF_TABW, 16, 1024);
+        if (!GLOBAL) {
+          const uint64_t hdesc = umma_desc_sw128(sbase + C::OFF_TABH, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_tab, k);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_tab, k);
+        }
+        const uint64_t wdesc = umma_desc_sw128(sbase + C::OFF_TABW, 16, 1024);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TW, qdesc + 2u * k, wdesc + 2u * k, idesc_tab, k);
         umma_commit(bar_tab);
       }
       if (GLOBAL) {
-        mbar_wait(bar_tab, 0);     // tables consumed: the K / V areas are free
-        for (int j = 0; j < C::NST && j < ntiles; ++j) load_k(j, j);
+        mbar_wait(bar_tab, 0);     // rel_pos_w table consumed: the V area is free
         for (int j = 0; j < C::NST && j < ntiles; ++j) load_v(j, j);
       }
-      auto issue_s = [&](int tile) {
-        const int st = tile % C::NST;
-        const uint64_t kdesc = umma_desc_sw128(sbase + C::OFF_K + st * KV_BYTES, 16, 1024);
-        const uint32_t idesc = (!GLOBAL && tile == 3) ? idesc_s16 : idesc_s64;
+      // S_t -> S buffer t & 1 (free once the softmax threads hold S_{t-2} in registers). The tensor pipe runs MMAs
+      // in issue order and a chain of dependent small MMAs has a long latency, so S_{j+2} is issued as soon as
+      // S_j has been read -- early in softmax tile j -- and never queues behind PV_j.
+      auto issue_s = [&](int t) {
+        const int st = t % C::NST, buf = t & 1;
+        mbar_wait(bar_kfull + 8 * st, (t / C::NST) & 1);
+        if (t >= 2) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(sbase + C::OFF_K + st * C::K_STAGE, 16, 1024);
+        const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
+        const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_S, qdesc + 2u * k, kdesc + 2u * k, idesc, k);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(d, qdesc + 2u * k, kdesc + 2u * k, idesc, k);
         umma_commit(bar_kempty + 8 * st);    // (the barrier somebody always waits on is committed last)
-        umma_commit(bar_s_full);
+        umma_commit(bar_s_full + 8 * buf);
       };
       mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S / O columns are free
-      mbar_wait(bar_kfull, 0);
       tc_fence_after();
       issue_s(0);
+      if (ntiles > 1) issue_s(1);
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) {
-          const int s1 = (j + 1) % C::NST;
-          mbar_wait(bar_kfull + 8 * s1, ((j + 1) / C::NST) & 1);
-          mbar_wait(bar_s_free, j & 1);           // S_j is in registers
-          tc_fence_after();
-          issue_s(j + 1);
-        }
+        if (j + 2 < ntiles) issue_s(j + 2);
         const int st = j % C::NST, pb = j & 1;
+        // refill the K stage of tile j right away (S_j was issued a whole tile ago): tile j+NST is needed by
+        // issue_s two iterations from now, so its TMA latency hides behind two softmax tiles
+        if (GLOBAL && j + C::NST < ntiles) {
+          mbar_wait(bar_kempty + 8 * st, (j / C::NST) & 1);
+          load_k(j + C::NST, st);
+        }
         mbar_wait(bar_vfull + 8 * st, (j / C::NST) & 1);
         mbar_wait(bar_p_full + 8 * pb, (j >> 1) & 1);
         tc_fence_after();
@@ -193,10 +217,6 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           umma_commit(bar_p_free + 8 * pb);
         }
         if (GLOBAL) {
-          if (j + C::NST < ntiles) {               // K stage of tile j was released by S_j long ago
-            mbar_wait(bar_kempty + 8 * st, (j / C::NST) & 1);
-            load_k(j + C::NST, st);
-          }
           if (j >= 1 && j - 1 + C::NST < ntiles) { // V stage of tile j-1: PV_{j-1} was issued one iteration ago
             const int sv = (j - 1) % C::NST;
             mbar_wait(bar_vempty + 8 * sv, ((j - 1) / C::NST) & 1);
@@ -266,16 +286,18 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // one KV tile: NW columns of S, the first NV of them valid keys
     auto do_tile = [&](auto nw_c, auto nv_c, int j, const float* b /* NW bias values (log2 units) */) {
       constexpr int NW = decltype(nw_c)::value, NV = decltype(nv_c)::value;
-      mbar_wait(bar_s_full, j & 1);
+      const int pb = j & 1;                       // S buffer and P buffer of this tile
+      mbar_wait(bar_s_full + 8 * pb, (j >> 1) & 1);
       tc_fence_after();
       uint32_t r[NW];
       float bh = 0.f;
       if (warp_active) {
-        if constexpr (NW == 64) { tmem_ld_x32p(tlane + C::COL_S, r); tmem_ld_x32p(tlane + C::COL_S + 32, r + 32); }
-        else tmem_ld_x16p(tlane + C::COL_S, r);
+        const uint32_t scol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N);
+        if constexpr (NW == 64) { tmem_ld_x32p(scol, r); tmem_ld_x32p(scol + 32, r + 32); }
+        else tmem_ld_x16p(scol, r);
         if (GLOBAL) {
           uint32_t rb;
-          tmem_ld_x1(tlane + C::COL_TH + static_cast<uint32_t>(qh + 63 - j), rb);   // warp-uniform column
+          tmem_ld_x1(scol + 64u + static_cast<uint32_t>(warp >> 1), rb);   // q . rel_pos_h[qh - j + 63]: warp-uniform column
           tmem_ld_wait();
           bh = __uint_as_float(rb);
         } else {
@@ -283,8 +305,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_s_free);
-      const int pb = j & 1;
+      mbar_arrive(bar_s_free + 8 * pb);
+      // P buffer pb was consumed by PV_{j-2}. Every thread waits (also the idle warps of a ragged window tile):
+      // S runs two tiles ahead, so without this an idle warp could arrive on bar_p_full for tile j while the
+      // barrier's phase of tile j-2 is still open.
+      if (j >= 2) mbar_wait(bar_p_free + 8 * pb, ((j - 2) >> 1) & 1);
       if (warp_active) {
         float2 y[NW / 2];
 #pragma unroll
@@ -317,7 +342,6 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
         const float c = bh - m_used;
         const float2 c2 = make_float2(c, c);
-        if (j >= 2) mbar_wait(bar_p_free + 8 * pb, ((j - 2) >> 1) & 1);    // P buffer consumed by PV_{j-2}
         const uint32_t p_row = p_row0 + pb * P_BYTES;
 #pragma unroll
         for (int ch = 0; ch < NW / 8; ++ch) {
@@ -417,13 +441,14 @@ void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, i
   const CUtensorMap tmKV = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BKV);
   const CUtensorMap tmKVtail = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, 16);
   const CUtensorMap tmRel = make_tmap_bf16_2d(rel_tab, 256, HD, HD, is_global ? 128 : 32);
+  const CUtensorMap tmRel8 = make_tmap_bf16_2d(rel_tab, 256, HD, HD, 8);
   AttnParams p;
   p.T = T; p.D = D; p.out = out; p.unwindow = unwindow ? 1 : 0;
   dim3 grid(ceil_div(T, BQ), heads, n_seq);
   if (is_global)
-    encoder_attention_kernel<true><<<grid, THREADS, Cfg<true>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, p);
+    encoder_attention_kernel<true><<<grid, THREADS, Cfg<true>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
   else
-    encoder_attention_kernel<false><<<grid, THREADS, Cfg<false>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, p);
+    encoder_attention_kernel<false><<<grid, THREADS, Cfg<false>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
   YSI_CUDA(cudaGetLastError());
 }
 
