@@ -62,3 +62,32 @@ def test_batch_equals_single(tiny_stage):
         single = tiny_stage.run(imgs[i], boxes[i])
         assert np.array_equal(both[i][0], single[0])
         assert both[i][1] == single[1]
+
+
+@pytest.mark.parametrize("H,W", [(2048, 2048), (348, 704)])
+def test_stage_end_to_end_other_sizes(tiny_stage, tiny_oracle, H, W):
+    """Config-5 sized frames (2x antialias downscale in, 1024->2048 second upsample out) and the aspect ratio of the
+    reference's example PNGs (upscale in, unpadded 506x1024 -> 348x704 downscale out)."""
+    from oracle import metrics_oracle as mo
+    from oracle import sam_oracle
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    g, b = synth_image(31, max(H, W), 2)
+    im = np.ascontiguousarray(gray_to_rgb_u8(g)[:H, :W])
+    b = np.clip(b, 0, [W - 1, H - 1, W - 1, H - 1]).astype(np.float32)
+    ref_masks, d = sam_oracle.run_stage(tiny_oracle, im, b, dump=True)
+    tiny_stage.on_empty = "zeros"
+    masks, mets, crops = tiny_stage.run(im, b)
+    assert masks.shape == ref_masks.shape == (2, H, W)
+    # a6 alone on the oracle's logits is exact at this geometry too
+    m6 = tiny_stage.postprocess(d["low_res_logits"], H, W)
+    assert np.array_equal(m6, ref_masks)
+    for k in range(2):
+        iou = np.logical_and(masks[k], ref_masks[k]).sum() / max(np.logical_or(masks[k], ref_masks[k]).sum(), 1)
+        assert iou > 0.97, iou
+        if masks[k].any():
+            ref = mo.calculate_metrics(im, masks[k])
+            for key, val in ref.items():
+                if isinstance(val, int):
+                    assert mets[k][key] == val, (key, mets[k][key], val)
+                else:
+                    assert mets[k][key] == pytest.approx(val, rel=1e-9, abs=1e-12), key

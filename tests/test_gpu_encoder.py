@@ -53,3 +53,16 @@ def test_encoder_batch_of_two_matches_single(tiny_stage, tiny_oracle):
     both = tiny_stage.encode(pv)
     one = tiny_stage.encode(pv[1:2])
     assert np.array_equal(both[1], one[0])          # images are independent: batching must not change results
+
+
+@pytest.mark.parametrize("H,W", [(2048, 2048), (348, 704), (300, 704), (1500, 2000), (640, 480), (1024, 700)])
+def test_preprocess_resize_is_bit_exact(tiny_stage, H, W):
+    """a1 for inputs that are not 1024x1024: the uint8 antialias resize (Pillow-style fixed point) + normalise +
+    zero pad must reproduce SamImageProcessor exactly (config 5 is 2048x2048, the reference's example PNGs 348x704)."""
+    from oracle import sam_oracle
+    rng = np.random.RandomState(H + W)
+    img = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    ref, orig, reshaped = sam_oracle.preprocess(img)
+    got = tiny_stage.preprocess([img])
+    assert orig == (H, W)
+    assert np.array_equal(got[0], ref[0].numpy())

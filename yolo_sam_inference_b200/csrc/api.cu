@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,9 @@ struct ysi_ctx {
   uint8_t* d_rgb = nullptr;        // [max_batch, H, W, 3]
   uint16_t* d_sum3 = nullptr;      // [max_batch, H, W]
   float* d_pix = nullptr;          // [max_batch, 3, 1024, 1024] (stage API only, lazily allocated)
+  uint8_t* d_rs_tmp = nullptr;     // [max_batch, max_image_h, 1024, 3] horizontally resized (lazily allocated)
+  uint8_t* d_rs = nullptr;         // [max_batch, 1024, 1024, 3] resized image (lazily allocated)
+  std::map<std::pair<int, int>, ResizeTablesDev> resize_tabs;   // (in, out) -> device tables
   float* d_emb = nullptr;          // [max_batch*4096, 256] token-major image embeddings
   float* d_low = nullptr;          // [max_boxes, 256, 256]
   uint8_t* d_masks = nullptr;      // [max_boxes, H, W]
@@ -355,6 +359,47 @@ void create_impl(ysi_ctx* c) {
   YSI_CUDA(cudaStreamSynchronize(c->stream));
 }
 
+const ResizeTablesDev& resize_tables(ysi_ctx* c, int in_size, int out_size) {
+  auto key = std::make_pair(in_size, out_size);
+  auto it = c->resize_tabs.find(key);
+  if (it != c->resize_tabs.end()) return it->second;
+  const ResizeTables t = build_resize_tables(in_size, out_size);
+  ResizeTablesDev d;
+  d.in_size = in_size; d.out_size = out_size; d.ksize = t.ksize; d.prec = t.prec;
+  int* xm = c->dalloc<int>(t.xmin.size());
+  int* xs = c->dalloc<int>(t.xsize.size());
+  int16_t* w = c->dalloc<int16_t>(t.weights.size());
+  YSI_CUDA(cudaMemcpy(xm, t.xmin.data(), t.xmin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  YSI_CUDA(cudaMemcpy(xs, t.xsize.data(), t.xsize.size() * sizeof(int), cudaMemcpyHostToDevice));
+  YSI_CUDA(cudaMemcpy(w, t.weights.data(), t.weights.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+  d.xmin = xm; d.xsize = xs; d.weights = w;
+  return c->resize_tabs.emplace(key, d).first->second;
+}
+
+// a1 on the device (image_processing_sam.py:205-250): resize longest edge to 1024 (uint8 antialias bilinear, skipped
+// when the size already matches), normalise, zero-pad to 1024x1024; emits pixel_values and/or the patch-embed A matrix.
+// rgb: dense device images [n, H, W, 3].
+void preprocess_images(ysi_ctx* c, const uint8_t* rgb, int n, int H, int W, float* pixel_values, bf16* a_patch) {
+  const PostGeom g = make_post_geom(H, W);
+  const uint8_t* src = rgb;
+  int sh = H, sw = W, pitch = W * 3;
+  size_t istride = static_cast<size_t>(H) * W * 3;
+  if (g.rw != W) {
+    if (!c->d_rs_tmp) c->d_rs_tmp = c->dalloc<uint8_t>(static_cast<size_t>(c->cfg.max_batch) * c->cfg.max_image_h * 1024 * 3);
+    launch_resize_h(src, n, H, pitch, istride, resize_tables(c, W, g.rw), c->d_rs_tmp, c->stream);
+    c->launches += 1;
+    src = c->d_rs_tmp; sw = g.rw; pitch = g.rw * 3; istride = static_cast<size_t>(H) * g.rw * 3;
+  }
+  if (g.rh != H) {
+    if (!c->d_rs) c->d_rs = c->dalloc<uint8_t>(static_cast<size_t>(c->cfg.max_batch) * 1024 * 1024 * 3);
+    launch_resize_v(src, n, pitch, istride, sw, resize_tables(c, H, g.rh), c->d_rs, c->stream);
+    c->launches += 1;
+    src = c->d_rs; sh = g.rh; istride = static_cast<size_t>(g.rh) * sw * 3;
+  }
+  launch_preprocess(src, n, sh, sw, pitch, istride, c->mean255, c->std255, pixel_values, a_patch, c->stream);
+  c->launches += 1;
+}
+
 // processing_sam.py:215-234: boxes (float32, original pixels) -> float64 in the resized frame
 void rescale_boxes(const float* boxes, int nb, int H, int W, std::vector<double>& out) {
   const PostGeom g = make_post_geom(H, W);
@@ -373,7 +418,6 @@ void check_batch(ysi_ctx* c, int n, int H, int W, int nb) {
   YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
   YSI_CHECK(nb >= 0 && nb <= c->cfg.max_boxes, "box count exceeds max_boxes");
   YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
-  YSI_CHECK(H == 1024 && W == 1024, "this build runs the fused preprocess for 1024x1024 inputs only");
 }
 
 void stage_impl(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
@@ -418,8 +462,8 @@ void compute_impl(ysi_ctx* c, ysi_timing* tm, bool sync = true) {
   if (nb > 0) {
     ProfScope ps(prof, KC_PREPROCESS);
     launch_sum3(d_rgb, n, H, W, W * 3, c->d_sum3, s);
-    launch_preprocess_1024(d_rgb, n, W * 3, c->mean255, c->std255, nullptr, c->ew.a_patch, s);
-    c->launches += 2;
+    c->launches += 1;
+    preprocess_images(c, d_rgb, n, H, W, nullptr, c->ew.a_patch);
   }
   YSI_CUDA(cudaEventRecord(c->ev[1], s));
   if (nb > 0) encoder_forward(c->enc, c->ew, n, c->d_emb, nullptr, s, &c->launches, prof);
@@ -624,14 +668,13 @@ int ysi_profile_read(ysi_ctx* c, int max_classes, const char** names, double* ms
 int ysi_preprocess(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, float* pixel_values_out) {
   return guarded(c, [&] {
     YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
-    YSI_CHECK(H == 1024 && W == 1024, "this build runs the fused preprocess for 1024x1024 inputs only");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
     if (!c->d_pix) c->d_pix = c->dalloc<float>(static_cast<size_t>(c->cfg.max_batch) * 3 * 1024 * 1024);
     const size_t img_bytes = static_cast<size_t>(H) * W * 3;
     for (int i = 0; i < n; ++i)
       YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
                                  static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->stream));
-    launch_preprocess_1024(c->d_rgb, n, W * 3, c->mean255, c->std255, c->d_pix, nullptr, c->stream);
-    c->launches += 1;
+    preprocess_images(c, c->d_rgb, n, H, W, c->d_pix, nullptr);
     YSI_CUDA(cudaMemcpyAsync(pixel_values_out, c->d_pix, sizeof(float) * n * 3 * 1024 * 1024, cudaMemcpyDeviceToHost, c->stream));
     YSI_CUDA(cudaStreamSynchronize(c->stream));
   });

@@ -1,19 +1,135 @@
 // SAM ViT image encoder assembly (modeling_sam.py:1058-1072): preprocessing, patch-embed im2col,
 // LayerNorm (+ window partition), neck; the contractions run on the tcgen05 GEMM / attention kernels.
 #include "kernels.h"
+#include <cmath>
+
 #include "ptx.cuh"
 
 namespace ysi {
 
 // ------------------------------------------------------------------------------------------------
-// a1 at 1024x1024 (identity resize): (x - 255*mean) / (255*std) in fp32, exactly as tvF.normalize
-// (image_processing_backends.py rescale_and_normalize: mean,std pre-multiplied by 1/rescale_factor).
+// a1, resize step: torchvision's uint8 bilinear resize with antialias=True (image_processing_sam.py:205-250 ->
+// image_processing_backends.py resize) is Pillow's fixed-point separable resampler: per output index a
+// window [xmin, xmin+xsize) of the input, triangle-filter weights normalised in double and quantised to
+// int16 with `prec` fractional bits (as many as keep the largest weight below 2^15), accumulation in int32,
+// (acc + 2^(prec-1)) >> prec clamped to uint8; horizontal pass first, then vertical, each rounding to uint8.
+// build_resize_tables restates aten/src/ATen/native/cpu/UpSampleKernel.cpp (_compute_indices_int16_weights_aa).
+// ------------------------------------------------------------------------------------------------
+ResizeTables build_resize_tables(int in_size, int out_size) {
+  ResizeTables t;
+  t.in_size = in_size; t.out_size = out_size;
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double support = scale >= 1.0 ? scale : 1.0;                 // interp_size / 2 = 1 for the triangle filter
+  const double invscale = scale >= 1.0 ? 1.0 / scale : 1.0;
+  t.ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  t.xmin.assign(out_size, 0); t.xsize.assign(out_size, 0);
+  std::vector<double> w(static_cast<size_t>(out_size) * t.ksize, 0.0);
+  double wmax = 0.0;
+  for (int i = 0; i < out_size; ++i) {
+    const double center = scale * (i + 0.5);
+    int lo = static_cast<int>(center - support + 0.5); if (lo < 0) lo = 0;
+    int hi = static_cast<int>(center + support + 0.5); if (hi > in_size) hi = in_size;
+    const int n = hi - lo;
+    t.xmin[i] = lo; t.xsize[i] = n;
+    double total = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const double x = (j + lo - center + 0.5) * invscale;
+      const double v = x < 0 ? 1.0 + x : 1.0 - x;
+      w[static_cast<size_t>(i) * t.ksize + j] = v > 0.0 ? v : 0.0;
+      total += w[static_cast<size_t>(i) * t.ksize + j];
+    }
+    for (int j = 0; j < n; ++j) {
+      if (total != 0.0) w[static_cast<size_t>(i) * t.ksize + j] /= total;
+      if (w[static_cast<size_t>(i) * t.ksize + j] > wmax) wmax = w[static_cast<size_t>(i) * t.ksize + j];
+    }
+  }
+  int prec = 0;
+  for (prec = 0; prec < 22; ++prec) {
+    const int next = static_cast<int>(0.5 + wmax * (1 << (prec + 1)));
+    if (next >= (1 << 15)) break;
+  }
+  t.prec = prec;
+  t.weights.assign(w.size(), 0);
+  for (size_t k = 0; k < w.size(); ++k) t.weights[k] = static_cast<int16_t>(w[k] * (1 << prec) + 0.5);   // weights are >= 0
+  return t;
+}
+
+// one thread = one output pixel (3 channels); horizontal: dst[b,y,i,:] from src[b,y,xmin[i]..,:]
+__global__ void resize_h_kernel(const uint8_t* __restrict__ src, int n, int H, int row_stride, size_t img_stride,
+                                const int* __restrict__ xmin, const int* __restrict__ xsize, const int16_t* __restrict__ wts,
+                                int ksize, int prec, int ow, uint8_t* __restrict__ dst) {
+  const long long total = static_cast<long long>(n) * H * ow;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % ow);
+    const long long t = idx / ow;
+    const int y = static_cast<int>(t % H), b = static_cast<int>(t / H);
+    const uint8_t* sp = src + b * img_stride + static_cast<size_t>(y) * row_stride + static_cast<size_t>(xmin[i]) * 3;
+    const int16_t* w = wts + static_cast<size_t>(i) * ksize;
+    const int cnt = xsize[i];
+    int a0 = 1 << (prec - 1), a1 = a0, a2 = a0;
+    for (int j = 0; j < cnt; ++j) {
+      const int wj = w[j];
+      a0 += sp[3 * j] * wj; a1 += sp[3 * j + 1] * wj; a2 += sp[3 * j + 2] * wj;
+    }
+    uint8_t* dp = dst + idx * 3;
+    dp[0] = static_cast<uint8_t>(min(max(a0 >> prec, 0), 255));
+    dp[1] = static_cast<uint8_t>(min(max(a1 >> prec, 0), 255));
+    dp[2] = static_cast<uint8_t>(min(max(a2 >> prec, 0), 255));
+  }
+}
+
+// vertical: dst[b,i,x,:] from src[b,ymin[i]..,x,:]   (src pitch = row_stride bytes)
+__global__ void resize_v_kernel(const uint8_t* __restrict__ src, int n, int row_stride, size_t img_stride, int W,
+                                const int* __restrict__ ymin, const int* __restrict__ ysize, const int16_t* __restrict__ wts,
+                                int ksize, int prec, int oh, uint8_t* __restrict__ dst) {
+  const long long total = static_cast<long long>(n) * oh * W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % W);
+    const long long t = idx / W;
+    const int i = static_cast<int>(t % oh), b = static_cast<int>(t / oh);
+    const uint8_t* sp = src + b * img_stride + static_cast<size_t>(ymin[i]) * row_stride + static_cast<size_t>(x) * 3;
+    const int16_t* w = wts + static_cast<size_t>(i) * ksize;
+    const int cnt = ysize[i];
+    int a0 = 1 << (prec - 1), a1 = a0, a2 = a0;
+    for (int j = 0; j < cnt; ++j) {
+      const int wj = w[j];
+      const uint8_t* q = sp + static_cast<size_t>(j) * row_stride;
+      a0 += q[0] * wj; a1 += q[1] * wj; a2 += q[2] * wj;
+    }
+    uint8_t* dp = dst + idx * 3;
+    dp[0] = static_cast<uint8_t>(min(max(a0 >> prec, 0), 255));
+    dp[1] = static_cast<uint8_t>(min(max(a1 >> prec, 0), 255));
+    dp[2] = static_cast<uint8_t>(min(max(a2 >> prec, 0), 255));
+  }
+}
+
+void launch_resize_h(const uint8_t* src, int n, int H, int row_stride, size_t img_stride, const ResizeTablesDev& t, uint8_t* dst,
+                     cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * H * t.out_size;
+  resize_h_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32)), 256, 0, s>>>(
+      src, n, H, row_stride, img_stride, t.xmin, t.xsize, t.weights, t.ksize, t.prec, t.out_size, dst);
+  YSI_CUDA(cudaGetLastError());
+}
+void launch_resize_v(const uint8_t* src, int n, int row_stride, size_t img_stride, int W, const ResizeTablesDev& t, uint8_t* dst,
+                     cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * t.out_size * W;
+  resize_v_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32)), 256, 0, s>>>(
+      src, n, row_stride, img_stride, W, t.xmin, t.xsize, t.weights, t.ksize, t.prec, t.out_size, dst);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1, normalise + pad + patchify: (x - 255*mean) / (255*std) in fp32, exactly as tvF.normalize
+// (image_processing_backends.py rescale_and_normalize: mean,std pre-multiplied by 1/rescale_factor); pixels
+// outside the resized image [src_h, src_w] are the zero padding applied AFTER normalisation (exactly 0.0).
 // One thread = 8 horizontally adjacent pixels of one channel of one patch row.
 // A row (token) = patch (py,px); column = c*256 + ky*16 + kx   (Conv2d weight [D,3,16,16] flattened)
 // ------------------------------------------------------------------------------------------------
-__global__ void preprocess_1024_kernel(const uint8_t* __restrict__ rgb, int n, int row_stride,
-                                       float m0, float m1, float m2, float s0, float s1, float s2,
-                                       float* __restrict__ pix, bf16* __restrict__ a_patch) {
+__global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, int n, int src_h, int src_w, int row_stride, size_t img_stride,
+                                  float m0, float m1, float m2, float s0, float s1, float s2,
+                                  float* __restrict__ pix, bf16* __restrict__ a_patch) {
   const long long total = static_cast<long long>(n) * 3 * 1024 * 128;   // 8-pixel groups
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -23,10 +139,11 @@ __global__ void preprocess_1024_kernel(const uint8_t* __restrict__ rgb, int n, i
     const int b = static_cast<int>(i / (3ll << 17));
     const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
     const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
-    const uint8_t* src = rgb + (static_cast<size_t>(b) * 1024 + y) * row_stride + static_cast<size_t>(xg) * 8 * 3 + c;
+    const uint8_t* src = rgb + b * img_stride + static_cast<size_t>(y) * row_stride + static_cast<size_t>(xg) * 8 * 3 + c;
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __fdiv_rn(__fsub_rn(static_cast<float>(src[3 * k]), mean), sd);
+    for (int k = 0; k < 8; ++k)
+      v[k] = (y < src_h && xg * 8 + k < src_w) ? __fdiv_rn(__fsub_rn(static_cast<float>(src[3 * k]), mean), sd) : 0.0f;
     if (pix) {
       float4* d = reinterpret_cast<float4*>(pix + ((static_cast<size_t>(b) * 3 + c) * 1024 + y) * 1024 + xg * 8);
       d[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -42,12 +159,12 @@ __global__ void preprocess_1024_kernel(const uint8_t* __restrict__ rgb, int n, i
   }
 }
 
-void launch_preprocess_1024(const uint8_t* rgb, int n, int row_stride, const float* mean255, const float* std255,
-                            float* pixel_values, bf16* a_patch, cudaStream_t s) {
+void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_stride, size_t img_stride, const float* mean255,
+                       const float* std255, float* pixel_values, bf16* a_patch, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  preprocess_1024_kernel<<<grid, 256, 0, s>>>(rgb, n, row_stride, mean255[0], mean255[1], mean255[2], std255[0],
-                                              std255[1], std255[2], pixel_values, a_patch);
+  preprocess_kernel<<<grid, 256, 0, s>>>(rgb, n, src_h, src_w, row_stride, img_stride, mean255[0], mean255[1], mean255[2],
+                                         std255[0], std255[1], std255[2], pixel_values, a_patch);
   YSI_CUDA(cudaGetLastError());
 }
 

@@ -84,10 +84,27 @@ struct EncoderWork {      // activation workspace for `cap` images
   const int* win_row_map; // [cap*4900] window row -> token row (or -1)
 };
 
-// uint8 RGB [n,1024,1024,3] (pitch row_stride bytes) -> normalised pixel_values fp32 [n,3,1024,1024] (optional)
-// and/or the patch-embed A matrix bf16 [n*4096, 768]
-void launch_preprocess_1024(const uint8_t* rgb, int n, int row_stride, const float* mean255, const float* std255,
-                            float* pixel_values, bf16* a_patch, cudaStream_t s);
+// torchvision / Pillow fixed-point antialias resampling tables for one axis (see encoder.cu)
+struct ResizeTables {
+  int in_size = 0, out_size = 0, ksize = 0, prec = 0;
+  std::vector<int> xmin, xsize;
+  std::vector<int16_t> weights;      // [out_size, ksize]
+};
+struct ResizeTablesDev {
+  int in_size = 0, out_size = 0, ksize = 0, prec = 0;
+  const int* xmin = nullptr; const int* xsize = nullptr; const int16_t* weights = nullptr;
+};
+ResizeTables build_resize_tables(int in_size, int out_size);
+// horizontal pass: src uint8 [n,H,*,3] (row pitch row_stride, image pitch img_stride bytes) -> dst dense [n,H,out,3]
+void launch_resize_h(const uint8_t* src, int n, int H, int row_stride, size_t img_stride, const ResizeTablesDev& t, uint8_t* dst,
+                     cudaStream_t s);
+// vertical pass: src uint8 [n,*,W,3] -> dst dense [n,out,W,3]
+void launch_resize_v(const uint8_t* src, int n, int row_stride, size_t img_stride, int W, const ResizeTablesDev& t, uint8_t* dst,
+                     cudaStream_t s);
+// resized uint8 RGB [n,src_h,src_w,3] (row pitch row_stride, image pitch img_stride bytes) -> normalised, zero-padded
+// pixel_values fp32 [n,3,1024,1024] (optional) and/or the patch-embed A matrix bf16 [n*4096, 768]
+void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_stride, size_t img_stride, const float* mean255,
+                       const float* std255, float* pixel_values, bf16* a_patch, cudaStream_t s);
 void launch_im2col_patch_f32(const float* pixel_values, int n, bf16* a_patch, cudaStream_t s);
 void launch_build_win_row_map(int* map, int n_images, cudaStream_t s);
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
