@@ -35,10 +35,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 BATCH = int(os.environ.get("YSI_BENCH_BATCH", "8"))   # images per step
+MODEL = os.environ.get("YSI_BENCH_MODEL", "vit_b")    # vit_b = BASELINE configs[1]; vit_h = configs[2]'s model
+ENC_FLOPS = {"vit_b": 937.6e9, "vit_l": 2837.0e9, "vit_h": 5641.8e9}
 POOL_IMAGES = 256            # BASELINE configs[1]: 256 synthetic 1024x1024 images
 ENC_FLOPS_VIT_B = 937.6e9    # algorithmic FLOPs / image
 DEC_FLOPS_BOX = 3.61e9
-METRIC = "SAM box-prompt images/s (ViT-B, 1024x1024, 1 box/image; masks/s == images/s)"
+METRIC = "SAM box-prompt images/s (%s, 1024x1024, 1 box/image; masks/s == images/s)" % {"vit_b": "ViT-B", "vit_l": "ViT-L", "vit_h": "ViT-H"}.get(MODEL, MODEL)
 
 
 def peaks():
@@ -147,7 +149,7 @@ def cpu_reference_images_per_s(n_images: int, warmup: int, threads: int, budget_
     import torch
     from oracle import metrics_oracle, sam_oracle
     torch.set_num_threads(threads)
-    model = sam_oracle.build_model("vit_b", 1234)
+    model = sam_oracle.build_model(MODEL, 1234)
     imgs, boxes = make_inputs(0, max(n_images, 1))
 
     def one(i):
@@ -224,7 +226,7 @@ def run_ours(args):
     pool_n = min(POOL_IMAGES, BATCH * max(K, 1))
     # folder partition: rank r owns images [r*POOL, (r+1)*POOL) of the global synthetic list
     imgs, boxes = make_inputs(rank * POOL_IMAGES, pool_n)
-    stage = SamStage("vit_b", device=f"cuda:{local}", state_dict=seeded_state_dict("vit_b", 1234), max_batch=BATCH,
+    stage = SamStage(MODEL, device=f"cuda:{local}", state_dict=seeded_state_dict(MODEL, 1234), max_batch=BATCH,
                      max_boxes=BATCH, max_image_hw=(1024, 1024), on_empty="zeros")
     stage.pool_upload(imgs)
     nbat = pool_n // BATCH
@@ -306,7 +308,7 @@ def run_ours(args):
                      for k, v in prof.items()}
         # whole-encoder tensor utilisation from the device-resident number
         enc_ms = sum(prof[c]["ms"] for c in gemm_classes + ["attn_window", "attn_global", "layernorm", "neck"]) / psteps
-        breakdown["_encoder_alg_tflops"] = ENC_FLOPS_VIT_B * BATCH / (enc_ms / 1e3) / 1e12 if enc_ms else None
+        breakdown["_encoder_alg_tflops"] = ENC_FLOPS[MODEL] * BATCH / (enc_ms / 1e3) / 1e12 if enc_ms else None
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu = None
@@ -323,14 +325,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: SAM ViT-B bf16 (fp32 accumulate/residual), 256 synthetic 1024x1024 "
+            "config": {"workload": ("configs[1]: SAM ViT-B" if MODEL == "vit_b" else f"SAM {MODEL}") + " bf16 (fp32 accumulate/residual), 256 synthetic 1024x1024 "
                                    f"images per GPU, 1 box/image, batch {BATCH} images per step",
                        "batch": BATCH, "pool_images_per_gpu": pool_n, "weights": "seeded random-init (no checkpoints offline)",
                        "l2": "inputs differ every step and the per-step working set (~0.9 GB of activations) exceeds the "
                              "126 MB L2, so no L2 flush is needed between timed iterations",
                        "parallelism": f"image-sharded x{world}, no collective"},
             "masks_per_s": value,
-            "alg_tflops": (ENC_FLOPS_VIT_B + DEC_FLOPS_BOX) * value / 1e12,
+            "alg_tflops": (ENC_FLOPS[MODEL] + DEC_FLOPS_BOX) * value / 1e12,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "cpu_baseline": cpu, "breakdown": breakdown,

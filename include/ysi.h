@@ -35,7 +35,7 @@ typedef struct ysi_ctx ysi_ctx;
 #define YSI_FLAG_CONTOUR_TRUNCATED 4u /* contour longer than the trace budget (never for H,W <= 4096) */
 
 typedef struct {
-  int32_t hidden_size;  /* ViT width D: 768 (B) / 1024 (L) / 1280 (H); head_dim must be 64 in this round */
+  int32_t hidden_size;  /* ViT width D: 768 (B) / 1024 (L) / 1280 (H); head_dim = D / num_heads must be 64 or 80 */
   int32_t num_layers;
   int32_t num_heads;
   int32_t mlp_dim;
@@ -151,10 +151,10 @@ YSI_API int ysi_metrics(ysi_ctx* ctx, const uint8_t* rgb, int H, int W, int row_
 YSI_API int ysi_gemm(ysi_ctx* ctx, const float* A, const float* W, const float* bias, int M, int N, int K, int act,
              float* C_out);
 /* windowed / global attention of one encoder layer on its own (modeling_sam.py:843-882):
- * qkv fp32 [n_seq, T, 3*heads*64] (T = 196 windowed, 4096 global), rel_pos_h/w fp32 [2S-1, 64]
- * -> out fp32 [n_seq, T, heads*64]. */
+ * qkv fp32 [n_seq, T, 3*heads*head_dim] (T = 196 windowed, 4096 global), rel_pos_h/w fp32 [2S-1, head_dim]
+ * -> out fp32 [n_seq, T, heads*head_dim]. head_dim 64 (ViT-B/L) or 80 (ViT-H). */
 YSI_API int ysi_attention(ysi_ctx* ctx, const float* qkv, const float* rel_pos_h, const float* rel_pos_w, int n_seq,
-                  int heads, int is_global, float* out);
+                  int heads, int head_dim, int is_global, float* out);
 
 /* the GEMM core through the production tile dispatcher, with the encoder's epilogue kinds:
  * out_kind 0: C = result (fp32); 1: C = bf16-rounded result; 2: C += result (the residual add of

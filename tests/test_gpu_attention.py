@@ -14,9 +14,9 @@ def _bf16(t):
 
 
 def reference_attention(qkv, rel_h, rel_w, heads, S):
-    """qkv [B, S*S, 3*heads*64] (already bf16-representable) -> [B, S*S, heads*64], fp32 math."""
+    """qkv [B, S*S, 3*heads*hd] (already bf16-representable) -> [B, S*S, heads*hd], fp32 math."""
     B, T, _ = qkv.shape
-    hd = 64
+    hd = qkv.shape[2] // (3 * heads)
     x = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, B * heads, T, hd)
     q, k, v = x[0], x[1], x[2]
     idx = torch.arange(S)[:, None] - torch.arange(S)[None, :] + (S - 1)
@@ -29,14 +29,15 @@ def reference_attention(qkv, rel_h, rel_w, heads, S):
     return out
 
 
-@pytest.mark.parametrize("is_global,n_seq,heads", [(False, 3, 3), (False, 50, 2), (True, 1, 2), (True, 2, 3)])
-def test_attention_matches_reference(tiny_stage, is_global, n_seq, heads):
+@pytest.mark.parametrize("is_global,n_seq,heads,hd", [(False, 3, 3, 64), (False, 50, 2, 64), (True, 1, 2, 64), (True, 2, 3, 64),
+                                                       (False, 27, 2, 80), (True, 1, 3, 80)])
+def test_attention_matches_reference(tiny_stage, is_global, n_seq, heads, hd):
     g = torch.Generator().manual_seed(7 + n_seq + heads)
     S = 64 if is_global else 14
     T = S * S
-    qkv = _bf16(torch.randn(n_seq, T, 3 * heads * 64, generator=g) * 1.2)
-    rel_h = _bf16(torch.randn(2 * S - 1, 64, generator=g) * 0.15)
-    rel_w = _bf16(torch.randn(2 * S - 1, 64, generator=g) * 0.15)
+    qkv = _bf16(torch.randn(n_seq, T, 3 * heads * hd, generator=g) * 1.2)
+    rel_h = _bf16(torch.randn(2 * S - 1, hd, generator=g) * 0.15)
+    rel_w = _bf16(torch.randn(2 * S - 1, hd, generator=g) * 0.15)
     ref = reference_attention(qkv, rel_h, rel_w, heads, S).numpy()
     out = tiny_stage.attention(qkv.numpy(), rel_h.numpy(), rel_w.numpy(), heads, is_global)
     assert np.isfinite(out).all()

@@ -84,7 +84,7 @@ EXPORTS = {
     "ysi_postprocess": (C.c_int, [_ctx, _f32p, C.c_int, C.c_int, C.c_int, _u8p, _f32p]),
     "ysi_metrics": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_void_p]),
     "ysi_gemm": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
-    "ysi_attention": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p]),
+    "ysi_attention": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "ysi_gemm_ex": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "ysi_gemm_bench": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ysi_get_image_pe": (C.c_int, [_ctx, _f32p]),

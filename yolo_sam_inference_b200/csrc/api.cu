@@ -152,7 +152,8 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   };
   // ---------------- encoder
   EncoderW& e = c->enc;
-  e.D = D; e.L = L; e.heads = heads; e.mlp = mlp;
+  e.D = D; e.L = L; e.heads = heads; e.mlp = mlp; e.head_dim = D / heads;
+  const int hd = e.head_dim, hdp = attn_table_cols(hd);
   if (const char* rm = getenv("YSI_RESIDUAL_MODE")) e.residual_mode = atoi(rm) == 1 ? 1 : 2;   // tuning knob (bench only)
   e.w_patch = b16("vision_encoder.patch_embed.projection.weight", {D, 3, 16, 16});
   e.b_patch = f32("vision_encoder.patch_embed.projection.bias", {D});
@@ -171,13 +172,13 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
     lw.w_proj = b16(p + "attn.proj.weight", {D, D}); lw.b_proj = f32(p + "attn.proj.bias", {D});
     lw.w_fc1 = b16(p + "mlp.lin1.weight", {mlp, D}); lw.b_fc1 = f32(p + "mlp.lin1.bias", {mlp});
     lw.w_fc2 = b16(p + "mlp.lin2.weight", {D, mlp}); lw.b_fc2 = f32(p + "mlp.lin2.bias", {D});
-    const HostTensor& rh = wm.get(p + "attn.rel_pos_h", {2 * S - 1, 64});
-    const HostTensor& rw = wm.get(p + "attn.rel_pos_w", {2 * S - 1, 64});
-    std::vector<bf16> tab(256 * 64, __float2bfloat16(0.f));
+    const HostTensor& rh = wm.get(p + "attn.rel_pos_h", {2 * S - 1, hd});
+    const HostTensor& rw = wm.get(p + "attn.rel_pos_w", {2 * S - 1, hd});
+    std::vector<bf16> tab(256 * hdp, __float2bfloat16(0.f));
     for (int r = 0; r < 2 * S - 1; ++r)
-      for (int k = 0; k < 64; ++k) {
-        tab[r * 64 + k] = __float2bfloat16(rh.data[r * 64 + k] * ATTN_LOG2E);
-        tab[(128 + r) * 64 + k] = __float2bfloat16(rw.data[r * 64 + k] * ATTN_LOG2E);
+      for (int k = 0; k < hd; ++k) {
+        tab[r * hdp + k] = __float2bfloat16(rh.data[r * hd + k] * ATTN_LOG2E);
+        tab[(128 + r) * hdp + k] = __float2bfloat16(rw.data[r * hd + k] * ATTN_LOG2E);
       }
     lw.rel_tab = c->upload_bf16(tab);
   }
@@ -280,9 +281,11 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
 
 void create_impl(ysi_ctx* c) {
   const ysi_config& cfg = c->cfg;
-  YSI_CHECK(cfg.hidden_size == cfg.num_heads * 64, "this build supports head_dim 64 only (ViT-B/L)");
-  YSI_CHECK(cfg.hidden_size % 64 == 0 && cfg.hidden_size <= 1280, "hidden_size must be a multiple of 64, <= 1280");
-  YSI_CHECK(cfg.mlp_dim % 64 == 0, "mlp_dim must be a multiple of 64");
+  YSI_CHECK(cfg.num_heads > 0 && cfg.hidden_size % cfg.num_heads == 0 &&
+                (cfg.hidden_size / cfg.num_heads == 64 || cfg.hidden_size / cfg.num_heads == 80),
+            "head_dim must be 64 (ViT-B/L) or 80 (ViT-H)");
+  YSI_CHECK(cfg.hidden_size % 32 == 0 && cfg.hidden_size <= 1280, "hidden_size must be a multiple of 32, <= 1280");
+  YSI_CHECK(cfg.mlp_dim % 32 == 0, "mlp_dim must be a multiple of 32");
   YSI_CHECK(cfg.num_global >= 0 && cfg.num_global <= YSI_MAX_GLOBAL_LAYERS, "too many global layers");
   YSI_CHECK(cfg.max_batch >= 1 && cfg.max_boxes >= 1, "max_batch and max_boxes must be positive");
   YSI_CHECK(cfg.max_image_h >= 16 && cfg.max_image_w >= 16 && cfg.max_image_h <= 4096 && cfg.max_image_w <= 4096,
@@ -850,25 +853,27 @@ int ysi_gemm_bench(ysi_ctx* c, int M, int N, int K, int pair, int mode, int iter
   });
 }
 
-int ysi_attention(ysi_ctx* c, const float* qkv, const float* rel_h, const float* rel_w, int n_seq, int heads,
+int ysi_attention(ysi_ctx* c, const float* qkv, const float* rel_h, const float* rel_w, int n_seq, int heads, int head_dim,
                   int is_global, float* out) {
   return guarded(c, [&] {
-    const int T = is_global ? 4096 : 196, S = is_global ? 64 : 14, D = heads * 64;
+    YSI_CHECK(head_dim == 64 || head_dim == 80, "head_dim must be 64 or 80");
+    const int T = is_global ? 4096 : 196, S = is_global ? 64 : 14, D = heads * head_dim, hdp = attn_table_cols(head_dim);
     const size_t rows = static_cast<size_t>(n_seq) * T;
     std::vector<bf16> q = to_bf16(qkv, rows * 3 * D);
+    const float ks = attn_k_scale(head_dim);
     for (size_t r = 0; r < rows; ++r)           // what the qkv GEMM epilogue does: K in log2 units
-      for (int k = D; k < 2 * D; ++k) q[r * 3 * D + k] = __float2bfloat16(qkv[r * 3 * D + k] * ATTN_K_SCALE);
-    std::vector<bf16> tab(256 * 64, __float2bfloat16(0.f));
+      for (int k = D; k < 2 * D; ++k) q[r * 3 * D + k] = __float2bfloat16(qkv[r * 3 * D + k] * ks);
+    std::vector<bf16> tab(256 * hdp, __float2bfloat16(0.f));
     for (int r = 0; r < 2 * S - 1; ++r)
-      for (int k = 0; k < 64; ++k) {
-        tab[r * 64 + k] = __float2bfloat16(rel_h[r * 64 + k] * ATTN_LOG2E);
-        tab[(128 + r) * 64 + k] = __float2bfloat16(rel_w[r * 64 + k] * ATTN_LOG2E);
+      for (int k = 0; k < head_dim; ++k) {
+        tab[r * hdp + k] = __float2bfloat16(rel_h[r * head_dim + k] * ATTN_LOG2E);
+        tab[(128 + r) * hdp + k] = __float2bfloat16(rel_w[r * head_dim + k] * ATTN_LOG2E);
       }
     bf16 *dq = nullptr, *dt = nullptr, *dout = nullptr;
     YSI_CUDA(cudaMalloc(&dq, q.size() * 2)); YSI_CUDA(cudaMalloc(&dt, tab.size() * 2)); YSI_CUDA(cudaMalloc(&dout, rows * D * 2));
     YSI_CUDA(cudaMemcpy(dq, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
     YSI_CUDA(cudaMemcpy(dt, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
-    launch_encoder_attention(dq, dt, dout, n_seq, T, heads, is_global != 0, false, c->stream);
+    launch_encoder_attention(dq, dt, dout, n_seq, T, heads, head_dim, is_global != 0, false, c->stream);
     c->launches += 1;
     std::vector<bf16> o(rows * D);
     YSI_CUDA(cudaMemcpyAsync(o.data(), dout, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));

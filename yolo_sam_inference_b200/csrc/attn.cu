@@ -32,55 +32,69 @@
 namespace ysi {
 
 namespace attn {
-constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int BQ = 128, BKV = 64;
 constexpr int THREADS = 160;
-constexpr int Q_BYTES = BQ * HD * 2;        // 16 KB
-constexpr int KV_BYTES = BKV * HD * 2;      // 8 KB
+constexpr int CH_Q = BQ * 128;              // one 64-column chunk of the Q tile: 128 rows x 128 B = 16 KB
+constexpr int KV_BYTES = BKV * 128;         // one 64-column chunk of a 64-key tile: 8 KB
 constexpr int P_BYTES = BQ * BKV * 2;       // 16 KB
 constexpr float LAZY_LOG2 = 8.0f;           // rescale O only when the row max grows by more than 2^8
 
-template <bool GLOBAL>
+// HD = 64 (ViT-B/L) or 80 (ViT-H). Operands are staged in 64-column, 128B-swizzled chunks; for HD = 80 a second
+// chunk holds columns 64..127 of which only the first 16 (one k-step) are used -- whatever follows them in the
+// qkv row (next head / next section / zero fill) is never touched by an MMA.
+template <bool GLOBAL, int HD>
 struct Cfg {
+  static constexpr int NCH = HD > 64 ? 2 : 1;                       // 64-column chunks per operand
+  static constexpr int NKS = HD / 16;                               // k-steps of Q K^T and of the table MMAs
   static constexpr int NST = GLOBAL ? 3 : 4;                        // K / V ring depth (window: whole window)
-  static constexpr int K_STAGE = GLOBAL ? 80 * 128 : KV_BYTES;      // global: 64 keys + 16 rows for the rel_pos_h "keys"
-  static constexpr int K_TOTAL = GLOBAL ? 3 * K_STAGE : 208 * 128;
-  static constexpr int V_TOTAL = GLOBAL ? 3 * KV_BYTES : 208 * 128;
+  static constexpr int K_CHUNK = GLOBAL ? 80 * 128 : 208 * 128;     // global: 64 keys + 16 rows for the rel_pos_h "keys"
+  static constexpr int K_STAGE = GLOBAL ? NCH * K_CHUNK : KV_BYTES; // global: a stage holds its chunks back to back;
+                                                                    // window: chunk c lives at OFF_K + c*K_CHUNK, tiles 8 KB apart
+  static constexpr int K_TOTAL = GLOBAL ? NST * K_STAGE : NCH * K_CHUNK;
+  static constexpr int V_CHUNK = GLOBAL ? KV_BYTES : 208 * 128;
+  static constexpr int V_STAGE = GLOBAL ? NCH * V_CHUNK : KV_BYTES;
+  static constexpr int V_TOTAL = GLOBAL ? NST * V_STAGE : NCH * V_CHUNK;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_K = OFF_Q + NCH * CH_Q;
   static constexpr int OFF_V = OFF_K + K_TOTAL;
   static constexpr int OFF_P = OFF_V + V_TOTAL;      // 2 x 16 KB; fp32 bias scratch [k][128] during setup
-  // rel-pos tables as TMA'd for the table MMA: global -> rel_pos_w in the V area (16 KB, the V loads wait for the MMA);
-  // windowed -> second P buffer (4 KB each), so the whole window's K / V can be requested up front with Q
+  // rel-pos tables as TMA'd for the table MMA: global -> rel_pos_w in the V area (16 KB per chunk, the V loads wait
+  // for the MMA); windowed -> second P buffer (4 KB per table chunk), so the whole window's K / V can be requested
+  // up front with Q
+  static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
+  static constexpr int TAB_CHUNK = TAB_ROWS * 128;
   static constexpr int OFF_TABH = GLOBAL ? OFF_K : OFF_P + P_BYTES;     // (unused when GLOBAL)
-  static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_P + P_BYTES + 4096;
+  static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_P + P_BYTES + NCH * TAB_CHUNK;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
-  static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
   static constexpr int TMEM_COLS = 256;
   static constexpr int S_N = GLOBAL ? 80 : 64;              // columns of one S buffer
   static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
   static constexpr int COL_O = 2 * S_N;
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
-  static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_STAGE % 1024 == 0, "swizzle atoms need 1 KB alignment");
-  static_assert(COL_O + 64 <= TMEM_COLS, "TMEM budget");
+  static constexpr int CTAS_PER_SM = HD > 64 ? 1 : 2;
+  static_assert(HD == 64 || HD == 80, "head_dim 64 or 80");
+  static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_CHUNK % 1024 == 0, "swizzle atoms need 1 KB alignment");
+  static_assert(GLOBAL || 2 * NCH * TAB_CHUNK <= P_BYTES, "window tables must fit the second P buffer");
+  static_assert(COL_O + HD <= TMEM_COLS, "TMEM budget");
 };
 }  // namespace attn
 
 struct AttnParams {
   int T;          // sequence length: 196 (window) or 4096 (global)
-  int D;          // heads * 64
+  int D;          // heads * head_dim
   int unwindow;   // windowed only: write rows in token order [img*4096 + y*64 + x] and drop the pad tokens
   bf16* out;      // [n_seq * T, D]  (or [n_img * 4096, D] when unwindow)
 };
 
-template <bool GLOBAL>
-__global__ void __launch_bounds__(attn::THREADS, 2)
+template <bool GLOBAL, int HD>
+__global__ void __launch_bounds__(attn::THREADS, attn::Cfg<GLOBAL, HD>::CTAS_PER_SM)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const __grid_constant__ CUtensorMap tmKVtail, const __grid_constant__ CUtensorMap tmRel,
                          const __grid_constant__ CUtensorMap tmRel8, AttnParams p) {
   using namespace attn;
-  using C = Cfg<GLOBAL>;
+  using C = Cfg<GLOBAL, HD>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -130,25 +144,40 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       constexpr uint32_t idesc_tab = umma_idesc_bf16(128, C::TAB_ROWS, 0, 0);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::S_N, 0, 0);
       constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);   // B (= V) is MN-major
-      constexpr int TAB_BYTES = C::TAB_ROWS * 128;
+      constexpr uint32_t idesc_pv64 = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
+      constexpr uint32_t idesc_pv16 = umma_idesc_bf16(128, 16, 0, 1);
+      constexpr int NCH = C::NCH, NKS = C::NKS;
+      // K-major operand, k-step k: chunk k/4 (64 columns each), +32 B per 16 columns inside the swizzle atom
+      auto kdesc_at = [&](uint32_t base, int chunk_bytes, int k) {
+        return umma_desc_sw128(base + static_cast<uint32_t>((k >> 2) * chunk_bytes), 16, 1024) + 2u * static_cast<uint32_t>(k & 3);
+      };
       // ---- setup: Q tile + rel-pos table(s)
-      mbar_arrive_expect_tx(bar_q, Q_BYTES + (GLOBAL ? 1 : 2) * TAB_BYTES);
-      tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
-      if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);      // rel_pos_h rows (zero padded)
-      tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);                 // rel_pos_w rows
+      mbar_arrive_expect_tx(bar_q, NCH * (CH_Q + (GLOBAL ? 1 : 2) * C::TAB_CHUNK));
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_2d(sbase + C::OFF_Q + c * CH_Q, &tmQ, bar_q, cq + 64 * c, row0 + qt * BQ);
+        if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 0);   // rel_pos_h rows (zero padded)
+        tma_load_2d(sbase + C::OFF_TABW + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 128);              // rel_pos_w rows
+      }
+      auto k_tile_addr = [&](int st, int c) {
+        return sbase + C::OFF_K + (GLOBAL ? st * C::K_STAGE + c * C::K_CHUNK : c * C::K_CHUNK + st * KV_BYTES);
+      };
+      auto v_tile_addr = [&](int st, int c) {
+        return sbase + C::OFF_V + (GLOBAL ? st * C::V_STAGE + c * C::V_CHUNK : c * C::V_CHUNK + st * KV_BYTES);
+      };
       auto load_k = [&](int tile, int st) {
         const bool tail = !GLOBAL && tile == 3;
-        const uint32_t dst = sbase + C::OFF_K + st * C::K_STAGE;
-        mbar_arrive_expect_tx(bar_kfull + 8 * st, GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES));
-        tma_load_2d(dst, tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck, row0 + tile * BKV);
-        // global: rows 64.. of the K tile = rel_pos_h[qh - kh + 63] for the CTA's two query rows (qh0 = 2 qt, kh = tile)
-        if (GLOBAL) tma_load_2d(dst + KV_BYTES, &tmRel8, bar_kfull + 8 * st, 0, 2 * qt - tile + 63);
+        mbar_arrive_expect_tx(bar_kfull + 8 * st, NCH * (GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES)));
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_2d(k_tile_addr(st, c), tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck + 64 * c, row0 + tile * BKV);
+          // global: rows 64.. of the K tile = rel_pos_h[qh - kh + 63] for the CTA's two query rows (qh0 = 2 qt, kh = tile)
+          if (GLOBAL) tma_load_2d(k_tile_addr(st, c) + KV_BYTES, &tmRel8, bar_kfull + 8 * st, 64 * c, 2 * qt - tile + 63);
+        }
       };
       auto load_v = [&](int tile, int st) {
         const bool tail = !GLOBAL && tile == 3;
-        mbar_arrive_expect_tx(bar_vfull + 8 * st, tail ? 16 * 128 : KV_BYTES);
-        tma_load_2d(sbase + C::OFF_V + st * KV_BYTES, tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv, row0 + tile * BKV);
+        mbar_arrive_expect_tx(bar_vfull + 8 * st, NCH * (tail ? 16 * 128 : KV_BYTES));
+        for (int c = 0; c < NCH; ++c)
+          tma_load_2d(v_tile_addr(st, c), tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv + 64 * c, row0 + tile * BKV);
       };
       if (!GLOBAL) {             // whole window: K / V do not alias the tables, request them right away
         for (int j = 0; j < 4; ++j) load_k(j, j);
@@ -158,35 +187,33 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       mbar_wait(bar_q, 0);
       tc_fence_after();
-      const uint64_t qdesc = umma_desc_sw128(sbase + C::OFF_Q, 16, 1024);
       {
         if (!GLOBAL) {
-          const uint64_t hdesc = umma_desc_sw128(sbase + C::OFF_TABH, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TH, qdesc + 2u * k, hdesc + 2u * k, idesc_tab, k);
+          for (int k = 0; k < NKS; ++k)
+            umma_bf16_ss(tmem_base + C::COL_TH, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
         }
-        const uint64_t wdesc = umma_desc_sw128(sbase + C::OFF_TABW, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + C::COL_TW, qdesc + 2u * k, wdesc + 2u * k, idesc_tab, k);
+        for (int k = 0; k < NKS; ++k)
+          umma_bf16_ss(tmem_base + C::COL_TW, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
         umma_commit(bar_tab);
       }
       if (GLOBAL) {
         mbar_wait(bar_tab, 0);     // rel_pos_w table consumed: the V area is free
         for (int j = 0; j < C::NST && j < ntiles; ++j) load_v(j, j);
       }
-      // S_t -> S buffer t & 1 (free once the softmax threads hold S_{t-2} in registers). The tensor pipe runs MMAs
-      // in issue order and a chain of dependent small MMAs has a long latency, so S_{j+2} is issued as soon as
-      // S_j has been read -- early in softmax tile j -- and never queues behind PV_j.
+      // S_t -> S buffer t & 1 (free once the softmax threads hold S_{t-2} in registers); issued two tiles ahead, as
+      // soon as S_{t-2} has been read, so it never queues behind a PV in the in-order tensor pipe.
       auto issue_s = [&](int t) {
         const int st = t % C::NST, buf = t & 1;
         mbar_wait(bar_kfull + 8 * st, (t / C::NST) & 1);
         if (t >= 2) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);
         tc_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(sbase + C::OFF_K + st * C::K_STAGE, 16, 1024);
         const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(d, qdesc + 2u * k, kdesc + 2u * k, idesc, k);
+        for (int k = 0; k < NKS; ++k)
+          umma_bf16_ss(d, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(k_tile_addr(st, 0), C::K_CHUNK, k), idesc, k);
         umma_commit(bar_kempty + 8 * st);    // (the barrier somebody always waits on is committed last)
         umma_commit(bar_s_full + 8 * buf);
       };
@@ -209,10 +236,15 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         {
           // O (+)= P_j V_j : A = P (K-major, K = keys), B = V_j (MN-major: key rows x 64 hd); 16 keys = 2048 B
           const uint64_t pdesc = umma_desc_sw128(sbase + C::OFF_P + pb * P_BYTES, 16, 1024);
-          const uint64_t vdesc = umma_desc_sw128(sbase + C::OFF_V + st * KV_BYTES, 1024, 1024);
+          const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
           const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ss(tmem_base + C::COL_O, pdesc + 2u * k, vdesc + 128u * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_base + C::COL_O, pdesc + 2u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
+          if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
+            const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_ss(tmem_base + C::COL_O + 64, pdesc + 2u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
+          }
           umma_commit(bar_vempty + 8 * st);
           umma_commit(bar_p_free + 8 * pb);
         }
@@ -327,7 +359,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int qr = 0; qr < 4; ++qr) {
+            for (int qr = 0; qr < HD / 16; ++qr) {
               uint32_t o[16];
               tmem_ld_x16p(tlane + C::COL_O + 16 * qr, o);
               tmem_ld_wait();
@@ -388,9 +420,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     if (warp_active) {
-      uint32_t o[64];
+      uint32_t o[HD];
       tmem_ld_x32p(tlane + C::COL_O, o);
       tmem_ld_x32p(tlane + C::COL_O + 32, o + 32);
+      if constexpr (HD > 64) tmem_ld_x16p(tlane + C::COL_O + 64, o + 64);
       tmem_ld_wait();
       const float inv = 1.0f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
       long long orow = -1;
@@ -406,7 +439,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (orow >= 0) {
         uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(orow) * p.D + head * HD);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < HD / 8; ++c) {
           uint4 v;
           v.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
           v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
@@ -419,36 +452,47 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, Cfg<GLOBAL>::TMEM_COLS);
+  if (warp == 4) tmem_dealloc(tmem_base, Cfg<GLOBAL, HD>::TMEM_COLS);
 }
 
-// qkv: bf16 [n_seq*T, 3D] with the K columns pre-scaled by 0.125*log2(e); rel_tab: bf16 [256, 64] pre-scaled by
-// log2(e) (rows 0..127 rel_pos_h zero-padded, 128..255 rel_pos_w). unwindow: see AttnParams.
-void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads,
-                              bool is_global, bool unwindow, cudaStream_t stream) {
-  using namespace attn;
+template <bool GLOBAL, int HD>
+static void launch_attn_t(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmKVtail, const CUtensorMap& tmRel,
+                          const CUtensorMap& tmRel8, const AttnParams& p, dim3 grid, cudaStream_t stream) {
+  using C = attn::Cfg<GLOBAL, HD>;
   static bool init = false;
   if (!init) {
-    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
-    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<GLOBAL, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     init = true;
   }
-  const int D = heads * HD;
+  encoder_attention_kernel<GLOBAL, HD><<<grid, attn::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
+}
+
+// qkv: bf16 [n_seq*T, 3D] with the K columns pre-scaled by hd^-0.5*log2(e); rel_tab: bf16 [256, HDP] pre-scaled by
+// log2(e) (rows 0..127 rel_pos_h zero-padded, 128..255 rel_pos_w; HDP = 64, or 128 with zero columns 80.. for
+// head_dim 80). unwindow: see AttnParams.
+void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads, int head_dim,
+                              bool is_global, bool unwindow, cudaStream_t stream) {
+  using namespace attn;
+  YSI_CHECK(head_dim == 64 || head_dim == 80, "attention kernel supports head_dim 64 (ViT-B/L) and 80 (ViT-H)");
+  const int D = heads * head_dim, HDP = head_dim == 64 ? 64 : 128;
   const long long rows = static_cast<long long>(n_seq) * T;
   YSI_CHECK(is_global ? T == 4096 : T == 196, "attention kernel supports T = 4096 (global) or 196 (window)");
   YSI_CHECK(!unwindow || (!is_global && n_seq % 25 == 0), "unwindow needs whole images of 25 windows");
   const CUtensorMap tmQ = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BQ);
   const CUtensorMap tmKV = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BKV);
   const CUtensorMap tmKVtail = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, 16);
-  const CUtensorMap tmRel = make_tmap_bf16_2d(rel_tab, 256, HD, HD, is_global ? 128 : 32);
-  const CUtensorMap tmRel8 = make_tmap_bf16_2d(rel_tab, 256, HD, HD, 8);
+  const CUtensorMap tmRel = make_tmap_bf16_2d(rel_tab, 256, HDP, HDP, is_global ? 128 : 32);
+  const CUtensorMap tmRel8 = make_tmap_bf16_2d(rel_tab, 256, HDP, HDP, 8);
   AttnParams p;
   p.T = T; p.D = D; p.out = out; p.unwindow = unwindow ? 1 : 0;
   dim3 grid(ceil_div(T, BQ), heads, n_seq);
-  if (is_global)
-    encoder_attention_kernel<true><<<grid, THREADS, Cfg<true>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
-  else
-    encoder_attention_kernel<false><<<grid, THREADS, Cfg<false>::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
+  if (head_dim == 64) {
+    if (is_global) launch_attn_t<true, 64>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
+    else launch_attn_t<false, 64>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
+  } else {
+    if (is_global) launch_attn_t<true, 80>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
+    else launch_attn_t<false, 80>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
+  }
   YSI_CUDA(cudaGetLastError());
 }
 

@@ -353,15 +353,15 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     {
       GemmEpilogue ep;
       ep.bias = lw.b_qkv; ep.out_bf16 = work.qkv; ep.ld_out_bf16 = 3 * D;
-      ep.col_scale = ATTN_K_SCALE; ep.scale_c0 = D; ep.scale_c1 = 2 * D;     // K in log2 units for the attention kernel
+      ep.col_scale = attn_k_scale(w.head_dim); ep.scale_c0 = D; ep.scale_c1 = 2 * D;     // K in log2 units for the attention kernel
       ProfScope ps(prof, KC_GEMM_QKV, 2.0 * T * 3 * D * D);
       gemm_bf16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
     }
     {
       const double S = glob ? 64.0 : 14.0, tok = glob ? 4096.0 : 196.0, nseq = glob ? n : n * 25.0;
       // QK^T + PV (4 * T^2 * hd per head) + rel-pos terms (2 * 2 * T * S * hd per head)
-      ProfScope ps(prof, glob ? KC_ATTN_GLOBAL : KC_ATTN_WINDOW, nseq * w.heads * (4.0 * tok * tok * 64 + 4.0 * tok * S * 64));
-      launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, glob, !glob, s); ++nl;
+      ProfScope ps(prof, glob ? KC_ATTN_GLOBAL : KC_ATTN_WINDOW, nseq * w.heads * (4.0 * tok * tok * w.head_dim + 4.0 * tok * S * w.head_dim));
+      launch_encoder_attention(work.qkv, lw.rel_tab, work.attn, glob ? n : n * 25, glob ? 4096 : 196, w.heads, w.head_dim, glob, !glob, s); ++nl;
     }
     {
       GemmEpilogue ep;   // x += attn * Wproj^T + b ; the attention kernel already un-partitioned the windows

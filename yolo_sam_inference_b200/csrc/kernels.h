@@ -3,6 +3,8 @@
 #include "../../include/ysi.h"
 #include "common.h"
 
+#include <cmath>
+
 namespace ysi {
 
 // ------------------------------------------------------------------ post-processing + morphometrics
@@ -43,21 +45,23 @@ void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16
 // fused flash-style attention with decomposed rel-pos bias (attn.cu)
 // qkv K columns pre-scaled by hd^-0.5 * log2(e), rel_tab pre-scaled by log2(e) (see attn.cu);
 // unwindow (windowed only): rows are written in token order and the 64->70 pad tokens are dropped
-constexpr float ATTN_K_SCALE = 0.125f * 1.4426950408889634f;
 constexpr float ATTN_LOG2E = 1.4426950408889634f;
-void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads,
+inline float attn_k_scale(int head_dim) { return static_cast<float>(1.0 / std::sqrt(static_cast<double>(head_dim))) * ATTN_LOG2E; }
+inline int attn_table_cols(int head_dim) { return head_dim == 64 ? 64 : 128; }    // rel-pos table row pitch (zero padded)
+void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads, int head_dim,
                               bool is_global, bool unwindow, cudaStream_t stream);
 
 struct EncoderLayerW {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   const bf16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
   const float *b_qkv, *b_proj, *b_fc1, *b_fc2;
-  const bf16* rel_tab;   // [256,64] * log2(e): rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
+  const bf16* rel_tab;   // [256,HDP] * log2(e): rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
   int is_global;
 };
 
 struct EncoderW {
   int D, L, heads, mlp;
+  int head_dim = 64;
   int residual_mode = 2;   // GemmEpilogue::accumulate for the two residual adds of a layer
   const bf16* w_patch;    // [D, 768]
   const float* b_patch;   // [D]

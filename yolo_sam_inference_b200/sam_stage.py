@@ -343,9 +343,10 @@ class SamStage:
     def attention(self, qkv: np.ndarray, rel_h: np.ndarray, rel_w: np.ndarray, heads: int, is_global: bool) -> np.ndarray:
         q = np.ascontiguousarray(qkv, np.float32)
         n_seq, T = q.shape[0], q.shape[1]
-        out = np.empty((n_seq, T, heads * 64), np.float32)
+        head_dim = q.shape[2] // (3 * heads)
+        out = np.empty((n_seq, T, heads * head_dim), np.float32)
         self._check(self._lib.ysi_attention(self._ctx, nat.as_f32p(q), nat.as_f32p(np.ascontiguousarray(rel_h, np.float32)),
-                                            nat.as_f32p(np.ascontiguousarray(rel_w, np.float32)), n_seq, heads,
+                                            nat.as_f32p(np.ascontiguousarray(rel_w, np.float32)), n_seq, heads, head_dim,
                                             1 if is_global else 0, nat.as_f32p(out)), "ysi_attention")
         return out
 

@@ -38,6 +38,7 @@ class SamVariant:
 # "vit_t" is a small test-only tower with the same head_dim so every kernel is exercised quickly.
 VARIANTS: Dict[str, SamVariant] = {
     "vit_t": SamVariant("vit_t", 192, 4, 3, (1, 3), 768),
+    "vit_t80": SamVariant("vit_t80", 160, 4, 2, (1, 3), 640),      # test-only tower with ViT-H's head_dim 80
     "vit_b": SamVariant("vit_b", 768, 12, 12, (2, 5, 8, 11), 3072, "facebook/sam-vit-base"),
     "vit_l": SamVariant("vit_l", 1024, 24, 16, (5, 11, 17, 23), 4096, "facebook/sam-vit-large"),
     "vit_h": SamVariant("vit_h", 1280, 32, 16, (7, 15, 23, 31), 5120, "facebook/sam-vit-huge"),
