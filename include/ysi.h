@@ -105,17 +105,21 @@ YSI_API int ysi_run_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb,
                   const float* boxes_xyxy, const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out,
                   ysi_mask_metrics* metrics_out, ysi_timing* timing);
 
-/* Split form of ysi_run_batch used by bench.py to time the device-resident leg separately:
- * stage = host->device copy of images+boxes, compute = all kernels, fetch = device->host of results. */
-YSI_API int ysi_stage_batch(ysi_ctx* ctx, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
-                    const float* boxes_xyxy, const int32_t* box_counts);
-YSI_API int ysi_compute_staged(ysi_ctx* ctx, ysi_timing* timing);
-YSI_API int ysi_fetch_staged(ysi_ctx* ctx, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out);
+/* Pipelined form of ysi_run_batch: a context has two slots; ysi_submit_batch enqueues a batch into `slot` (0/1) and
+ * returns at once, ysi_wait_batch blocks until that slot's results are in the host buffers. Submitting batch i+1 before
+ * waiting for batch i overlaps its host->device copy and encoder with the decoder / metrics / device->host copy of
+ * batch i (four CUDA streams inside the context). The host buffers (pinned for true overlap) must stay valid until the
+ * matching wait; a slot must be waited for before it is reused. */
+YSI_API int ysi_submit_batch(ysi_ctx* ctx, int slot, int n_images, const uint8_t* const* rgb, int H, int W, int row_stride,
+                     const float* boxes_xyxy, const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out,
+                     ysi_mask_metrics* metrics_out);
+YSI_API int ysi_wait_batch(ysi_ctx* ctx, int slot, ysi_timing* timing);
 
 /* ---- measurement support (bench.py) ------------------------------------------------------------- */
 /* resident input pool: images uploaded once, then processed straight from HBM (device-resident leg) */
 YSI_API int ysi_pool_upload(ysi_ctx* ctx, int pool_size, int idx, const uint8_t* rgb, int H, int W, int row_stride);
-/* run images [first_idx, first_idx+n) of the pool; sync == 0 only enqueues (results stay on the device) */
+/* run images [first_idx, first_idx+n) of the pool through the same two-slot pipeline; sync == 0 only enqueues
+ * (results stay on the device) */
 YSI_API int ysi_compute_pool(ysi_ctx* ctx, int first_idx, int n, const float* boxes_xyxy, const int32_t* box_counts, int sync,
                      ysi_timing* timing);
 /* CUDA events on the context's own stream (torch.cuda.Event would only see torch's stream) */

@@ -91,3 +91,23 @@ def test_stage_end_to_end_other_sizes(tiny_stage, tiny_oracle, H, W):
                     assert mets[k][key] == val, (key, mets[k][key], val)
                 else:
                     assert mets[k][key] == pytest.approx(val, rel=1e-9, abs=1e-12), key
+
+
+def test_run_stream_equals_run_batch(tiny_stage):
+    """The two-slot pipelined API (copies / encoder / decoder of neighbouring batches overlap on four streams) must
+    return exactly what the synchronous call returns, batch by batch, including a zero-box batch in the middle."""
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    tiny_stage.on_empty = "zeros"
+    batches = []
+    for i, nbx in enumerate((1, 2, 0, 3, 1)):
+        imgs, boxes = [], []
+        for k in range(2):
+            g, b = synth_image(40 + 2 * i + k, 1024, max(nbx, 1))
+            imgs.append(gray_to_rgb_u8(g)); boxes.append(b if nbx else np.zeros((0, 4), np.float32))
+        batches.append((imgs, boxes))
+    ref = [tiny_stage.run_batch(im, bx) for im, bx in batches]
+    got = list(tiny_stage.run_stream(iter(batches)))
+    assert len(got) == len(ref)
+    for r, g in zip(ref, got):
+        for (rm, rmet, rc), (gm, gmet, gc) in zip(r, g):
+            assert np.array_equal(rm, gm) and rmet == gmet and len(rc) == len(gc)

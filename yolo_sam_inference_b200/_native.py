@@ -68,9 +68,9 @@ EXPORTS = {
                           C.POINTER(YsiTiming)]),
     "ysi_run_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p, _u8p, _u8p,
                                 C.c_void_p, C.POINTER(YsiTiming)]),
-    "ysi_stage_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
-    "ysi_compute_staged": (C.c_int, [_ctx, C.POINTER(YsiTiming)]),
-    "ysi_fetch_staged": (C.c_int, [_ctx, _u8p, _u8p, C.c_void_p]),
+    "ysi_submit_batch": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p,
+                                   _u8p, _u8p, C.c_void_p]),
+    "ysi_wait_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(YsiTiming)]),
     "ysi_pool_upload": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]),
     "ysi_compute_pool": (C.c_int, [_ctx, C.c_int, C.c_int, _f32p, _i32p, C.c_int, C.POINTER(YsiTiming)]),
     "ysi_timer_record": (C.c_int, [_ctx, C.c_int]),

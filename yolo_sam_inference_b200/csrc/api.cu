@@ -67,16 +67,31 @@ struct ysi_ctx {
   int pool_cap = 0, pool_H = 0, pool_W = 0;
   Profiler prof;
   cudaEvent_t timers[8]{};
+  cudaEvent_t join_ev = nullptr;
   // pinned ring for the small per-step box arrays (lets ysi_compute_pool enqueue steps without syncing)
   static constexpr int RING = 64;
   double* h_boxes = nullptr;   // [RING, max_boxes, 4]
   int* h_box_img = nullptr;    // [RING, max_boxes]
   int ring_pos = 0;
 
-  // staged batch (ysi_stage_batch)
-  const uint8_t* st_rgb = nullptr;
-  int st_n = 0, st_H = 0, st_W = 0, st_nb = 0;
-  cudaEvent_t ev[8]{};
+  // Two-slot software pipeline: H2D of batch i+1 (s_in) | preprocess + encoder of batch i (stream) |
+  // decoder + upsample + metrics of batch i-1 (s_aux) | D2H of batch i-1 (s_out). A slot owns the buffers that
+  // cross a stage boundary; encoder / decoder workspaces are single because each lives on one stream.
+  struct Slot {
+    uint8_t* d_rgb = nullptr;       // [max_batch, H, W, 3]
+    uint16_t* d_sum3 = nullptr;     // [max_batch, H, W]
+    float* d_emb = nullptr;         // [max_batch*4096, 256]
+    uint8_t* d_masks = nullptr;     // [max_boxes, H, W]
+    uint8_t* d_packed = nullptr;    // [max_boxes, ceil(H*W/8)] (lazily allocated)
+    ysi_mask_metrics* d_metrics = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_enc = nullptr, ev_dec = nullptr, ev_d2h = nullptr;
+    cudaEvent_t t[8]{};             // stage timing: in0, enc0, enc_pre, enc1, dec0, dec1, post1, out0
+    int n = 0, H = 0, W = 0, nb = 0;
+    bool host_in = false, host_out = false;
+  };
+  Slot slots[2];
+  int next_slot = 0;
+  cudaStream_t s_aux = nullptr, s_in = nullptr, s_out = nullptr;
 
   template <class T>
   T* dalloc(size_t n) {
@@ -294,8 +309,8 @@ void create_impl(ysi_ctx* c) {
   YSI_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, c->device));
   YSI_CHECK(cc_major == 10, "libysi.so is built for sm_100a only (needs a B200-class GPU)");
   YSI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (auto& e : c->ev) YSI_CUDA(cudaEventCreate(&e));
   for (auto& e : c->timers) YSI_CUDA(cudaEventCreate(&e));
+  YSI_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
   c->prof.stream = c->stream;
   // (x - mean*255) / (std*255) with the fp32 products tvF.normalize sees
   const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
@@ -343,15 +358,24 @@ void create_impl(ysi_ctx* c) {
   dw.tok_ws = c->dalloc<float>(NB * (7 * (6 * 256 + 2048) + 2 * 256 + 8 * 4 * 126));
   dw.boxes1024 = c->dalloc<double>(NB * 4);
   dw.box_img = c->dalloc<int>(NB);
-  c->d_rgb = c->dalloc<uint8_t>(B * HW * 3);
-  c->d_sum3 = c->dalloc<uint16_t>(B * HW);
-  c->d_emb = c->dalloc<float>(B * 4096 * 256);
+  for (auto& sl : c->slots) {
+    sl.d_rgb = c->dalloc<uint8_t>(B * HW * 3);
+    sl.d_sum3 = c->dalloc<uint16_t>(B * HW);
+    sl.d_emb = c->dalloc<float>(B * 4096 * 256);
+    sl.d_masks = c->dalloc<uint8_t>(NB * HW);
+    sl.d_metrics = c->dalloc<ysi_mask_metrics>(NB);
+    for (cudaEvent_t* e : {&sl.ev_h2d, &sl.ev_enc, &sl.ev_dec, &sl.ev_d2h}) YSI_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (auto& e : sl.t) YSI_CUDA(cudaEventCreate(&e));
+  }
+  // the stage-level entry points (parity tests) work on slot 0's buffers
+  c->d_rgb = c->slots[0].d_rgb; c->d_sum3 = c->slots[0].d_sum3; c->d_emb = c->slots[0].d_emb;
+  c->d_masks = c->slots[0].d_masks; c->d_metrics = c->slots[0].d_metrics;
   c->d_low = c->dalloc<float>(NB * 65536);
-  c->d_masks = c->dalloc<uint8_t>(NB * HW);
-  c->d_packed = c->dalloc<uint8_t>(NB * ((HW + 7) / 8));
   c->d_stats = c->dalloc<MaskStatsDev>(NB);
-  c->d_metrics = c->dalloc<ysi_mask_metrics>(NB);
   c->d_mask_img = c->dalloc<int>(NB);
+  YSI_CUDA(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+  YSI_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  YSI_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   {
     void* p = nullptr;
     YSI_CUDA(cudaHostAlloc(&p, sizeof(double) * 4 * NB * ysi_ctx::RING, cudaHostAllocDefault));
@@ -423,96 +447,134 @@ void check_batch(ysi_ctx* c, int n, int H, int W, int nb) {
   YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
 }
 
-void stage_impl(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
-                const int32_t* box_counts) {
+// Enqueue one batch into `slot` (see ysi_ctx::Slot). Images come from host memory (rgb != null; pinned memory makes the
+// copy asynchronous) or are already resident on the device (dev_src). Results are copied to the host buffers when any
+// is given, else they stay on the device. Returns immediately; wait_impl() blocks until the slot's batch is done.
+void submit_impl(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, const uint8_t* dev_src, int H, int W, int row_stride,
+                 const float* boxes, const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out,
+                 ysi_mask_metrics* metrics_out) {
   int nb = 0;
   for (int i = 0; i < n; ++i) nb += box_counts[i];
   check_batch(c, n, H, W, nb);
+  YSI_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
+  YSI_CHECK(rgb || dev_src, "no input images");
   YSI_CHECK(!rgb || row_stride >= 3 * W, "row_stride smaller than 3*W");
-  c->st_n = n; c->st_H = H; c->st_W = W; c->st_nb = nb;
-  const size_t img_bytes = static_cast<size_t>(H) * W * 3;
+  ysi_ctx::Slot& sl = c->slots[slot];
+  sl.n = n; sl.H = H; sl.W = W; sl.nb = nb;
+  sl.host_in = rgb != nullptr;
+  sl.host_out = masks_out || packed_out || metrics_out;
+  Profiler* prof = c->prof.active ? &c->prof : nullptr;
+  cudaStream_t sm = c->stream;
+  cudaStream_t sd = prof ? c->stream : c->s_aux;     // per-class profiling needs one timeline
+  const size_t img_bytes = static_cast<size_t>(H) * W * 3, HW = static_cast<size_t>(H) * W;
+  const uint8_t* src = dev_src;
+  // ---- stage 1: H2D (s_in). d_rgb of this slot was last read by the encoder stage of the previous batch in the slot.
   if (rgb) {
+    YSI_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_enc, 0));
+    YSI_CUDA(cudaEventRecord(sl.t[0], c->s_in));
     for (int i = 0; i < n; ++i)
-      YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
-                                 static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->stream));
-    c->st_rgb = c->d_rgb;
+      YSI_CUDA(cudaMemcpy2DAsync(sl.d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
+                                 static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->s_in));
+    YSI_CUDA(cudaEventRecord(sl.ev_h2d, c->s_in));
+    YSI_CUDA(cudaStreamWaitEvent(sm, sl.ev_h2d, 0));
+    src = sl.d_rgb;
   }
+  // ---- stage 2: preprocess + encoder (main stream). d_sum3 / d_emb of this slot were last read by its decoder stage.
+  YSI_CUDA(cudaStreamWaitEvent(sm, sl.ev_dec, 0));
+  YSI_CUDA(cudaEventRecord(sl.t[1], sm));
   if (nb > 0) {
-    const int slot = c->ring_pos;
+    ProfScope ps(prof, KC_PREPROCESS);
+    launch_sum3(src, n, H, W, W * 3, sl.d_sum3, sm);
+    c->launches += 1;
+    preprocess_images(c, src, n, H, W, nullptr, c->ew.a_patch);
+  }
+  YSI_CUDA(cudaEventRecord(sl.t[2], sm));
+  if (nb > 0) encoder_forward(c->enc, c->ew, n, sl.d_emb, nullptr, sm, &c->launches, prof);
+  YSI_CUDA(cudaEventRecord(sl.t[3], sm));
+  YSI_CUDA(cudaEventRecord(sl.ev_enc, sm));
+  // ---- stage 3: prompt encoder + decoder + upsample + metrics (s_aux). d_masks / d_metrics were last read by the D2H.
+  YSI_CUDA(cudaStreamWaitEvent(sd, sl.ev_enc, 0));
+  YSI_CUDA(cudaStreamWaitEvent(sd, sl.ev_d2h, 0));
+  YSI_CUDA(cudaEventRecord(sl.t[4], sd));
+  if (nb > 0) {
+    const int rs = c->ring_pos;
     c->ring_pos = (c->ring_pos + 1) % ysi_ctx::RING;
-    double* hb = c->h_boxes + static_cast<size_t>(slot) * 4 * c->cfg.max_boxes;
-    int* hi = c->h_box_img + static_cast<size_t>(slot) * c->cfg.max_boxes;
+    double* hb = c->h_boxes + static_cast<size_t>(rs) * 4 * c->cfg.max_boxes;
+    int* hi = c->h_box_img + static_cast<size_t>(rs) * c->cfg.max_boxes;
     std::vector<double> b1024;
     rescale_boxes(boxes, nb, H, W, b1024);
     std::memcpy(hb, b1024.data(), sizeof(double) * 4 * nb);
     int k = 0;
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < box_counts[i]; ++j) hi[k++] = i;
-    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, hb, sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, c->stream));
-    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
-    YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, hb, sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, sd));
+    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, sd));
+    YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, sd));
+    decoder_forward(c->dec, c->dw, sl.d_emb, n, nb, c->d_low, nullptr, sd, &c->launches, prof);
   }
-  if (rgb) YSI_CUDA(cudaStreamSynchronize(c->stream));   // the caller may reuse its image buffers
+  YSI_CUDA(cudaEventRecord(sl.t[5], sd));
+  if (nb > 0) {
+    {
+      ProfScope ps(prof, KC_POST_UPSAMPLE);
+      launch_init_stats(c->d_stats, nb, sd);
+      launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), sl.d_sum3, c->d_mask_img, sl.d_masks, nullptr, c->d_stats, sd);
+      c->launches += 2;
+    }
+    YSI_CUDA(cudaEventRecord(sl.t[6], sd));
+    {
+      ProfScope ps(prof, KC_POST_HULL);
+      launch_contour_hull_disk(sl.d_masks, nb, H, W, sl.d_sum3, c->d_mask_img, c->d_stats, sl.d_metrics, sd);
+      c->launches += 1;
+    }
+    if (packed_out) {
+      if (!sl.d_packed)
+        sl.d_packed = c->dalloc<uint8_t>(static_cast<size_t>(c->cfg.max_boxes) * ((static_cast<size_t>(c->cfg.max_image_h) * c->cfg.max_image_w + 7) / 8));
+      launch_packbits(sl.d_masks, sl.d_packed, nb, static_cast<long long>(HW), sd);
+      c->launches += 1;
+    }
+  } else {
+    YSI_CUDA(cudaEventRecord(sl.t[6], sd));
+  }
+  YSI_CUDA(cudaEventRecord(sl.ev_dec, sd));
+  // ---- stage 4: D2H (s_out)
+  YSI_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_dec, 0));
+  YSI_CUDA(cudaEventRecord(sl.t[7], c->s_out));
+  if (nb > 0) {
+    if (packed_out)
+      YSI_CUDA(cudaMemcpyAsync(packed_out, sl.d_packed, static_cast<size_t>(nb) * ((HW + 7) / 8), cudaMemcpyDeviceToHost, c->s_out));
+    if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, sl.d_masks, nb * HW, cudaMemcpyDeviceToHost, c->s_out));
+    if (metrics_out)
+      YSI_CUDA(cudaMemcpyAsync(metrics_out, sl.d_metrics, sizeof(ysi_mask_metrics) * nb, cudaMemcpyDeviceToHost, c->s_out));
+  }
+  YSI_CUDA(cudaEventRecord(sl.ev_d2h, c->s_out));
 }
 
-void compute_impl(ysi_ctx* c, ysi_timing* tm, bool sync = true) {
-  const int n = c->st_n, H = c->st_H, W = c->st_W, nb = c->st_nb;
-  YSI_CHECK(n > 0 && c->st_rgb, "no staged batch");
-  cudaStream_t s = c->stream;
-  Profiler* prof = c->prof.active ? &c->prof : nullptr;
-  const uint8_t* d_rgb = c->st_rgb;
-  YSI_CUDA(cudaEventRecord(c->ev[0], s));
-  if (nb > 0) {
-    ProfScope ps(prof, KC_PREPROCESS);
-    launch_sum3(d_rgb, n, H, W, W * 3, c->d_sum3, s);
-    c->launches += 1;
-    preprocess_images(c, d_rgb, n, H, W, nullptr, c->ew.a_patch);
-  }
-  YSI_CUDA(cudaEventRecord(c->ev[1], s));
-  if (nb > 0) encoder_forward(c->enc, c->ew, n, c->d_emb, nullptr, s, &c->launches, prof);
-  YSI_CUDA(cudaEventRecord(c->ev[2], s));
-  if (nb > 0) decoder_forward(c->dec, c->dw, c->d_emb, n, nb, c->d_low, nullptr, s, &c->launches, prof);
-  YSI_CUDA(cudaEventRecord(c->ev[3], s));
-  if (nb > 0) {
-    ProfScope ps(prof, KC_POST_UPSAMPLE);
-    launch_init_stats(c->d_stats, nb, s);
-    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), c->d_sum3, c->d_mask_img, c->d_masks, nullptr, c->d_stats, s);
-    c->launches += 2;
-  }
-  YSI_CUDA(cudaEventRecord(c->ev[4], s));
-  if (nb > 0) {
-    ProfScope ps(prof, KC_POST_HULL);
-    launch_contour_hull_disk(c->d_masks, nb, H, W, c->d_sum3, c->d_mask_img, c->d_stats, c->d_metrics, s);
-    c->launches += 1;
-  }
-  YSI_CUDA(cudaEventRecord(c->ev[5], s));
-  if (!sync) return;
-  YSI_CUDA(cudaStreamSynchronize(s));
+void wait_impl(ysi_ctx* c, int slot, ysi_timing* tm) {
+  YSI_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
+  ysi_ctx::Slot& sl = c->slots[slot];
+  YSI_CUDA(cudaEventSynchronize(sl.ev_d2h));
   if (tm) {
     std::memset(tm, 0, sizeof(*tm));
-    YSI_CUDA(cudaEventElapsedTime(&tm->preprocess_ms, c->ev[0], c->ev[1]));
-    YSI_CUDA(cudaEventElapsedTime(&tm->encoder_ms, c->ev[1], c->ev[2]));
-    YSI_CUDA(cudaEventElapsedTime(&tm->decoder_ms, c->ev[2], c->ev[3]));
-    YSI_CUDA(cudaEventElapsedTime(&tm->postprocess_ms, c->ev[3], c->ev[4]));
-    YSI_CUDA(cudaEventElapsedTime(&tm->metrics_ms, c->ev[4], c->ev[5]));
-    YSI_CUDA(cudaEventElapsedTime(&tm->total_ms, c->ev[0], c->ev[5]));
+    if (sl.n > 0) {
+      // (stage times of this batch on their own streams; with batches in flight the stages of different batches overlap)
+      YSI_CUDA(cudaEventSynchronize(sl.t[7]));
+      if (sl.host_in) { YSI_CUDA(cudaEventElapsedTime(&tm->h2d_ms, sl.t[0], sl.t[1])); }
+      YSI_CUDA(cudaEventElapsedTime(&tm->preprocess_ms, sl.t[1], sl.t[2]));
+      YSI_CUDA(cudaEventElapsedTime(&tm->encoder_ms, sl.t[2], sl.t[3]));
+      YSI_CUDA(cudaEventElapsedTime(&tm->decoder_ms, sl.t[4], sl.t[5]));
+      YSI_CUDA(cudaEventElapsedTime(&tm->postprocess_ms, sl.t[5], sl.t[6]));
+      YSI_CUDA(cudaEventElapsedTime(&tm->metrics_ms, sl.t[6], sl.t[7]));
+      tm->total_ms = tm->h2d_ms + tm->preprocess_ms + tm->encoder_ms + tm->decoder_ms + tm->postprocess_ms + tm->metrics_ms;
+    }
   }
 }
 
-void fetch_impl(ysi_ctx* c, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
-  const int nb = c->st_nb;
-  if (nb <= 0) return;
-  const size_t HW = static_cast<size_t>(c->st_H) * c->st_W;
-  cudaStream_t s = c->stream;
-  if (packed_out) {
-    launch_packbits(c->d_masks, c->d_packed, nb, static_cast<long long>(HW), s);
-    c->launches += 1;
-    YSI_CUDA(cudaMemcpyAsync(packed_out, c->d_packed, static_cast<size_t>(nb) * ((HW + 7) / 8), cudaMemcpyDeviceToHost, s));
-  }
-  if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, c->d_masks, nb * HW, cudaMemcpyDeviceToHost, s));
-  if (metrics_out)
-    YSI_CUDA(cudaMemcpyAsync(metrics_out, c->d_metrics, sizeof(ysi_mask_metrics) * nb, cudaMemcpyDeviceToHost, s));
-  YSI_CUDA(cudaStreamSynchronize(s));
+// every stream of the context idle
+void sync_all(ysi_ctx* c) {
+  YSI_CUDA(cudaStreamSynchronize(c->s_in));
+  YSI_CUDA(cudaStreamSynchronize(c->stream));
+  YSI_CUDA(cudaStreamSynchronize(c->s_aux));
+  YSI_CUDA(cudaStreamSynchronize(c->s_out));
 }
 
 }  // namespace
@@ -546,9 +608,17 @@ void ysi_destroy(ysi_ctx* c) {
   cudaDeviceSynchronize();
   for (void* p : c->allocs) cudaFree(p);
   for (void* p : c->host_allocs) cudaFreeHost(p);
-  for (auto& e : c->ev)
+  for (auto& sl : c->slots) {
+    for (cudaEvent_t e : {sl.ev_h2d, sl.ev_enc, sl.ev_dec, sl.ev_d2h})
+      if (e) cudaEventDestroy(e);
+    for (auto& e : sl.t)
+      if (e) cudaEventDestroy(e);
+  }
+  for (auto& e : c->timers)
     if (e) cudaEventDestroy(e);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->join_ev) cudaEventDestroy(c->join_ev);
+  for (cudaStream_t st : {c->s_aux, c->s_in, c->s_out, c->stream})
+    if (st) cudaStreamDestroy(st);
   delete c;
 }
 
@@ -560,37 +630,21 @@ int ysi_load_weights(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   return guarded(c, [&] { load_weights_impl(c, tensors, n); });
 }
 
-int ysi_stage_batch(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
-                    const int32_t* box_counts) {
-  return guarded(c, [&] { stage_impl(c, n, rgb, H, W, row_stride, boxes, box_counts); });
+int ysi_submit_batch(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
+                     const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
+  return guarded(c, [&] { submit_impl(c, slot, n, rgb, nullptr, H, W, row_stride, boxes, box_counts, masks_out, packed_out, metrics_out); });
 }
 
-int ysi_compute_staged(ysi_ctx* c, ysi_timing* tm) {
-  return guarded(c, [&] { compute_impl(c, tm); });
-}
-
-int ysi_fetch_staged(ysi_ctx* c, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
-  return guarded(c, [&] { fetch_impl(c, masks_out, packed_out, metrics_out); });
+int ysi_wait_batch(ysi_ctx* c, int slot, ysi_timing* tm) {
+  return guarded(c, [&] { wait_impl(c, slot, tm); });
 }
 
 int ysi_run_batch(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
                   const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out,
                   ysi_timing* tm) {
   return guarded(c, [&] {
-    cudaEvent_t e0 = c->ev[6], e1 = c->ev[7];
-    YSI_CUDA(cudaEventRecord(e0, c->stream));
-    stage_impl(c, n, rgb, H, W, row_stride, boxes, box_counts);
-    YSI_CUDA(cudaEventRecord(e1, c->stream));
-    ysi_timing t{};
-    compute_impl(c, &t);
-    YSI_CUDA(cudaEventElapsedTime(&t.h2d_ms, e0, e1));
-    YSI_CUDA(cudaEventRecord(e0, c->stream));
-    fetch_impl(c, masks_out, packed_out, metrics_out);
-    YSI_CUDA(cudaEventRecord(e1, c->stream));
-    YSI_CUDA(cudaEventSynchronize(e1));
-    YSI_CUDA(cudaEventElapsedTime(&t.d2h_ms, e0, e1));
-    t.total_ms += t.h2d_ms + t.d2h_ms;
-    if (tm) *tm = t;
+    submit_impl(c, 0, n, rgb, nullptr, H, W, row_stride, boxes, box_counts, masks_out, packed_out, metrics_out);
+    wait_impl(c, 0, tm);
   });
 }
 
@@ -622,15 +676,22 @@ int ysi_pool_upload(ysi_ctx* c, int pool_size, int idx, const uint8_t* rgb, int 
 int ysi_compute_pool(ysi_ctx* c, int first_idx, int n, const float* boxes, const int32_t* box_counts, int sync, ysi_timing* tm) {
   return guarded(c, [&] {
     YSI_CHECK(c->d_pool && first_idx >= 0 && first_idx + n <= c->pool_cap, "pool range out of bounds");
-    stage_impl(c, n, nullptr, c->pool_H, c->pool_W, 0, boxes, box_counts);
-    c->st_rgb = c->d_pool + static_cast<size_t>(first_idx) * c->pool_H * c->pool_W * 3;
-    compute_impl(c, tm, sync != 0);
+    const int slot = c->next_slot;
+    c->next_slot ^= 1;
+    submit_impl(c, slot, n, nullptr, c->d_pool + static_cast<size_t>(first_idx) * c->pool_H * c->pool_W * 3, c->pool_H, c->pool_W, 0,
+                boxes, box_counts, nullptr, nullptr, nullptr);
+    if (sync) wait_impl(c, slot, tm);
   });
 }
 
 int ysi_timer_record(ysi_ctx* c, int slot) {
   return guarded(c, [&] {
     YSI_CHECK(slot >= 0 && slot < 8, "timer slot out of range");
+    // the timer follows everything enqueued so far on every stream of the context
+    for (cudaStream_t st : {c->s_in, c->s_aux, c->s_out}) {
+      YSI_CUDA(cudaEventRecord(c->join_ev, st));
+      YSI_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+    }
     YSI_CUDA(cudaEventRecord(c->timers[slot], c->stream));
   });
 }
@@ -643,12 +704,12 @@ int ysi_timer_elapsed_ms(ysi_ctx* c, int slot_a, int slot_b, float* ms) {
 }
 
 int ysi_sync(ysi_ctx* c) {
-  return guarded(c, [&] { YSI_CUDA(cudaStreamSynchronize(c->stream)); });
+  return guarded(c, [&] { sync_all(c); });
 }
 
 int ysi_profile(ysi_ctx* c, int enable) {
   return guarded(c, [&] {
-    YSI_CUDA(cudaStreamSynchronize(c->stream));
+    sync_all(c);
     c->prof.reset();
     c->prof.active = enable != 0;
   });

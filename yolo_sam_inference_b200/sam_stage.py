@@ -130,6 +130,7 @@ class SamStage:
             self._ctx = None
             raise RuntimeError(f"ysi_create failed ({rc}): {msg.decode() if msg else '?'}")
         self.last_timing: Dict[str, float] = {}
+        self._pinned: Dict[Any, Any] = {}
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -216,31 +217,74 @@ class SamStage:
             k += c
         return out
 
-    # split form (bench.py times the device-resident leg on its own)
-    def stage_batch(self, images: Sequence[np.ndarray], boxes: Sequence[np.ndarray]) -> int:
-        n = len(images)
-        H, W = images[0].shape[:2]
-        counts = np.array([len(b) for b in boxes], dtype=np.int32)
-        allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
-        ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in images])
-        self._check(self._lib.ysi_stage_batch(self._ctx, n, ptrs, H, W, images[0].strides[0], nat.as_f32p(allb),
-                                              nat.as_i32p(counts)), "ysi_stage_batch")
-        self._staged = (int(counts.sum()), H, W)
-        return int(counts.sum())
+    # ------------------------------------------------------------------ pipelined form
+    def run_stream(self, batches, want_masks: bool = True, raw: bool = False):
+        """Generator over ``batches`` (an iterable of (images, boxes) with same-sized images per batch) that keeps two
+        batches in flight: the H2D copy and the encoder of batch i+1 overlap the decoder, metrics and D2H copy of
+        batch i (ysi_submit_batch / ysi_wait_batch). Yields, per batch, what ``run_batch`` returns."""
+        pending = []                      # [(slot, images, boxes, counts, masks, rows, keepalive)]
+        slot = 0
 
-    def compute_staged(self) -> Dict[str, float]:
-        tm = nat.YsiTiming()
-        self._check(self._lib.ysi_compute_staged(self._ctx, C.byref(tm)), "ysi_compute_staged")
-        self.last_timing = tm.as_dict()
-        return self.last_timing
+        def finish(item):
+            sl, images, boxes, counts, masks, rows, _keep = item
+            tm = nat.YsiTiming()
+            self._check(self._lib.ysi_wait_batch(self._ctx, sl, C.byref(tm)), "ysi_wait_batch")
+            self.last_timing = tm.as_dict()
+            return self._unpack(images, boxes, counts, masks, rows, want_masks, raw)
 
-    def fetch_staged(self, want_masks: bool = True):
-        nb, H, W = self._staged
-        masks = np.empty((nb, H, W), np.uint8) if want_masks else None
-        rows = np.zeros(nb, dtype=nat.METRICS_DTYPE)
-        self._check(self._lib.ysi_fetch_staged(self._ctx, nat.as_u8p(masks), None, rows.ctypes.data_as(C.c_void_p)),
-                    "ysi_fetch_staged")
+        for images, boxes in batches:
+            n = len(images)
+            H, W = images[0].shape[:2]
+            imgs = [im if im.strides[2] == 1 and im.strides[1] == 3 else np.ascontiguousarray(im) for im in images]
+            counts = np.array([len(b) for b in boxes], dtype=np.int32)
+            nb = int(counts.sum())
+            if nb == 0:
+                while pending:
+                    yield finish(pending.pop(0))
+                yield [(np.zeros((0, H, W), bool), [], []) for _ in range(n)]
+                continue
+            if len(pending) == 2:
+                yield finish(pending.pop(0))
+            allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
+            ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in imgs])
+            masks, rows = self._out_buffers(slot, nb, H, W, want_masks)
+            self._check(self._lib.ysi_submit_batch(self._ctx, slot, n, ptrs, H, W, imgs[0].strides[0], nat.as_f32p(allb),
+                                                   nat.as_i32p(counts), nat.as_u8p(masks), None,
+                                                   rows.ctypes.data_as(C.c_void_p)), "ysi_submit_batch")
+            pending.append((slot, images, boxes, counts, masks, rows, (imgs, allb, ptrs)))
+            slot ^= 1
+        while pending:
+            yield finish(pending.pop(0))
+
+    def _out_buffers(self, slot: int, nb: int, H: int, W: int, want_masks: bool):
+        """Pinned host buffers for a slot's results (true copy/compute overlap needs page-locked memory)."""
+        import torch
+        key = (slot, H, W, want_masks)
+        buf = self._pinned.get(key)
+        if buf is None:
+            m = torch.empty((self.max_boxes, H, W), dtype=torch.uint8).pin_memory() if want_masks else None
+            r = torch.empty((self.max_boxes * nat.METRICS_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
+            buf = self._pinned[key] = (m, r)
+        m, r = buf
+        masks = m.numpy()[:nb] if want_masks else None
+        rows = r.numpy()[:nb * nat.METRICS_DTYPE.itemsize].view(nat.METRICS_DTYPE)
         return masks, rows
+
+    def _unpack(self, images, boxes, counts, masks, rows, want_masks, raw):
+        out = []
+        k = 0
+        for i in range(len(images)):
+            c = int(counts[i])
+            m = masks[k:k + c].view(bool).copy() if want_masks else None
+            r = rows[k:k + c].copy()
+            mets = r if raw else [metrics_from_raw(r[j], self.on_empty) for j in range(c)]
+            crops = []
+            for bx in np.asarray(boxes[i], np.float32).reshape(-1, 4):
+                x1, y1, x2, y2 = bx.astype(int)
+                crops.append(images[i][max(y1, 0):max(y2, 0), max(x1, 0):max(x2, 0)])
+            out.append((m, mets, crops))
+            k += c
+        return out
 
     # ------------------------------------------------------------------ measurement support (bench.py)
     def pool_upload(self, images: Sequence[np.ndarray]) -> None:
