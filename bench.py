@@ -35,6 +35,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 BATCH = int(os.environ.get("YSI_BENCH_BATCH", "8"))   # images per step
+BOXES = int(os.environ.get("YSI_BENCH_BOXES", "1"))    # boxes per image: 1 = configs[1]; 32 = configs[3] (decoder / metrics dominated)
 MODEL = os.environ.get("YSI_BENCH_MODEL", "vit_b")    # vit_b = BASELINE configs[1]; vit_h = configs[2]'s model
 ENC_FLOPS = {"vit_b": 937.6e9, "vit_l": 2837.0e9, "vit_h": 5641.8e9}
 POOL_IMAGES = 256            # BASELINE configs[1]: 256 synthetic 1024x1024 images
@@ -135,7 +136,7 @@ def make_inputs(first_index: int, count: int):
     from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
     imgs, boxes = [], []
     for i in range(first_index, first_index + count):
-        g, b = synth_image(i, 1024, 1)
+        g, b = synth_image(i, 1024, BOXES)
         imgs.append(gray_to_rgb_u8(g))
         boxes.append(b)
     return imgs, boxes
@@ -227,7 +228,7 @@ def run_ours(args):
     # folder partition: rank r owns images [r*POOL, (r+1)*POOL) of the global synthetic list
     imgs, boxes = make_inputs(rank * POOL_IMAGES, pool_n)
     stage = SamStage(MODEL, device=f"cuda:{local}", state_dict=seeded_state_dict(MODEL, 1234), max_batch=BATCH,
-                     max_boxes=BATCH, max_image_hw=(1024, 1024), on_empty="zeros")
+                     max_boxes=BATCH * BOXES, max_image_hw=(1024, 1024), on_empty="zeros")
     stage.pool_upload(imgs)
     nbat = pool_n // BATCH
 
@@ -284,8 +285,8 @@ def run_ours(args):
     assert n_out == K * BATCH
     e2e_s = max_over_ranks(dist, e2e_s, dev)
     e2e_value = world * K * BATCH / e2e_s
-    h2d = BATCH * 1024 * 1024 * 3 + BATCH * (4 * 8 + 8)
-    d2h = BATCH * 1024 * 1024 + BATCH * 1192
+    h2d = BATCH * 1024 * 1024 * 3 + BATCH * BOXES * (4 * 8 + 8)
+    d2h = BATCH * BOXES * (1024 * 1024 + 1192)
 
     # ---- profiled pass: per-launch CUDA events by kernel class (roofline + breakdown) ---------------------
     roof, breakdown = None, None
@@ -333,13 +334,13 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": ("configs[1]: SAM ViT-B" if MODEL == "vit_b" else f"SAM {MODEL}") + " bf16 (fp32 accumulate/residual), 256 synthetic 1024x1024 "
-                                   f"images per GPU, 1 box/image, batch {BATCH} images per step",
+                                   f"images per GPU, {BOXES} box(es)/image, batch {BATCH} images per step",
                        "batch": BATCH, "pool_images_per_gpu": pool_n, "weights": "seeded random-init (no checkpoints offline)",
                        "l2": "inputs differ every step and the per-step working set (~0.9 GB of activations) exceeds the "
                              "126 MB L2, so no L2 flush is needed between timed iterations",
                        "parallelism": f"image-sharded x{world}, no collective"},
-            "masks_per_s": value,
-            "alg_tflops": (ENC_FLOPS[MODEL] + DEC_FLOPS_BOX) * value / 1e12,
+            "masks_per_s": value * BOXES, "boxes_per_image": BOXES,
+            "alg_tflops": (ENC_FLOPS[MODEL] + DEC_FLOPS_BOX * BOXES) * value / 1e12,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "cpu_baseline": cpu, "breakdown": breakdown,

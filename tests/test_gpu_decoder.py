@@ -24,7 +24,7 @@ def test_prompt_encoder_and_image_pe(tiny_stage, tiny_oracle):
     assert np.abs(tiny_stage.image_pe() - dumps["image_pe"]).max() < 1e-5
 
 
-@pytest.mark.parametrize("n_boxes", [1, 5])
+@pytest.mark.parametrize("n_boxes", [1, 5, 40])     # 40 boxes: 280 token rows -> tiled fp32 token GEMM path
 def test_decoder_logits_parity(tiny_stage, tiny_oracle, n_boxes):
     img, boxes, dumps, b1024 = _case(tiny_oracle, 5 + n_boxes, n_boxes)
     low = tiny_stage.decode(dumps["image_embeddings"], b1024)

@@ -188,6 +188,74 @@ tok_linear_kernel(TokLin3 P, int R) {
   }
 }
 
+// Same contract as tok_linear_kernel for many rows (config 4: 32 boxes/image -> R = 7*256): classic shared-memory
+// tiled fp32 GEMM, 64 x 64 output tile per CTA, 4 x 4 outputs per thread, K in slabs of 32, so weights and
+// activations are each read from L2 once per tile row / column instead of once per 8 x 8 block.
+constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32;
+
+__global__ void __launch_bounds__(256)
+tok_gemm_kernel(TokLin3 P, int R) {
+  const TokLin& p = P.t[blockIdx.z];
+  __shared__ float Xs[TG_BM][TG_BK + 1];
+  __shared__ float Ws[TG_BN][TG_BK + 1];
+  const int n0 = blockIdx.x * TG_BN, r0 = blockIdx.y * TG_BM;
+  if (n0 >= p.N) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loader mapping: 256 threads x 2 float4 = 64 rows x 32 k
+  const int lrow = tid >> 3, lk4 = tid & 7;          // rows lrow, lrow+32; k = lk4*4..+3
+  for (int k0 = 0; k0 < p.K; k0 += TG_BK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rr = lrow + 32 * h;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + rr < R) {
+        x = __ldg(reinterpret_cast<const float4*>(p.X + static_cast<size_t>(r0 + rr) * p.ldx + k0) + lk4);
+        if (p.Xadd) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.Xadd + static_cast<size_t>(r0 + rr) * p.ldx + k0) + lk4);
+          x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+        }
+      }
+      Xs[rr][lk4 * 4] = x.x; Xs[rr][lk4 * 4 + 1] = x.y; Xs[rr][lk4 * 4 + 2] = x.z; Xs[rr][lk4 * 4 + 3] = x.w;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + rr < p.N) w = __ldg(reinterpret_cast<const float4*>(p.W + static_cast<size_t>(n0 + rr) * p.K + k0) + lk4);
+      Ws[rr][lk4 * 4] = w.x; Ws[rr][lk4 * 4 + 1] = w.y; Ws[rr][lk4 * 4 + 2] = w.z; Ws[rr][lk4 * 4 + 3] = w.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TG_BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Xs[ty * 4 + i][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[tx + 16 * j][k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= p.N) continue;
+      float v = acc[i][j] + (p.b ? __ldg(p.b + n) : 0.f);
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.res) v += p.res[static_cast<size_t>(r) * p.ldres + n];
+      p.Y[static_cast<size_t>(r) * p.ldy + n] = v;
+    }
+  }
+}
+
 // LayerNorm over rows of 256 (warp per row) -> out, and optionally out + pe
 __global__ void __launch_bounds__(256)
 tok_layernorm_kernel(const float* __restrict__ in, int R, const float* __restrict__ g, const float* __restrict__ b, float eps,
@@ -505,11 +573,14 @@ static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s)
   for (int i = 0; i < 3; ++i) {
     P.t[i] = t[i < count ? i : 0];
     if (i < count) {
-      YSI_CHECK(t[i].K % 128 == 0 && t[i].K <= 2048 && t[i].N % 8 == 0, "token linear shape");
+      YSI_CHECK(t[i].K % 128 == 0 && t[i].K <= 2048 && t[i].N % 8 == 0 && t[i].ldx % 4 == 0, "token linear shape");
       nmax = t[i].N > nmax ? t[i].N : nmax;
     }
   }
-  tok_linear_kernel<<<dim3(nmax / 8, ceil_div(R, TOK_ROWS), count), 256, 0, s>>>(P, R);
+  if (R >= 256)
+    tok_gemm_kernel<<<dim3(ceil_div(nmax, TG_BN), ceil_div(R, TG_BM), count), 256, 0, s>>>(P, R);
+  else
+    tok_linear_kernel<<<dim3(nmax / 8, ceil_div(R, TOK_ROWS), count), 256, 0, s>>>(P, R);
 }
 
 void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb, int n_img, int nb, float* low_res_out,

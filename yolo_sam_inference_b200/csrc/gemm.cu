@@ -133,6 +133,13 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int
       es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
       es.f32_add = 1;
       launch_gemm2(tmA, tmB, M, N, K, es, stream);
+    } else if (use_staged && plain && ep.out_f32 && !ep.out_bf16 && !ep.accumulate && ep.act == ACT_NONE && ep.scale_c1 <= ep.scale_c0) {
+      // plain fp32 output (decoder image-side projections): staged 128-byte rows, TMA store
+      EpiStaged es;
+      es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
+      es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
+      es.f32_add = 2;
+      launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else {
       launch_gemm2(tmA, tmB, M, N, K, epi, stream);
     }

@@ -180,7 +180,7 @@ struct alignas(64) EpiStaged {
   int act;
   float col_scale;
   int scale_c0, scale_c1;
-  int f32_add;
+  int f32_add;     // 0: bf16 store, 1: fp32 reduce-add, 2: fp32 store
   __device__ __forceinline__ void finish(EpiCtx& ctx) const {
     if (ctx.lane == 0) bulk_wait_read<0>();
   }
@@ -198,7 +198,7 @@ struct alignas(64) EpiStaged {
     fence_proxy_async_smem();
     __syncwarp();
     if (ctx.lane == 0) {
-      if (f32_add) tma_reduce_add_2d(&tm_out, buf, col0, ctx.row0); else tma_store_2d(&tm_out, buf, col0, ctx.row0);
+      if (f32_add == 1) tma_reduce_add_2d(&tm_out, buf, col0, ctx.row0); else tma_store_2d(&tm_out, buf, col0, ctx.row0);
       bulk_commit();
     }
     ++ctx.nbuf;
