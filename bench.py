@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 
 BATCH = int(os.environ.get("YSI_BENCH_BATCH", "8"))   # images per step
 BOXES = int(os.environ.get("YSI_BENCH_BOXES", "1"))    # boxes per image: 1 = configs[1]; 32 = configs[3] (decoder / metrics dominated)
+PRECISION = os.environ.get("YSI_PRECISION", "fp16")    # 16-bit operand encoding of the tensor-core contractions (fp16 | bf16)
 MODEL = os.environ.get("YSI_BENCH_MODEL", "vit_b")    # vit_b = BASELINE configs[1]; vit_h = configs[2]'s model
 ENC_FLOPS = {"vit_b": 937.6e9, "vit_l": 2837.0e9, "vit_h": 5641.8e9}
 POOL_IMAGES = 256            # BASELINE configs[1]: 256 synthetic 1024x1024 images
@@ -228,7 +229,7 @@ def run_ours(args):
     # folder partition: rank r owns images [r*POOL, (r+1)*POOL) of the global synthetic list
     imgs, boxes = make_inputs(rank * POOL_IMAGES, pool_n)
     stage = SamStage(MODEL, device=f"cuda:{local}", state_dict=seeded_state_dict(MODEL, 1234), max_batch=BATCH,
-                     max_boxes=BATCH * BOXES, max_image_hw=(1024, 1024), on_empty="zeros")
+                     max_boxes=BATCH * BOXES, max_image_hw=(1024, 1024), on_empty="zeros", precision=PRECISION)
     stage.pool_upload(imgs)
     nbat = pool_n // BATCH
 
@@ -304,7 +305,7 @@ def run_ours(args):
         g_n = sum(prof[c]["records"] for c in gemm_classes)
         tot_ms = sum(v["ms"] for v in prof.values())
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,EpiGeneric> (tcgen05 GEMM of the ViT linears)",
+        roof = {"bound": "tensor", "kernel": "gemm2_op16_kernel / gemm_op16_kernel (tcgen05 GEMMs of the ViT linears)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "frac_of_burst": achieved / pk["bf16_tflops"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
@@ -332,8 +333,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": ("configs[1]: SAM ViT-B" if MODEL == "vit_b" else f"SAM {MODEL}") + " bf16 (fp32 accumulate/residual), 256 synthetic 1024x1024 "
+            "dtype": PRECISION, "data": "synthetic",
+            "config": {"workload": ("configs[1]: SAM ViT-B" if MODEL == "vit_b" else f"SAM {MODEL}") + f" {PRECISION} operands (tcgen05 kind::f16, fp32 accumulate/residual), 256 synthetic 1024x1024 "
                                    f"images per GPU, {BOXES} box(es)/image, batch {BATCH} images per step",
                        "batch": BATCH, "pool_images_per_gpu": pool_n, "weights": "seeded random-init (no checkpoints offline)",
                        "l2": "inputs differ every step and the per-step working set (~0.9 GB of activations) exceeds the "

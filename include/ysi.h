@@ -175,6 +175,9 @@ YSI_API int ysi_get_image_pe(ysi_ctx* ctx, float* out);
 YSI_API int64_t ysi_launch_count(const ysi_ctx* ctx);
 /* last completed timing of the run entry points */
 YSI_API int ysi_version(void);
+/* 16-bit encoding of the tensor-core operands this library was compiled for: "bf16" (libysi.so) or "fp16"
+ * (libysi_fp16.so); accumulation, residual stream, LayerNorm and softmax statistics are fp32 in both. */
+YSI_API const char* ysi_operand_dtype(void);
 
 #ifdef __cplusplus
 }

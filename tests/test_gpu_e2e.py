@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import rel_l2
+from conftest import iou_gate, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -45,9 +45,9 @@ def test_stage_end_to_end(tiny_stage, tiny_oracle):
             x1, y1, x2, y2 = b[k].astype(int)
             assert np.array_equal(crops[k], im[y1:y2, x1:x2])
     print("end-to-end mask IoU vs fp32 oracle (random-init noise-field logits):", ["%.4f" % i for i in ious])
-    # random-init logits are a zero-mean noise field: bf16 operands cannot reach 0.999 on
-    # them; the gate here is the documented bf16 floor, the 0.999 gate is checked on identical logits (a6).
-    assert min(ious) > 0.97
+    # random-init logits are a zero-mean noise field, the hardest case for a thresholded-mask
+    # IoU: north-star gate 0.999 with fp16 operands; bf16 operands have their own measured floor (conftest.iou_gate)
+    assert min(ious) >= iou_gate(tiny_stage.precision)
 
 
 def test_batch_equals_single(tiny_stage):
@@ -83,7 +83,7 @@ def test_stage_end_to_end_other_sizes(tiny_stage, tiny_oracle, H, W):
     assert np.array_equal(m6, ref_masks)
     for k in range(2):
         iou = np.logical_and(masks[k], ref_masks[k]).sum() / max(np.logical_or(masks[k], ref_masks[k]).sum(), 1)
-        assert iou > 0.97, iou
+        assert iou >= iou_gate(tiny_stage.precision), iou
         if masks[k].any():
             ref = mo.calculate_metrics(im, masks[k])
             for key, val in ref.items():

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import rel_l2
+from conftest import iou_gate, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -33,7 +33,7 @@ def test_vit_b_stage_parity():
         print("vit_b embeddings %.2e | logits dec-only %.2e e2e %.2e | IoU %.4f (ref positive frac %.3f)"
               % (e_emb, e_dec, e_e2e, iou, frac_pos))
         assert max(errs) < 2e-2 and e_emb < 2e-2 and e_dec < 2e-2 and e_e2e < 2e-2
-        assert iou > 0.97
+        assert iou >= iou_gate(stage.precision)
     finally:
         stage.close()
 
@@ -59,7 +59,7 @@ def test_head_dim_80_tower_parity():
         masks, mets, _ = stage.run(img, boxes)
         for k in range(2):
             iou = np.logical_and(masks[k], ref_masks[k]).sum() / max(np.logical_or(masks[k], ref_masks[k]).sum(), 1)
-            assert iou > 0.97
+            assert iou >= iou_gate(stage.precision)
     finally:
         stage.close()
 
@@ -87,6 +87,6 @@ def test_vit_h_stage_parity():
         print("vit_h per-layer rel-L2 (every 4th):", ["%.1e" % e for e in errs[::4]], "last %.1e" % errs[-1])
         print("vit_h embeddings %.2e | IoU %.4f" % (e_emb, iou))
         assert max(errs) < 2e-2 and e_emb < 2e-2
-        assert iou > 0.97
+        assert iou >= iou_gate(stage.precision)
     finally:
         stage.close()

@@ -60,6 +60,7 @@ _ctx = C.c_void_p
 
 EXPORTS = {
     "ysi_version": (C.c_int, []),
+    "ysi_operand_dtype": (C.c_char_p, []),
     "ysi_create": (C.c_int, [C.c_int, C.POINTER(YsiConfig), C.POINTER(_ctx)]),
     "ysi_load_weights": (C.c_int, [_ctx, C.POINTER(YsiTensorDesc), C.c_size_t]),
     "ysi_destroy": (None, [_ctx]),
@@ -91,30 +92,40 @@ EXPORTS = {
     "ysi_launch_count": (C.c_int64, [_ctx]),
 }
 
-_LIB: Optional[C.CDLL] = None
+PRECISIONS = ("bf16", "fp16")      # 16-bit operand encoding of the tensor-core contractions (csrc/common.h)
+_LIBS: dict = {}
 
 
-def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libysi.so")
+def default_precision() -> str:
+    return os.environ.get("YSI_PRECISION", "fp16")
 
 
-def load(build_if_missing: bool = True) -> C.CDLL:
-    """Load libysi.so and bind every symbol of include/ysi.h (raises if any is missing)."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = lib_path()
+def lib_path(precision: str = "bf16") -> str:
+    from .build import lib_path as _lp
+    return _lp(precision)
+
+
+def load(build_if_missing: bool = True, precision: Optional[str] = None) -> C.CDLL:
+    """Load the library of one operand precision and bind every symbol of include/ysi.h (raises if any is missing)."""
+    precision = precision or default_precision()
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
+    if precision in _LIBS:
+        return _LIBS[precision]
+    path = lib_path(precision)
     if not os.path.exists(path):
         if not build_if_missing:
             raise RuntimeError(f"{path} is missing: run `python -m yolo_sam_inference_b200.build`")
         from .build import build
-        build()
+        build(precision=precision)
     lib = C.CDLL(path)
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    _LIB = lib
+    if lib.ysi_operand_dtype().decode() != precision:
+        raise RuntimeError(f"{path} was built for {lib.ysi_operand_dtype().decode()} operands, expected {precision}")
+    _LIBS[precision] = lib
     return lib
 
 

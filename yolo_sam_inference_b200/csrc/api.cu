@@ -105,18 +105,18 @@ struct ysi_ctx {
     YSI_CUDA(cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice));
     return d;
   }
-  bf16* upload_bf16(const std::vector<bf16>& h) {
-    bf16* d = dalloc<bf16>(h.size());
-    YSI_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  op16* upload_op16(const std::vector<op16>& h) {
+    op16* d = dalloc<op16>(h.size());
+    YSI_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(op16), cudaMemcpyHostToDevice));
     return d;
   }
 };
 
 namespace {
 
-std::vector<bf16> to_bf16(const float* p, size_t n) {
-  std::vector<bf16> v(n);
-  for (size_t i = 0; i < n; ++i) v[i] = __float2bfloat16(p[i]);
+std::vector<op16> to_op16(const float* p, size_t n) {
+  std::vector<op16> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = f2op(p[i]);
   return v;
 }
 
@@ -163,14 +163,20 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   };
   auto b16 = [&](const std::string& name, std::initializer_list<int64_t> shape) {
     const HostTensor& t = wm.get(name, shape);
-    return c->upload_bf16(to_bf16(t.data, t.numel()));
+    return c->upload_op16(to_op16(t.data, t.numel()));
   };
   // ---------------- encoder
   EncoderW& e = c->enc;
   e.D = D; e.L = L; e.heads = heads; e.mlp = mlp; e.head_dim = D / heads;
   const int hd = e.head_dim, hdp = attn_table_cols(hd);
   if (const char* rm = getenv("YSI_RESIDUAL_MODE")) e.residual_mode = atoi(rm) == 1 ? 1 : 2;   // tuning knob (bench only)
-  e.w_patch = b16("vision_encoder.patch_embed.projection.weight", {D, 3, 16, 16});
+  {
+    const HostTensor& t = wm.get("vision_encoder.patch_embed.projection.weight", {D, 3, 16, 16});
+    std::vector<op16> wv(static_cast<size_t>(D) * PATCH_K);        // [W | W]: the pixel hi and lo terms share the weights
+    for (int o = 0; o < D; ++o)
+      for (int k = 0; k < 768; ++k) wv[static_cast<size_t>(o) * PATCH_K + k] = wv[static_cast<size_t>(o) * PATCH_K + 768 + k] = f2op(t.data[o * 768 + k]);
+    e.w_patch = c->upload_op16(wv);
+  }
   e.b_patch = f32("vision_encoder.patch_embed.projection.bias", {D});
   e.pos_embed = f32("vision_encoder.pos_embed", {1, 64, 64, D});
   c->enc_layers.resize(L);
@@ -189,25 +195,32 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
     lw.w_fc2 = b16(p + "mlp.lin2.weight", {D, mlp}); lw.b_fc2 = f32(p + "mlp.lin2.bias", {D});
     const HostTensor& rh = wm.get(p + "attn.rel_pos_h", {2 * S - 1, hd});
     const HostTensor& rw = wm.get(p + "attn.rel_pos_w", {2 * S - 1, hd});
-    std::vector<bf16> tab(256 * hdp, __float2bfloat16(0.f));
+    std::vector<op16> tab(256 * hdp, f2op(0.f));
     for (int r = 0; r < 2 * S - 1; ++r)
       for (int k = 0; k < hd; ++k) {
-        tab[r * hdp + k] = __float2bfloat16(rh.data[r * hd + k] * ATTN_LOG2E);
-        tab[(128 + r) * hdp + k] = __float2bfloat16(rw.data[r * hd + k] * ATTN_LOG2E);
+        tab[r * hdp + k] = f2op(rh.data[r * hd + k] * ATTN_LOG2E);
+        tab[(128 + r) * hdp + k] = f2op(rw.data[r * hd + k] * ATTN_LOG2E);
       }
-    lw.rel_tab = c->upload_bf16(tab);
+    lw.rel_tab = c->upload_op16(tab);
   }
   e.layers = c->enc_layers.data();
-  e.w_neck1 = b16("vision_encoder.neck.conv1.weight", {256, D, 1, 1});
+  {
+    const HostTensor& t = wm.get("vision_encoder.neck.conv1.weight", {256, D, 1, 1});
+    std::vector<op16> wv(static_cast<size_t>(256) * 2 * D);        // [W | W] against the [hi | lo] input split
+    for (int o = 0; o < 256; ++o)
+      for (int k = 0; k < D; ++k) wv[static_cast<size_t>(o) * 2 * D + k] = wv[static_cast<size_t>(o) * 2 * D + D + k] = f2op(t.data[o * D + k]);
+    e.w_neck1 = c->upload_op16(wv);
+  }
   e.neck_ln1_g = f32("vision_encoder.neck.layer_norm1.weight", {256});
   e.neck_ln1_b = f32("vision_encoder.neck.layer_norm1.bias", {256});
   {
     const HostTensor& t = wm.get("vision_encoder.neck.conv2.weight", {256, 256, 3, 3});
-    std::vector<bf16> wv(256 * 2304);
+    std::vector<op16> wv(256 * NECK_K2);
     for (int o = 0; o < 256; ++o)
       for (int ci = 0; ci < 256; ++ci)
-        for (int tap = 0; tap < 9; ++tap) wv[o * 2304 + tap * 256 + ci] = __float2bfloat16(t.data[(o * 256 + ci) * 9 + tap]);
-    e.w_neck2 = c->upload_bf16(wv);
+        for (int tap = 0; tap < 9; ++tap)
+          wv[o * NECK_K2 + tap * NECK_C2 + ci] = wv[o * NECK_K2 + tap * NECK_C2 + 256 + ci] = f2op(t.data[(o * 256 + ci) * 9 + tap]);
+    e.w_neck2 = c->upload_op16(wv);
   }
   e.neck_ln2_g = f32("vision_encoder.neck.layer_norm2.weight", {256});
   e.neck_ln2_b = f32("vision_encoder.neck.layer_norm2.bias", {256});
@@ -247,9 +260,9 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
     lw.w_fc2 = f32(p + ".mlp.lin2.weight", {256, 2048}); lw.b_fc2 = f32(p + ".mlp.lin2.bias", {256});
     const HostTensor& wk = wm.get(p + ".cross_attn_token_to_image.k_proj.weight", {128, 256});
     const HostTensor& wq = wm.get(p + ".cross_attn_image_to_token.q_proj.weight", {128, 256});
-    std::vector<bf16> kq(256 * 256);
-    for (int k = 0; k < 128 * 256; ++k) { kq[k] = __float2bfloat16(wk.data[k]); kq[128 * 256 + k] = __float2bfloat16(wq.data[k]); }
-    lw.w_kq_img = c->upload_bf16(kq);
+    std::vector<op16> kq(256 * 256);
+    for (int k = 0; k < 128 * 256; ++k) { kq[k] = f2op(wk.data[k]); kq[128 * 256 + k] = f2op(wq.data[k]); }
+    lw.w_kq_img = c->upload_op16(kq);
     std::vector<float> bkq(256);
     std::memcpy(bkq.data(), wm.get(p + ".cross_attn_token_to_image.k_proj.bias", {128}).data, 128 * sizeof(float));
     std::memcpy(bkq.data() + 128, wm.get(p + ".cross_attn_image_to_token.q_proj.bias", {128}).data, 128 * sizeof(float));
@@ -265,17 +278,17 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   {
     // ConvTranspose2d weight [in, out, kh, kw] -> GEMM weight [(dy*2+dx)*out + o][in]
     const HostTensor& t1 = wm.get("mask_decoder.upscale_conv1.weight", {256, 64, 2, 2});
-    std::vector<bf16> w1(256 * 256);
+    std::vector<op16> w1(256 * 512);      // [W | W]: the keys arrive as a two-term split [hi | lo]
     for (int i = 0; i < 256; ++i)
       for (int o = 0; o < 64; ++o)
-        for (int sp = 0; sp < 4; ++sp) w1[(sp * 64 + o) * 256 + i] = __float2bfloat16(t1.data[(i * 64 + o) * 4 + sp]);
-    d.w_ct1 = c->upload_bf16(w1);
+        for (int sp = 0; sp < 4; ++sp) w1[(sp * 64 + o) * 512 + i] = w1[(sp * 64 + o) * 512 + 256 + i] = f2op(t1.data[(i * 64 + o) * 4 + sp]);
+    d.w_ct1 = c->upload_op16(w1);
     const HostTensor& t2 = wm.get("mask_decoder.upscale_conv2.weight", {64, 32, 2, 2});
-    std::vector<bf16> w2(128 * 64);
+    std::vector<op16> w2(128 * 128);      // [W | W]
     for (int i = 0; i < 64; ++i)
       for (int o = 0; o < 32; ++o)
-        for (int sp = 0; sp < 4; ++sp) w2[(sp * 32 + o) * 64 + i] = __float2bfloat16(t2.data[(i * 32 + o) * 4 + sp]);
-    d.w_ct2 = c->upload_bf16(w2);
+        for (int sp = 0; sp < 4; ++sp) w2[(sp * 32 + o) * 128 + i] = w2[(sp * 32 + o) * 128 + 64 + i] = f2op(t2.data[(i * 32 + o) * 4 + sp]);
+    d.w_ct2 = c->upload_op16(w2);
   }
   d.b_ct1 = f32("mask_decoder.upscale_conv1.bias", {64});
   d.b_ct2 = f32("mask_decoder.upscale_conv2.bias", {32});
@@ -321,15 +334,15 @@ void create_impl(ysi_ctx* c) {
   const size_t HW = static_cast<size_t>(cfg.max_image_h) * cfg.max_image_w;
   EncoderWork& ew = c->ew;
   ew.cap = cfg.max_batch;
-  ew.a_patch = c->dalloc<bf16>(B * 4096 * 768);
+  ew.a_patch = c->dalloc<op16>(B * 4096 * PATCH_K);
   ew.x = c->dalloc<float>(B * 4096 * D);
-  ew.h = c->dalloc<bf16>(B * 4900 * D);
-  ew.qkv = c->dalloc<bf16>(B * 4900 * 3 * D);
-  ew.attn = c->dalloc<bf16>(B * 4096 * D);
-  ew.u = c->dalloc<bf16>(B * 4096 * cfg.mlp_dim);
+  ew.h = c->dalloc<op16>(B * 4900 * D);
+  ew.qkv = c->dalloc<op16>(B * 4900 * 3 * D);
+  ew.attn = c->dalloc<op16>(B * 4096 * D);
+  ew.u = c->dalloc<op16>(B * 4096 * cfg.mlp_dim);
   ew.n1 = c->dalloc<float>(B * 4096 * 256);
-  ew.n1b = c->dalloc<bf16>(B * 4096 * 256);
-  ew.a_neck = c->dalloc<bf16>(B * 4096 * 2304);
+  ew.n1b = c->dalloc<op16>(B * 4096 * NECK_C2);
+  ew.a_neck = c->dalloc<op16>(B * 4096 * NECK_K2);
   ew.n2 = c->dalloc<float>(B * 4096 * 256);
   int* map = c->dalloc<int>(B * 4900);
   launch_build_win_row_map(map, cfg.max_batch, c->stream);
@@ -337,17 +350,17 @@ void create_impl(ysi_ctx* c) {
   DecoderWork& dw = c->dw;
   dw.cap_img = cfg.max_batch; dw.cap_box = cfg.max_boxes;
   dw.keys0 = c->dalloc<float>(B * 4096 * 256);
-  dw.keys0_bf = c->dalloc<bf16>(B * 4096 * 256);
-  dw.keyspos0_bf = c->dalloc<bf16>(B * 4096 * 256);
+  dw.keys0_bf = c->dalloc<op16>(B * 4096 * 256);
+  dw.keyspos0_bf = c->dalloc<op16>(B * 4096 * 256);
   dw.kq0 = c->dalloc<float>(B * 4096 * 256);
   dw.v0 = c->dalloc<float>(B * 4096 * 128);
   dw.keys = c->dalloc<float>(NB * 4096 * 256);
-  dw.keys_bf = c->dalloc<bf16>(NB * 4096 * 256);
-  dw.keyspos_bf = c->dalloc<bf16>(NB * 4096 * 256);
+  dw.keys_bf = c->dalloc<op16>(NB * 4096 * 512);
+  dw.keyspos_bf = c->dalloc<op16>(NB * 4096 * 256);
   dw.kq = c->dalloc<float>(NB * 4096 * 256);
   dw.v = c->dalloc<float>(NB * 4096 * 128);
-  dw.attn_i2t = c->dalloc<bf16>(NB * 4096 * 128);
-  dw.up1 = c->dalloc<bf16>(NB * 16384 * 64);
+  dw.attn_i2t = c->dalloc<op16>(NB * 4096 * 128);
+  dw.up1 = c->dalloc<op16>(NB * 16384 * 128);
   dw.tok0 = c->dalloc<float>(NB * 7 * 256);
   dw.queries = c->dalloc<float>(NB * 7 * 256);
   dw.q_t2i = c->dalloc<float>(NB * 7 * 128);
@@ -406,7 +419,7 @@ const ResizeTablesDev& resize_tables(ysi_ctx* c, int in_size, int out_size) {
 // a1 on the device (image_processing_sam.py:205-250): resize longest edge to 1024 (uint8 antialias bilinear, skipped
 // when the size already matches), normalise, zero-pad to 1024x1024; emits pixel_values and/or the patch-embed A matrix.
 // rgb: dense device images [n, H, W, 3].
-void preprocess_images(ysi_ctx* c, const uint8_t* rgb, int n, int H, int W, float* pixel_values, bf16* a_patch) {
+void preprocess_images(ysi_ctx* c, const uint8_t* rgb, int n, int H, int W, float* pixel_values, op16* a_patch) {
   const PostGeom g = make_post_geom(H, W);
   const uint8_t* src = rgb;
   int sh = H, sw = W, pitch = W * 3;
@@ -582,6 +595,7 @@ void sync_all(ysi_ctx* c) {
 extern "C" {
 
 int ysi_version(void) { return 1; }
+const char* ysi_operand_dtype(void) { return YSI_OP_NAME; }
 
 int ysi_create(int device, const ysi_config* cfg, ysi_ctx** out) {
   if (!cfg || !out) return -1;
@@ -830,8 +844,8 @@ int ysi_metrics(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, co
 
 int ysi_gemm(ysi_ctx* c, const float* A, const float* W, const float* bias, int M, int N, int K, int act, float* C_out) {
   return guarded(c, [&] {
-    std::vector<bf16> a = to_bf16(A, static_cast<size_t>(M) * K), w = to_bf16(W, static_cast<size_t>(N) * K);
-    bf16 *dA = nullptr, *dW = nullptr;
+    std::vector<op16> a = to_op16(A, static_cast<size_t>(M) * K), w = to_op16(W, static_cast<size_t>(N) * K);
+    op16 *dA = nullptr, *dW = nullptr;
     float *dC = nullptr, *dB = nullptr;
     YSI_CUDA(cudaMalloc(&dA, a.size() * 2)); YSI_CUDA(cudaMalloc(&dW, w.size() * 2));
     YSI_CUDA(cudaMalloc(&dC, sizeof(float) * M * N));
@@ -840,7 +854,7 @@ int ysi_gemm(ysi_ctx* c, const float* A, const float* W, const float* bias, int 
     if (bias) { YSI_CUDA(cudaMalloc(&dB, sizeof(float) * N)); YSI_CUDA(cudaMemcpy(dB, bias, sizeof(float) * N, cudaMemcpyHostToDevice)); }
     GemmEpilogue ep;
     ep.bias = dB; ep.act = act; ep.out_f32 = dC; ep.ld_out = N;
-    gemm_bf16(dA, K, dW, K, M, N, K, ep, c->stream);
+    gemm_op16(dA, K, dW, K, M, N, K, ep, c->stream);
     c->launches += 1;
     YSI_CUDA(cudaMemcpyAsync(C_out, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c->stream));
     YSI_CUDA(cudaStreamSynchronize(c->stream));
@@ -849,29 +863,29 @@ int ysi_gemm(ysi_ctx* c, const float* A, const float* W, const float* bias, int 
 }
 
 // GEMM through the production dispatcher with the epilogue kinds the encoder uses:
-// out_kind 0: C = fp32 result; 1: C = bf16-rounded result (K-scale style column scaling off); 2: C += result (residual add)
+// out_kind 0: C = fp32 result; 1: C = op16-rounded result (K-scale style column scaling off); 2: C += result (residual add)
 int ysi_gemm_ex(ysi_ctx* c, const float* A, const float* W, const float* bias, int M, int N, int K, int act, int out_kind,
                 float* C_inout) {
   return guarded(c, [&] {
-    std::vector<bf16> a = to_bf16(A, static_cast<size_t>(M) * K), w = to_bf16(W, static_cast<size_t>(N) * K);
-    bf16 *dA = nullptr, *dW = nullptr, *dO = nullptr;
+    std::vector<op16> a = to_op16(A, static_cast<size_t>(M) * K), w = to_op16(W, static_cast<size_t>(N) * K);
+    op16 *dA = nullptr, *dW = nullptr, *dO = nullptr;
     float *dC = nullptr, *dB = nullptr;
     YSI_CUDA(cudaMalloc(&dA, a.size() * 2)); YSI_CUDA(cudaMalloc(&dW, w.size() * 2));
-    YSI_CUDA(cudaMalloc(&dC, sizeof(float) * M * N)); YSI_CUDA(cudaMalloc(&dO, sizeof(bf16) * M * N));
+    YSI_CUDA(cudaMalloc(&dC, sizeof(float) * M * N)); YSI_CUDA(cudaMalloc(&dO, sizeof(op16) * M * N));
     YSI_CUDA(cudaMemcpy(dA, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
     YSI_CUDA(cudaMemcpy(dW, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
     YSI_CUDA(cudaMemcpy(dC, C_inout, sizeof(float) * M * N, cudaMemcpyHostToDevice));
     if (bias) { YSI_CUDA(cudaMalloc(&dB, sizeof(float) * N)); YSI_CUDA(cudaMemcpy(dB, bias, sizeof(float) * N, cudaMemcpyHostToDevice)); }
     GemmEpilogue ep;
     ep.bias = dB; ep.act = act;
-    if (out_kind == 1) { ep.out_bf16 = dO; ep.ld_out_bf16 = N; } else { ep.out_f32 = dC; ep.ld_out = N; ep.accumulate = out_kind == 2 ? 2 : 0; }
-    gemm_bf16(dA, K, dW, K, M, N, K, ep, c->stream);
+    if (out_kind == 1) { ep.out_op16 = dO; ep.ld_out_op16 = N; } else { ep.out_f32 = dC; ep.ld_out = N; ep.accumulate = out_kind == 2 ? 2 : 0; }
+    gemm_op16(dA, K, dW, K, M, N, K, ep, c->stream);
     c->launches += 1;
     if (out_kind == 1) {
-      std::vector<bf16> o(static_cast<size_t>(M) * N);
+      std::vector<op16> o(static_cast<size_t>(M) * N);
       YSI_CUDA(cudaMemcpyAsync(o.data(), dO, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));
       YSI_CUDA(cudaStreamSynchronize(c->stream));
-      for (size_t i = 0; i < o.size(); ++i) C_inout[i] = __bfloat162float(o[i]);
+      for (size_t i = 0; i < o.size(); ++i) C_inout[i] = op2f(o[i]);
     } else {
       YSI_CUDA(cudaMemcpyAsync(C_inout, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c->stream));
       YSI_CUDA(cudaStreamSynchronize(c->stream));
@@ -881,24 +895,24 @@ int ysi_gemm_ex(ysi_ctx* c, const float* A, const float* W, const float* bias, i
 }
 
 // measurement support: time `iters` back-to-back launches of one GEMM shape on device-resident operands.
-// mode 0: bf16 output epilogue; 1: fp32 red-add epilogue; 2: drain-only epilogue (mainloop speed). pair: CTA-pair kernel.
+// mode 0: op16 output epilogue; 1: fp32 red-add epilogue; 2: drain-only epilogue (mainloop speed). pair: CTA-pair kernel.
 int ysi_gemm_bench(ysi_ctx* c, int M, int N, int K, int pair, int mode, int iters, float* ms_per_iter) {
   return guarded(c, [&] {
-    bf16 *dA = nullptr, *dW = nullptr, *dO = nullptr;
+    op16 *dA = nullptr, *dW = nullptr, *dO = nullptr;
     float* dF = nullptr;
     YSI_CUDA(cudaMalloc(&dA, static_cast<size_t>(M) * K * 2)); YSI_CUDA(cudaMalloc(&dW, static_cast<size_t>(N) * K * 2));
     YSI_CUDA(cudaMalloc(&dO, static_cast<size_t>(M) * N * 2)); YSI_CUDA(cudaMalloc(&dF, static_cast<size_t>(M) * N * 4));
     YSI_CUDA(cudaMemset(dA, 0x3c, static_cast<size_t>(M) * K * 2)); YSI_CUDA(cudaMemset(dW, 0x3c, static_cast<size_t>(N) * K * 2));
     YSI_CUDA(cudaMemset(dF, 0, static_cast<size_t>(M) * N * 4));
-    const CUtensorMap tmA = make_tmap_bf16_2d(dA, M, K, K, GEMM_BM);
-    const CUtensorMap tmB = make_tmap_bf16_2d(dW, N, K, K, pair ? 128 : 256);
+    const CUtensorMap tmA = make_tmap_op16_2d(dA, M, K, K, GEMM_BM);
+    const CUtensorMap tmB = make_tmap_op16_2d(dW, N, K, K, pair ? 128 : 256);
     GemmEpilogue ep;
-    if (mode == 0) { ep.out_bf16 = dO; ep.ld_out_bf16 = N; } else { ep.out_f32 = dF; ep.ld_out = N; ep.accumulate = 2; }
+    if (mode == 0) { ep.out_op16 = dO; ep.ld_out_op16 = N; } else { ep.out_f32 = dF; ep.ld_out = N; ep.accumulate = 2; }
     EpiGeneric eg{ep};
     EpiDrain ed{dF};
     auto run = [&] {
       if (mode == 2) { if (pair) launch_gemm2(tmA, tmB, M, N, K, ed, c->stream); else launch_gemm<256>(tmA, tmB, M, N, K, ed, c->stream); }
-      else if (pair == 2) gemm_bf16(dA, K, dW, K, M, N, K, ep, c->stream);      // production dispatch (staged epilogue)
+      else if (pair == 2) gemm_op16(dA, K, dW, K, M, N, K, ep, c->stream);      // production dispatch (staged epilogue)
       else { if (pair) launch_gemm2(tmA, tmB, M, N, K, eg, c->stream); else launch_gemm<256>(tmA, tmB, M, N, K, eg, c->stream); }
     };
     for (int i = 0; i < 3; ++i) run();
@@ -920,26 +934,26 @@ int ysi_attention(ysi_ctx* c, const float* qkv, const float* rel_h, const float*
     YSI_CHECK(head_dim == 64 || head_dim == 80, "head_dim must be 64 or 80");
     const int T = is_global ? 4096 : 196, S = is_global ? 64 : 14, D = heads * head_dim, hdp = attn_table_cols(head_dim);
     const size_t rows = static_cast<size_t>(n_seq) * T;
-    std::vector<bf16> q = to_bf16(qkv, rows * 3 * D);
+    std::vector<op16> q = to_op16(qkv, rows * 3 * D);
     const float ks = attn_k_scale(head_dim);
     for (size_t r = 0; r < rows; ++r)           // what the qkv GEMM epilogue does: K in log2 units
-      for (int k = D; k < 2 * D; ++k) q[r * 3 * D + k] = __float2bfloat16(qkv[r * 3 * D + k] * ks);
-    std::vector<bf16> tab(256 * hdp, __float2bfloat16(0.f));
+      for (int k = D; k < 2 * D; ++k) q[r * 3 * D + k] = f2op(qkv[r * 3 * D + k] * ks);
+    std::vector<op16> tab(256 * hdp, f2op(0.f));
     for (int r = 0; r < 2 * S - 1; ++r)
       for (int k = 0; k < head_dim; ++k) {
-        tab[r * hdp + k] = __float2bfloat16(rel_h[r * head_dim + k] * ATTN_LOG2E);
-        tab[(128 + r) * hdp + k] = __float2bfloat16(rel_w[r * head_dim + k] * ATTN_LOG2E);
+        tab[r * hdp + k] = f2op(rel_h[r * head_dim + k] * ATTN_LOG2E);
+        tab[(128 + r) * hdp + k] = f2op(rel_w[r * head_dim + k] * ATTN_LOG2E);
       }
-    bf16 *dq = nullptr, *dt = nullptr, *dout = nullptr;
+    op16 *dq = nullptr, *dt = nullptr, *dout = nullptr;
     YSI_CUDA(cudaMalloc(&dq, q.size() * 2)); YSI_CUDA(cudaMalloc(&dt, tab.size() * 2)); YSI_CUDA(cudaMalloc(&dout, rows * D * 2));
     YSI_CUDA(cudaMemcpy(dq, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
     YSI_CUDA(cudaMemcpy(dt, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
     launch_encoder_attention(dq, dt, dout, n_seq, T, heads, head_dim, is_global != 0, false, c->stream);
     c->launches += 1;
-    std::vector<bf16> o(rows * D);
+    std::vector<op16> o(rows * D);
     YSI_CUDA(cudaMemcpyAsync(o.data(), dout, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));
     YSI_CUDA(cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < o.size(); ++i) out[i] = __bfloat162float(o[i]);
+    for (size_t i = 0; i < o.size(); ++i) out[i] = op2f(o[i]);
     cudaFree(dq); cudaFree(dt); cudaFree(dout);
   });
 }

@@ -8,7 +8,7 @@
 // One CTA = 128 queries of one (sequence, head); keys/values stream through in tiles of 64.
 //   warp 4 (one lane) : TMA loads (Q, rel-pos tables, K and V rings) + every tcgen05.mma
 //   warps 0-3         : one query row per thread; S from TMEM, bias add (FADD2), max (FMNMX3), exp2 (MUFU),
-//                       P -> bf16 -> 128B-swizzled smem (double buffered)
+//                       P -> op16 -> 128B-swizzled smem (double buffered)
 // Tensor-core work per tile: S = Q K^T (128x64x64, both K-major) and O += P V (128x64x64, V is the MN-major B
 // operand straight out of the qkv activation). O stays in TMEM for the whole CTA: it is rescaled in place
 // (tcgen05.ld / tcgen05.st) only when the running row maximum grows by more than 2^8 ("lazy rescale"), so the
@@ -85,7 +85,7 @@ struct AttnParams {
   int T;          // sequence length: 196 (window) or 4096 (global)
   int D;          // heads * head_dim
   int unwindow;   // windowed only: write rows in token order [img*4096 + y*64 + x] and drop the pad tokens
-  bf16* out;      // [n_seq * T, D]  (or [n_img * 4096, D] when unwindow)
+  op16* out;      // [n_seq * T, D]  (or [n_img * 4096, D] when unwindow)
 };
 
 template <bool GLOBAL, int HD>
@@ -141,11 +141,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp == 4) {
     if (lane == 0) {
-      constexpr uint32_t idesc_tab = umma_idesc_bf16(128, C::TAB_ROWS, 0, 0);
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::S_N, 0, 0);
-      constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16, 0, 0);
-      constexpr uint32_t idesc_pv64 = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
-      constexpr uint32_t idesc_pv16 = umma_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t idesc_tab = umma_idesc_op16(128, C::TAB_ROWS, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_op16(128, C::S_N, 0, 0);
+      constexpr uint32_t idesc_s16 = umma_idesc_op16(128, 16, 0, 0);
+      constexpr uint32_t idesc_pv64 = umma_idesc_op16(128, 64, 0, 1);   // B (= V) is MN-major
+      constexpr uint32_t idesc_pv16 = umma_idesc_op16(128, 16, 0, 1);
       constexpr int NCH = C::NCH, NKS = C::NKS;
       // K-major operand, k-step k: chunk k/4 (64 columns each), +32 B per 16 columns inside the swizzle atom
       auto kdesc_at = [&](uint32_t base, int chunk_bytes, int k) {
@@ -191,11 +191,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         if (!GLOBAL) {
 #pragma unroll
           for (int k = 0; k < NKS; ++k)
-            umma_bf16_ss(tmem_base + C::COL_TH, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
+            umma_op16_ss(tmem_base + C::COL_TH, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
         }
 #pragma unroll
         for (int k = 0; k < NKS; ++k)
-          umma_bf16_ss(tmem_base + C::COL_TW, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
+          umma_op16_ss(tmem_base + C::COL_TW, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
         umma_commit(bar_tab);
       }
       if (GLOBAL) {
@@ -213,7 +213,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
 #pragma unroll
         for (int k = 0; k < NKS; ++k)
-          umma_bf16_ss(d, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(k_tile_addr(st, 0), C::K_CHUNK, k), idesc, k);
+          umma_op16_ss(d, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(k_tile_addr(st, 0), C::K_CHUNK, k), idesc, k);
         umma_commit(bar_kempty + 8 * st);    // (the barrier somebody always waits on is committed last)
         umma_commit(bar_s_full + 8 * buf);
       };
@@ -239,11 +239,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
           const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ss(tmem_base + C::COL_O, pdesc + 2u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
+            umma_op16_ss(tmem_base + C::COL_O, pdesc + 2u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
           if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
             const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
             for (int k = 0; k < ksteps; ++k)
-              umma_bf16_ss(tmem_base + C::COL_O + 64, pdesc + 2u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
+              umma_op16_ss(tmem_base + C::COL_O + 64, pdesc + 2u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(bar_vempty + 8 * st);
           umma_commit(bar_p_free + 8 * pb);
@@ -385,7 +385,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
             e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
             if (h & 1) l2b = add2(l2b, e); else l2a = add2(l2a, e);
-            pk[h] = pack_bf16x2(e.x, e.y);
+            pk[h] = pack_op16x2(e.x, e.y);
           }
           // K-major, 128B swizzle: 16-byte chunk ch of row t lands at chunk ch ^ (t & 7)
           const uint32_t addr = p_row + ((static_cast<uint32_t>(ch) ^ swz) << 4);
@@ -441,10 +441,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
         for (int c = 0; c < HD / 8; ++c) {
           uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-          v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-          v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-          v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          v.x = pack_op16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          v.y = pack_op16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          v.z = pack_op16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          v.w = pack_op16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
           dst[c] = v;
         }
       }
@@ -467,10 +467,10 @@ static void launch_attn_t(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const
   encoder_attention_kernel<GLOBAL, HD><<<grid, attn::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
 }
 
-// qkv: bf16 [n_seq*T, 3D] with the K columns pre-scaled by hd^-0.5*log2(e); rel_tab: bf16 [256, HDP] pre-scaled by
+// qkv: op16 [n_seq*T, 3D] with the K columns pre-scaled by hd^-0.5*log2(e); rel_tab: op16 [256, HDP] pre-scaled by
 // log2(e) (rows 0..127 rel_pos_h zero-padded, 128..255 rel_pos_w; HDP = 64, or 128 with zero columns 80.. for
 // head_dim 80). unwindow: see AttnParams.
-void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads, int head_dim,
+void launch_encoder_attention(const op16* qkv, const op16* rel_tab, op16* out, int n_seq, int T, int heads, int head_dim,
                               bool is_global, bool unwindow, cudaStream_t stream) {
   using namespace attn;
   YSI_CHECK(head_dim == 64 || head_dim == 80, "attention kernel supports head_dim 64 (ViT-B/L) and 80 (ViT-H)");
@@ -478,11 +478,11 @@ void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, i
   const long long rows = static_cast<long long>(n_seq) * T;
   YSI_CHECK(is_global ? T == 4096 : T == 196, "attention kernel supports T = 4096 (global) or 196 (window)");
   YSI_CHECK(!unwindow || (!is_global && n_seq % 25 == 0), "unwindow needs whole images of 25 windows");
-  const CUtensorMap tmQ = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BQ);
-  const CUtensorMap tmKV = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, BKV);
-  const CUtensorMap tmKVtail = make_tmap_bf16_2d(qkv, rows, 3 * D, 3 * D, 16);
-  const CUtensorMap tmRel = make_tmap_bf16_2d(rel_tab, 256, HDP, HDP, is_global ? 128 : 32);
-  const CUtensorMap tmRel8 = make_tmap_bf16_2d(rel_tab, 256, HDP, HDP, 8);
+  const CUtensorMap tmQ = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, BQ);
+  const CUtensorMap tmKV = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, BKV);
+  const CUtensorMap tmKVtail = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, 16);
+  const CUtensorMap tmRel = make_tmap_op16_2d(rel_tab, 256, HDP, HDP, is_global ? 128 : 32);
+  const CUtensorMap tmRel8 = make_tmap_op16_2d(rel_tab, 256, HDP, HDP, 8);
   AttnParams p;
   p.T = T; p.D = D; p.out = out; p.unwindow = unwindow ? 1 : 0;
   dim3 grid(ceil_div(T, BQ), heads, n_seq);

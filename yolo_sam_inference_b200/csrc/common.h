@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,7 +12,25 @@
 
 namespace ysi {
 
-typedef __nv_bfloat16 bf16;
+// The 16-bit operand type of every tensor-core contraction (tcgen05 kind::f16 takes either encoding at the same
+// rate; accumulation is always fp32 in TMEM).  Chosen at compile time: build.py emits one library per encoding.
+//   bf16 (default)          : 8 significand bits  -- the north-star's nominal dtype
+//   fp16 (-DYSI_OP_FP16=1)  : 11 significand bits -- 8x less operand rounding; activations of this path (LayerNorm
+//                             outputs, q/k/v, GELU hidden, softmax P <= 2^8, normalised pixels) sit far inside
+//                             fp16's range and the residual stream / statistics stay fp32
+#ifdef YSI_OP_FP16
+typedef __half op16;
+#define YSI_OP_NAME "fp16"
+#define OP16_TMAP_TYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+__host__ __device__ inline op16 f2op(float v) { return __float2half_rn(v); }
+__host__ __device__ inline float op2f(op16 v) { return __half2float(v); }
+#else
+typedef __nv_bfloat16 op16;
+#define YSI_OP_NAME "bf16"
+#define OP16_TMAP_TYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+__host__ __device__ inline op16 f2op(float v) { return __float2bfloat16(v); }
+__host__ __device__ inline float op2f(op16 v) { return __bfloat162float(v); }
+#endif
 
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
@@ -35,9 +54,9 @@ struct CudaError : std::runtime_error {
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// Row-major bf16 matrix [rows, cols] (row pitch ld elements) -> 2-D TMA map with a {box_cols, box_rows}
+// Row-major op16 matrix [rows, cols] (row pitch ld elements) -> 2-D TMA map with a {box_cols, box_rows}
 // box and 128-byte swizzle. box_cols must be 64 (=128 B). Out-of-bounds reads return zero.
-CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+CUtensorMap make_tmap_op16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                               uint32_t box_cols = 64);
 
 // Row-major fp32 matrix -> 2-D TMA map with a {32 cols, box_rows} box (128 B inner extent), 128-byte swizzle;
@@ -59,13 +78,13 @@ struct GemmEpilogue {
   int accumulate = 0;            // 1: out_f32 += value (load/add/store); 2: same sum through red.global.add (L2 atomics)
   float col_scale = 1.0f;        // columns [scale_c0, scale_c1) are multiplied by col_scale after the bias
   int scale_c0 = 0, scale_c1 = 0;  //   (multiples of 32; used to hand K to the attention kernel in log2 units)
-  bf16* out_bf16 = nullptr;      // optional bf16 destination [*, ld_out_bf16]
+  op16* out_op16 = nullptr;      // optional op16 destination [*, ld_out_op16]
   int ld_out = 0;
-  int ld_out_bf16 = 0;
+  int ld_out_op16 = 0;
 };
 
-// C[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation in TMEM. A: row pitch lda, W: row pitch ldw.
-void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+// C[M,N] = A[M,K] * W[N,K]^T, op16 operands, fp32 accumulation in TMEM. A: row pitch lda, W: row pitch ldw.
+void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                cudaStream_t stream);
 
 int sm_count();

@@ -65,10 +65,10 @@ __global__ void prompt_tokens_kernel(const double* __restrict__ boxes1024, Decod
   }
 }
 
-// keys0 = emb + no_mask_embed ; bf16 copies of keys0 and keys0 + pe   (:499, :320-321)
+// keys0 = emb + no_mask_embed ; op16 copies of keys0 and keys0 + pe   (:499, :320-321)
 __global__ void prep_keys_kernel(const float* __restrict__ emb, const float* __restrict__ no_mask,
                                  const float* __restrict__ pe, long long n4, float* __restrict__ keys,
-                                 bf16* __restrict__ keys_bf, bf16* __restrict__ keyspos_bf) {
+                                 op16* __restrict__ keys_bf, op16* __restrict__ keyspos_bf) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c4 = static_cast<int>(i & 63);
@@ -79,18 +79,21 @@ __global__ void prep_keys_kernel(const float* __restrict__ emb, const float* __r
     e.x += nm.x; e.y += nm.y; e.z += nm.z; e.w += nm.w;
     reinterpret_cast<float4*>(keys)[i] = e;
     uint2 o;
-    o.x = pack_bf16x2(e.x, e.y); o.y = pack_bf16x2(e.z, e.w);
+    o.x = pack_op16x2(e.x, e.y); o.y = pack_op16x2(e.z, e.w);
     reinterpret_cast<uint2*>(keys_bf)[i] = o;
-    o.x = pack_bf16x2(e.x + p.x, e.y + p.y); o.y = pack_bf16x2(e.z + p.z, e.w + p.w);
+    o.x = pack_op16x2(e.x + p.x, e.y + p.y); o.y = pack_op16x2(e.z + p.z, e.w + p.w);
     reinterpret_cast<uint2*>(keyspos_bf)[i] = o;
   }
 }
 
-// LayerNorm4 over per-box keys (warp per row) -> fp32 keys + bf16(keys) + bf16(keys + pe)   (:343-347)
+// LayerNorm4 over per-box keys (warp per row) -> fp32 keys + op16 keys as a two-term split [hi(256) | lo(256)] (row
+// pitch KEYS_LD; the attention projections read the hi half, the upscaler both) + op16(keys + pe)   (:343-347)
+constexpr int KEYS_LD = 512;
+
 __global__ void __launch_bounds__(256)
 keys_ln_kernel(const float* __restrict__ in, long long rows, const float* __restrict__ g, const float* __restrict__ bta,
-               const float* __restrict__ pe, float* __restrict__ keys, bf16* __restrict__ keys_bf,
-               bf16* __restrict__ keyspos_bf) {
+               const float* __restrict__ pe, float* __restrict__ keys, op16* __restrict__ keys_bf,
+               op16* __restrict__ keyspos_bf) {
   const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -119,9 +122,11 @@ keys_ln_kernel(const float* __restrict__ in, long long rows, const float* __rest
     y.z = (v[k].z - mean) * rstd * gg.z + bb.z; y.w = (v[k].w - mean) * rstd * gg.w + bb.w;
     reinterpret_cast<float4*>(keys + row * C)[i] = y;
     uint2 o;
-    o.x = pack_bf16x2(y.x, y.y); o.y = pack_bf16x2(y.z, y.w);
-    reinterpret_cast<uint2*>(keys_bf + row * C)[i] = o;
-    o.x = pack_bf16x2(y.x + p.x, y.y + p.y); o.y = pack_bf16x2(y.z + p.z, y.w + p.w);
+    o.x = pack_op16x2(y.x, y.y); o.y = pack_op16x2(y.z, y.w);
+    reinterpret_cast<uint2*>(keys_bf + row * KEYS_LD)[i] = o;
+    o.x = pack_op16x2(y.x - op2f(f2op(y.x)), y.y - op2f(f2op(y.y))); o.y = pack_op16x2(y.z - op2f(f2op(y.z)), y.w - op2f(f2op(y.w)));
+    reinterpret_cast<uint2*>(keys_bf + row * KEYS_LD + C)[i] = o;
+    o.x = pack_op16x2(y.x + p.x, y.y + p.y); o.y = pack_op16x2(y.z + p.z, y.w + p.w);
     reinterpret_cast<uint2*>(keyspos_bf + row * C)[i] = o;
   }
 }
@@ -444,7 +449,7 @@ t2i_merge_kernel(const float* __restrict__ part, float* __restrict__ attn_out) {
 // Q: fp32 [*,ldq] (columns 128..255 of the fused k|q projection). One thread = (token, head).
 __global__ void __launch_bounds__(256)
 i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict__ group, const float* __restrict__ k_tok,
-                     const float* __restrict__ v_tok, bf16* __restrict__ out) {
+                     const float* __restrict__ v_tok, op16* __restrict__ out) {
   __shared__ float s_k[NT * 128], s_v[NT * 128];
   const int b = blockIdx.y, t = threadIdx.x;
   for (int i = t; i < NT * 128; i += 256) {
@@ -481,8 +486,8 @@ i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict
   }
   uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * 4096 + tok) * 128 + h * 16);
   uint4 v0, v1;
-  v0.x = pack_bf16x2(o[0], o[1]); v0.y = pack_bf16x2(o[2], o[3]); v0.z = pack_bf16x2(o[4], o[5]); v0.w = pack_bf16x2(o[6], o[7]);
-  v1.x = pack_bf16x2(o[8], o[9]); v1.y = pack_bf16x2(o[10], o[11]); v1.z = pack_bf16x2(o[12], o[13]); v1.w = pack_bf16x2(o[14], o[15]);
+  v0.x = pack_op16x2(o[0], o[1]); v0.y = pack_op16x2(o[2], o[3]); v0.z = pack_op16x2(o[4], o[5]); v0.w = pack_op16x2(o[6], o[7]);
+  v1.x = pack_op16x2(o[8], o[9]); v1.y = pack_op16x2(o[10], o[11]); v1.z = pack_op16x2(o[12], o[13]); v1.w = pack_op16x2(o[14], o[15]);
   dst[0] = v0;
   dst[1] = v1;
 }
@@ -491,10 +496,10 @@ i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict
 // upscaler epilogues
 // ---------------------------------------------------------------------------------------------------
 // ConvTranspose2d(256->64,k2,s2) as a GEMM with N = 4 sub-positions x 64 channels; per sub-position:
-// + bias, LayerNorm over the 64 channels (eps 1e-6), GELU, bf16, stored pixel-shuffled   (:515-520)
+// + bias, LayerNorm over the 64 channels (eps 1e-6), GELU, op16, stored pixel-shuffled   (:515-520)
 struct EpiConvT1 {
   const float *bias, *g, *b;
-  bf16* out;   // [nb*16384, 64]
+  op16* out;   // [nb*16384, 128]: 64 channels as a two-term split [hi | lo]
   __device__ __forceinline__ void finish(EpiCtx&) const {}
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     const bool active = row < M;
@@ -518,7 +523,7 @@ struct EpiConvT1 {
       for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; sq += d * d; }
       const float rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-6f);
       const int dy = sp >> 1, dx = sp & 1;
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(box) * 16384 + (2 * y + dy) * 128 + (2 * x + dx)) * 64);
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(box) * 16384 + (2 * y + dy) * 128 + (2 * x + dx)) * 128);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float u[8];
@@ -528,8 +533,12 @@ struct EpiConvT1 {
           u[k] = gelu_erf((v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i));
         }
         uint4 o;
-        o.x = pack_bf16x2(u[0], u[1]); o.y = pack_bf16x2(u[2], u[3]); o.z = pack_bf16x2(u[4], u[5]); o.w = pack_bf16x2(u[6], u[7]);
+        o.x = pack_op16x2(u[0], u[1]); o.y = pack_op16x2(u[2], u[3]); o.z = pack_op16x2(u[4], u[5]); o.w = pack_op16x2(u[6], u[7]);
         dst[c] = o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] -= op2f(f2op(u[k]));
+        o.x = pack_op16x2(u[0], u[1]); o.y = pack_op16x2(u[2], u[3]); o.z = pack_op16x2(u[4], u[5]); o.w = pack_op16x2(u[6], u[7]);
+        dst[8 + c] = o;
       }
     }
   }
@@ -614,8 +623,8 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     const bool first = li == 0;
     const bool per_img = li == 0;                       // block 0: keys are shared by all boxes of an image
     const int rows = per_img ? TI : TB;
-    const bf16* a_keys = per_img ? wk.keys0_bf : wk.keys_bf;
-    const bf16* a_keyspos = per_img ? wk.keyspos0_bf : wk.keyspos_bf;
+    const op16* a_keys = per_img ? wk.keys0_bf : wk.keys_bf;
+    const op16* a_keyspos = per_img ? wk.keyspos0_bf : wk.keyspos_bf;
     float* kq = per_img ? wk.kq0 : wk.kq;
     float* v = per_img ? wk.v0 : wk.v;
     const int* group = per_img ? wk.box_img : nullptr;
@@ -640,10 +649,10 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       ProfScope ps(prof, KC_DEC_GEMM, 2.0 * rows * 384 * 256);
       GemmEpilogue ep;
       ep.bias = lw.b_kq_img; ep.out_f32 = kq; ep.ld_out = 256;
-      gemm_bf16(a_keyspos, C, lw.w_kq_img, C, rows, 256, C, ep, s); ++nl;
+      gemm_op16(a_keyspos, C, lw.w_kq_img, C, rows, 256, C, ep, s); ++nl;
       GemmEpilogue ev;
       ev.bias = lw.t2i.bv; ev.out_f32 = v; ev.ld_out = 128;
-      gemm_bf16(a_keys, C, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
+      gemm_op16(a_keys, per_img ? C : KEYS_LD, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
     }
     { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(wk.q_t2i, kq, 256, v, 128, group, t_part); ++nl;
       t2i_merge_kernel<<<nb, 256, 0, s>>>(t_part, wk.attn_t2i); ++nl; }
@@ -673,7 +682,7 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       ep.add_src = per_img ? wk.keys0 : wk.keys; ep.ld_add = 256;
       if (per_img) { ep.add_mod = 4096; ep.add_group = wk.box_img; } else { ep.add_mod = TB; }
       // block 1 reads kq (q columns) in i2t above, which is complete before this GEMM starts (same stream)
-      gemm_bf16(wk.attn_i2t, 128, lw.w_i2t_out, 128, TB, 256, 128, ep, s); ++nl;
+      gemm_op16(wk.attn_i2t, 128, lw.w_i2t_out, 128, TB, 256, 128, ep, s); ++nl;
       keys_ln_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(wk.kq, TB, lw.ln4_g, lw.ln4_b, w.image_pe, wk.keys, wk.keys_bf, wk.keyspos_bf); ++nl;
       YSI_CUDA(cudaGetLastError());
     }
@@ -688,10 +697,10 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 256);
     GemmEpilogue ek;
     ek.bias = w.final_attn.bk; ek.out_f32 = wk.kq; ek.ld_out = 256;    // K in columns 0..127 of kq
-    gemm_bf16(wk.keyspos_bf, C, w.w_k_final, C, TB, 128, C, ek, s); ++nl;
+    gemm_op16(wk.keyspos_bf, C, w.w_k_final, C, TB, 128, C, ek, s); ++nl;
     GemmEpilogue ev;
     ev.bias = w.final_attn.bv; ev.out_f32 = wk.v; ev.ld_out = 128;
-    gemm_bf16(wk.keys_bf, C, w.w_v_final, C, TB, 128, C, ev, s); ++nl;
+    gemm_op16(wk.keys_bf, KEYS_LD, w.w_v_final, C, TB, 128, C, ev, s); ++nl;
   }
   { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, t_part); ++nl;
     t2i_merge_kernel<<<nb, 256, 0, s>>>(t_part, wk.attn_t2i); ++nl; }
@@ -712,15 +721,17 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   // upscaler (:515-531)
   {
     ProfScope ps(prof, KC_DEC_UPSCALE, 2.0 * TB * 256 * 256 + 2.0 * nb * 16384.0 * 128 * 64);
-    const CUtensorMap tmA = make_tmap_bf16_2d(wk.keys_bf, TB, C, C, GEMM_BM);
-    const CUtensorMap tmB = make_tmap_bf16_2d(w.w_ct1, 256, C, C, 256);
+    // both transposed convolutions contract [hi | lo] input splits against [W | W]: these two inputs feed the logits
+    // directly, so their op16 rounding would otherwise dominate the decoder's error
+    const CUtensorMap tmA = make_tmap_op16_2d(wk.keys_bf, TB, KEYS_LD, KEYS_LD, GEMM_BM);
+    const CUtensorMap tmB = make_tmap_op16_2d(w.w_ct1, 256, KEYS_LD, KEYS_LD, 256);
     EpiConvT1 e1{w.b_ct1, w.lnu_g, w.lnu_b, wk.up1};
-    launch_gemm<256>(tmA, tmB, TB, 256, C, e1, s); ++nl;
+    launch_gemm<256>(tmA, tmB, TB, 256, KEYS_LD, e1, s); ++nl;
     const int M2 = nb * 16384;
-    const CUtensorMap tmA2 = make_tmap_bf16_2d(wk.up1, M2, 64, 64, GEMM_BM);
-    const CUtensorMap tmB2 = make_tmap_bf16_2d(w.w_ct2, 128, 64, 64, 128);
+    const CUtensorMap tmA2 = make_tmap_op16_2d(wk.up1, M2, 128, 128, GEMM_BM);
+    const CUtensorMap tmB2 = make_tmap_op16_2d(w.w_ct2, 128, 128, 128, 128);
     EpiConvT2 e2{w.b_ct2, wk.hyper, low_res_out};
-    launch_gemm<128>(tmA2, tmB2, M2, 128, 64, e2, s); ++nl;
+    launch_gemm<128>(tmA2, tmB2, M2, 128, 128, e2, s); ++nl;
   }
   *launches += nl;
 }

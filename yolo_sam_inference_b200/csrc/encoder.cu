@@ -127,9 +127,26 @@ void launch_resize_v(const uint8_t* src, int n, int row_stride, size_t img_strid
 // One thread = 8 horizontally adjacent pixels of one channel of one patch row.
 // A row (token) = patch (py,px); column = c*256 + ky*16 + kx   (Conv2d weight [D,3,16,16] flattened)
 // ------------------------------------------------------------------------------------------------
+// The patch-embed A operand carries every pixel as a two-term split  v = hi + lo  (both op16, lo = the rounding
+// residual of hi): columns [0,768) hold hi, [768,1536) hold lo, and the weight matrix is [W | W], so the tensor
+// core sums hi*W + lo*W in fp32 and the input rounding of this one GEMM -- the largest single error term of the
+// encoder, since its output IS the residual stream -- drops from 2^-9 / 2^-12 to fp32 level for 0.1 ms per step.
+__device__ __forceinline__ void store_patch_hi_lo(op16* dst, const float (&v)[8]) {
+  float lo[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) lo[k] = v[k] - op2f(f2op(v[k]));
+  uint4 o;
+  o.x = pack_op16x2(v[0], v[1]); o.y = pack_op16x2(v[2], v[3]);
+  o.z = pack_op16x2(v[4], v[5]); o.w = pack_op16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = o;
+  o.x = pack_op16x2(lo[0], lo[1]); o.y = pack_op16x2(lo[2], lo[3]);
+  o.z = pack_op16x2(lo[4], lo[5]); o.w = pack_op16x2(lo[6], lo[7]);
+  *reinterpret_cast<uint4*>(dst + 768) = o;
+}
+
 __global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, int n, int src_h, int src_w, int row_stride, size_t img_stride,
                                   float m0, float m1, float m2, float s0, float s1, float s2,
-                                  float* __restrict__ pix, bf16* __restrict__ a_patch) {
+                                  float* __restrict__ pix, op16* __restrict__ a_patch) {
   const long long total = static_cast<long long>(n) * 3 * 1024 * 128;   // 8-pixel groups
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -151,16 +168,13 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, int n, int sr
     }
     if (a_patch) {
       const int py = y >> 4, ky = y & 15, px = xg >> 1, kx0 = (xg & 1) * 8;
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(a_patch + (static_cast<size_t>(b) * 4096 + py * 64 + px) * 768 + c * 256 + ky * 16 + kx0) = o;
+      store_patch_hi_lo(a_patch + (static_cast<size_t>(b) * 4096 + py * 64 + px) * PATCH_K + c * 256 + ky * 16 + kx0, v);
     }
   }
 }
 
 void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_stride, size_t img_stride, const float* mean255,
-                       const float* std255, float* pixel_values, bf16* a_patch, cudaStream_t s) {
+                       const float* std255, float* pixel_values, op16* a_patch, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
   preprocess_kernel<<<grid, 256, 0, s>>>(rgb, n, src_h, src_w, row_stride, img_stride, mean255[0], mean255[1], mean255[2],
@@ -168,7 +182,7 @@ void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_
   YSI_CUDA(cudaGetLastError());
 }
 
-__global__ void im2col_patch_f32_kernel(const float* __restrict__ pix, int n, bf16* __restrict__ a_patch) {
+__global__ void im2col_patch_f32_kernel(const float* __restrict__ pix, int n, op16* __restrict__ a_patch) {
   const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -179,14 +193,12 @@ __global__ void im2col_patch_f32_kernel(const float* __restrict__ pix, int n, bf
     const float4* sp = reinterpret_cast<const float4*>(pix + ((static_cast<size_t>(b) * 3 + c) * 1024 + y) * 1024 + xg * 8);
     const float4 a = sp[0], d = sp[1];
     const int py = y >> 4, ky = y & 15, px = xg >> 1, kx0 = (xg & 1) * 8;
-    uint4 o;
-    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-    o.z = pack_bf16x2(d.x, d.y); o.w = pack_bf16x2(d.z, d.w);
-    *reinterpret_cast<uint4*>(a_patch + (static_cast<size_t>(b) * 4096 + py * 64 + px) * 768 + c * 256 + ky * 16 + kx0) = o;
+    const float v[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    store_patch_hi_lo(a_patch + (static_cast<size_t>(b) * 4096 + py * 64 + px) * PATCH_K + c * 256 + ky * 16 + kx0, v);
   }
 }
 
-void launch_im2col_patch_f32(const float* pixel_values, int n, bf16* a_patch, cudaStream_t s) {
+void launch_im2col_patch_f32(const float* pixel_values, int n, op16* a_patch, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * 3 * 1024 * 128;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
   im2col_patch_f32_kernel<<<grid, 256, 0, s>>>(pixel_values, n, a_patch);
@@ -197,7 +209,7 @@ void launch_im2col_patch_f32(const float* pixel_values, int n, bf16* a_patch, cu
 // LayerNorm over the last dim of fp32 rows, one warp per OUTPUT row.
 //   WINDOWED: output rows are in window-partition order (25 windows x 196 per image, 64->70 zero pad,
 //             modeling_sam.py:900-922); pad rows are written as zeros (they become q=k=v=bias).
-// Output bf16 (GEMM operand) and/or fp32.
+// Output op16 (GEMM operand) and/or fp32.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int window_row_to_token(int wrow) {   // row within one image's 4900 -> token or -1
   const int w = wrow / 196, l = wrow - w * 196;
@@ -206,10 +218,11 @@ __device__ __forceinline__ int window_row_to_token(int wrow) {   // row within o
   return (y < 64 && x < 64) ? y * 64 + x : -1;
 }
 
-template <bool WINDOWED>
+// SPLIT: the op16 output row is [hi(D) | lo(D)] (two-term split, see store_patch_hi_lo) for the neck's convolutions.
+template <bool WINDOWED, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, bf16* __restrict__ out_bf, float* __restrict__ out_f) {
+                 const float* __restrict__ beta, float eps, op16* __restrict__ out_bf, float* __restrict__ out_f) {
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= rows_out) return;
@@ -266,19 +279,29 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
       if (out_f) reinterpret_cast<float4*>(out_f + static_cast<size_t>(warp_global) * D)[i] = y;
       if (out_bf) {
         uint2 o;
-        o.x = pack_bf16x2(y.x, y.y);
-        o.y = pack_bf16x2(y.z, y.w);
-        reinterpret_cast<uint2*>(out_bf + static_cast<size_t>(warp_global) * D)[i] = o;
+        o.x = pack_op16x2(y.x, y.y);
+        o.y = pack_op16x2(y.z, y.w);
+        if (SPLIT) {
+          op16* orow = out_bf + static_cast<size_t>(warp_global) * 2 * D;
+          reinterpret_cast<uint2*>(orow)[i] = o;
+          o.x = pack_op16x2(y.x - op2f(f2op(y.x)), y.y - op2f(f2op(y.y)));
+          o.y = pack_op16x2(y.z - op2f(f2op(y.z)), y.w - op2f(f2op(y.w)));
+          reinterpret_cast<uint2*>(orow + D)[i] = o;
+        } else {
+          reinterpret_cast<uint2*>(out_bf + static_cast<size_t>(warp_global) * D)[i] = o;
+        }
       }
     }
   }
 }
 
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
-                      bf16* out_bf, float* out_f, bool windowed, cudaStream_t s) {
+                      op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split) {
   YSI_CHECK(D % 8 == 0 && D <= 1280, "LayerNorm width must be a multiple of 8 and <= 1280");
   const int blocks = ceil_div(rows_out, 8);
-  if (windowed)
+  if (split)
+    layernorm_kernel<false, true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
+  else if (windowed)
     layernorm_kernel<true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
   else
     layernorm_kernel<false><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
@@ -299,33 +322,39 @@ void launch_build_win_row_map(int* map, int n_images, cudaStream_t s) {
   YSI_CUDA(cudaGetLastError());
 }
 
-// 3x3 / pad 1 im2col over the 64x64 token grid, 256 channels, tap-major columns:
-//   A[t, (ky*3+kx)*256 + c] = in[(y+ky-1, x+kx-1), c]  (zero outside the grid)
-__global__ void im2col_3x3_kernel(const bf16* __restrict__ in, int n, bf16* __restrict__ out) {
-  const long long total = static_cast<long long>(n) * 4096 * 9 * 32;   // uint4 (8 channel) groups
+// 3x3 / pad 1 im2col over the 64x64 token grid, tap-major columns; a row of `in` is the 256 channels as a two-term
+// split [hi(256) | lo(256)] (NECK_C2 = 512 values):
+//   A[t, (ky*3+kx)*512 + c] = in[(y+ky-1, x+kx-1), c]  (zero outside the grid)
+__global__ void im2col_3x3_kernel(const op16* __restrict__ in, int n, op16* __restrict__ out) {
+  const long long total = static_cast<long long>(n) * 4096 * 9 * 64;   // uint4 (8 value) groups
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i & 31);
-    const int tap = static_cast<int>((i >> 5) % 9);
-    const long long t = i / (9 * 32);
+    const int cg = static_cast<int>(i & 63);
+    const int tap = static_cast<int>((i >> 6) % 9);
+    const long long t = i / (9 * 64);
     const int tok = static_cast<int>(t & 4095);
     const int b = static_cast<int>(t >> 12);
     const int y = (tok >> 6) + tap / 3 - 1, x = (tok & 63) + tap % 3 - 1;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (y >= 0 && y < 64 && x >= 0 && x < 64)
-      v = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(b) * 4096 + y * 64 + x) * 256 + cg * 8);
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * 2304 + tap * 256 + cg * 8) = v;
+      v = *reinterpret_cast<const uint4*>(in + (static_cast<size_t>(b) * 4096 + y * 64 + x) * NECK_C2 + cg * 8);
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * NECK_K2 + tap * NECK_C2 + cg * 8) = v;
   }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n8) {
+// fp32 [rows, D] -> op16 [rows, 2D] = [hi | lo] (two-term split, see store_patch_hi_lo)
+__global__ void cast_split_op16_kernel(const float* __restrict__ in, op16* __restrict__ out, long long n8, int d8) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    const long long row = i / d8, c8 = i - row * d8;
     uint4 o;
-    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
-    reinterpret_cast<uint4*>(out)[i] = o;
+    o.x = pack_op16x2(a.x, a.y); o.y = pack_op16x2(a.z, a.w);
+    o.z = pack_op16x2(b.x, b.y); o.w = pack_op16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(out)[row * 2 * d8 + c8] = o;
+    o.x = pack_op16x2(a.x - op2f(f2op(a.x)), a.y - op2f(f2op(a.y))); o.y = pack_op16x2(a.z - op2f(f2op(a.z)), a.w - op2f(f2op(a.w)));
+    o.z = pack_op16x2(b.x - op2f(f2op(b.x)), b.y - op2f(f2op(b.y))); o.w = pack_op16x2(b.z - op2f(f2op(b.z)), b.w - op2f(f2op(b.w)));
+    reinterpret_cast<uint4*>(out)[row * 2 * d8 + d8 + c8] = o;
   }
 }
 
@@ -340,8 +369,8 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     GemmEpilogue ep;
     ep.bias = w.b_patch; ep.add_src = w.pos_embed; ep.add_mod = 4096; ep.ld_add = D;
     ep.out_f32 = work.x; ep.ld_out = D;
-    ProfScope ps(prof, KC_GEMM_PATCH, 2.0 * T * D * 768);
-    gemm_bf16(work.a_patch, 768, w.w_patch, 768, T, D, 768, ep, s); ++nl;
+    ProfScope ps(prof, KC_GEMM_PATCH, 2.0 * T * D * 768);      // algorithmic FLOPs: the lo term is overhead
+    gemm_op16(work.a_patch, PATCH_K, w.w_patch, PATCH_K, T, D, PATCH_K, ep, s); ++nl;
   }
   if (hidden_dump) YSI_CUDA(cudaMemcpyAsync(hidden_dump, work.x, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, s));
   for (int li = 0; li < w.L; ++li) {
@@ -352,10 +381,10 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s); ++nl; }
     {
       GemmEpilogue ep;
-      ep.bias = lw.b_qkv; ep.out_bf16 = work.qkv; ep.ld_out_bf16 = 3 * D;
+      ep.bias = lw.b_qkv; ep.out_op16 = work.qkv; ep.ld_out_op16 = 3 * D;
       ep.col_scale = attn_k_scale(w.head_dim); ep.scale_c0 = D; ep.scale_c1 = 2 * D;     // K in log2 units for the attention kernel
       ProfScope ps(prof, KC_GEMM_QKV, 2.0 * T * 3 * D * D);
-      gemm_bf16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
+      gemm_op16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
     }
     {
       const double S = glob ? 64.0 : 14.0, tok = glob ? 4096.0 : 196.0, nseq = glob ? n : n * 25.0;
@@ -367,41 +396,44 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
       GemmEpilogue ep;   // x += attn * Wproj^T + b ; the attention kernel already un-partitioned the windows
       ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
       ProfScope ps(prof, KC_GEMM_PROJ, 2.0 * T * D * D);
-      gemm_bf16(work.attn, D, lw.w_proj, D, T, D, D, ep, s); ++nl;
+      gemm_op16(work.attn, D, lw.w_proj, D, T, D, D, ep, s); ++nl;
     }
     { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s); ++nl; }
     {
       GemmEpilogue ep;
-      ep.bias = lw.b_fc1; ep.act = ACT_GELU; ep.out_bf16 = work.u; ep.ld_out_bf16 = w.mlp;
+      ep.bias = lw.b_fc1; ep.act = ACT_GELU; ep.out_op16 = work.u; ep.ld_out_op16 = w.mlp;
       ProfScope ps(prof, KC_GEMM_FC1, 2.0 * T * w.mlp * D);
-      gemm_bf16(work.h, D, lw.w_fc1, D, T, w.mlp, D, ep, s); ++nl;
+      gemm_op16(work.h, D, lw.w_fc1, D, T, w.mlp, D, ep, s); ++nl;
     }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
       ProfScope ps(prof, KC_GEMM_FC2, 2.0 * T * w.mlp * D);
-      gemm_bf16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
+      gemm_op16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
     }
     if (hidden_dump)
       YSI_CUDA(cudaMemcpyAsync(hidden_dump + static_cast<size_t>(li + 1) * T * D, work.x, sizeof(float) * T * D,
                                cudaMemcpyDeviceToDevice, s));
   }
-  // neck (modeling_sam.py:985-992): 1x1 conv -> LN2d -> 3x3 conv -> LN2d, all in token-major (NHWC) layout
+  // neck (modeling_sam.py:985-992): 1x1 conv -> LN2d -> 3x3 conv -> LN2d, all in token-major (NHWC) layout.
+  // Both convolutions take their input as a two-term op16 split [hi | lo] against [W | W]: their input roundings
+  // would otherwise be the two largest error terms of the image embedding (they act on the whole residual stream /
+  // the whole normalised map, not on a small branch), and the neck is < 2 % of the encoder's FLOPs.
   {
     ProfScope ps(prof, KC_NECK, 2.0 * T * 256 * (D + 2304.0));
     const long long n8 = static_cast<long long>(T) * D / 8;
-    cast_bf16_kernel<<<static_cast<int>(std::min<long long>((n8 + 255) / 256, 148 * 16)), 256, 0, s>>>(work.x, work.h, n8);
+    cast_split_op16_kernel<<<static_cast<int>(std::min<long long>((n8 + 255) / 256, 148 * 16)), 256, 0, s>>>(work.x, work.u, n8, D / 8);
     YSI_CUDA(cudaGetLastError()); ++nl;
     GemmEpilogue ep;
     ep.out_f32 = work.n1; ep.ld_out = 256;
-    gemm_bf16(work.h, D, w.w_neck1, D, T, 256, D, ep, s); ++nl;
-    launch_layernorm(work.n1, T, 256, w.neck_ln1_g, w.neck_ln1_b, 1e-6f, work.n1b, nullptr, false, s); ++nl;
-    const long long tot = static_cast<long long>(T) * 9 * 32;
+    gemm_op16(work.u, 2 * D, w.w_neck1, 2 * D, T, 256, 2 * D, ep, s); ++nl;
+    launch_layernorm(work.n1, T, 256, w.neck_ln1_g, w.neck_ln1_b, 1e-6f, work.n1b, nullptr, false, s, /*split=*/true); ++nl;
+    const long long tot = static_cast<long long>(T) * 9 * 64;
     im2col_3x3_kernel<<<static_cast<int>(std::min<long long>((tot + 255) / 256, 148 * 16)), 256, 0, s>>>(work.n1b, n, work.a_neck);
     YSI_CUDA(cudaGetLastError()); ++nl;
     GemmEpilogue ep2;
     ep2.out_f32 = work.n2; ep2.ld_out = 256;
-    gemm_bf16(work.a_neck, 2304, w.w_neck2, 2304, T, 256, 2304, ep2, s); ++nl;
+    gemm_op16(work.a_neck, NECK_K2, w.w_neck2, NECK_K2, T, 256, NECK_K2, ep2, s); ++nl;
     launch_layernorm(work.n2, T, 256, w.neck_ln2_g, w.neck_ln2_b, 1e-6f, nullptr, emb_out, false, s); ++nl;
   }
   *launches += nl;

@@ -27,7 +27,7 @@ static PFN_encodeTiled get_encode_fn() {
 static CUtensorMap make_tmap_2d(const void* base, int esize, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                                 uint32_t box_cols);
 
-CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+CUtensorMap make_tmap_op16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                               uint32_t box_cols) {
   return make_tmap_2d(base, 2, rows, cols, ld, box_rows, box_cols);
 }
@@ -56,7 +56,7 @@ static CUtensorMap make_tmap_2d(const void* base, int esize, uint64_t rows, uint
   cuuint64_t gstride[1] = {ld * static_cast<uint64_t>(esize)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode_fn()(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
+  CUresult r = get_encode_fn()(&m, esize == 2 ? OP16_TMAP_TYPE : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   YSI_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
@@ -106,34 +106,34 @@ int sm_count() {
   return n;
 }
 
-void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                cudaStream_t stream) {
   YSI_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   YSI_CHECK(N % 32 == 0, "GEMM N must be a multiple of 32");
   YSI_CHECK(K % 8 == 0, "GEMM K must be a multiple of 8");
   EpiGeneric epi{ep};
-  const CUtensorMap tmA = make_tmap_bf16_2d(A, M, K, lda, GEMM_BM);
+  const CUtensorMap tmA = make_tmap_op16_2d(A, M, K, lda, GEMM_BM);
   static const int use_pair = [] { const char* e = getenv("YSI_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   if (use_pair && N % 256 == 0 && M >= 2048) {
     // big GEMMs: CTA pairs (cta_group::2), each CTA loads half of the B tile
-    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 128);
+    const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 128);
     static const int use_staged = [] { const char* e = getenv("YSI_GEMM_STAGED"); return e ? atoi(e) : 1; }();
     const bool plain = !ep.row_map && !ep.add_src && ep.act != ACT_RELU;
-    if (use_staged && plain && ep.out_bf16 && !ep.out_f32) {
-      // bf16 activation output: tile staged in shared memory, written with TMA stores
+    if (use_staged && plain && ep.out_op16 && !ep.out_f32) {
+      // op16 activation output: tile staged in shared memory, written with TMA stores
       EpiStaged es;
-      es.tm_out = make_tmap_bf16_2d(ep.out_bf16, M, N, ep.ld_out_bf16, 32);
+      es.tm_out = make_tmap_op16_2d(ep.out_op16, M, N, ep.ld_out_op16, 32);
       es.bias = ep.bias; es.act = ep.act; es.col_scale = ep.col_scale; es.scale_c0 = ep.scale_c0; es.scale_c1 = ep.scale_c1;
       es.f32_add = 0;
       launch_gemm2(tmA, tmB, M, N, K, es, stream);
-    } else if (use_staged && plain && ep.out_f32 && !ep.out_bf16 && ep.accumulate && ep.act == ACT_NONE) {
+    } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && ep.accumulate && ep.act == ACT_NONE) {
       // residual add: x += tile through cp.reduce.async.bulk (fp32 add in the L2, 128-byte rows)
       EpiStaged es;
       es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
       es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
       es.f32_add = 1;
       launch_gemm2(tmA, tmB, M, N, K, es, stream);
-    } else if (use_staged && plain && ep.out_f32 && !ep.out_bf16 && !ep.accumulate && ep.act == ACT_NONE && ep.scale_c1 <= ep.scale_c0) {
+    } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && !ep.accumulate && ep.act == ACT_NONE && ep.scale_c1 <= ep.scale_c0) {
       // plain fp32 output (decoder image-side projections): staged 128-byte rows, TMA store
       EpiStaged es;
       es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
@@ -147,13 +147,13 @@ void gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int
   }
   // widest tile that does not waste more than a quarter of its columns
   if (N % 256 == 0 || N > 512) {
-    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 256);
+    const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 256);
     launch_gemm<256>(tmA, tmB, M, N, K, epi, stream);
   } else if (N % 128 == 0) {
-    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 128);
+    const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 128);
     launch_gemm<128>(tmA, tmB, M, N, K, epi, stream);
   } else {
-    const CUtensorMap tmB = make_tmap_bf16_2d(W, N, K, ldw, 64);
+    const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 64);
     launch_gemm<64>(tmA, tmB, M, N, K, epi, stream);
   }
 }

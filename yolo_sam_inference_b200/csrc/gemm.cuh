@@ -1,5 +1,5 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T
-//   bf16 operands (K-major, TMA-loaded into 128B-swizzled shared memory), fp32 accumulators in TMEM.
+//   op16 operands (K-major, TMA-loaded into 128B-swizzled shared memory), fp32 accumulators in TMEM.
 //   warp 0   : TMA producer (one elected lane)          -- STAGES-deep smem ring, full/empty mbarriers
 //   warp 1   : TMEM allocator + MMA issuer (one lane)    -- tcgen05.mma 128 x BN x 16, commit -> mbarriers
 //   warps 2-9: epilogue (TMEM -> registers -> global)    -- double-buffered accumulator (2 x BN columns);
@@ -75,7 +75,7 @@ struct EpiCtx {
   int lane;
 };
 
-// Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_bf16.
+// Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_op16.
 struct EpiGeneric {
   GemmEpilogue p;
   __device__ __forceinline__ void finish(EpiCtx&) const {}
@@ -152,15 +152,15 @@ struct EpiGeneric {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
-      if (p.out_bf16) {
-        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(drow) * p.ld_out_bf16 + col0);
+      if (p.out_op16) {
+        uint4* o4 = reinterpret_cast<uint4*>(p.out_op16 + static_cast<size_t>(drow) * p.ld_out_op16 + col0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-          o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-          o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-          o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          o.x = pack_op16x2(v[8 * i], v[8 * i + 1]);
+          o.y = pack_op16x2(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_op16x2(v[8 * i + 4], v[8 * i + 5]);
+          o.w = pack_op16x2(v[8 * i + 6], v[8 * i + 7]);
           o4[i] = o;
         }
       }
@@ -170,7 +170,7 @@ struct EpiGeneric {
 
 // Staged epilogue (CTA-pair kernel): each warp converts a 32-row x 128-byte slab of its accumulator quarter,
 // writes it to 128B-swizzled shared memory (conflict free) and one lane hands it to the TMA:
-//   bf16 activations -> cp.async.bulk.tensor store (64 columns per slab)
+//   op16 activations -> cp.async.bulk.tensor store (64 columns per slab)
 //   fp32 residual    -> cp.reduce.async.bulk.tensor .add (32 columns per slab): x += acc + bias, added in the L2
 // Global writes are full 128-byte rows instead of 32 scattered 16-byte pieces per instruction, and rows past M
 // are clipped by the tensor map.
@@ -180,7 +180,7 @@ struct alignas(64) EpiStaged {
   int act;
   float col_scale;
   int scale_c0, scale_c1;
-  int f32_add;     // 0: bf16 store, 1: fp32 reduce-add, 2: fp32 store
+  int f32_add;     // 0: op16 store, 1: fp32 reduce-add, 2: fp32 store
   __device__ __forceinline__ void finish(EpiCtx& ctx) const {
     if (ctx.lane == 0) bulk_wait_read<0>();
   }
@@ -256,7 +256,7 @@ struct alignas(64) EpiStaged {
             }
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[16 * h + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          for (int i = 0; i < 16; ++i) pk[16 * h + i] = pack_op16x2(v[2 * i], v[2 * i + 1]);
         }
         slab_out(ctx, pk, col0);
       }
@@ -284,7 +284,7 @@ struct EpiDrain {
 
 template <int BN, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  Epi epi) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -346,7 +346,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_op16(GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -364,7 +364,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 B per 16-element K step inside the 128 B swizzle atom (encoded >> 4 => +2)
-            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_op16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
@@ -422,7 +422,7 @@ struct Gemm2Cfg {
 
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                   const __grid_constant__ Epi epi) {
   using Cfg = Gemm2Cfg;
   constexpr int BN = Cfg::BN;
@@ -487,7 +487,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_op16(2 * GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -504,7 +504,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_op16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_cg2_mc(empty_bar(stage), 3);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -542,7 +542,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <class Epi>
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
-  auto kern = gemm2_bf16_kernel<Epi>;
+  auto kern = gemm2_op16_kernel<Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -558,7 +558,7 @@ template <int BN, class Epi>
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi,
                  cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, Epi>;
+  auto kern = gemm_op16_kernel<BN, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));

@@ -48,14 +48,18 @@ void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16
 constexpr float ATTN_LOG2E = 1.4426950408889634f;
 inline float attn_k_scale(int head_dim) { return static_cast<float>(1.0 / std::sqrt(static_cast<double>(head_dim))) * ATTN_LOG2E; }
 inline int attn_table_cols(int head_dim) { return head_dim == 64 ? 64 : 128; }    // rel-pos table row pitch (zero padded)
-void launch_encoder_attention(const bf16* qkv, const bf16* rel_tab, bf16* out, int n_seq, int T, int heads, int head_dim,
+void launch_encoder_attention(const op16* qkv, const op16* rel_tab, op16* out, int n_seq, int T, int heads, int head_dim,
                               bool is_global, bool unwindow, cudaStream_t stream);
+
+constexpr int NECK_C2 = 512;        // neck 3x3 conv input row: 256 channels as [hi | lo]
+constexpr int NECK_K2 = 9 * NECK_C2;  // its im2col contraction length
+constexpr int PATCH_K = 2 * 768;   // patch-embed contraction length: 3*16*16 pixel hi terms + as many lo terms
 
 struct EncoderLayerW {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  const bf16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
+  const op16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
   const float *b_qkv, *b_proj, *b_fc1, *b_fc2;
-  const bf16* rel_tab;   // [256,HDP] * log2(e): rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
+  const op16* rel_tab;   // [256,HDP] * log2(e): rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
   int is_global;
 };
 
@@ -63,27 +67,27 @@ struct EncoderW {
   int D, L, heads, mlp;
   int head_dim = 64;
   int residual_mode = 2;   // GemmEpilogue::accumulate for the two residual adds of a layer
-  const bf16* w_patch;    // [D, 768]
+  const op16* w_patch;    // [D, PATCH_K] = [W | W] (hi / lo split of the pixels, encoder.cu)
   const float* b_patch;   // [D]
   const float* pos_embed; // [4096, D]
   const EncoderLayerW* layers;   // host array, L entries
-  const bf16* w_neck1;    // [256, D]
+  const op16* w_neck1;    // [256, 2D] = [W | W]
   const float *neck_ln1_g, *neck_ln1_b;
-  const bf16* w_neck2;    // [256, 9*256]  (tap-major: [(ky*3+kx)*256 + cin])
+  const op16* w_neck2;    // [256, NECK_K2]  (tap-major: [(ky*3+kx)*512 + cin] and the same weight again at +256)
   const float *neck_ln2_g, *neck_ln2_b;
 };
 
 struct EncoderWork {      // activation workspace for `cap` images
   int cap;
-  bf16* a_patch;          // [cap*4096, 768]
+  op16* a_patch;          // [cap*4096, PATCH_K]: pixel hi terms | lo terms
   float* x;               // [cap*4096, D]   fp32 residual stream
-  bf16* h;                // [cap*4900, D]
-  bf16* qkv;              // [cap*4900, 3D]
-  bf16* attn;             // [cap*4096, D]  attention output in token order
-  bf16* u;                // [cap*4096, mlp]
+  op16* h;                // [cap*4900, D]
+  op16* qkv;              // [cap*4900, 3D]
+  op16* attn;             // [cap*4096, D]  attention output in token order
+  op16* u;                // [cap*4096, mlp]
   float* n1;              // [cap*4096, 256]
-  bf16* n1b;              // [cap*4096, 256]
-  bf16* a_neck;           // [cap*4096, 2304]
+  op16* n1b;              // [cap*4096, NECK_C2]  hi | lo
+  op16* a_neck;           // [cap*4096, NECK_K2]
   float* n2;              // [cap*4096, 256]
   const int* win_row_map; // [cap*4900] window row -> token row (or -1)
 };
@@ -106,13 +110,13 @@ void launch_resize_h(const uint8_t* src, int n, int H, int row_stride, size_t im
 void launch_resize_v(const uint8_t* src, int n, int row_stride, size_t img_stride, int W, const ResizeTablesDev& t, uint8_t* dst,
                      cudaStream_t s);
 // resized uint8 RGB [n,src_h,src_w,3] (row pitch row_stride, image pitch img_stride bytes) -> normalised, zero-padded
-// pixel_values fp32 [n,3,1024,1024] (optional) and/or the patch-embed A matrix bf16 [n*4096, 768]
+// pixel_values fp32 [n,3,1024,1024] (optional) and/or the patch-embed A matrix op16 [n*4096, 768]
 void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_stride, size_t img_stride, const float* mean255,
-                       const float* std255, float* pixel_values, bf16* a_patch, cudaStream_t s);
-void launch_im2col_patch_f32(const float* pixel_values, int n, bf16* a_patch, cudaStream_t s);
+                       const float* std255, float* pixel_values, op16* a_patch, cudaStream_t s);
+void launch_im2col_patch_f32(const float* pixel_values, int n, op16* a_patch, cudaStream_t s);
 void launch_build_win_row_map(int* map, int n_images, cudaStream_t s);
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
-                      bf16* out_bf, float* out_f, bool windowed, cudaStream_t s);
+                      op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split = false);
 // runs the whole encoder on work.a_patch (n images); result: image embeddings fp32 token-major [n*4096, 256].
 // hidden_dump (optional, device) fp32 [(L+1), n*4096, D]
 void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* emb_out, float* hidden_dump,
@@ -126,10 +130,10 @@ struct DecLayerW {
   DecAttnW self_attn, t2i, i2t;
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b, *ln4_g, *ln4_b;
   const float *w_fc1, *b_fc1, *w_fc2, *b_fc2;       // 256 -> 2048 -> 256 (ReLU)
-  const bf16* w_kq_img;    // [256,256]: rows 0..127 t2i.k_proj, rows 128..255 i2t.q_proj  (input keys + pos)
+  const op16* w_kq_img;    // [256,256]: rows 0..127 t2i.k_proj, rows 128..255 i2t.q_proj  (input keys + pos)
   const float* b_kq_img;   // [256]
-  const bf16* w_v_img;     // [128,256] t2i.v_proj (input keys)
-  const bf16* w_i2t_out;   // [256,128] i2t.out_proj
+  const op16* w_v_img;     // [128,256] t2i.v_proj (input keys)
+  const op16* w_i2t_out;   // [256,128] i2t.out_proj
 };
 struct DecoderW {
   const float* gauss;          // [2,128] shared_image_embedding.positional_embedding
@@ -139,23 +143,23 @@ struct DecoderW {
   const float* mask_tokens;    // [4,256]
   DecLayerW layers[2];
   DecAttnW final_attn;
-  const bf16 *w_k_final, *w_v_final;     // [128,256]
+  const op16 *w_k_final, *w_v_final;     // [128,256]
   const float *lnf_g, *lnf_b;
-  const bf16* w_ct1;           // [256 = (dy,dx,o64), 256]
+  const op16* w_ct1;           // [256 = (dy,dx,o64), 512]  [W | W]
   const float *b_ct1, *lnu_g, *lnu_b;    // [64]
-  const bf16* w_ct2;           // [128 = (dy,dx,o32), 64]
+  const op16* w_ct2;           // [128 = (dy,dx,o32), 128]  [W | W]
   const float* b_ct2;          // [32]
   const float *hy_w0, *hy_b0, *hy_w1, *hy_b1, *hy_w2, *hy_b2;   // hypernetwork MLP of mask token 0
   const float* image_pe;       // [4096,256] token-major, built at weight load
 };
 struct DecoderWork {           // workspace for cap_img images and cap_box boxes
   int cap_img, cap_box;
-  float* keys0;  bf16* keys0_bf;  bf16* keyspos0_bf;    // [cap_img*4096, 256]
+  float* keys0;  op16* keys0_bf;  op16* keyspos0_bf;    // [cap_img*4096, 256]
   float* kq0;    float* v0;                              // [cap_img*4096, 256] / [cap_img*4096,128]
-  float* keys;   bf16* keys_bf;   bf16* keyspos_bf;      // [cap_box*4096, 256] per-box keys
+  float* keys;   op16* keys_bf;   op16* keyspos_bf;      // [cap_box*4096, 256] per-box keys
   float* kq;     float* v;                               // [cap_box*4096, 256] / [.,128]
-  bf16* attn_i2t;                                        // [cap_box*4096, 128]
-  bf16* up1;                                             // [cap_box*16384, 64]
+  op16* attn_i2t;                                        // [cap_box*4096, 128]
+  op16* up1;                                             // [cap_box*16384, 128]  hi | lo
   float *tok0, *queries, *q_t2i, *attn_t2i, *k_tok, *v_tok, *hyper;   // token-side [cap_box, 7, *]
   float* tok_ws;                                         // token-side scratch: cap_box * (7*(6*256 + 2048) + 2*256 + 8*4*126) floats
   double* boxes1024;  int* box_img;                      // [cap_box,4] / [cap_box]

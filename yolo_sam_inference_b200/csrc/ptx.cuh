@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -113,9 +114,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4     bits [46,48) version = 1 (Blackwell)
 //   bits [61,64) layout type: 2 = SWIZZLE_128B
-// K-major operand tile (rows x 64 bf16, TMA box {64, rows}): 8-row groups are 1024 B apart (SBO),
+// K-major operand tile (rows x 64 op16, TMA box {64, rows}): 8-row groups are 1024 B apart (SBO),
 //   LBO is unused for swizzled K-major (encoded 1). Advancing K by 16 elements = +32 B on the start.
-// MN-major operand tile (k-rows x 64 bf16, TMA box {64, krows}): 8 k-rows per 1024 B group (SBO),
+// MN-major operand tile (k-rows x 64 op16, TMA box {64, krows}): 8 k-rows per 1024 B group (SBO),
 //   LBO = distance between 64-element MN blocks (unused when MN extent == 64). Advancing K by 16 rows
 //   = +2048 B on the start.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -128,17 +129,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
-//   bits [4,6) D format (1 = f32)   [7,10) A format (1 = bf16)   [10,13) B format (1 = bf16)
+// Instruction descriptor for kind::f16 with op16 A/B and fp32 accumulation.
+//   bits [4,6) D format (1 = f32)   [7,10) A format (1 = op16)   [10,13) B format (1 = op16)
 //   bit 15 A major (0 = K, 1 = MN)  bit 16 B major               [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t umma_idesc_op16(int M, int N, int a_mn_major, int b_mn_major) {
+#ifdef YSI_OP_FP16
+  constexpr uint32_t fmt = 0u;
+#else
+  constexpr uint32_t fmt = 1u;
+#endif
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_op16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -148,9 +154,9 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, ui
       : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = TMEM lanes, K-major, two bf16 per 32-bit column)
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = TMEM lanes, K-major, two op16 per 32-bit column)
 // is read from tensor memory, so only B costs shared-memory bandwidth.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_op16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -200,7 +206,7 @@ __device__ __forceinline__ void tmem_relinquish_cg2() {
 __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_ss_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_op16_ss_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                  uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -320,8 +326,13 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// two fp32 -> one packed pair of 16-bit operands (round to nearest even), lo in the low half
+__device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi) {
+#ifdef YSI_OP_FP16
+  __half2 v = __floats2half2_rn(lo, hi);
+#else
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+#endif
   return *reinterpret_cast<uint32_t*>(&v);
 }
 

@@ -109,12 +109,16 @@ class SamStage:
 
     def __init__(self, sam_model_type: str = "facebook/sam-vit-huge", device: str = "cuda",
                  state_dict: Optional[Dict[str, Any]] = None, max_batch: int = 8, max_boxes: int = 64,
-                 max_image_hw: Tuple[int, int] = (1024, 1024), on_empty: str = "raise"):
+                 max_image_hw: Tuple[int, int] = (1024, 1024), on_empty: str = "raise",
+                 precision: Optional[str] = None):
+        """``precision``: 16-bit encoding of the tensor-core operands, "fp16" or "bf16" (default: $YSI_PRECISION, else
+        fp16); accumulation, residual stream and statistics are fp32 either way (csrc/common.h)."""
         self.variant: SamVariant = variant_of(sam_model_type)
+        self.precision = precision or nat.default_precision()
         self.device_index = parse_device(device)
         self.on_empty = on_empty
         self.max_batch, self.max_boxes = int(max_batch), int(max_boxes)
-        self._lib = nat.load()
+        self._lib = nat.load(precision=self.precision)
         cfg = nat.YsiConfig()
         v = self.variant
         cfg.hidden_size, cfg.num_layers, cfg.num_heads, cfg.mlp_dim = v.hidden_size, v.num_layers, v.num_heads, v.mlp_dim
