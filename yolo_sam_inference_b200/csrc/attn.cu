@@ -6,9 +6,16 @@
 // the K columns arrive pre-multiplied by hd^-0.5 * log2(e) and the rel-pos tables by log2(e); p = 2^(x - m).
 //
 // One CTA = 128 queries of one (sequence, head); keys/values stream through in tiles of 64.
-//   warp 4 (one lane) : TMA loads (Q, rel-pos tables, K and V rings) + every tcgen05.mma
-//   warps 0-3         : one query row per thread; S from TMEM, bias add (FADD2), max (FMNMX3), exp2 (MUFU),
-//                       P -> op16 -> 128B-swizzled smem (double buffered)
+//   warps 8-10 (one lane each): TMA loads (Q, rel-pos tables, K and V rings) | table + S MMAs | P.V MMAs
+//   warps 0-7         : TWO threads per query row: warp w owns rows 32 (w & 3) .. +31 (its TMEM lane quarter) and
+//                       the key columns 32 (w >> 2) .. +31 of every tile: S from TMEM, bias add (FADD2), max
+//                       (FMNMX3), exp2 (MUFU), P -> op16 -> TENSOR MEMORY (tcgen05.st), which P.V reads as its A operand.
+//                       16 softmax warps per SM (2 CTAs) keep the MUFU pipe fed while other warps sit in TMEM
+//                       loads / barriers; a thread holds 32 bias + 32 score registers instead of 64 + 64.
+//   The two threads of a row must scale P by the same running maximum. They exchange their half-row maxima
+//   through shared memory + an mbarrier, but OFF the critical path: every thread publishes its maximum, computes
+//   its exponentials speculatively against the current (lazily updated) maximum, and only then reads its
+//   partner's value; the tile is redone in the rare case (first tiles of a row) that the maximum had to move.
 // Tensor-core work per tile: S = Q K^T (128x64x64, both K-major) and O += P V (128x64x64, V is the MN-major B
 // operand straight out of the qkv activation). O stays in TMEM for the whole CTA: it is rescaled in place
 // (tcgen05.ld / tcgen05.st) only when the running row maximum grows by more than 2^8 ("lazy rescale"), so the
@@ -33,7 +40,13 @@ namespace ysi {
 
 namespace attn {
 constexpr int BQ = 128, BKV = 64;
-constexpr int THREADS = 160;
+constexpr int SM_WARPS = 8;                  // softmax warps (two warpgroups)
+constexpr int THREADS = 32 * (SM_WARPS + 4); // + one producer warpgroup: TMA warp, S-MMA warp, PV-MMA warp, and a register donor
+// Register budget per SM sub-partition (16384 registers = 512 per lane): two CTAs put 4 softmax warps and 2 producer
+// warps on each. The kernel launches with <= 80 registers per thread (6 x 80 = 480); the producer warpgroup then
+// shrinks to REG_PRODUCER and the softmax warpgroups grow to REG_SOFTMAX with setmaxnreg. The pool is per CTA:
+// 8 x 104 + 4 x 32 = 960 = 12 warps x 80 (asking for more than the CTA released deadlocks the allocation).
+constexpr int REG_SOFTMAX = 104, REG_PRODUCER = 32;
 constexpr int CH_Q = BQ * 128;              // one 64-column chunk of the Q tile: 128 rows x 128 B = 16 KB
 constexpr int KV_BYTES = BKV * 128;         // one 64-column chunk of a 64-key tile: 8 KB
 constexpr int P_BYTES = BQ * BKV * 2;       // 16 KB
@@ -46,38 +59,51 @@ template <bool GLOBAL, int HD>
 struct Cfg {
   static constexpr int NCH = HD > 64 ? 2 : 1;                       // 64-column chunks per operand
   static constexpr int NKS = HD / 16;                               // k-steps of Q K^T and of the table MMAs
-  static constexpr int NST = GLOBAL ? 3 : 4;                        // K / V ring depth (window: whole window)
+  // K / V ring depths (window: whole window resident). A K tile is requested NSTK - 2 softmax tiles before the S MMA
+  // that consumes it (S runs two tiles ahead of the softmax), a V tile NSTV - 1 tiles ahead: at ~1 us per tile one
+  // tile of lead time does not cover the L2 round trip of the TMA, and a late K tile stalls the single MMA-issuing
+  // thread -- and with it every P.V queued behind it.
+  static constexpr int NSTK = GLOBAL ? 5 : 4;
+  static constexpr int NSTV = 4;
   static constexpr int K_CHUNK = GLOBAL ? 80 * 128 : 208 * 128;     // global: 64 keys + 16 rows for the rel_pos_h "keys"
   static constexpr int K_STAGE = GLOBAL ? NCH * K_CHUNK : KV_BYTES; // global: a stage holds its chunks back to back;
                                                                     // window: chunk c lives at OFF_K + c*K_CHUNK, tiles 8 KB apart
-  static constexpr int K_TOTAL = GLOBAL ? NST * K_STAGE : NCH * K_CHUNK;
+  static constexpr int K_TOTAL = GLOBAL ? NSTK * K_STAGE : NCH * K_CHUNK;
   static constexpr int V_CHUNK = GLOBAL ? KV_BYTES : 208 * 128;
   static constexpr int V_STAGE = GLOBAL ? NCH * V_CHUNK : KV_BYTES;
-  static constexpr int V_TOTAL = GLOBAL ? NST * V_STAGE : NCH * V_CHUNK;
+  static constexpr int V_TOTAL = GLOBAL ? NSTV * V_STAGE : NCH * V_CHUNK;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NCH * CH_Q;
   static constexpr int OFF_V = OFF_K + K_TOTAL;
-  static constexpr int OFF_P = OFF_V + V_TOTAL;      // 2 x 16 KB; fp32 bias scratch [k][128] during setup
-  // rel-pos tables as TMA'd for the table MMA: global -> rel_pos_w in the V area (16 KB per chunk, the V loads wait
-  // for the MMA); windowed -> second P buffer (4 KB per table chunk), so the whole window's K / V can be requested
-  // up front with Q
+  // 32 KB of setup scratch: fp32 bias values [k][128] (P itself lives in TMEM). Global: aliases the V ring, whose first
+  // loads wait until every softmax thread has its bias in registers (bar_rel). Windowed: its own region.
+  static constexpr int SCRATCH = 32768;
+  static constexpr int OFF_P = GLOBAL ? OFF_V : OFF_V + V_TOTAL;
+  // rel-pos tables as TMA'd for the table MMA: global -> rel_pos_w in the V area (16 KB per chunk; consumed by the table
+  // MMA before the scratch is written); windowed -> second half of the scratch (4 KB per table chunk), so the whole
+  // window's K / V can be requested up front with Q
   static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
   static constexpr int TAB_CHUNK = TAB_ROWS * 128;
   static constexpr int OFF_TABH = GLOBAL ? OFF_K : OFF_P + P_BYTES;     // (unused when GLOBAL)
   static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_P + P_BYTES + NCH * TAB_CHUNK;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = 256;
+  static constexpr int OFF_BAR = GLOBAL ? OFF_V + V_TOTAL : OFF_P + SCRATCH;       // 512 B of mbarriers
+  static constexpr int OFF_XM = OFF_BAR + 512;              // fp32 [2][128][2]: half-row maxima of tile parity 0 / 1
+  static constexpr int OFF_XL = OFF_XM + 2048;              // fp32 [128][2]: half-row sums at the end
+  static constexpr int SMEM_BYTES = OFF_XL + 1024 + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = HD > 64 ? 512 : 256;     // 2 S buffers + O + P (head_dim 80 runs one CTA per SM anyway)
   static constexpr int S_N = GLOBAL ? 80 : 64;              // columns of one S buffer
   static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
   static constexpr int COL_O = 2 * S_N;
+  static constexpr int COL_P = COL_O + HD;                  // P tile as the TMEM A operand of P.V: 64 op16 keys = 32 columns
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
   static constexpr int CTAS_PER_SM = HD > 64 ? 1 : 2;
   static_assert(HD == 64 || HD == 80, "head_dim 64 or 80");
   static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_CHUNK % 1024 == 0, "swizzle atoms need 1 KB alignment");
-  static_assert(GLOBAL || 2 * NCH * TAB_CHUNK <= P_BYTES, "window tables must fit the second P buffer");
-  static_assert(COL_O + HD <= TMEM_COLS, "TMEM budget");
+  static_assert(GLOBAL || 2 * NCH * TAB_CHUNK <= P_BYTES, "window tables must fit the second half of the scratch");
+  static_assert(!GLOBAL || V_TOTAL >= SCRATCH, "the bias scratch aliases the V ring");
+  static_assert(NSTK <= 8 && NSTV <= 8, "barrier arrays");
+  static_assert(COL_P + 32 <= TMEM_COLS, "TMEM budget");
 };
 }  // namespace attn
 
@@ -103,33 +129,40 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t bar_q = bar, bar_tab = bar + 8, bar_rel = bar + 16;
   const uint32_t bar_s_full = bar + 24;    // [2]
   const uint32_t bar_s_free = bar + 40;    // [2]
-  const uint32_t bar_p_full = bar + 56;    // [2]
-  const uint32_t bar_p_free = bar + 72;    // [2]
-  const uint32_t bar_kfull = bar + 88;     // [4]
-  const uint32_t bar_kempty = bar + 120;   // [4]
-  const uint32_t bar_vfull = bar + 152;    // [4]
-  const uint32_t bar_vempty = bar + 184;   // [4]
-  const uint32_t tmem_ptr_smem = bar + 216;
+  const uint32_t bar_p_full = bar + 56;    // P_j is in TMEM (phase j & 1)
+  const uint32_t bar_p_free = bar + 64;    // P.V_j has completed (phase j & 1): P may be overwritten, O is up to date
+  const uint32_t bar_kfull = bar + 72;     // [8]
+  const uint32_t bar_kempty = bar + 136;   // [8]
+  const uint32_t bar_vfull = bar + 200;    // [8]
+  const uint32_t bar_vempty = bar + 264;   // [8]
+  const uint32_t bar_pair = bar + 328;     // [4 row quarters][2 tile parities]: the two warps sharing 32 rows
+  const uint32_t bar_fin = bar + 392;      // [4 row quarters]
+  const uint32_t tmem_ptr_smem = bar + 424;
+  float* xm = reinterpret_cast<float*>(sgen + C::OFF_XM);
+  float* xl = reinterpret_cast<float*>(sgen + C::OFF_XL);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int row0 = seq * p.T;                 // first row of this sequence in the qkv matrix
   const int ntiles = GLOBAL ? p.T / BKV : 4;
   const int cq = head * HD, ck = p.D + head * HD, cv = 2 * p.D + head * HD;
+  constexpr int NSM = 32 * SM_WARPS;          // softmax threads
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, 128);
+    mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, NSM);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_free + 8 * i, 128);
-      mbar_init(bar_p_full + 8 * i, 128); mbar_init(bar_p_free + 8 * i, 1);
+      mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_free + 8 * i, NSM);
     }
-    for (int i = 0; i < 4; ++i) {
+    mbar_init(bar_p_full, NSM); mbar_init(bar_p_free, 1);
+    for (int i = 0; i < 8; ++i) {
       mbar_init(bar_kfull + 8 * i, 1); mbar_init(bar_kempty + 8 * i, 1);
       mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
+      mbar_init(bar_pair + 8 * i, 64);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 64);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == SM_WARPS) {
     tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
     tmem_relinquish();
   }
@@ -139,31 +172,31 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_tab = umma_idesc_op16(128, C::TAB_ROWS, 0, 0);
-      constexpr uint32_t idesc_s = umma_idesc_op16(128, C::S_N, 0, 0);
-      constexpr uint32_t idesc_s16 = umma_idesc_op16(128, 16, 0, 0);
-      constexpr uint32_t idesc_pv64 = umma_idesc_op16(128, 64, 0, 1);   // B (= V) is MN-major
-      constexpr uint32_t idesc_pv16 = umma_idesc_op16(128, 16, 0, 1);
-      constexpr int NCH = C::NCH, NKS = C::NKS;
-      // K-major operand, k-step k: chunk k/4 (64 columns each), +32 B per 16 columns inside the swizzle atom
-      auto kdesc_at = [&](uint32_t base, int chunk_bytes, int k) {
-        return umma_desc_sw128(base + static_cast<uint32_t>((k >> 2) * chunk_bytes), 16, 1024) + 2u * static_cast<uint32_t>(k & 3);
-      };
-      // ---- setup: Q tile + rel-pos table(s)
+  if (warp >= SM_WARPS) {
+    // ------------------------------------------------------------------ producer warpgroup
+    // Three single-lane roles, one per warp, so that no role's serial instruction stream (barrier polls, descriptor
+    // arithmetic, uniform-datapath issue sequences: ~80 SASS instructions per tile each) paces the softmax:
+    //   warp 8: TMA loads   warp 9: table + S = Q K^T MMAs   warp 10: O += P V MMAs   (warp 11 only donates registers)
+    if (C::CTAS_PER_SM == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_PRODUCER));
+    constexpr int NCH = C::NCH, NKS = C::NKS;
+    auto k_tile_addr = [&](int st, int c) {
+      return sbase + C::OFF_K + (GLOBAL ? st * C::K_STAGE + c * C::K_CHUNK : c * C::K_CHUNK + st * KV_BYTES);
+    };
+    auto v_tile_addr = [&](int st, int c) {
+      return sbase + C::OFF_V + (GLOBAL ? st * C::V_STAGE + c * C::V_CHUNK : c * C::V_CHUNK + st * KV_BYTES);
+    };
+    // K-major operand, k-step k: chunk k/4 (64 columns each), +32 B per 16 columns inside the swizzle atom
+    auto kdesc_at = [&](uint32_t base, int chunk_bytes, int k) {
+      return umma_desc_sw128(base + static_cast<uint32_t>((k >> 2) * chunk_bytes), 16, 1024) + 2u * static_cast<uint32_t>(k & 3);
+    };
+    if (warp == SM_WARPS && lane == 0) {
+      // ---- TMA: Q tile + rel-pos table(s), then the K / V rings
       mbar_arrive_expect_tx(bar_q, NCH * (CH_Q + (GLOBAL ? 1 : 2) * C::TAB_CHUNK));
       for (int c = 0; c < NCH; ++c) {
         tma_load_2d(sbase + C::OFF_Q + c * CH_Q, &tmQ, bar_q, cq + 64 * c, row0 + qt * BQ);
         if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 0);   // rel_pos_h rows (zero padded)
         tma_load_2d(sbase + C::OFF_TABW + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 128);              // rel_pos_w rows
       }
-      auto k_tile_addr = [&](int st, int c) {
-        return sbase + C::OFF_K + (GLOBAL ? st * C::K_STAGE + c * C::K_CHUNK : c * C::K_CHUNK + st * KV_BYTES);
-      };
-      auto v_tile_addr = [&](int st, int c) {
-        return sbase + C::OFF_V + (GLOBAL ? st * C::V_STAGE + c * C::V_CHUNK : c * C::V_CHUNK + st * KV_BYTES);
-      };
       auto load_k = [&](int tile, int st) {
         const bool tail = !GLOBAL && tile == 3;
         mbar_arrive_expect_tx(bar_kfull + 8 * st, NCH * (GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES)));
@@ -179,101 +212,105 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int c = 0; c < NCH; ++c)
           tma_load_2d(v_tile_addr(st, c), tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv + 64 * c, row0 + tile * BKV);
       };
-      if (!GLOBAL) {             // whole window: K / V do not alias the tables, request them right away
+      if (!GLOBAL) {             // whole window resident: K / V do not alias the tables, request everything right away
         for (int j = 0; j < 4; ++j) load_k(j, j);
         for (int j = 0; j < 4; ++j) load_v(j, j);
-      } else {                   // the K ring does not alias the rel_pos_w table
-        for (int j = 0; j < C::NST && j < ntiles; ++j) load_k(j, j);
+      } else {
+        for (int j = 0; j < C::NSTK && j < ntiles; ++j) load_k(j, j);      // the K ring does not alias the rel_pos_w table
+        mbar_wait(bar_rel, 0);   // every softmax thread has its bias values: the scratch (= V ring) is free
+        for (int j = 0; j < C::NSTV && j < ntiles; ++j) load_v(j, j);
+        // refill a K stage once its S MMA has completed and a V stage once its P.V has (S runs two tiles ahead of
+        // P.V, so waiting in this order never delays a K tile that is needed soon)
+        int sk = 0, sv = 0;
+        uint32_t pk = 0, pv = 0;
+        for (int j = 0; j < ntiles; ++j) {
+          if (j + C::NSTK < ntiles) { mbar_wait(bar_kempty + 8 * sk, pk); load_k(j + C::NSTK, sk); }
+          if (j + C::NSTV < ntiles) { mbar_wait(bar_vempty + 8 * sv, pv); load_v(j + C::NSTV, sv); }
+          if (++sk == C::NSTK) { sk = 0; pk ^= 1u; }
+          if (++sv == C::NSTV) { sv = 0; pv ^= 1u; }
+        }
       }
+    } else if (warp == SM_WARPS + 1 && lane == 0) {
+      // ---- rel-pos table MMA(s), then S_t = Q K_t^T into S buffer t & 1 as soon as the softmax threads hold S_{t-2}
+      // in registers (two tiles ahead of the softmax, so S never queues behind a P.V in the in-order tensor pipe)
+      constexpr uint32_t idesc_tab = umma_idesc_op16(128, C::TAB_ROWS, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_op16(128, C::S_N, 0, 0);
+      constexpr uint32_t idesc_s16 = umma_idesc_op16(128, 16, 0, 0);
+      uint64_t qdesc[NKS];
+#pragma unroll
+      for (int k = 0; k < NKS; ++k) qdesc[k] = kdesc_at(sbase + C::OFF_Q, CH_Q, k);
       mbar_wait(bar_q, 0);
       tc_fence_after();
-      {
-        if (!GLOBAL) {
-#pragma unroll
-          for (int k = 0; k < NKS; ++k)
-            umma_op16_ss(tmem_base + C::COL_TH, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
-        }
+      if (!GLOBAL) {
 #pragma unroll
         for (int k = 0; k < NKS; ++k)
-          umma_op16_ss(tmem_base + C::COL_TW, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
-        umma_commit(bar_tab);
+          umma_op16_ss(tmem_base + C::COL_TH, qdesc[k], kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
       }
-      if (GLOBAL) {
-        mbar_wait(bar_tab, 0);     // rel_pos_w table consumed: the V area is free
-        for (int j = 0; j < C::NST && j < ntiles; ++j) load_v(j, j);
-      }
-      // S_t -> S buffer t & 1 (free once the softmax threads hold S_{t-2} in registers); issued two tiles ahead, as
-      // soon as S_{t-2} has been read, so it never queues behind a PV in the in-order tensor pipe.
-      auto issue_s = [&](int t) {
-        const int st = t % C::NST, buf = t & 1;
-        mbar_wait(bar_kfull + 8 * st, (t / C::NST) & 1);
+#pragma unroll
+      for (int k = 0; k < NKS; ++k)
+        umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
+      umma_commit(bar_tab);
+      mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(bar_kfull + 8 * st, ph);
         if (t >= 2) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
+        const uint32_t kbase = k_tile_addr(st, 0);
 #pragma unroll
-        for (int k = 0; k < NKS; ++k)
-          umma_op16_ss(d, kdesc_at(sbase + C::OFF_Q, CH_Q, k), kdesc_at(k_tile_addr(st, 0), C::K_CHUNK, k), idesc, k);
-        umma_commit(bar_kempty + 8 * st);    // (the barrier somebody always waits on is committed last)
+        for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, C::K_CHUNK, k), idesc, k);
+        umma_commit(bar_kempty + 8 * st);
         umma_commit(bar_s_full + 8 * buf);
-      };
-      mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S / O columns are free
-      tc_fence_after();
-      issue_s(0);
-      if (ntiles > 1) issue_s(1);
+        if (++st == C::NSTK) { st = 0; ph ^= 1u; }
+      }
+    } else if (warp == SM_WARPS + 2 && lane == 0) {
+      // ---- O (+)= P_j V_j : A = P straight out of TENSOR MEMORY (row = lane, two op16 keys per 32-bit column, 8 columns
+      // per 16-key k-step) -- no shared-memory round trip for P; B = V_j (MN-major: key rows x 64 hd), 16 keys = 2048 B
+      constexpr uint32_t idesc_pv64 = umma_idesc_op16(128, 64, 0, 1);   // B (= V) is MN-major
+      constexpr uint32_t idesc_pv16 = umma_idesc_op16(128, 16, 0, 1);
+      const uint32_t ptm = tmem_base + C::COL_P, otm = tmem_base + C::COL_O;
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 2 < ntiles) issue_s(j + 2);
-        const int st = j % C::NST, pb = j & 1;
-        // refill the K stage of tile j right away (S_j was issued a whole tile ago): tile j+NST is needed by
-        // issue_s two iterations from now, so its TMA latency hides behind two softmax tiles
-        if (GLOBAL && j + C::NST < ntiles) {
-          mbar_wait(bar_kempty + 8 * st, (j / C::NST) & 1);
-          load_k(j + C::NST, st);
-        }
-        mbar_wait(bar_vfull + 8 * st, (j / C::NST) & 1);
-        mbar_wait(bar_p_full + 8 * pb, (j >> 1) & 1);
+        mbar_wait(bar_vfull + 8 * st, ph);
+        mbar_wait(bar_p_full, j & 1);
         tc_fence_after();
-        {
-          // O (+)= P_j V_j : A = P (K-major, K = keys), B = V_j (MN-major: key rows x 64 hd); 16 keys = 2048 B
-          const uint64_t pdesc = umma_desc_sw128(sbase + C::OFF_P + pb * P_BYTES, 16, 1024);
-          const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
-          const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
-          for (int k = 0; k < ksteps; ++k)
-            umma_op16_ss(tmem_base + C::COL_O, pdesc + 2u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
-          if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
-            const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
-            for (int k = 0; k < ksteps; ++k)
-              umma_op16_ss(tmem_base + C::COL_O + 64, pdesc + 2u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(bar_vempty + 8 * st);
-          umma_commit(bar_p_free + 8 * pb);
+        const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
+        const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
+        for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm, ptm + 8u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
+        if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
+          const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
+          for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
         }
-        if (GLOBAL) {
-          if (j >= 1 && j - 1 + C::NST < ntiles) { // V stage of tile j-1: PV_{j-1} was issued one iteration ago
-            const int sv = (j - 1) % C::NST;
-            mbar_wait(bar_vempty + 8 * sv, ((j - 1) / C::NST) & 1);
-            load_v(j - 1 + C::NST, sv);
-          }
-        }
+        umma_commit(bar_vempty + 8 * st);
+        umma_commit(bar_p_free);
+        if (++st == C::NSTV) { st = 0; ph ^= 1u; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps: thread = query row
-    const int t = threadIdx.x;                       // 0..127, TMEM lane
-    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // ------------------------------------------------------------------ softmax warps: two threads per query row
+    if (C::CTAS_PER_SM == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_SOFTMAX));
+    const int rq = warp & 3;                         // row quarter = TMEM lane quarter of this warp
+    const int half = warp >> 2;                      // which 32 key columns of every 64-key tile
+    const int t = rq * 32 + lane;                    // query row inside the tile = TMEM lane
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
     const int lq = qt * BQ + t;                      // query index inside the sequence
     const bool q_valid = lq < p.T;
-    const bool warp_active = GLOBAL || (qt * BQ + warp * 32) < p.T;   // warps with no valid query only keep the barriers moving
+    const bool warp_active = GLOBAL || (qt * BQ + rq * 32) < p.T;   // warps with no valid query only keep the barriers moving
     int qh, qw;
     if (GLOBAL) { qh = lq >> 6; qw = lq & 63; } else { const int l = lq < 196 ? lq : 195; qh = l / 14; qw = l - qh * 14; }
     constexpr int S = GLOBAL ? 64 : 14;
-    constexpr int NB = GLOBAL ? 64 : 28;             // bias registers: rel_w[64] | rel_h[14] + rel_w[14]
+    constexpr int NB = GLOBAL ? 32 : 28;             // bias registers: rel_w of this thread's 32 keys | rel_h[14] + rel_w[14]
     float bias[NB];
 
     mbar_wait(bar_tab, 0);
     tc_fence_after();
     // Q.table^T sits in TMEM as [query][table row]; thread t needs column (q_pos - k_pos + S-1) for every key
-    // position: scatter through smem scratch [k][t] (the column is thread dependent), then keep it in registers.
+    // position it owns: scatter through smem scratch [k][t] (the column is thread dependent), then keep it in registers.
     if (GLOBAL) {
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -283,53 +320,59 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kw = qw + (S - 1) - (c0 + i);
-          if (kw >= 0 && kw < S) rel_s[kw * 128 + t] = __uint_as_float(r[i]);
+          if ((kw >> 5) == half) rel_s[kw * 128 + t] = __uint_as_float(r[i]);     // 0 <= kw < 64 and in this thread's half
         }
       }
 #pragma unroll
-      for (int i = 0; i < 64; ++i) bias[i] = rel_s[i * 128 + t];
+      for (int i = 0; i < 32; ++i) bias[i] = rel_s[(32 * half + i) * 128 + t];
     } else {
+      // both threads of a row keep all 28 values; each writes / reads its own scratch column block
+      float* my = rel_s + half * (28 * 128);
       uint32_t r[32];
       tmem_ld_x32p(tlane + C::COL_TH, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int kh = qh + (S - 1) - i;
-        if (kh >= 0 && kh < S) rel_s[kh * 128 + t] = __uint_as_float(r[i]);
+        if (kh >= 0 && kh < S) my[kh * 128 + t] = __uint_as_float(r[i]);
       }
       tmem_ld_x32p(tlane + C::COL_TW, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int kw = qw + (S - 1) - i;
-        if (kw >= 0 && kw < S) rel_s[(14 + kw) * 128 + t] = __uint_as_float(r[i]);
+        if (kw >= 0 && kw < S) my[(14 + kw) * 128 + t] = __uint_as_float(r[i]);
       }
 #pragma unroll
-      for (int i = 0; i < 28; ++i) bias[i] = rel_s[i * 128 + t];
+      for (int i = 0; i < 28; ++i) bias[i] = my[i * 128 + t];
     }
     tc_fence_before();
     mbar_arrive(bar_rel);
 
     float m_used = -INFINITY;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
-    const uint32_t p_row0 = sbase + C::OFF_P + static_cast<uint32_t>(t) * 128u;
-    const uint32_t swz = static_cast<uint32_t>(t & 7);
+    constexpr int OH = HD / 2;                       // O columns owned by this thread
+    const uint32_t ocol = tlane + C::COL_O + static_cast<uint32_t>(half * OH);
 
-    // one KV tile: NW columns of S, the first NV of them valid keys
-    auto do_tile = [&](auto nw_c, auto nv_c, int j, const float* b /* NW bias values (log2 units) */) {
+    // one KV tile: this thread owns NW columns of S starting at column c0 (NW = 0: nothing, only the barriers),
+    // the first NV of them valid keys; bfn(i) = bias of column i (log2 units; i is a compile-time constant after unrolling)
+    auto do_tile = [&](auto nw_c, auto nv_c, int j, auto bfn, int c0) {
       constexpr int NW = decltype(nw_c)::value, NV = decltype(nv_c)::value;
+      constexpr int NR = NW > 0 ? NW : 2;
       const int pb = j & 1;                       // S buffer and P buffer of this tile
-      mbar_wait(bar_s_full + 8 * pb, (j >> 1) & 1);
+      const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
+      mbar_wait(bar_s_full + 8 * pb, par);
       tc_fence_after();
-      uint32_t r[NW];
+      uint32_t r[NR];
       float bh = 0.f;
-      if (warp_active) {
+      const bool act = warp_active && NW > 0;
+      if (act) {
         const uint32_t scol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N);
-        if constexpr (NW == 64) { tmem_ld_x32p(scol, r); tmem_ld_x32p(scol + 32, r + 32); }
-        else tmem_ld_x16p(scol, r);
+        if constexpr (NW == 32) tmem_ld_x32p(scol + c0, r);
+        else if constexpr (NW == 16) tmem_ld_x16p(scol + c0, r);
         if (GLOBAL) {
           uint32_t rb;
-          tmem_ld_x1(scol + 64u + static_cast<uint32_t>(warp >> 1), rb);   // q . rel_pos_h[qh - j + 63]: warp-uniform column
+          tmem_ld_x1(scol + 64u + static_cast<uint32_t>(rq >> 1), rb);   // q . rel_pos_h[qh - j + 63]: warp-uniform column
           tmem_ld_wait();
           bh = __uint_as_float(rb);
         } else {
@@ -338,94 +381,110 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       tc_fence_before();
       mbar_arrive(bar_s_free + 8 * pb);
-      // P buffer pb was consumed by PV_{j-2}. Every thread waits (also the idle warps of a ragged window tile):
-      // S runs two tiles ahead, so without this an idle warp could arrive on bar_p_full for tile j while the
-      // barrier's phase of tile j-2 is still open.
-      if (j >= 2) mbar_wait(bar_p_free + 8 * pb, ((j - 2) >> 1) & 1);
-      if (warp_active) {
-        float2 y[NW / 2];
+      float2 y[NR / 2];
+      float m_half = -INFINITY;
+      if (act) {
 #pragma unroll
         for (int i = 0; i < NW / 2; ++i)
-          y[i] = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(b[2 * i], b[2 * i + 1]));
+          y[i] = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bfn(2 * i), bfn(2 * i + 1)));
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < NV / 2; ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
-        const float m_cand = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
-        if (__any_sync(0xFFFFFFFFu, m_cand > m_used + LAZY_LOG2)) {
-          const float m_new = fmaxf(m_used, m_cand);
-          if (j > 0) {
-            // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed, PV_j has not been issued
-            const float f = ex2_approx(m_used - m_new);
-            mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int qr = 0; qr < HD / 16; ++qr) {
-              uint32_t o[16];
-              tmem_ld_x16p(tlane + C::COL_O + 16 * qr, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-              tmem_st_x16p(tlane + C::COL_O + 16 * qr, o);
-            }
-            tmem_st_wait();
-            l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
-          }
-          m_used = m_new;
-        }
-        const float c = bh - m_used;
+        m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
+      }
+      // publish this half-row maximum; the partner's is read after the (speculative) exponentials
+      xm[(pb * 128 + t) * 2 + half] = m_half;
+      mbar_arrive(bar_pair + 8 * (rq * 2 + pb));
+      uint32_t pk[NR / 2];
+      float2 ta, tb;
+      auto exps = [&](float c) {
         const float2 c2 = make_float2(c, c);
-        const uint32_t p_row = p_row0 + pb * P_BYTES;
+        ta = make_float2(0.f, 0.f); tb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int ch = 0; ch < NW / 8; ++ch) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int i = ch * 4 + h;                 // pair index
-            float2 e = add2(y[i], c2);
-            e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
-            e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
-            if (h & 1) l2b = add2(l2b, e); else l2a = add2(l2a, e);
-            pk[h] = pack_op16x2(e.x, e.y);
-          }
-          // K-major, 128B swizzle: 16-byte chunk ch of row t lands at chunk ch ^ (t & 7)
-          const uint32_t addr = p_row + ((static_cast<uint32_t>(ch) ^ swz) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                       : "memory");
+        for (int i = 0; i < NW / 2; ++i) {
+          float2 e = add2(y[i], c2);
+          e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
+          e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
+          if (i & 1) tb = add2(tb, e); else ta = add2(ta, e);
+          pk[i] = pack_op16x2(e.x, e.y);
         }
-        fence_proxy_async_smem();
+      };
+      if (act && j > 0) exps(bh - m_used);
+      mbar_wait(bar_pair + 8 * (rq * 2 + pb), par);
+      const float m_cand = fmaxf(m_half, xm[(pb * 128 + t) * 2 + (half ^ 1)]);
+      // identical in both warps of the pair: they see the same 32 pairs of half-row maxima
+      if (__any_sync(0xFFFFFFFFu, m_cand > m_used + LAZY_LOG2)) {
+        const float m_new = fmaxf(m_used, m_cand);
+        if (j > 0) {
+          // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed, PV_j has not been issued
+          const float f = ex2_approx(m_used - m_new);
+          mbar_wait(bar_p_free, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int qr = 0; qr < OH / 8; ++qr) {
+            uint32_t o[8];
+            tmem_ld_x8p(ocol + 8 * qr, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_x8p(ocol + 8 * qr, o);
+          }
+          tmem_st_wait();
+          l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
+        }
+        m_used = m_new;
+        if (act) exps(bh - m_used);
+      }
+      // P (single TMEM buffer) was consumed by P.V_{j-1}, issued when the last thread finished tile j-1 -- a whole
+      // softmax tile ago. Every thread waits (also idle ones), so nobody can arrive on bar_p_full for tile j while the
+      // barrier's phase of tile j-1 is still open.
+      if (j >= 1) mbar_wait(bar_p_free, (j - 1) & 1);
+      if (act) {
+        l2a = add2(l2a, ta); l2b = add2(l2b, tb);
+        tc_fence_after();
+        const uint32_t pcol = tlane + C::COL_P + static_cast<uint32_t>(c0 / 2);
+        if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
+        else if constexpr (NW == 16) tmem_st_x8p(pcol, pk);
+        tmem_st_wait();
         tc_fence_before();
       }
-      mbar_arrive(bar_p_full + 8 * pb);
+      mbar_arrive(bar_p_full);
     };
 
+    using I32 = std::integral_constant<int, 32>;
+    using I16 = std::integral_constant<int, 16>;
+    using I4 = std::integral_constant<int, 4>;
+    using I0 = std::integral_constant<int, 0>;
     if (GLOBAL) {
-      for (int j = 0; j < ntiles; ++j) do_tile(std::integral_constant<int, 64>{}, std::integral_constant<int, 64>{}, j, bias);
+      for (int j = 0; j < ntiles; ++j) do_tile(I32{}, I32{}, j, [&](int i) { return bias[i]; }, 32 * half);
     } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // key k = 64 j + i of the window: kh = k / 14, kw = k % 14 (compile-time after unrolling)
-        if (j < 3) {
-          float b[64];
-#pragma unroll
-          for (int i = 0; i < 64; ++i) b[i] = bias[(64 * j + i) / 14] + bias[14 + (64 * j + i) % 14];
-          do_tile(std::integral_constant<int, 64>{}, std::integral_constant<int, 64>{}, j, b);
-        } else {
-          float b[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) b[i] = i < 4 ? bias[(192 + i) / 14] + bias[14 + (192 + i) % 14] : 0.f;
-          do_tile(std::integral_constant<int, 16>{}, std::integral_constant<int, 4>{}, j, b);
-        }
-      }
+      // key k = 64 j + 32 half + i of the window: kh = k / 14, kw = k % 14 (compile-time after unrolling)
+      auto window_tiles = [&](auto half_c) {
+        constexpr int HF = decltype(half_c)::value;
+        auto tile = [&](auto j_c) {
+          constexpr int K0 = 64 * decltype(j_c)::value + 32 * HF;
+          do_tile(I32{}, I32{}, decltype(j_c)::value, [&](int i) { return bias[(K0 + i) / 14] + bias[14 + (K0 + i) % 14]; }, 32 * HF);
+        };
+        tile(std::integral_constant<int, 0>{}); tile(std::integral_constant<int, 1>{}); tile(std::integral_constant<int, 2>{});
+        if (HF == 0)        // ragged last tile (keys 192..195 + 12 masked columns): the first half of the pair takes it
+          do_tile(I16{}, I4{}, 3, [&](int i) { return i < 4 ? bias[(192 + i) / 14] + bias[14 + (192 + i) % 14] : 0.f; }, 0);
+        else
+          do_tile(I0{}, I0{}, 3, [&](int) { return 0.f; }, 0);
+      };
+      if (half == 0) window_tiles(std::integral_constant<int, 0>{}); else window_tiles(std::integral_constant<int, 1>{});
     }
-    mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
+    // row sum = both halves
+    xl[t * 2 + half] = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+    mbar_arrive(bar_fin + 8 * rq);
+    mbar_wait(bar_p_free, (ntiles - 1) & 1);
     tc_fence_after();
+    mbar_wait(bar_fin + 8 * rq, 0);
     if (warp_active) {
-      uint32_t o[HD];
-      tmem_ld_x32p(tlane + C::COL_O, o);
-      tmem_ld_x32p(tlane + C::COL_O + 32, o + 32);
-      if constexpr (HD > 64) tmem_ld_x16p(tlane + C::COL_O + 64, o + 64);
+      uint32_t o[OH];
+      tmem_ld_x32p(ocol, o);
+      if constexpr (OH > 32) tmem_ld_x8p(ocol + 32, o + 32);
       tmem_ld_wait();
-      const float inv = 1.0f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
+      const float inv = 1.0f / (xl[t * 2] + xl[t * 2 + 1]);
       long long orow = -1;
       if (q_valid) {
         if (!GLOBAL && p.unwindow) {
@@ -437,9 +496,9 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       if (orow >= 0) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(orow) * p.D + head * HD);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(orow) * p.D + head * HD + half * OH);
 #pragma unroll
-        for (int c = 0; c < HD / 8; ++c) {
+        for (int c = 0; c < OH / 8; ++c) {
           uint4 v;
           v.x = pack_op16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
           v.y = pack_op16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
@@ -452,7 +511,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, Cfg<GLOBAL, HD>::TMEM_COLS);
+  if (warp == attn::SM_WARPS) tmem_dealloc(tmem_base, Cfg<GLOBAL, HD>::TMEM_COLS);
 }
 
 template <bool GLOBAL, int HD>
