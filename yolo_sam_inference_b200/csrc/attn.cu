@@ -149,17 +149,19 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   constexpr int NSM = 32 * SM_WARPS;          // softmax threads
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, NSM);
+    // the softmax warps arrive ONCE PER WARP (lane 0 after __syncwarp): per-thread arrivals -- ~800 per tile and CTA --
+    // serialise in the SM's barrier unit and were the bottleneck of the whole kernel
+    mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, SM_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_free + 8 * i, NSM);
+      mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_free + 8 * i, SM_WARPS);
     }
-    mbar_init(bar_p_full, NSM); mbar_init(bar_p_free, 1);
+    mbar_init(bar_p_full, SM_WARPS); mbar_init(bar_p_free, 1);
     for (int i = 0; i < 8; ++i) {
       mbar_init(bar_kfull + 8 * i, 1); mbar_init(bar_kempty + 8 * i, 1);
       mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
-      mbar_init(bar_pair + 8 * i, 64);
+      mbar_init(bar_pair + 8 * i, 2);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 64);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 2);
     fence_mbar_init();
   }
   if (warp == SM_WARPS) {
@@ -189,15 +191,20 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto kdesc_at = [&](uint32_t base, int chunk_bytes, int k) {
       return umma_desc_sw128(base + static_cast<uint32_t>((k >> 2) * chunk_bytes), 16, 1024) + 2u * static_cast<uint32_t>(k & 3);
     };
-    if (warp == SM_WARPS && lane == 0) {
+    // Each role runs with the whole warp converged (all lanes poll the barriers) and one elected lane issuing.
+    if (warp == SM_WARPS) {
+      const bool lead = elect_one();
       // ---- TMA: Q tile + rel-pos table(s), then the K / V rings
-      mbar_arrive_expect_tx(bar_q, NCH * (CH_Q + (GLOBAL ? 1 : 2) * C::TAB_CHUNK));
-      for (int c = 0; c < NCH; ++c) {
-        tma_load_2d(sbase + C::OFF_Q + c * CH_Q, &tmQ, bar_q, cq + 64 * c, row0 + qt * BQ);
-        if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 0);   // rel_pos_h rows (zero padded)
-        tma_load_2d(sbase + C::OFF_TABW + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 128);              // rel_pos_w rows
+      if (lead) {
+        mbar_arrive_expect_tx(bar_q, NCH * (CH_Q + (GLOBAL ? 1 : 2) * C::TAB_CHUNK));
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_2d(sbase + C::OFF_Q + c * CH_Q, &tmQ, bar_q, cq + 64 * c, row0 + qt * BQ);
+          if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 0);   // rel_pos_h rows (zero padded)
+          tma_load_2d(sbase + C::OFF_TABW + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 128);              // rel_pos_w rows
+        }
       }
       auto load_k = [&](int tile, int st) {
+        if (!lead) return;
         const bool tail = !GLOBAL && tile == 3;
         mbar_arrive_expect_tx(bar_kfull + 8 * st, NCH * (GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES)));
         for (int c = 0; c < NCH; ++c) {
@@ -207,6 +214,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       };
       auto load_v = [&](int tile, int st) {
+        if (!lead) return;
         const bool tail = !GLOBAL && tile == 3;
         mbar_arrive_expect_tx(bar_vfull + 8 * st, NCH * (tail ? 16 * 128 : KV_BYTES));
         for (int c = 0; c < NCH; ++c)
@@ -230,7 +238,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (++sv == C::NSTV) { sv = 0; pv ^= 1u; }
         }
       }
-    } else if (warp == SM_WARPS + 1 && lane == 0) {
+    } else if (warp == SM_WARPS + 1) {
+      const bool lead = elect_one();
       // ---- rel-pos table MMA(s), then S_t = Q K_t^T into S buffer t & 1 as soon as the softmax threads hold S_{t-2}
       // in registers (two tiles ahead of the softmax, so S never queues behind a P.V in the in-order tensor pipe)
       constexpr uint32_t idesc_tab = umma_idesc_op16(128, C::TAB_ROWS, 0, 0);
@@ -241,15 +250,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int k = 0; k < NKS; ++k) qdesc[k] = kdesc_at(sbase + C::OFF_Q, CH_Q, k);
       mbar_wait(bar_q, 0);
       tc_fence_after();
-      if (!GLOBAL) {
+      if (lead) {
+        if (!GLOBAL) {
+#pragma unroll
+          for (int k = 0; k < NKS; ++k)
+            umma_op16_ss(tmem_base + C::COL_TH, qdesc[k], kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
+        }
 #pragma unroll
         for (int k = 0; k < NKS; ++k)
-          umma_op16_ss(tmem_base + C::COL_TH, qdesc[k], kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
+          umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
+        umma_commit(bar_tab);
       }
-#pragma unroll
-      for (int k = 0; k < NKS; ++k)
-        umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
-      umma_commit(bar_tab);
       mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
       int st = 0;
       uint32_t ph = 0;
@@ -261,13 +272,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
         const uint32_t kbase = k_tile_addr(st, 0);
+        if (lead) {
 #pragma unroll
-        for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, C::K_CHUNK, k), idesc, k);
-        umma_commit(bar_kempty + 8 * st);
-        umma_commit(bar_s_full + 8 * buf);
+          for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, C::K_CHUNK, k), idesc, k);
+          umma_commit(bar_kempty + 8 * st);
+          umma_commit(bar_s_full + 8 * buf);
+        }
+        __syncwarp();
         if (++st == C::NSTK) { st = 0; ph ^= 1u; }
       }
-    } else if (warp == SM_WARPS + 2 && lane == 0) {
+    } else if (warp == SM_WARPS + 2) {
+      const bool lead = elect_one();
       // ---- O (+)= P_j V_j : A = P straight out of TENSOR MEMORY (row = lane, two op16 keys per 32-bit column, 8 columns
       // per 16-key k-step) -- no shared-memory round trip for P; B = V_j (MN-major: key rows x 64 hd), 16 keys = 2048 B
       constexpr uint32_t idesc_pv64 = umma_idesc_op16(128, 64, 0, 1);   // B (= V) is MN-major
@@ -279,15 +294,23 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(bar_vfull + 8 * st, ph);
         mbar_wait(bar_p_full, j & 1);
         tc_fence_after();
-        const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
-        const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
-        for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm, ptm + 8u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
-        if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
-          const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
-          for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
+        if (lead) {
+          const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
+          if (GLOBAL || j < 3) {
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k) umma_op16_ts(otm, ptm + 8u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
+          } else {
+            umma_op16_ts(otm, ptm, vdesc, idesc_pv64, 1u);
+          }
+          if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
+            const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
+            const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
+            for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_vempty + 8 * st);
+          umma_commit(bar_p_free);
         }
-        umma_commit(bar_vempty + 8 * st);
-        umma_commit(bar_p_free);
+        __syncwarp();
         if (++st == C::NSTV) { st = 0; ph ^= 1u; }
       }
     }
@@ -347,7 +370,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int i = 0; i < 28; ++i) bias[i] = my[i * 128 + t];
     }
     tc_fence_before();
-    mbar_arrive(bar_rel);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_rel);
 
     float m_used = -INFINITY;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
@@ -380,7 +404,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_s_free + 8 * pb);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_free + 8 * pb);
       float2 y[NR / 2];
       float m_half = -INFINITY;
       if (act) {
@@ -394,7 +419,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       // publish this half-row maximum; the partner's is read after the (speculative) exponentials
       xm[(pb * 128 + t) * 2 + half] = m_half;
-      mbar_arrive(bar_pair + 8 * (rq * 2 + pb));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pair + 8 * (rq * 2 + pb));
       uint32_t pk[NR / 2];
       float2 ta, tb;
       auto exps = [&](float c) {
@@ -448,7 +474,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tmem_st_wait();
         tc_fence_before();
       }
-      mbar_arrive(bar_p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
     };
 
     using I32 = std::integral_constant<int, 32>;
@@ -475,7 +502,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
     // row sum = both halves
     xl[t * 2 + half] = (l2a.x + l2a.y) + (l2b.x + l2b.y);
-    mbar_arrive(bar_fin + 8 * rq);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_fin + 8 * rq);
     mbar_wait(bar_p_free, (ntiles - 1) & 1);
     tc_fence_after();
     mbar_wait(bar_fin + 8 * rq, 0);
