@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False, precision: str = "all") ->
         for v in VARIANTS:
             build(force, verbose, v)
         return LIB
-    lib, defines = lib_path(precision), VARIANTS[precision][1]
+    lib, defines = lib_path(precision), VARIANTS[precision][1] + os.environ.get("YSI_NVCC_DEFINES", "").split()
     if not force and not _stale(lib):
         return lib
     nvcc = _nvcc()

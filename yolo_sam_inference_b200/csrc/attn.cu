@@ -32,6 +32,7 @@
 //                    keys >= 196 of the last tile are masked.
 // 2 CTAs/SM overlap one CTA's softmax with the other's MMAs; the kernel is MUFU(ex2)-bound by design.
 #include "kernels.h"
+#include <cstdio>
 #include <type_traits>
 
 #include "ptx.cuh"
@@ -90,11 +91,10 @@ struct Cfg {
   static constexpr int OFF_XM = OFF_BAR + 512;              // fp32 [2][128][2]: half-row maxima of tile parity 0 / 1
   static constexpr int OFF_XL = OFF_XM + 2048;              // fp32 [128][2]: half-row sums at the end
   static constexpr int SMEM_BYTES = OFF_XL + 1024 + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = HD > 64 ? 512 : 256;     // 2 S buffers + O + P (head_dim 80 runs one CTA per SM anyway)
+  static constexpr int TMEM_COLS = 256;                     // 2 S buffers (P_j overwrites the first 32 columns of S_j) + O
   static constexpr int S_N = GLOBAL ? 80 : 64;              // columns of one S buffer
   static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
   static constexpr int COL_O = 2 * S_N;
-  static constexpr int COL_P = COL_O + HD;                  // P tile as the TMEM A operand of P.V: 64 op16 keys = 32 columns
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
   static constexpr int CTAS_PER_SM = HD > 64 ? 1 : 2;
@@ -103,9 +103,18 @@ struct Cfg {
   static_assert(GLOBAL || 2 * NCH * TAB_CHUNK <= P_BYTES, "window tables must fit the second half of the scratch");
   static_assert(!GLOBAL || V_TOTAL >= SCRATCH, "the bias scratch aliases the V ring");
   static_assert(NSTK <= 8 && NSTV <= 8, "barrier arrays");
-  static_assert(COL_P + 32 <= TMEM_COLS, "TMEM budget");
+  static_assert(COL_O + HD <= TMEM_COLS, "TMEM budget");
 };
 }  // namespace attn
+
+// Optional timing trace of one CTA (build with -DYSI_ATTN_TRACE, run scripts/gpu_attn_trace.sh): clock64 at the phase
+// boundaries of every softmax warp and producer role, printed by the CTA at exit. Not compiled into the product library.
+#ifdef YSI_ATTN_TRACE
+__device__ long long g_attn_trace[12][64][8];
+#define ATTN_TRACE(w, tile, ev) do { if (trace && lane == 0) g_attn_trace[w][(tile) & 63][ev] = clock64(); } while (0)
+#else
+#define ATTN_TRACE(w, tile, ev) do { } while (0)
+#endif
 
 struct AttnParams {
   int T;          // sequence length: 196 (window) or 4096 (global)
@@ -128,9 +137,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t bar = sbase + C::OFF_BAR;
   const uint32_t bar_q = bar, bar_tab = bar + 8, bar_rel = bar + 16;
   const uint32_t bar_s_full = bar + 24;    // [2]
-  const uint32_t bar_s_free = bar + 40;    // [2]
-  const uint32_t bar_p_full = bar + 56;    // P_j is in TMEM (phase j & 1)
-  const uint32_t bar_p_free = bar + 64;    // P.V_j has completed (phase j & 1): P may be overwritten, O is up to date
+  const uint32_t bar_p_full = bar + 40;    // [2] P_j is in TMEM (in S buffer j & 1)
+  const uint32_t bar_p_free = bar + 56;    // [2] P.V_j has completed: S buffer j & 1 may be overwritten by S_{j+2}, O is up to date
   const uint32_t bar_kfull = bar + 72;     // [8]
   const uint32_t bar_kempty = bar + 136;   // [8]
   const uint32_t bar_vfull = bar + 200;    // [8]
@@ -147,15 +155,18 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int ntiles = GLOBAL ? p.T / BKV : 4;
   const int cq = head * HD, ck = p.D + head * HD, cv = 2 * p.D + head * HD;
   constexpr int NSM = 32 * SM_WARPS;          // softmax threads
+#ifdef YSI_ATTN_TRACE
+  const bool trace = GLOBAL && blockIdx.x == 7 && blockIdx.y == 3 && blockIdx.z == 0;
+#endif
 
   if (threadIdx.x == 0) {
     // the softmax warps arrive ONCE PER WARP (lane 0 after __syncwarp): per-thread arrivals -- ~800 per tile and CTA --
     // serialise in the SM's barrier unit and were the bottleneck of the whole kernel
     mbar_init(bar_q, 1); mbar_init(bar_tab, 1); mbar_init(bar_rel, SM_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_free + 8 * i, SM_WARPS);
+      mbar_init(bar_s_full + 8 * i, 1);
+      mbar_init(bar_p_full + 8 * i, SM_WARPS); mbar_init(bar_p_free + 8 * i, 1);
     }
-    mbar_init(bar_p_full, SM_WARPS); mbar_init(bar_p_free, 1);
     for (int i = 0; i < 8; ++i) {
       mbar_init(bar_kfull + 8 * i, 1); mbar_init(bar_kempty + 8 * i, 1);
       mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
@@ -164,6 +175,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 2);
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < 512; i += THREADS) reinterpret_cast<uint32_t*>(xm)[i] = 0xFFFFFFFFu;   // tag 0xFF: nothing published yet
   if (warp == SM_WARPS) {
     tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
     tmem_relinquish();
@@ -232,16 +244,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         int sk = 0, sv = 0;
         uint32_t pk = 0, pv = 0;
         for (int j = 0; j < ntiles; ++j) {
-          if (j + C::NSTK < ntiles) { mbar_wait(bar_kempty + 8 * sk, pk); load_k(j + C::NSTK, sk); }
-          if (j + C::NSTV < ntiles) { mbar_wait(bar_vempty + 8 * sv, pv); load_v(j + C::NSTV, sv); }
+          if (j + C::NSTK < ntiles) { mbar_wait(bar_kempty + 8 * sk, pk); ATTN_TRACE(8, j, 0); load_k(j + C::NSTK, sk); }
+          if (j + C::NSTV < ntiles) { mbar_wait(bar_vempty + 8 * sv, pv); ATTN_TRACE(8, j, 1); load_v(j + C::NSTV, sv); }
           if (++sk == C::NSTK) { sk = 0; pk ^= 1u; }
           if (++sv == C::NSTV) { sv = 0; pv ^= 1u; }
         }
       }
     } else if (warp == SM_WARPS + 1) {
       const bool lead = elect_one();
-      // ---- rel-pos table MMA(s), then S_t = Q K_t^T into S buffer t & 1 as soon as the softmax threads hold S_{t-2}
-      // in registers (two tiles ahead of the softmax, so S never queues behind a P.V in the in-order tensor pipe)
+      // ---- rel-pos table MMA(s), then S_t = Q K_t^T into S buffer t & 1 as soon as P.V_{t-2} -- whose A operand P_{t-2}
+      // sits in the first columns of that buffer -- has completed: about one softmax tile before S_t is needed
       constexpr uint32_t idesc_tab = umma_idesc_op16(128, C::TAB_ROWS, 0, 0);
       constexpr uint32_t idesc_s = umma_idesc_op16(128, C::S_N, 0, 0);
       constexpr uint32_t idesc_s16 = umma_idesc_op16(128, 16, 0, 0);
@@ -267,7 +279,9 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         mbar_wait(bar_kfull + 8 * st, ph);
-        if (t >= 2) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);
+        ATTN_TRACE(9, t, 0);
+        if (t >= 2) mbar_wait(bar_p_free + 8 * buf, ((t >> 1) - 1) & 1);     // P.V_{t-2} done: S / P buffer t & 1 is free
+        ATTN_TRACE(9, t, 1);
         tc_fence_after();
         const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
@@ -279,6 +293,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           umma_commit(bar_s_full + 8 * buf);
         }
         __syncwarp();
+        ATTN_TRACE(9, t, 2);
         if (++st == C::NSTK) { st = 0; ph ^= 1u; }
       }
     } else if (warp == SM_WARPS + 2) {
@@ -287,13 +302,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       // per 16-key k-step) -- no shared-memory round trip for P; B = V_j (MN-major: key rows x 64 hd), 16 keys = 2048 B
       constexpr uint32_t idesc_pv64 = umma_idesc_op16(128, 64, 0, 1);   // B (= V) is MN-major
       constexpr uint32_t idesc_pv16 = umma_idesc_op16(128, 16, 0, 1);
-      const uint32_t ptm = tmem_base + C::COL_P, otm = tmem_base + C::COL_O;
+      const uint32_t otm = tmem_base + C::COL_O;
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < ntiles; ++j) {
         mbar_wait(bar_vfull + 8 * st, ph);
-        mbar_wait(bar_p_full, j & 1);
+        ATTN_TRACE(10, j, 0);
+        mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
+        ATTN_TRACE(10, j, 1);
         tc_fence_after();
+        const uint32_t ptm = tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
         if (lead) {
           const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
           if (GLOBAL || j < 3) {
@@ -308,9 +326,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(bar_vempty + 8 * st);
-          umma_commit(bar_p_free);
+          umma_commit(bar_p_free + 8 * (j & 1));
         }
         __syncwarp();
+        ATTN_TRACE(10, j, 2);
         if (++st == C::NSTV) { st = 0; ph ^= 1u; }
       }
     }
@@ -373,6 +392,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_rel);
 
+    bool s_ready = false;                            // S of the next tile already seen complete (probed a tile early)
     float m_used = -INFINITY;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
     constexpr int OH = HD / 2;                       // O columns owned by this thread
@@ -385,7 +405,9 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       constexpr int NR = NW > 0 ? NW : 2;
       const int pb = j & 1;                       // S buffer and P buffer of this tile
       const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
-      mbar_wait(bar_s_full + 8 * pb, par);
+      ATTN_TRACE(warp, j, 0);
+      if (!s_ready) mbar_wait(bar_s_full + 8 * pb, par);
+      ATTN_TRACE(warp, j, 1);
       tc_fence_after();
       uint32_t r[NR];
       float bh = 0.f;
@@ -403,9 +425,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           tmem_ld_wait();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_s_free + 8 * pb);
+      ATTN_TRACE(warp, j, 2);
       float2 y[NR / 2];
       float m_half = -INFINITY;
       if (act) {
@@ -417,10 +437,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int i = 0; i < NV / 2; ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
         m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
       }
-      // publish this half-row maximum; the partner's is read after the (speculative) exponentials
-      xm[(pb * 128 + t) * 2 + half] = m_half;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pair + 8 * (rq * 2 + pb));
+      // publish this half-row maximum; the partner's is read after the (speculative) exponentials. One 32-bit word
+      // carries value and flag: the low mantissa byte is replaced by the tile index (both threads then use the same
+      // truncated values, so they take identical decisions) -- no barrier round trip on the per-tile path.
+      const uint32_t tag = static_cast<uint32_t>(j);
+      const uint32_t mine = (__float_as_uint(m_half) & 0xFFFFFF00u) | tag;
+      const uint32_t xaddr = smem_u32(xm) + static_cast<uint32_t>(((pb * 128 + t) * 2) * 4);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(xaddr + 4u * half), "r"(mine) : "memory");
       uint32_t pk[NR / 2];
       float2 ta, tb;
       auto exps = [&](float c) {
@@ -436,15 +459,20 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       };
       if (act && j > 0) exps(bh - m_used);
-      mbar_wait(bar_pair + 8 * (rq * 2 + pb), par);
-      const float m_cand = fmaxf(m_half, xm[(pb * 128 + t) * 2 + (half ^ 1)]);
+      ATTN_TRACE(warp, j, 3);
+      uint32_t theirs;
+      do {
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(theirs) : "r"(xaddr + 4u * (half ^ 1)) : "memory");
+      } while ((theirs & 0xFFu) != tag);
+      ATTN_TRACE(warp, j, 4);
+      const float m_cand = fmaxf(__uint_as_float(mine & 0xFFFFFF00u), __uint_as_float(theirs & 0xFFFFFF00u));
       // identical in both warps of the pair: they see the same 32 pairs of half-row maxima
       if (__any_sync(0xFFFFFFFFu, m_cand > m_used + LAZY_LOG2)) {
         const float m_new = fmaxf(m_used, m_cand);
         if (j > 0) {
           // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed, PV_j has not been issued
           const float f = ex2_approx(m_used - m_new);
-          mbar_wait(bar_p_free, (j - 1) & 1);
+          mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll
           for (int qr = 0; qr < OH / 8; ++qr) {
@@ -461,21 +489,25 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         m_used = m_new;
         if (act) exps(bh - m_used);
       }
-      // P (single TMEM buffer) was consumed by P.V_{j-1}, issued when the last thread finished tile j-1 -- a whole
-      // softmax tile ago. Every thread waits (also idle ones), so nobody can arrive on bar_p_full for tile j while the
-      // barrier's phase of tile j-1 is still open.
-      if (j >= 1) mbar_wait(bar_p_free, (j - 1) & 1);
+      // P_j goes into the first 32 columns of S buffer pb. They are free: S_j (this buffer) was only issued after
+      // P.V_{j-2} had completed, this thread has its own S columns in registers, and the partner (whose S columns the
+      // second half of the pair overwrites) published its maximum -- i.e. finished its TMEM load -- before the pair
+      // exchange above completed. No wait on the tensor pipe in steady state.
+      ATTN_TRACE(warp, j, 5);
+      // probe the next tile's S now: the barrier unit's round trip overlaps the P store below
+      s_ready = mbar_test_wait(bar_s_full + 8 * (pb ^ 1), static_cast<uint32_t>(((j + 1) >> 1) & 1));
       if (act) {
         l2a = add2(l2a, ta); l2b = add2(l2b, tb);
         tc_fence_after();
-        const uint32_t pcol = tlane + C::COL_P + static_cast<uint32_t>(c0 / 2);
+        const uint32_t pcol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
         if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
         else if constexpr (NW == 16) tmem_st_x8p(pcol, pk);
         tmem_st_wait();
         tc_fence_before();
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full);
+      if (lane == 0) mbar_arrive(bar_p_full + 8 * pb);
+      ATTN_TRACE(warp, j, 6);
     };
 
     using I32 = std::integral_constant<int, 32>;
@@ -504,7 +536,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     xl[t * 2 + half] = (l2a.x + l2a.y) + (l2b.x + l2b.y);
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_fin + 8 * rq);
-    mbar_wait(bar_p_free, (ntiles - 1) & 1);
+    mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     mbar_wait(bar_fin + 8 * rq, 0);
     if (warp_active) {
@@ -539,6 +571,20 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+#ifdef YSI_ATTN_TRACE
+  if (trace && threadIdx.x == 0) {
+    const long long t0 = g_attn_trace[0][20][0];
+    for (int j = 20; j < 23; ++j) {
+      for (int w = 0; w < 8; ++w)
+        printf("TR tile %d warp %d: start %lld s_full %lld ld %lld exps %lld pair %lld p_free %lld done %lld\n", j, w, g_attn_trace[w][j][0] - t0,
+               g_attn_trace[w][j][1] - t0, g_attn_trace[w][j][2] - t0, g_attn_trace[w][j][3] - t0, g_attn_trace[w][j][4] - t0,
+               g_attn_trace[w][j][5] - t0, g_attn_trace[w][j][6] - t0);
+      printf("TR tile %d S-issue: kfull %lld s_free %lld issued %lld | PV: vfull %lld p_full %lld issued %lld | TMA: kempty %lld vempty %lld\n", j,
+             g_attn_trace[9][j][0] - t0, g_attn_trace[9][j][1] - t0, g_attn_trace[9][j][2] - t0, g_attn_trace[10][j][0] - t0,
+             g_attn_trace[10][j][1] - t0, g_attn_trace[10][j][2] - t0, g_attn_trace[8][j][0] - t0, g_attn_trace[8][j][1] - t0);
+    }
+  }
+#endif
   if (warp == attn::SM_WARPS) tmem_dealloc(tmem_base, Cfg<GLOBAL, HD>::TMEM_COLS);
 }
 
