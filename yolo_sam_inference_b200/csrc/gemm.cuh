@@ -181,12 +181,13 @@ struct alignas(64) EpiStaged {
   float col_scale;
   int scale_c0, scale_c1;
   int f32_add;     // 0: op16 store, 1: fp32 reduce-add, 2: fp32 store
+  // bulk async-groups belong to the issuing thread: elect.sync picks the same lane for the same (full) mask every time
   __device__ __forceinline__ void finish(EpiCtx& ctx) const {
-    if (ctx.lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
   }
   __device__ __forceinline__ void slab_out(EpiCtx& ctx, const uint32_t (&pk)[32], int col0) const {
     const uint32_t buf = ctx.smem + (ctx.nbuf & 1u) * 4096u;
-    if (ctx.lane == 0) bulk_wait_read<1>();       // the slab stored from this buffer two steps ago has been read
+    if (elect_one()) bulk_wait_read<1>();       // the slab stored from this buffer two steps ago has been read
     __syncwarp();
     const uint32_t rowp = buf + static_cast<uint32_t>(ctx.lane) * 128u;
     const uint32_t swz = static_cast<uint32_t>(ctx.lane & 7);
@@ -197,7 +198,7 @@ struct alignas(64) EpiStaged {
                    : "memory");
     fence_proxy_async_smem();
     __syncwarp();
-    if (ctx.lane == 0) {
+    if (elect_one()) {
       if (f32_add == 1) tma_reduce_add_2d(&tm_out, buf, col0, ctx.row0); else tma_store_2d(&tm_out, buf, col0, ctx.row0);
       bulk_commit();
     }
@@ -327,8 +328,12 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+  // The two single-thread roles run with their whole warp converged and one ELECTED lane issuing: the compiler then
+  // emits the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) back to back instead of wrapping each one in
+  // a per-lane waterfall loop, which otherwise makes the issuing thread -- not the tensor pipe -- the pacemaker.
   if (warp == 0) {
-    if (lane == 0) {
+    const bool lead = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -336,16 +341,20 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (lead) {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool lead = elect_one();
+    {
       constexpr uint32_t idesc = umma_idesc_op16(GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -358,18 +367,22 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+          if (lead) {
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // +32 B per 16-element K step inside the 128 B swizzle atom (encoded >> 4 => +2)
-            umma_op16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // +32 B per 16-element K step inside the 128 B swizzle atom (encoded >> 4 => +2)
+              umma_op16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
           }
-          umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (lead) umma_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -469,7 +482,8 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool lead = elect_one();      // converged warp + elected lane, see gemm_op16_kernel
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -477,16 +491,20 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
-          tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (lead) {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    const bool lead = elect_one();
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_op16(2 * GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -499,16 +517,20 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+          if (lead) {
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_op16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_cg2_mc(empty_bar(stage), 3);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_op16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_cg2_mc(empty_bar(stage), 3);
+          }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_cg2_mc(tfull_bar(acc), 3);
+        if (lead) umma_commit_cg2_mc(tfull_bar(acc), 3);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
