@@ -80,6 +80,7 @@ struct ysi_ctx {
   struct Slot {
     uint8_t* d_rgb = nullptr;       // [max_batch, H, W, 3]
     uint16_t* d_sum3 = nullptr;     // [max_batch, H, W]
+    uint8_t* d_gray = nullptr;      // [max_batch, H, W]  floor((R+G+B)/3)
     float* d_emb = nullptr;         // [max_batch*4096, 256]
     uint8_t* d_masks = nullptr;     // [max_boxes, H, W]
     uint8_t* d_packed = nullptr;    // [max_boxes, ceil(H*W/8)] (lazily allocated)
@@ -374,6 +375,7 @@ void create_impl(ysi_ctx* c) {
   for (auto& sl : c->slots) {
     sl.d_rgb = c->dalloc<uint8_t>(B * HW * 3);
     sl.d_sum3 = c->dalloc<uint16_t>(B * HW);
+    sl.d_gray = c->dalloc<uint8_t>(B * HW);
     sl.d_emb = c->dalloc<float>(B * 4096 * 256);
     sl.d_masks = c->dalloc<uint8_t>(NB * HW);
     sl.d_metrics = c->dalloc<ysi_mask_metrics>(NB);
@@ -497,7 +499,7 @@ void submit_impl(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, const u
   YSI_CUDA(cudaEventRecord(sl.t[1], sm));
   if (nb > 0) {
     ProfScope ps(prof, KC_PREPROCESS);
-    launch_sum3(src, n, H, W, W * 3, sl.d_sum3, sm);
+    launch_sum3(src, n, H, W, W * 3, sl.d_sum3, sl.d_gray, sm);
     c->launches += 1;
     preprocess_images(c, src, n, H, W, nullptr, c->ew.a_patch);
   }
@@ -530,7 +532,7 @@ void submit_impl(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, const u
     {
       ProfScope ps(prof, KC_POST_UPSAMPLE);
       launch_init_stats(c->d_stats, nb, sd);
-      launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), sl.d_sum3, c->d_mask_img, sl.d_masks, nullptr, c->d_stats, sd);
+      launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), sl.d_sum3, sl.d_gray, c->d_mask_img, sl.d_masks, nullptr, c->d_stats, sd);
       c->launches += 2;
     }
     YSI_CUDA(cudaEventRecord(sl.t[6], sd));
@@ -814,7 +816,7 @@ int ysi_postprocess(ysi_ctx* c, const float* low_res, int nb, int H, int W, uint
     float* d_up = nullptr;
     if (upsampled_out) { YSI_CUDA(cudaMalloc(&d_up, sizeof(float) * nb * HW)); }
     launch_init_stats(c->d_stats, nb, c->stream);
-    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), nullptr, nullptr, c->d_masks, d_up, c->d_stats, c->stream);
+    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), nullptr, nullptr, nullptr, c->d_masks, d_up, c->d_stats, c->stream);
     c->launches += 2;
     if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, c->d_masks, nb * HW, cudaMemcpyDeviceToHost, c->stream));
     if (upsampled_out) YSI_CUDA(cudaMemcpyAsync(upsampled_out, d_up, sizeof(float) * nb * HW, cudaMemcpyDeviceToHost, c->stream));
@@ -832,7 +834,7 @@ int ysi_metrics(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, co
     YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb, static_cast<size_t>(W) * 3, rgb, row_stride, static_cast<size_t>(W) * 3, H,
                                cudaMemcpyHostToDevice, c->stream));
     YSI_CUDA(cudaMemcpyAsync(c->d_masks, masks, nb * HW, cudaMemcpyHostToDevice, c->stream));
-    launch_sum3(c->d_rgb, 1, H, W, W * 3, c->d_sum3, c->stream);
+    launch_sum3(c->d_rgb, 1, H, W, W * 3, c->d_sum3, nullptr, c->stream);
     launch_init_stats(c->d_stats, nb, c->stream);
     launch_mask_stats(c->d_masks, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->stream);
     launch_contour_hull_disk(c->d_masks, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->d_metrics, c->stream);

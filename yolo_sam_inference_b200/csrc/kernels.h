@@ -27,8 +27,9 @@ void launch_init_stats(MaskStatsDev* stats, int nmask, cudaStream_t s);
 // a6 (+ first half of a7): low-res logits [nmask,256,256] -> mask bytes [nmask,H,W] + stats.
 // sum3: per-image R+G+B planes uint16 [n_img,H,W] (may be null: no intensity histogram),
 // mask_image[m]: image index of mask m (null => all image 0). up_logits optional fp32 [nmask,H,W].
-void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const int* mask_image,
-                           uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s);
+// gray: floor((R+G+B)/3) uint8 planes [n_img,H,W] (histogram bins; required with sum3 for the 1024x1024 fast path).
+void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const uint8_t* gray,
+                           const int* mask_image, uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s);
 // same statistics from given mask bytes (a7 alone)
 void launch_mask_stats(const uint8_t* masks_in, int nmask, int H, int W, const uint16_t* sum3, const int* mask_image,
                        MaskStatsDev* stats, cudaStream_t s);
@@ -39,7 +40,7 @@ void launch_contour_hull_disk(const uint8_t* masks, int nmask, int H, int W, con
 // np.packbits(mask.reshape(-1)) per mask: [nmask, ceil(H*W/8)]
 void launch_packbits(const uint8_t* masks, uint8_t* packed, int nmask, long long npix, cudaStream_t s);
 // uint8 RGB [n,H,W,3] (pitch row_stride) -> R+G+B uint16 planes
-void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, cudaStream_t s);
+void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, uint8_t* gray, cudaStream_t s);
 
 // ------------------------------------------------------------------ encoder
 // fused flash-style attention with decomposed rel-pos bias (attn.cu)

@@ -254,9 +254,248 @@ upsample_stats_kernel(const float* __restrict__ low_all, const uint8_t* __restri
   }
 }
 
-void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const int* mask_image,
-                           uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s) {
+// ---------------------------------------------------------------------------------------------------
+// Fast path of K1 for the dominant geometry (H = W = 1024: the second resize of post_process_masks is the identity,
+// the first is an exact x4 upsample): bit-parallel, ~10 instructions per output pixel instead of ~300.
+//
+//  * x4 bilinear with align_corners=False has a fixed pattern: output rows 4G-2 .. 4G+1 ("row group" G) blend low
+//    rows G-1 and G with l1 = 1/8, 3/8, 5/8, 7/8 (rows 0,1 and 1022,1023 degenerate to one low row through the
+//    index clamps); columns likewise.  The taps, their order and the fma contraction are those of lin_index /
+//    lerp_torch above, so the result is bit-identical to the generic kernel (and to ATen's CPU kernel).
+//  * a lane owns 32 consecutive output columns: it reads 8 floats of a low row (the warp reads the whole 1 KB row,
+//    coalesced) + one neighbour each side by shuffle, interpolates horizontally once per low row (kept in registers
+//    for the next group) and vertically 4 rows per group, and thresholds straight into a 32-bit row word.
+//  * everything downstream works on row words: area / centroid sums by POPC, bounding box by OR-accumulation,
+//    border = W & ~(up & down & left & right), the neighbour counts of skimage's perimeter code as bit-sliced adders
+//    (LOP3 full adders) and one POPC per code bin, the first mixed 2x2 cell by XORs; the mask bytes are expanded from
+//    the row words and written 16 bytes per lane, 512 contiguous bytes per instruction.
+//  * a warp walks down a band of rows with a two-row delay line (codes of row r need the border of rows r-1 .. r+1,
+//    which needs the mask of rows r-2 .. r+2); one row group above and one below the band are recomputed as halo.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FAST_WARPS = 8;
+
+__device__ __forceinline__ unsigned int shl_in(unsigned int w, unsigned int prev_lane_word) {   // columns c-1 -> bit c
+  return (w << 1) | (prev_lane_word >> 31);
+}
+__device__ __forceinline__ unsigned int shr_in(unsigned int w, unsigned int next_lane_word) {   // columns c+1 -> bit c
+  return (w >> 1) | (next_lane_word << 31);
+}
+
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __restrict__ gray_all,
+                           const int* __restrict__ mask_image, uint8_t* __restrict__ masks_out,
+                           MaskStatsDev* __restrict__ stats, int groups_per_warp) {
+  constexpr int H = 1024, W = 1024;
+  __shared__ unsigned int s_hist[FAST_WARPS][2][256];
+  const int m = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* low = low_all + static_cast<size_t>(m) * 65536;
+  const bool want_hist = gray_all != nullptr;
+  const uint8_t* gray = want_hist ? gray_all + static_cast<size_t>(mask_image ? mask_image[m] : 0) * H * W : nullptr;
+  uint8_t* mout = masks_out + static_cast<size_t>(m) * H * W;
+  if (want_hist)
+    for (int i = threadIdx.x; i < FAST_WARPS * 2 * 256; i += FAST_WARPS * 32) (&s_hist[0][0][0])[i] = 0;
+  __syncthreads();
+  unsigned int* my_hist = &s_hist[warp][lane & 1][0];
+
+  // band of this warp: row groups [ga, gb) -> output rows [4 ga - 2, 4 gb - 2), clipped to the image
+  const int ga = (blockIdx.x * FAST_WARPS + warp) * groups_per_warp;
+  const int gb = min(ga + groups_per_warp, 257);
+  const int R0 = max(4 * ga - 2, 0), R1 = min(4 * gb - 2, H);
+
+  unsigned long long area = 0, sum_r = 0, sum_c = 0;
+  unsigned int colmask = 0;                 // OR of all finalised row words: min / max column of this lane
+  int mnr = INT_MAX, mxr = -1;
+  unsigned int first = 0xFFFFFFFFu;
+  unsigned int pc[YSI_PERIM_BINS];
+#pragma unroll
+  for (int b = 0; b < YSI_PERIM_BINS; ++b) pc[b] = 0;
+
+  if (ga < gb) {
+    // horizontal interpolation of one low row into this lane's 32 output columns
+    auto hrow = [&](int lr, float (&h)[32]) {
+      const float4* src = reinterpret_cast<const float4*>(low + lr * 256 + lane * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      float p[10];
+      p[1] = a.x; p[2] = a.y; p[3] = a.z; p[4] = a.w; p[5] = b.x; p[6] = b.y; p[7] = b.z; p[8] = b.w;
+      p[0] = __shfl_up_sync(0xFFFFFFFFu, p[8], 1);
+      p[9] = __shfl_down_sync(0xFFFFFFFFu, p[1], 1);
+      if (lane == 31) p[9] = p[8];                      // i1 clamps to the last low column
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int j0 = (k + 2) >> 2;                    // p index of the left tap (low column 8 lane - 1 + j0)
+        const int i = (k + 2) & 3;
+        const float l1 = 0.125f + 0.25f * i, l0 = 1.0f - l1;
+        h[k] = lerp_torch(l0, p[j0], l1, p[j0 + 1]);
+      }
+      if (lane == 0) {                                  // output columns 0, 1: src clamps to 0 -> weights (1, 0)
+        h[0] = lerp_torch(1.0f, p[1], 0.0f, p[2]);
+        h[1] = h[0];
+      }
+    };
+    float hA[32], hB[32];
+    // delay line: mask words of the two previous rows, border words (and their column-shifted copies) of rows -3, -2
+    unsigned int Wp1 = 0, Wp2 = 0, Bp2 = 0, Bp3 = 0, BLp2 = 0, BRp2 = 0, BLp3 = 0, BRp3 = 0;
+    const int g_first = ga - 1, g_last = gb;            // halo groups included
+    {
+      const int la = min(max(g_first - 1, 0), 255);
+      hrow(la, hA);
+    }
+    for (int G = g_first; G <= g_last; ++G) {
+      const int lb = min(max(G, 0), 255);
+      hrow(lb, hB);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rn = 4 * G - 2 + i;                   // row generated in this step (may be outside the image)
+        unsigned int Wn = 0;
+        if (rn >= 0 && rn < H) {
+          const float l1 = 0.125f + 0.25f * i, l0 = 1.0f - l1;
+          const bool top = rn < 2;                      // rows 0, 1: weights (1, 0) on low rows (0, 1)
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = top ? lerp_torch(1.0f, hB[k], 0.0f, hB[k]) : lerp_torch(l0, hA[k], l1, hB[k]);
+            Wn |= (x > 0.0f) ? (1u << k) : 0u;
+          }
+          if (rn >= R0 && rn < R1) {
+            // bytes of this row: lane L writes columns 16 L .. +15 and 512 + 16 L .. +15
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const unsigned int ws = __shfl_sync(0xFFFFFFFFu, Wn, (lane >> 1) + 16 * hh);
+              const unsigned int bits = (ws >> (16 * (lane & 1))) & 0xFFFFu;
+              uint4 o;
+              o.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+              o.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+              o.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+              o.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+              *reinterpret_cast<uint4*>(mout + static_cast<size_t>(rn) * W + 512 * hh + 16 * lane) = o;
+            }
+          }
+        }
+        // ---- border of row rn-1 (mask rows rn-2, rn-1, rn)
+        unsigned int wl = __shfl_up_sync(0xFFFFFFFFu, Wp1, 1), wr = __shfl_down_sync(0xFFFFFFFFu, Wp1, 1);
+        if (lane == 0) wl = 0;
+        if (lane == 31) wr = 0;
+        const unsigned int Bp1 = Wp1 & ~(Wp2 & Wn & shl_in(Wp1, wl) & shr_in(Wp1, wr));
+        unsigned int bl = __shfl_up_sync(0xFFFFFFFFu, Bp1, 1), br = __shfl_down_sync(0xFFFFFFFFu, Bp1, 1);
+        if (lane == 0) bl = 0;
+        if (lane == 31) br = 0;
+        const unsigned int BLp1 = shl_in(Bp1, bl), BRp1 = shr_in(Bp1, br);
+        // ---- finalise row f = rn-2: mask word Wp2, border rows f-1 (p3), f (p2), f+1 (p1)
+        const int f = rn - 2;
+        if (f >= R0 && f < R1) {
+          const unsigned int Wf = Wp2;
+          if (__any_sync(0xFFFFFFFFu, Wf != 0)) {
+            const unsigned int n = __popc(Wf);
+            area += n;
+            sum_r += static_cast<unsigned long long>(n) * f;
+            unsigned int si = __popc(Wf & 0xAAAAAAAAu) + 2 * __popc(Wf & 0xCCCCCCCCu) + 4 * __popc(Wf & 0xF0F0F0F0u) +
+                              8 * __popc(Wf & 0xFF00FF00u) + 16 * __popc(Wf & 0xFFFF0000u);
+            sum_c += static_cast<unsigned long long>(n) * (32 * lane) + si;
+            colmask |= Wf;
+            mnr = min(mnr, f); mxr = max(mxr, f);     // warp-uniform: some lane of the warp has a pixel in row f
+            // perimeter code = 1 + 2 n4 + 10 nd over border neighbours; bit-sliced counts n4, nd in {0..4}
+            const unsigned int B = Bp2;
+            if (__any_sync(0xFFFFFFFFu, B != 0)) {
+              const unsigned int a0 = Bp3, a1 = Bp1, a2 = BLp2, a3 = BRp2;          // up, down, left, right
+              const unsigned int s1 = a0 ^ a1 ^ a2, c1 = (a0 & a1) | (a2 & (a0 ^ a1));
+              const unsigned int n4_0 = s1 ^ a3, c2 = s1 & a3;
+              const unsigned int n4_1 = c1 ^ c2, n4_2 = c1 & c2;
+              const unsigned int d0 = BLp3, d1 = BRp3, d2 = BLp1, d3 = BRp1;        // diagonals
+              const unsigned int t1 = d0 ^ d1 ^ d2, e1 = (d0 & d1) | (d2 & (d0 ^ d1));
+              const unsigned int nd_0 = t1 ^ d3, e2 = t1 & d3;
+              const unsigned int nd_1 = e1 ^ e2, nd_2 = e1 & e2;
+              // selectors n4 == v / nd == v for the values that occur in weighted codes (5,7,13,15,17,21,23,25,27,33)
+              const unsigned int n4e0 = ~(n4_0 | n4_1 | n4_2), n4e1 = n4_0 & ~n4_1 & ~n4_2, n4e2 = ~n4_0 & n4_1 & ~n4_2,
+                                 n4e3 = n4_0 & n4_1 & ~n4_2;
+              const unsigned int nde0 = ~(nd_0 | nd_1 | nd_2), nde1 = nd_0 & ~nd_1 & ~nd_2, nde2 = ~nd_0 & nd_1 & ~nd_2,
+                                 nde3 = nd_0 & nd_1 & ~nd_2;
+              pc[0] += __popc(B & n4e2 & nde0);   // code 5
+              pc[1] += __popc(B & n4e3 & nde0);   // 7
+              pc[2] += __popc(B & n4e1 & nde1);   // 13
+              pc[3] += __popc(B & n4e2 & nde1);   // 15
+              pc[4] += __popc(B & n4e3 & nde1);   // 17
+              pc[5] += __popc(B & n4e0 & nde2);   // 21
+              pc[6] += __popc(B & n4e1 & nde2);   // 23
+              pc[7] += __popc(B & n4e2 & nde2);   // 25
+              pc[8] += __popc(B & n4e3 & nde2);   // 27
+              pc[9] += __popc(B & n4e1 & nde3);   // 33
+            }
+            // intensity histogram over the mask pixels of this row word
+            if (want_hist && Wf != 0) {
+              const uint4* gp = reinterpret_cast<const uint4*>(gray + static_cast<size_t>(f) * W + 32 * lane);
+              const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+              const unsigned int gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (Wf & (1u << k)) atomicAdd(&my_hist[(gw[k >> 2] >> (8 * (k & 3))) & 0xFFu], 1u);
+            }
+          }
+          // first mixed 2x2 cell with (f, c) as its upper-left pixel, c < W-1, f < H-1 (rows f, f+1 = Wp2, Wp1)
+          if (first == 0xFFFFFFFFu && f < H - 1) {
+            unsigned int nf = __shfl_down_sync(0xFFFFFFFFu, Wf, 1), n1 = __shfl_down_sync(0xFFFFFFFFu, Wp1, 1);
+            if (lane == 31) { nf = Wf >> 31 << 0; n1 = Wp1 >> 31; }   // column 1024 does not exist: replicate -> never mixed
+            const unsigned int Wfr = shr_in(Wf, lane == 31 ? (Wf >> 31) : nf), W1r = shr_in(Wp1, lane == 31 ? (Wp1 >> 31) : n1);
+            unsigned int mixed = (Wf ^ Wfr) | (Wf ^ Wp1) | (Wf ^ W1r);
+            if (lane == 31) mixed &= 0x7FFFFFFFu;     // c = 1023 is not an upper-left corner
+            const unsigned int ball = __ballot_sync(0xFFFFFFFFu, mixed != 0);
+            if (ball) {
+              const int l0 = __ffs(ball) - 1;
+              const unsigned int mw = __shfl_sync(0xFFFFFFFFu, mixed, l0);
+              first = static_cast<unsigned int>(f) * W + 32 * l0 + (__ffs(mw) - 1);
+            }
+          }
+        }
+        Wp2 = Wp1; Wp1 = Wn;
+        Bp3 = Bp2; Bp2 = Bp1; BLp3 = BLp2; BRp3 = BRp2; BLp2 = BLp1; BRp2 = BRp1;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) hA[k] = hB[k];
+    }
+  }
+  // ---- reduce: lanes -> warp -> global
+  int mnc = INT_MAX, mxc = -1;
+  if (colmask) { mnc = 32 * lane + __ffs(colmask) - 1; mxc = 32 * lane + 31 - __clz(colmask); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    area += __shfl_xor_sync(0xFFFFFFFFu, area, o);
+    sum_r += __shfl_xor_sync(0xFFFFFFFFu, sum_r, o);
+    sum_c += __shfl_xor_sync(0xFFFFFFFFu, sum_c, o);
+    mnc = min(mnc, __shfl_xor_sync(0xFFFFFFFFu, mnc, o));
+    mxc = max(mxc, __shfl_xor_sync(0xFFFFFFFFu, mxc, o));
+#pragma unroll
+    for (int b = 0; b < YSI_PERIM_BINS; ++b) pc[b] += __shfl_xor_sync(0xFFFFFFFFu, pc[b], o);
+  }
+  MaskStatsDev* st = stats + m;
+  if (lane == 0) {
+    if (area) {
+      atomicAdd(&st->area, area); atomicAdd(&st->sum_r, sum_r); atomicAdd(&st->sum_c, sum_c);
+      atomicMin(&st->min_r, mnr); atomicMin(&st->min_c, mnc); atomicMax(&st->max_r, mxr); atomicMax(&st->max_c, mxc);
+    }
+    if (first != 0xFFFFFFFFu) atomicMin(&st->first_cell, first);
+#pragma unroll
+    for (int b = 0; b < YSI_PERIM_BINS; ++b)
+      if (pc[b]) atomicAdd(&st->perim_hist[b], pc[b]);
+  }
+  if (want_hist) {
+    __syncthreads();
+    unsigned int hsum = 0;
+#pragma unroll
+    for (int w = 0; w < FAST_WARPS; ++w) hsum += s_hist[w][0][threadIdx.x] + s_hist[w][1][threadIdx.x];
+    if (hsum) atomicAdd(&st->mask_hist[threadIdx.x], hsum);
+  }
+}
+
+void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const uint8_t* gray,
+                           const int* mask_image, uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s) {
   if (nmask <= 0) return;
+  if (g.H == 1024 && g.W == 1024 && g.rh == 1024 && g.rw == 1024 && masks && !up_logits && (sum3 == nullptr || gray != nullptr)) {
+    // enough warps to fill the GPU for few masks, long bands (little halo recomputation) for many
+    const int gpw = nmask >= 64 ? 16 : (nmask >= 16 ? 8 : 4);       // row groups (4 rows each) per warp
+    const int ctas = ceil_div(257, FAST_WARPS * gpw);
+    upsample_stats_fast_kernel<<<dim3(ctas, nmask), FAST_WARPS * 32, 0, s>>>(low, sum3 ? gray : nullptr, mask_image, masks, stats, gpw);
+    YSI_CUDA(cudaGetLastError());
+    return;
+  }
   PostParams p;
   p.g = g;
   p.sh = static_cast<float>(g.rh) / static_cast<float>(g.H);
@@ -658,18 +897,24 @@ void launch_packbits(const uint8_t* masks, uint8_t* packed, int nmask, long long
   YSI_CUDA(cudaGetLastError());
 }
 
-__global__ void sum3_kernel(const uint8_t* __restrict__ rgb, int H, int W, int row_stride, uint16_t* __restrict__ out) {
+// R+G+B per pixel (uint16, the centre-disk sums square it) and floor((R+G+B)/3) (uint8, the mask histogram's bin)
+__global__ void sum3_kernel(const uint8_t* __restrict__ rgb, int H, int W, int row_stride, uint16_t* __restrict__ out,
+                            uint8_t* __restrict__ gray) {
   const int n = blockIdx.z;
   const int r = blockIdx.y;
   const uint8_t* row = rgb + (static_cast<size_t>(n) * H + r) * row_stride;
   uint16_t* orow = out + (static_cast<size_t>(n) * H + r) * W;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < W; c += gridDim.x * blockDim.x)
-    orow[c] = static_cast<uint16_t>(row[3 * c] + row[3 * c + 1] + row[3 * c + 2]);
+  uint8_t* grow = gray ? gray + (static_cast<size_t>(n) * H + r) * W : nullptr;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < W; c += gridDim.x * blockDim.x) {
+    const unsigned int v = row[3 * c] + row[3 * c + 1] + row[3 * c + 2];
+    orow[c] = static_cast<uint16_t>(v);
+    if (grow) grow[c] = static_cast<uint8_t>(v / 3);
+  }
 }
 
-void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, cudaStream_t s) {
+void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, uint8_t* gray, cudaStream_t s) {
   dim3 grid(ceil_div(W, 256), H, n);
-  sum3_kernel<<<grid, 256, 0, s>>>(rgb, H, W, row_stride, sum3);
+  sum3_kernel<<<grid, 256, 0, s>>>(rgb, H, W, row_stride, sum3, gray);
   YSI_CUDA(cudaGetLastError());
 }
 
