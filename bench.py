@@ -271,14 +271,14 @@ def run_ours(args):
             b = (i % nbat) * BATCH
             yield host_imgs[b:b + BATCH], boxes[b:b + BATCH]
 
-    for _ in stage.run_stream(host_batches(3), raw=True):        # warm-up (also allocates the pinned result buffers)
+    for _ in stage.run_stream(host_batches(3), raw=True, copy_masks=False):        # warm-up (also allocates the pinned result buffers)
         pass
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     n_out = 0
-    for out in stage.run_stream(host_batches(K), raw=True):      # public pipelined API: masks + metric rows per batch
+    for out in stage.run_stream(host_batches(K), raw=True, copy_masks=False):   # public pipelined API: masks (views into the pinned result ring) + metric rows per batch
         n_out += len(out)
     stage.sync()
     torch.cuda.synchronize()
@@ -309,6 +309,8 @@ def run_ours(args):
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "frac_of_burst": achieved / pk["bf16_tflops"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
+                "traffic_note": "ncu --set full (profiles/r01b_ncu_top.txt): fc1-shaped launch 378 MB DRAM r+w for 256 MB algorithmic, "
+                                "fc2-shaped 329 MB, qkv-shaped 188 MB; a class-wide per-launch average is not captured",
                 "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1),
                 "share_of_step": g_ms / tot_ms if tot_ms else None, "traffic": None,
                 "how": f"CUDA events around every launch, {psteps} profiled steps after the timed region"}

@@ -222,10 +222,14 @@ class SamStage:
         return out
 
     # ------------------------------------------------------------------ pipelined form
-    def run_stream(self, batches, want_masks: bool = True, raw: bool = False):
+    def run_stream(self, batches, want_masks: bool = True, raw: bool = False, copy_masks: bool = True):
         """Generator over ``batches`` (an iterable of (images, boxes) with same-sized images per batch) that keeps two
         batches in flight: the H2D copy and the encoder of batch i+1 overlap the decoder, metrics and D2H copy of
-        batch i (ysi_submit_batch / ysi_wait_batch). Yields, per batch, what ``run_batch`` returns."""
+        batch i (ysi_submit_batch / ysi_wait_batch). Yields, per batch, what ``run_batch`` returns.
+
+        ``copy_masks=False`` yields the masks as views into the slot's pinned host buffer instead of copies (at 32
+        boxes per image the copies are 268 MB of host memcpy per batch and dominate); such a view is valid only until
+        the generator is advanced again (the slot's buffer is then handed to the next batch)."""
         pending = []                      # [(slot, images, boxes, counts, masks, rows, keepalive)]
         slot = 0
 
@@ -234,7 +238,7 @@ class SamStage:
             tm = nat.YsiTiming()
             self._check(self._lib.ysi_wait_batch(self._ctx, sl, C.byref(tm)), "ysi_wait_batch")
             self.last_timing = tm.as_dict()
-            return self._unpack(images, boxes, counts, masks, rows, want_masks, raw)
+            return self._unpack(images, boxes, counts, masks, rows, want_masks, raw, copy_masks)
 
         for images, boxes in batches:
             n = len(images)
@@ -274,12 +278,12 @@ class SamStage:
         rows = r.numpy()[:nb * nat.METRICS_DTYPE.itemsize].view(nat.METRICS_DTYPE)
         return masks, rows
 
-    def _unpack(self, images, boxes, counts, masks, rows, want_masks, raw):
+    def _unpack(self, images, boxes, counts, masks, rows, want_masks, raw, copy_masks=True):
         out = []
         k = 0
         for i in range(len(images)):
             c = int(counts[i])
-            m = masks[k:k + c].view(bool).copy() if want_masks else None
+            m = (masks[k:k + c].view(bool).copy() if copy_masks else masks[k:k + c].view(bool)) if want_masks else None
             r = rows[k:k + c].copy()
             mets = r if raw else [metrics_from_raw(r[j], self.on_empty) for j in range(c)]
             crops = []
