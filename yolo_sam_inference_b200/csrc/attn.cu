@@ -143,9 +143,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t bar_kempty = bar + 136;   // [8]
   const uint32_t bar_vfull = bar + 200;    // [8]
   const uint32_t bar_vempty = bar + 264;   // [8]
-  const uint32_t bar_pair = bar + 328;     // [4 row quarters][2 tile parities]: the two warps sharing 32 rows
-  const uint32_t bar_fin = bar + 392;      // [4 row quarters]
-  const uint32_t tmem_ptr_smem = bar + 424;
+  const uint32_t bar_fin = bar + 328;      // [4 row quarters]: the two warps sharing 32 rows exchange their row sums
+  const uint32_t tmem_ptr_smem = bar + 360;
   float* xm = reinterpret_cast<float*>(sgen + C::OFF_XM);
   float* xl = reinterpret_cast<float*>(sgen + C::OFF_XL);
 
@@ -170,7 +169,6 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int i = 0; i < 8; ++i) {
       mbar_init(bar_kfull + 8 * i, 1); mbar_init(bar_kempty + 8 * i, 1);
       mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
-      mbar_init(bar_pair + 8 * i, 2);
     }
     for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 2);
     fence_mbar_init();

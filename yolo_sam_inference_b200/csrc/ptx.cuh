@@ -53,22 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// Same, for single-lane producer roles that mostly wait: the suspend-time hint lets the hardware park the thread until
-// the phase completes (or the hint expires) instead of re-issuing the poll, so the producer warps stop competing with
-// the compute warps for issue slots. Wake-up on completion is immediate, so no latency is added to the chain.
-__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)
-        : "memory");
-  } while (!ok);
-}
-
 // one lane of a fully converged warp (elect.sync): lets the compiler issue the uniform-datapath instructions of a
 // single-thread role (UTCHMMA, UTMALDG, UTCBAR) directly instead of wrapping each in a per-lane waterfall loop
 __device__ __forceinline__ bool elect_one() {
