@@ -93,7 +93,7 @@ constexpr int KEYS_LD = 512;
 __global__ void __launch_bounds__(256)
 keys_ln_kernel(const float* __restrict__ in, long long rows, const float* __restrict__ g, const float* __restrict__ bta,
                const float* __restrict__ pe, float* __restrict__ keys, op16* __restrict__ keys_bf,
-               op16* __restrict__ keyspos_bf) {
+               op16* __restrict__ keyspos_bf, int want_lo) {
   const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -120,12 +120,14 @@ keys_ln_kernel(const float* __restrict__ in, long long rows, const float* __rest
     float4 y;
     y.x = (v[k].x - mean) * rstd * gg.x + bb.x; y.y = (v[k].y - mean) * rstd * gg.y + bb.y;
     y.z = (v[k].z - mean) * rstd * gg.z + bb.z; y.w = (v[k].w - mean) * rstd * gg.w + bb.w;
-    reinterpret_cast<float4*>(keys + row * C)[i] = y;
+    if (keys) reinterpret_cast<float4*>(keys + row * C)[i] = y;       // fp32 copy: only the next block's residual needs it
     uint2 o;
     o.x = pack_op16x2(y.x, y.y); o.y = pack_op16x2(y.z, y.w);
     reinterpret_cast<uint2*>(keys_bf + row * KEYS_LD)[i] = o;
-    o.x = pack_op16x2(y.x - op2f(f2op(y.x)), y.y - op2f(f2op(y.y))); o.y = pack_op16x2(y.z - op2f(f2op(y.z)), y.w - op2f(f2op(y.w)));
-    reinterpret_cast<uint2*>(keys_bf + row * KEYS_LD + C)[i] = o;
+    if (want_lo) {                                                   // lo terms: only the upscaler (after the last block) reads them
+      o.x = pack_op16x2(y.x - op2f(f2op(y.x)), y.y - op2f(f2op(y.y))); o.y = pack_op16x2(y.z - op2f(f2op(y.z)), y.w - op2f(f2op(y.w)));
+      reinterpret_cast<uint2*>(keys_bf + row * KEYS_LD + C)[i] = o;
+    }
     o.x = pack_op16x2(y.x + p.x, y.y + p.y); o.y = pack_op16x2(y.z + p.z, y.w + p.w);
     reinterpret_cast<uint2*>(keyspos_bf + row * C)[i] = o;
   }
@@ -424,6 +426,99 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
   if (t < NT * 16) pout[2 * NT + t] = s_part[t] + s_part[NT * 16 + t];
 }
 
+// Many boxes (configs[3]: 32 per image): one CTA per (head, box) streams all 4096 keys ONCE through shared memory
+// (coalesced float4 loads, 256 keys per tile) and keeps a running (max, sum, P.V) per query row in registers -- lane =
+// (key lane 0..3, row 0..7): the 8 row-lanes of a key read its K / V slice as one broadcast -- instead of writing the
+// 7 x 1024 scores to shared memory, re-reading them twice and fetching V element-wise seven times.
+constexpr int T2O_TK = 256;
+
+__global__ void __launch_bounds__(256)
+t2i_attention_online_kernel(const float* __restrict__ q_t2i, const float* __restrict__ K, int ldk, const float* __restrict__ V,
+                            int ldv, const int* __restrict__ group, float* __restrict__ attn_out) {
+  __shared__ float4 s_k[T2O_TK][4];
+  __shared__ float4 s_v[T2O_TK][4];
+  __shared__ float s_red[8][NT][18];
+  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int r = lane & 7, kl = lane >> 3;
+  const size_t seq = group ? group[b] : b;
+  const float* Kb = K + seq * 4096 * ldk + h * 16;
+  const float* Vb = V + seq * 4096 * ldv + h * 16;
+  float q[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)      // scale 16^-0.5 and log2(e): softmax in base 2 (ex2.approx is one MUFU)
+    q[i] = r < NT ? (0.25f * 1.4426950408889634f) * q_t2i[(static_cast<size_t>(b) * NT + r) * 128 + h * 16 + i] : 0.f;
+  float m = -INFINITY, l = 0.f, o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.f;
+  for (int tile = 0; tile < 4096 / T2O_TK; ++tile) {
+    {
+      const size_t key = static_cast<size_t>(tile) * T2O_TK + t;
+      const float4* kp = reinterpret_cast<const float4*>(Kb + key * ldk);
+      const float4* vp = reinterpret_cast<const float4*>(Vb + key * ldv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s_k[t][i] = __ldg(kp + i); s_v[t][i] = __ldg(vp + i); }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      const int kk = warp * 32 + kl + 4 * i;
+      float sc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 k4 = s_k[kk][j];
+        sc = fmaf(q[4 * j], k4.x, sc); sc = fmaf(q[4 * j + 1], k4.y, sc);
+        sc = fmaf(q[4 * j + 2], k4.z, sc); sc = fmaf(q[4 * j + 3], k4.w, sc);
+      }
+      if (sc > m) {                         // new running maximum of this lane's key subset: rescale (rare after the first keys)
+        const float f = ex2_approx(m - sc);
+        l *= f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] *= f;
+        m = sc;
+      }
+      const float pv = ex2_approx(sc - m);
+      l += pv;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v4 = s_v[kk][j];
+        o[4 * j] = fmaf(pv, v4.x, o[4 * j]); o[4 * j + 1] = fmaf(pv, v4.y, o[4 * j + 1]);
+        o[4 * j + 2] = fmaf(pv, v4.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(pv, v4.w, o[4 * j + 3]);
+      }
+    }
+    __syncthreads();
+  }
+  // merge the 4 key lanes of the warp (every lane has seen keys: m is finite), then the 8 warps
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m, off), l2 = __shfl_xor_sync(0xFFFFFFFFu, l, off);
+    const float mn = fmaxf(m, m2), f1 = ex2_approx(m - mn), f2 = ex2_approx(m2 - mn);
+    l = l * f1 + l2 * f2;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = o[d] * f1 + __shfl_xor_sync(0xFFFFFFFFu, o[d], off) * f2;
+    m = mn;
+  }
+  if (kl == 0 && r < NT) {
+    s_red[warp][r][0] = m; s_red[warp][r][1] = l;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) s_red[warp][r][2 + d] = o[d];
+  }
+  __syncthreads();
+  if (t < NT * 16) {
+    const int rr = t / 16, d = t % 16;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mm = fmaxf(mm, s_red[w][rr][0]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float f = ex2_approx(s_red[w][rr][0] - mm);
+      ll = fmaf(f, s_red[w][rr][1], ll);
+      oo = fmaf(f, s_red[w][rr][2 + d], oo);
+    }
+    attn_out[(static_cast<size_t>(b) * NT + rr) * 128 + h * 16 + d] = oo / ll;
+  }
+}
+
 // combine the key ranges: out[b][r][h*16+d] = sum_s e^(m_s-m) o_s / sum_s e^(m_s-m) l_s
 __global__ void __launch_bounds__(256)
 t2i_merge_kernel(const float* __restrict__ part, float* __restrict__ attn_out) {
@@ -450,40 +545,54 @@ t2i_merge_kernel(const float* __restrict__ part, float* __restrict__ attn_out) {
 __global__ void __launch_bounds__(256)
 i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict__ group, const float* __restrict__ k_tok,
                      const float* __restrict__ v_tok, op16* __restrict__ out) {
-  __shared__ float s_k[NT * 128], s_v[NT * 128];
+  // k / v of the box's 7 tokens, head h at floats [h*20, h*20+16) of a 160-float row: the 8 heads of a quarter-warp
+  // then read their 16-byte pieces from 8 different bank groups (a 64-byte head stride would be a 4-way conflict)
+  __shared__ __align__(16) float s_k[NT * 160], s_v[NT * 160];
   const int b = blockIdx.y, t = threadIdx.x;
   for (int i = t; i < NT * 128; i += 256) {
-    s_k[i] = k_tok[static_cast<size_t>(b) * NT * 128 + i];
-    s_v[i] = v_tok[static_cast<size_t>(b) * NT * 128 + i];
+    const int rr = i >> 7, c = i & 127, j = rr * 160 + (c >> 4) * 20 + (c & 15);
+    s_k[j] = k_tok[static_cast<size_t>(b) * NT * 128 + i];
+    s_v[j] = v_tok[static_cast<size_t>(b) * NT * 128 + i];
   }
   __syncthreads();
   const int tok = blockIdx.x * 32 + (t >> 3), h = t & 7;
   const size_t seq = group ? group[b] : b;
   const float4* qp = reinterpret_cast<const float4*>(Q + (seq * 4096 + tok) * ldq + h * 16);
-  float q[16];
+  float4 q[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const float4 v = __ldg(qp + i); q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w; }
+  for (int i = 0; i < 4; ++i) q[i] = __ldg(qp + i);
   float sc[NT], m = -INFINITY;
 #pragma unroll
   for (int r = 0; r < NT; ++r) {
+    const float4* kp = reinterpret_cast<const float4*>(s_k + r * 160 + h * 20);
     float a = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) a = fmaf(q[d], s_k[r * 128 + h * 16 + d], a);
-    sc[r] = a * 0.25f;
+    for (int j = 0; j < 4; ++j) {
+      const float4 k4 = kp[j];
+      a = fmaf(q[j].x, k4.x, a); a = fmaf(q[j].y, k4.y, a); a = fmaf(q[j].z, k4.z, a); a = fmaf(q[j].w, k4.w, a);
+    }
+    sc[r] = a * (0.25f * 1.4426950408889634f);     // scale 16^-0.5, base-2 softmax
     m = fmaxf(m, sc[r]);
   }
   float sum = 0.f;
 #pragma unroll
-  for (int r = 0; r < NT; ++r) { sc[r] = expf(sc[r] - m); sum += sc[r]; }
+  for (int r = 0; r < NT; ++r) { sc[r] = ex2_approx(sc[r] - m); sum += sc[r]; }
   const float inv = 1.0f / sum;
   float o[16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    float a = 0.f;
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
 #pragma unroll
-    for (int r = 0; r < NT; ++r) a = fmaf(sc[r], s_v[r * 128 + h * 16 + d], a);
-    o[d] = a * inv;
+  for (int r = 0; r < NT; ++r) {
+    const float4* vp = reinterpret_cast<const float4*>(s_v + r * 160 + h * 20);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v4 = vp[j];
+      o[4 * j] = fmaf(sc[r], v4.x, o[4 * j]); o[4 * j + 1] = fmaf(sc[r], v4.y, o[4 * j + 1]);
+      o[4 * j + 2] = fmaf(sc[r], v4.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(sc[r], v4.w, o[4 * j + 3]);
+    }
   }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] *= inv;
   uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * 4096 + tok) * 128 + h * 16);
   uint4 v0, v1;
   v0.x = pack_op16x2(o[0], o[1]); v0.y = pack_op16x2(o[2], o[3]); v0.z = pack_op16x2(o[4], o[5]); v0.w = pack_op16x2(o[6], o[7]);
@@ -592,6 +701,19 @@ static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s)
     tok_linear_kernel<<<dim3(nmax / 8, ceil_div(R, TOK_ROWS), count), 256, 0, s>>>(P, R);
 }
 
+// token -> image attention: few boxes -> key ranges split over CTAs + merge (parallelism); many -> one streaming CTA
+// per (head, box)
+static int launch_t2i(const float* q, const float* K, int ldk, const float* V, int ldv, const int* group, float* part,
+                      float* attn_out, int nb, cudaStream_t s) {
+  if (nb >= 16) {
+    t2i_attention_online_kernel<<<dim3(8, nb), 256, 0, s>>>(q, K, ldk, V, ldv, group, attn_out);
+    return 1;
+  }
+  t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(q, K, ldk, V, ldv, group, part);
+  t2i_merge_kernel<<<nb, 256, 0, s>>>(part, attn_out);
+  return 2;
+}
+
 void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb, int n_img, int nb, float* low_res_out,
                      float* sparse_out, cudaStream_t s, int64_t* launches, Profiler* prof) {
   YSI_CHECK(n_img >= 1 && n_img <= wk.cap_img && nb >= 1 && nb <= wk.cap_box, "decoder batch exceeds the workspace");
@@ -654,8 +776,7 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       ev.bias = lw.t2i.bv; ev.out_f32 = v; ev.ld_out = 128;
       gemm_op16(a_keys, per_img ? C : KEYS_LD, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
     }
-    { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(wk.q_t2i, kq, 256, v, 128, group, t_part); ++nl;
-      t2i_merge_kernel<<<nb, 256, 0, s>>>(t_part, wk.attn_t2i); ++nl; }
+    { ProfScope ps(prof, KC_DEC_ATTN); nl += launch_t2i(wk.q_t2i, kq, 256, v, 128, group, t_part, wk.attn_t2i, nb, s); }
     {
       // queries += out_proj(attn); LN2; MLP; LN3; image->token key / value projections   (:328-341)
       ProfScope ps(prof, KC_DEC_TOKEN);
@@ -683,7 +804,9 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       if (per_img) { ep.add_mod = 4096; ep.add_group = wk.box_img; } else { ep.add_mod = TB; }
       // block 1 reads kq (q columns) in i2t above, which is complete before this GEMM starts (same stream)
       gemm_op16(wk.attn_i2t, 128, lw.w_i2t_out, 128, TB, 256, 128, ep, s); ++nl;
-      keys_ln_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(wk.kq, TB, lw.ln4_g, lw.ln4_b, w.image_pe, wk.keys, wk.keys_bf, wk.keyspos_bf); ++nl;
+      const bool last = li == 1;
+      keys_ln_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(wk.kq, TB, lw.ln4_g, lw.ln4_b, w.image_pe, last ? nullptr : wk.keys, wk.keys_bf,
+                                                     wk.keyspos_bf, last ? 1 : 0); ++nl;
       YSI_CUDA(cudaGetLastError());
     }
   }
@@ -702,8 +825,7 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     ev.bias = w.final_attn.bv; ev.out_f32 = wk.v; ev.ld_out = 128;
     gemm_op16(wk.keys_bf, KEYS_LD, w.w_v_final, C, TB, 128, C, ev, s); ++nl;
   }
-  { ProfScope ps(prof, KC_DEC_ATTN); t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, t_part); ++nl;
-    t2i_merge_kernel<<<nb, 256, 0, s>>>(t_part, wk.attn_t2i); ++nl; }
+  { ProfScope ps(prof, KC_DEC_ATTN); nl += launch_t2i(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, t_part, wk.attn_t2i, nb, s); }
   {
     // queries += out_proj(attn); layer_norm_final_attn (eps 1e-5); hypernetwork MLP of mask token 0 (= token row 1)
     ProfScope ps(prof, KC_DEC_TOKEN);
