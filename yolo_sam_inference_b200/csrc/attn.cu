@@ -53,41 +53,48 @@ constexpr int KV_BYTES = BKV * 128;         // one 64-column chunk of a 64-key t
 constexpr int P_BYTES = BQ * BKV * 2;       // 16 KB
 constexpr float LAZY_LOG2 = 8.0f;           // rescale O only when the row max grows by more than 2^8
 
-// HD = 64 (ViT-B/L) or 80 (ViT-H). Operands are staged in 64-column, 128B-swizzled chunks; for HD = 80 a second
-// chunk holds columns 64..127 of which only the first 16 (one k-step) are used -- whatever follows them in the
-// qkv row (next head / next section / zero fill) is never touched by an MMA.
+// HD = 64 (ViT-B/L) or 80 (ViT-H). Operands are staged as a 64-column, 128B-swizzled chunk; for HD = 80 the trailing
+// 16 columns (one k-step) are a second chunk with 32-byte rows (32B swizzle), a quarter of the first one's size.
 template <bool GLOBAL, int HD>
 struct Cfg {
-  static constexpr int NCH = HD > 64 ? 2 : 1;                       // 64-column chunks per operand
+  static constexpr bool HAS1 = HD > 64;                             // head_dim 80: a second, 16-column chunk per operand
   static constexpr int NKS = HD / 16;                               // k-steps of Q K^T and of the table MMAs
-  // K / V ring depths (window: whole window resident). A K tile is requested NSTK - 2 softmax tiles before the S MMA
-  // that consumes it (S runs two tiles ahead of the softmax), a V tile NSTV - 1 tiles ahead: at ~1 us per tile one
-  // tile of lead time does not cover the L2 round trip of the TMA, and a late K tile stalls the single MMA-issuing
-  // thread -- and with it every P.V queued behind it.
-  static constexpr int NSTK = GLOBAL ? 5 : 4;
+  // K / V ring depths (window: whole window resident). A K tile is requested well before the S MMA that consumes it
+  // and a V tile NSTV - 1 tiles ahead: one tile of lead time (~1 us) does not cover the L2 round trip of the TMA.
+  static constexpr int NSTK = GLOBAL ? (HAS1 ? 3 : 5) : 4;
   static constexpr int NSTV = 4;
+  // chunk 0: columns 0..63 (128-byte rows, SWIZZLE_128B); chunk 1 (HAS1): columns 64..79 (32-byte rows, SWIZZLE_32B)
+  static constexpr int Q1_BYTES = HAS1 ? BQ * 32 : 0;
   static constexpr int K_CHUNK = GLOBAL ? 80 * 128 : 208 * 128;     // global: 64 keys + 16 rows for the rel_pos_h "keys"
-  static constexpr int K_STAGE = GLOBAL ? NCH * K_CHUNK : KV_BYTES; // global: a stage holds its chunks back to back;
-                                                                    // window: chunk c lives at OFF_K + c*K_CHUNK, tiles 8 KB apart
-  static constexpr int K_TOTAL = GLOBAL ? NSTK * K_STAGE : NCH * K_CHUNK;
+  static constexpr int K1_CHUNK = HAS1 ? K_CHUNK / 4 : 0;
+  static constexpr int K_TOTAL = GLOBAL ? NSTK * K_CHUNK : K_CHUNK; // window: tiles 8 KB (chunk 1: 2 KB) apart
+  static constexpr int K1_TOTAL = ((GLOBAL ? NSTK * K1_CHUNK : K1_CHUNK) + 1023) / 1024 * 1024;
   static constexpr int V_CHUNK = GLOBAL ? KV_BYTES : 208 * 128;
-  static constexpr int V_STAGE = GLOBAL ? NCH * V_CHUNK : KV_BYTES;
-  static constexpr int V_TOTAL = GLOBAL ? NSTV * V_STAGE : NCH * V_CHUNK;
+  static constexpr int V1_CHUNK = HAS1 ? V_CHUNK / 4 : 0;
+  static constexpr int V_TOTAL = GLOBAL ? NSTV * V_CHUNK : V_CHUNK;
+  static constexpr int V1_TOTAL = ((GLOBAL ? NSTV * V1_CHUNK : V1_CHUNK) + 1023) / 1024 * 1024;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + NCH * CH_Q;
-  static constexpr int OFF_V = OFF_K + K_TOTAL;
-  // 32 KB of setup scratch: fp32 bias values [k][128] (P itself lives in TMEM). Global: aliases the V ring, whose first
-  // loads wait until every softmax thread has its bias in registers (bar_rel). Windowed: its own region.
+  static constexpr int OFF_Q1 = OFF_Q + CH_Q;
+  static constexpr int OFF_K = OFF_Q1 + Q1_BYTES;
+  static constexpr int OFF_K1 = OFF_K + K_TOTAL;
+  static constexpr int OFF_V = OFF_K1 + K1_TOTAL;
+  static constexpr int OFF_V1 = OFF_V + V_TOTAL;
+  // 32 KB of setup scratch: fp32 bias values [k][128] (P itself lives in TMEM). Global layers and head_dim 80: aliases
+  // the V area, whose first loads wait until every softmax thread has its bias in registers (bar_rel). Windowed
+  // head_dim 64: its own region, so the whole window's K / V can be requested up front with Q.
   static constexpr int SCRATCH = 32768;
-  static constexpr int OFF_P = GLOBAL ? OFF_V : OFF_V + V_TOTAL;
-  // rel-pos tables as TMA'd for the table MMA: global -> rel_pos_w in the V area (16 KB per chunk; consumed by the table
-  // MMA before the scratch is written); windowed -> second half of the scratch (4 KB per table chunk), so the whole
-  // window's K / V can be requested up front with Q
+  static constexpr bool ALIAS_V = GLOBAL || HAS1;
+  static constexpr int OFF_P = ALIAS_V ? OFF_V : OFF_V1 + V1_TOTAL;
+  // rel-pos tables as TMA'd for the table MMA (consumed before the scratch is written): global -> rel_pos_w at the
+  // start of the V area; windowed -> 16 KB into the scratch
   static constexpr int TAB_ROWS = GLOBAL ? 128 : 32;        // rows of each rel-pos table fed to the table MMA
   static constexpr int TAB_CHUNK = TAB_ROWS * 128;
+  static constexpr int TAB1_CHUNK = HAS1 ? TAB_ROWS * 32 : 0;
   static constexpr int OFF_TABH = GLOBAL ? OFF_K : OFF_P + P_BYTES;     // (unused when GLOBAL)
-  static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_P + P_BYTES + NCH * TAB_CHUNK;
-  static constexpr int OFF_BAR = GLOBAL ? OFF_V + V_TOTAL : OFF_P + SCRATCH;       // 512 B of mbarriers
+  static constexpr int OFF_TABW = GLOBAL ? OFF_V : OFF_TABH + TAB_CHUNK;
+  static constexpr int OFF_TABH1 = OFF_TABW + TAB_CHUNK;                 // (unused when GLOBAL)
+  static constexpr int OFF_TABW1 = GLOBAL ? OFF_TABW + TAB_CHUNK : OFF_TABH1 + TAB1_CHUNK;
+  static constexpr int OFF_BAR = ALIAS_V ? OFF_V1 + V1_TOTAL : OFF_P + SCRATCH;       // 512 B of mbarriers
   static constexpr int OFF_XM = OFF_BAR + 512;              // fp32 [2][128][2]: half-row maxima of tile parity 0 / 1
   static constexpr int OFF_XL = OFF_XM + 2048;              // fp32 [128][2]: half-row sums at the end
   static constexpr int SMEM_BYTES = OFF_XL + 1024 + 1024;   // + alignment slack
@@ -97,11 +104,13 @@ struct Cfg {
   static constexpr int COL_O = 2 * S_N;
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
-  static constexpr int CTAS_PER_SM = HD > 64 ? 1 : 2;
+  static constexpr int CTAS_PER_SM = 2;
   static_assert(HD == 64 || HD == 80, "head_dim 64 or 80");
   static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_CHUNK % 1024 == 0, "swizzle atoms need 1 KB alignment");
-  static_assert(GLOBAL || 2 * NCH * TAB_CHUNK <= P_BYTES, "window tables must fit the second half of the scratch");
-  static_assert(!GLOBAL || V_TOTAL >= SCRATCH, "the bias scratch aliases the V ring");
+  static_assert(OFF_K1 % 256 == 0 && OFF_V1 % 256 == 0 && OFF_Q1 % 256 == 0 && K1_CHUNK % 256 == 0 && V1_CHUNK % 256 == 0, "32B-swizzle atoms need 256 B alignment");
+  static_assert(OFF_TABW1 + TAB1_CHUNK <= OFF_P + (ALIAS_V ? V_TOTAL + V1_TOTAL : SCRATCH), "tables must fit the scratch / V area");
+  static_assert(!ALIAS_V || V_TOTAL + V1_TOTAL >= (GLOBAL ? SCRATCH : 2 * 28 * 128 * 4), "the bias scratch aliases the V area");
+  static_assert(2 * (OFF_BAR + 512 + 2048 + 1024 + 1024 + 1024) <= 232448, "two CTAs per SM");
   static_assert(NSTK <= 8 && NSTV <= 8, "barrier arrays");
   static_assert(COL_O + HD <= TMEM_COLS, "TMEM budget");
 };
@@ -127,7 +136,10 @@ template <bool GLOBAL, int HD>
 __global__ void __launch_bounds__(attn::THREADS, attn::Cfg<GLOBAL, HD>::CTAS_PER_SM)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const __grid_constant__ CUtensorMap tmKVtail, const __grid_constant__ CUtensorMap tmRel,
-                         const __grid_constant__ CUtensorMap tmRel8, AttnParams p) {
+                         const __grid_constant__ CUtensorMap tmRel8, const __grid_constant__ CUtensorMap tmQ1,
+                         const __grid_constant__ CUtensorMap tmKV1, const __grid_constant__ CUtensorMap tmKVtail1,
+                         const __grid_constant__ CUtensorMap tmRel1, const __grid_constant__ CUtensorMap tmRel8_1,
+                         AttnParams p) {
   using namespace attn;
   using C = Cfg<GLOBAL, HD>;
   extern __shared__ uint8_t smem_raw[];
@@ -190,48 +202,56 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // arithmetic, uniform-datapath issue sequences: ~80 SASS instructions per tile each) paces the softmax:
     //   warp 8: TMA loads   warp 9: table + S = Q K^T MMAs   warp 10: O += P V MMAs   (warp 11 only donates registers)
     if (C::CTAS_PER_SM == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_PRODUCER));
-    constexpr int NCH = C::NCH, NKS = C::NKS;
-    auto k_tile_addr = [&](int st, int c) {
-      return sbase + C::OFF_K + (GLOBAL ? st * C::K_STAGE + c * C::K_CHUNK : c * C::K_CHUNK + st * KV_BYTES);
-    };
-    auto v_tile_addr = [&](int st, int c) {
-      return sbase + C::OFF_V + (GLOBAL ? st * C::V_STAGE + c * C::V_CHUNK : c * C::V_CHUNK + st * KV_BYTES);
-    };
-    // K-major operand, k-step k: chunk k/4 (64 columns each), +32 B per 16 columns inside the swizzle atom
-    auto kdesc_at = [&](uint32_t base, int chunk_bytes, int k) {
-      return umma_desc_sw128(base + static_cast<uint32_t>((k >> 2) * chunk_bytes), 16, 1024) + 2u * static_cast<uint32_t>(k & 3);
+    constexpr int NKS = C::NKS;
+    constexpr bool HAS1 = C::HAS1;
+    // chunk 0 / chunk 1 of a K or V tile (global: ring stage st; window: tile st of the resident window)
+    auto k_tile_addr = [&](int st) { return sbase + C::OFF_K + st * (GLOBAL ? C::K_CHUNK : KV_BYTES); };
+    auto k1_tile_addr = [&](int st) { return sbase + C::OFF_K1 + st * (GLOBAL ? C::K1_CHUNK : KV_BYTES / 4); };
+    auto v_tile_addr = [&](int st) { return sbase + C::OFF_V + st * (GLOBAL ? C::V_CHUNK : KV_BYTES); };
+    auto v1_tile_addr = [&](int st) { return sbase + C::OFF_V1 + st * (GLOBAL ? C::V1_CHUNK : KV_BYTES / 4); };
+    // K-major operand, k-step k: steps 0..3 = +32 B per 16 columns inside the 128B swizzle atom of chunk 0, step 4 = chunk 1
+    auto kdesc_at = [&](uint32_t base0, uint32_t base1, int k) {
+      return k < 4 ? umma_desc_sw128(base0, 16, 1024) + 2u * static_cast<uint32_t>(k) : umma_desc_sw32(base1, 16, 256);
     };
     // Each role runs with the whole warp converged (all lanes poll the barriers) and one elected lane issuing.
     if (warp == SM_WARPS) {
       const bool lead = elect_one();
       // ---- TMA: Q tile + rel-pos table(s), then the K / V rings
       if (lead) {
-        mbar_arrive_expect_tx(bar_q, NCH * (CH_Q + (GLOBAL ? 1 : 2) * C::TAB_CHUNK));
-        for (int c = 0; c < NCH; ++c) {
-          tma_load_2d(sbase + C::OFF_Q + c * CH_Q, &tmQ, bar_q, cq + 64 * c, row0 + qt * BQ);
-          if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 0);   // rel_pos_h rows (zero padded)
-          tma_load_2d(sbase + C::OFF_TABW + c * C::TAB_CHUNK, &tmRel, bar_q, 64 * c, 128);              // rel_pos_w rows
+        mbar_arrive_expect_tx(bar_q, CH_Q + C::Q1_BYTES + (GLOBAL ? 1 : 2) * (C::TAB_CHUNK + C::TAB1_CHUNK));
+        tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
+        if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);        // rel_pos_h rows (zero padded)
+        tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);                   // rel_pos_w rows
+        if (HAS1) {
+          tma_load_2d(sbase + C::OFF_Q1, &tmQ1, bar_q, cq + 64, row0 + qt * BQ);
+          if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH1, &tmRel1, bar_q, 64, 0);
+          tma_load_2d(sbase + C::OFF_TABW1, &tmRel1, bar_q, 64, 128);
         }
       }
       auto load_k = [&](int tile, int st) {
         if (!lead) return;
         const bool tail = !GLOBAL && tile == 3;
-        mbar_arrive_expect_tx(bar_kfull + 8 * st, NCH * (GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES)));
-        for (int c = 0; c < NCH; ++c) {
-          tma_load_2d(k_tile_addr(st, c), tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck + 64 * c, row0 + tile * BKV);
-          // global: rows 64.. of the K tile = rel_pos_h[qh - kh + 63] for the CTA's two query rows (qh0 = 2 qt, kh = tile)
-          if (GLOBAL) tma_load_2d(k_tile_addr(st, c) + KV_BYTES, &tmRel8, bar_kfull + 8 * st, 64 * c, 2 * qt - tile + 63);
+        const int bytes0 = GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES);
+        mbar_arrive_expect_tx(bar_kfull + 8 * st, bytes0 + (HAS1 ? bytes0 / 4 : 0));
+        tma_load_2d(k_tile_addr(st), tail ? &tmKVtail : &tmKV, bar_kfull + 8 * st, ck, row0 + tile * BKV);
+        // global: rows 64.. of the K tile = rel_pos_h[qh - kh + 63] for the CTA's two query rows (qh0 = 2 qt, kh = tile)
+        if (GLOBAL) tma_load_2d(k_tile_addr(st) + KV_BYTES, &tmRel8, bar_kfull + 8 * st, 0, 2 * qt - tile + 63);
+        if (HAS1) {
+          tma_load_2d(k1_tile_addr(st), tail ? &tmKVtail1 : &tmKV1, bar_kfull + 8 * st, ck + 64, row0 + tile * BKV);
+          if (GLOBAL) tma_load_2d(k1_tile_addr(st) + KV_BYTES / 4, &tmRel8_1, bar_kfull + 8 * st, 64, 2 * qt - tile + 63);
         }
       };
       auto load_v = [&](int tile, int st) {
         if (!lead) return;
         const bool tail = !GLOBAL && tile == 3;
-        mbar_arrive_expect_tx(bar_vfull + 8 * st, NCH * (tail ? 16 * 128 : KV_BYTES));
-        for (int c = 0; c < NCH; ++c)
-          tma_load_2d(v_tile_addr(st, c), tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv + 64 * c, row0 + tile * BKV);
+        const int bytes0 = tail ? 16 * 128 : KV_BYTES;
+        mbar_arrive_expect_tx(bar_vfull + 8 * st, bytes0 + (HAS1 ? bytes0 / 4 : 0));
+        tma_load_2d(v_tile_addr(st), tail ? &tmKVtail : &tmKV, bar_vfull + 8 * st, cv, row0 + tile * BKV);
+        if (HAS1) tma_load_2d(v1_tile_addr(st), tail ? &tmKVtail1 : &tmKV1, bar_vfull + 8 * st, cv + 64, row0 + tile * BKV);
       };
-      if (!GLOBAL) {             // whole window resident: K / V do not alias the tables, request everything right away
+      if (!GLOBAL) {             // whole window resident: K does not alias the tables, request it right away
         for (int j = 0; j < 4; ++j) load_k(j, j);
+        if (C::ALIAS_V) mbar_wait(bar_rel, 0);     // the bias scratch sits in the V area: wait until it has been read
         for (int j = 0; j < 4; ++j) load_v(j, j);
       } else {
         for (int j = 0; j < C::NSTK && j < ntiles; ++j) load_k(j, j);      // the K ring does not alias the rel_pos_w table
@@ -257,18 +277,18 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       constexpr uint32_t idesc_s16 = umma_idesc_op16(128, 16, 0, 0);
       uint64_t qdesc[NKS];
 #pragma unroll
-      for (int k = 0; k < NKS; ++k) qdesc[k] = kdesc_at(sbase + C::OFF_Q, CH_Q, k);
+      for (int k = 0; k < NKS; ++k) qdesc[k] = kdesc_at(sbase + C::OFF_Q, sbase + C::OFF_Q1, k);
       mbar_wait(bar_q, 0);
       tc_fence_after();
       if (lead) {
         if (!GLOBAL) {
 #pragma unroll
           for (int k = 0; k < NKS; ++k)
-            umma_op16_ss(tmem_base + C::COL_TH, qdesc[k], kdesc_at(sbase + C::OFF_TABH, C::TAB_CHUNK, k), idesc_tab, k);
+            umma_op16_ss(tmem_base + C::COL_TH, qdesc[k], kdesc_at(sbase + C::OFF_TABH, sbase + C::OFF_TABH1, k), idesc_tab, k);
         }
 #pragma unroll
         for (int k = 0; k < NKS; ++k)
-          umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, C::TAB_CHUNK, k), idesc_tab, k);
+          umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, sbase + C::OFF_TABW1, k), idesc_tab, k);
         umma_commit(bar_tab);
       }
       mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
@@ -283,10 +303,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tc_fence_after();
         const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
-        const uint32_t kbase = k_tile_addr(st, 0);
+        const uint32_t kbase = k_tile_addr(st), kbase1 = k1_tile_addr(st);
         if (lead) {
 #pragma unroll
-          for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, C::K_CHUNK, k), idesc, k);
+          for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, kbase1, k), idesc, k);
           umma_commit(bar_kempty + 8 * st);
           umma_commit(bar_s_full + 8 * buf);
         }
@@ -311,17 +331,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tc_fence_after();
         const uint32_t ptm = tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
         if (lead) {
-          const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st, 0), 1024, 1024);
+          const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st), 1024, 1024);
           if (GLOBAL || j < 3) {
 #pragma unroll
             for (int k = 0; k < BKV / 16; ++k) umma_op16_ts(otm, ptm + 8u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
           } else {
             umma_op16_ts(otm, ptm, vdesc, idesc_pv64, 1u);
           }
-          if (NCH == 2) {            // head columns 64..79: a second, 16-wide MMA from the second V chunk
-            const uint64_t vdesc1 = umma_desc_sw128(v_tile_addr(st, 1), 1024, 1024);
+          if (HAS1) {                // head columns 64..79: a second, 16-wide MMA from the V chunk with 32-byte rows
+            const uint64_t vdesc1 = umma_desc_sw32(v1_tile_addr(st), 256, 256);      // MN-major: 8 key rows per 256 B group
             const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
-            for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 128u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 32u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(bar_vempty + 8 * st);
           umma_commit(bar_p_free + 8 * (j & 1));
@@ -588,14 +608,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
 template <bool GLOBAL, int HD>
 static void launch_attn_t(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmKVtail, const CUtensorMap& tmRel,
-                          const CUtensorMap& tmRel8, const AttnParams& p, dim3 grid, cudaStream_t stream) {
+                          const CUtensorMap& tmRel8, const CUtensorMap& tmQ1, const CUtensorMap& tmKV1, const CUtensorMap& tmKVtail1,
+                          const CUtensorMap& tmRel1, const CUtensorMap& tmRel8_1, const AttnParams& p, dim3 grid, cudaStream_t stream) {
   using C = attn::Cfg<GLOBAL, HD>;
   static bool init = false;
   if (!init) {
     YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<GLOBAL, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     init = true;
   }
-  encoder_attention_kernel<GLOBAL, HD><<<grid, attn::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p);
+  encoder_attention_kernel<GLOBAL, HD><<<grid, attn::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, tmQ1, tmKV1, tmKVtail1,
+                                                                                      tmRel1, tmRel8_1, p);
 }
 
 // qkv: op16 [n_seq*T, 3D] with the K columns pre-scaled by hd^-0.5*log2(e); rel_tab: op16 [256, HDP] pre-scaled by
@@ -614,15 +636,22 @@ void launch_encoder_attention(const op16* qkv, const op16* rel_tab, op16* out, i
   const CUtensorMap tmKVtail = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, 16);
   const CUtensorMap tmRel = make_tmap_op16_2d(rel_tab, 256, HDP, HDP, is_global ? 128 : 32);
   const CUtensorMap tmRel8 = make_tmap_op16_2d(rel_tab, 256, HDP, HDP, 8);
+  // head_dim 80: columns 64..79 as 16-column boxes (32-byte rows, 32B swizzle); head_dim 64 never touches them
+  const uint32_t c1 = head_dim == 64 ? 64 : 16;
+  const CUtensorMap tmQ1 = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, BQ, c1);
+  const CUtensorMap tmKV1 = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, BKV, c1);
+  const CUtensorMap tmKVtail1 = make_tmap_op16_2d(qkv, rows, 3 * D, 3 * D, 16, c1);
+  const CUtensorMap tmRel1 = make_tmap_op16_2d(rel_tab, 256, HDP, HDP, is_global ? 128 : 32, c1);
+  const CUtensorMap tmRel8_1 = make_tmap_op16_2d(rel_tab, 256, HDP, HDP, 8, c1);
   AttnParams p;
   p.T = T; p.D = D; p.out = out; p.unwindow = unwindow ? 1 : 0;
   dim3 grid(ceil_div(T, BQ), heads, n_seq);
   if (head_dim == 64) {
-    if (is_global) launch_attn_t<true, 64>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
-    else launch_attn_t<false, 64>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
+    if (is_global) launch_attn_t<true, 64>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, tmQ1, tmKV1, tmKVtail1, tmRel1, tmRel8_1, p, grid, stream);
+    else launch_attn_t<false, 64>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, tmQ1, tmKV1, tmKVtail1, tmRel1, tmRel8_1, p, grid, stream);
   } else {
-    if (is_global) launch_attn_t<true, 80>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
-    else launch_attn_t<false, 80>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, p, grid, stream);
+    if (is_global) launch_attn_t<true, 80>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, tmQ1, tmKV1, tmKVtail1, tmRel1, tmRel8_1, p, grid, stream);
+    else launch_attn_t<false, 80>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, tmQ1, tmKV1, tmKVtail1, tmRel1, tmRel8_1, p, grid, stream);
   }
   YSI_CUDA(cudaGetLastError());
 }

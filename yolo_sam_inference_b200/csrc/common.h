@@ -55,7 +55,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Row-major op16 matrix [rows, cols] (row pitch ld elements) -> 2-D TMA map with a {box_cols, box_rows}
-// box and 128-byte swizzle. box_cols must be 64 (=128 B). Out-of-bounds reads return zero.
+// box: box_cols = 64 (128-byte rows, 128B swizzle) or 16 (32-byte rows, 32B swizzle). Out-of-bounds reads return zero.
 CUtensorMap make_tmap_op16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                               uint32_t box_cols = 64);
 

@@ -49,7 +49,8 @@ static CUtensorMap make_tmap_2d(const void* base, int esize, uint64_t rows, uint
   }
   YSI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
   YSI_CHECK((ld * esize) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
-  YSI_CHECK(box_cols * esize == 128, "128B swizzle needs a 128-byte inner box");
+  YSI_CHECK(box_cols * esize == 128 || box_cols * esize == 32, "inner box must be 128 bytes (128B swizzle) or 32 bytes (32B swizzle)");
+  const CUtensorMapSwizzle swz = box_cols * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   YSI_CHECK(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
   CUtensorMap m;
   cuuint64_t gdim[2] = {cols, rows};
@@ -57,7 +58,7 @@ static CUtensorMap make_tmap_2d(const void* base, int esize, uint64_t rows, uint
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(&m, esize == 2 ? OP16_TMAP_TYPE : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
-                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   YSI_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
   std::lock_guard<std::mutex> g(mu);

@@ -152,6 +152,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// Same for SWIZZLE_32B tiles (rows of 16 op16 = 32 B; 8-row groups are 256 B apart): layout type 6. Used for the 16
+// trailing columns of head_dim 80 operands, which would otherwise occupy a full 128-byte-wide chunk.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 with op16 A/B and fp32 accumulation.
 //   bits [4,6) D format (1 = f32)   [7,10) A format (1 = op16)   [10,13) B format (1 = op16)
 //   bit 15 A major (0 = K, 1 = MN)  bit 16 B major               [17,23) N >> 3   [24,29) M >> 4
