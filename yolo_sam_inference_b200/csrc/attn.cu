@@ -6,21 +6,21 @@
 // the K columns arrive pre-multiplied by hd^-0.5 * log2(e) and the rel-pos tables by log2(e); p = 2^(x - m).
 //
 // One CTA = 128 queries of one (sequence, head); keys/values stream through in tiles of 64.
-//   warps 8-10 (one lane each): TMA loads (Q, rel-pos tables, K and V rings) | table + S MMAs | P.V MMAs
-//   warps 0-7         : TWO threads per query row: warp w owns rows 32 (w & 3) .. +31 (its TMEM lane quarter) and
-//                       the key columns 32 (w >> 2) .. +31 of every tile: S from TMEM, bias add (FADD2), max
+//   3 producer warps (one elected lane each): TMA loads (Q, rel-pos tables, K and V rings) | table + S MMAs | P.V MMAs
+//   softmax warps     : warp w owns rows 32 (w & 3) .. +31 (its TMEM lane quarter): S from TMEM, bias add (FADD2), max
 //                       (FMNMX3), exp2 (MUFU), P -> op16 -> TENSOR MEMORY (tcgen05.st), which P.V reads as its A operand.
-//                       16 softmax warps per SM (2 CTAs) keep the MUFU pipe fed while other warps sit in TMEM
-//                       loads / barriers; a thread holds 32 bias + 32 score registers instead of 64 + 64.
-//   The two threads of a row must scale P by the same running maximum. They exchange their half-row maxima
-//   through shared memory + an mbarrier, but OFF the critical path: every thread publishes its maximum, computes
-//   its exponentials speculatively against the current (lazily updated) maximum, and only then reads its
-//   partner's value; the tile is redone in the rare case (first tiles of a row) that the maximum had to move.
+//                       One thread per query row by default (SPLIT = 1, 4 warps); optionally two (SPLIT = 2, 8 warps,
+//                       32 key columns each) -- see SPLIT below. The producer warpgroup hands its registers to the
+//                       softmax warps (setmaxnreg), two CTAs per SM.
+//   With SPLIT = 2 the two threads of a row must scale P by the same running maximum: every thread publishes its
+//   half-row maximum (one flagged shared-memory word), computes its exponentials speculatively against the current
+//   (lazily updated) maximum, and only then reads its partner's value; the tile is redone in the rare case (first
+//   tiles of a row) that the maximum had to move.
 // Tensor-core work per tile: S = Q K^T (128x64x64, both K-major) and O += P V (128x64x64, V is the MN-major B
 // operand straight out of the qkv activation). O stays in TMEM for the whole CTA: it is rescaled in place
 // (tcgen05.ld / tcgen05.st) only when the running row maximum grows by more than 2^8 ("lazy rescale"), so the
-// softmax threads never wait on the PV MMA in steady state. S is double buffered in TMEM and each buffer is
-// released as soon as it is in registers, so S_{j+1} is complete before the softmax of tile j ends.
+// softmax threads never wait on the PV MMA in steady state. S is double buffered in TMEM; P_j overwrites the first 32
+// columns of S_j (it is the TMEM A operand of P.V_j), and S_{j+2} is issued into that buffer when P.V_j completes.
 // The rel-pos terms:
 //   global   (S=64): rel_w = one extra MMA per CTA (Q . Rw^T) whose TMEM result is re-indexed per query into
 //                    64 registers per thread (same for every tile). rel_h of tile j (key row kh = j) only
@@ -41,13 +41,23 @@ namespace ysi {
 
 namespace attn {
 constexpr int BQ = 128, BKV = 64;
-constexpr int SM_WARPS = 8;                  // softmax warps (two warpgroups)
+#ifndef YSI_ATTN_SPLIT
+#define YSI_ATTN_SPLIT 1
+#endif
+// Threads per query row. 1 (default): 4 softmax warps of 216 registers, a thread owns its row's 64 key columns of a tile
+// and nothing has to be exchanged. 2 (-DYSI_ATTN_SPLIT=2): 8 softmax warps of 104 registers, 32 columns each, the two
+// threads of a row agree on the running maximum through a flagged shared-memory word. Measured on one box, alternating
+// builds (scripts/gpu_ab_split.sh): global layers equal (2.92 ms per 8-image step), windowed 1.05 vs 1.19 ms,
+// head_dim 80 windowed 5.7 vs 6.9 ms -- the per-tile fixed costs are paid by half as many warps.
+constexpr int SPLIT = YSI_ATTN_SPLIT;
+constexpr int TW = BKV / SPLIT;              // key columns of a tile owned by one thread
+constexpr int SM_WARPS = 4 * SPLIT;          // softmax warps
 constexpr int THREADS = 32 * (SM_WARPS + 4); // + one producer warpgroup: TMA warp, S-MMA warp, PV-MMA warp, and a register donor
 // Register budget per SM sub-partition (16384 registers = 512 per lane): two CTAs put 4 softmax warps and 2 producer
 // warps on each. The kernel launches with <= 80 registers per thread (6 x 80 = 480); the producer warpgroup then
 // shrinks to REG_PRODUCER and the softmax warpgroups grow to REG_SOFTMAX with setmaxnreg. The pool is per CTA:
 // 8 x 104 + 4 x 32 = 960 = 12 warps x 80 (asking for more than the CTA released deadlocks the allocation).
-constexpr int REG_SOFTMAX = 104, REG_PRODUCER = 32;
+constexpr int REG_SOFTMAX = SPLIT == 2 ? 104 : 216, REG_PRODUCER = 32;     // SPLIT 1: 8 warps x 128 = 4 x 216 + 4 x 32 + slack
 constexpr int CH_Q = BQ * 128;              // one 64-column chunk of the Q tile: 128 rows x 128 B = 16 KB
 constexpr int KV_BYTES = BKV * 128;         // one 64-column chunk of a 64-key tile: 8 KB
 constexpr int P_BYTES = BQ * BKV * 2;       // 16 KB
@@ -355,7 +365,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // ------------------------------------------------------------------ softmax warps: two threads per query row
     if (C::CTAS_PER_SM == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_SOFTMAX));
     const int rq = warp & 3;                         // row quarter = TMEM lane quarter of this warp
-    const int half = warp >> 2;                      // which 32 key columns of every 64-key tile
+    const int half = SPLIT == 2 ? warp >> 2 : 0;     // which TW key columns of every 64-key tile
     const int t = rq * 32 + lane;                    // query row inside the tile = TMEM lane
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(rq * 32) << 16);
     const int lq = qt * BQ + t;                      // query index inside the sequence
@@ -364,7 +374,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     int qh, qw;
     if (GLOBAL) { qh = lq >> 6; qw = lq & 63; } else { const int l = lq < 196 ? lq : 195; qh = l / 14; qw = l - qh * 14; }
     constexpr int S = GLOBAL ? 64 : 14;
-    constexpr int NB = GLOBAL ? 32 : 28;             // bias registers: rel_w of this thread's 32 keys | rel_h[14] + rel_w[14]
+    constexpr int NB = GLOBAL ? TW : 28;             // bias registers: rel_w of this thread's TW keys | rel_h[14] + rel_w[14]
     float bias[NB];
 
     mbar_wait(bar_tab, 0);
@@ -380,11 +390,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kw = qw + (S - 1) - (c0 + i);
-          if ((kw >> 5) == half) rel_s[kw * 128 + t] = __uint_as_float(r[i]);     // 0 <= kw < 64 and in this thread's half
+          if (kw >= 0 && kw < 64 && kw / TW == half) rel_s[kw * 128 + t] = __uint_as_float(r[i]);     // in this thread's columns
         }
       }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) bias[i] = rel_s[(32 * half + i) * 128 + t];
+      for (int i = 0; i < TW; ++i) bias[i] = rel_s[(TW * half + i) * 128 + t];
     } else {
       // both threads of a row keep all 28 values; each writes / reads its own scratch column block
       float* my = rel_s + half * (28 * 128);
@@ -413,7 +423,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     bool s_ready = false;                            // S of the next tile already seen complete (probed a tile early)
     float m_used = -INFINITY;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
-    constexpr int OH = HD / 2;                       // O columns owned by this thread
+    constexpr int OH = HD / SPLIT;                   // O columns owned by this thread
     const uint32_t ocol = tlane + C::COL_O + static_cast<uint32_t>(half * OH);
 
     // one KV tile: this thread owns NW columns of S starting at column c0 (NW = 0: nothing, only the barriers),
@@ -432,7 +442,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const bool act = warp_active && NW > 0;
       if (act) {
         const uint32_t scol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N);
-        if constexpr (NW == 32) tmem_ld_x32p(scol + c0, r);
+        if constexpr (NW == 64) { tmem_ld_x32p(scol + c0, r); tmem_ld_x32p(scol + c0 + 32, r + 32); }
+        else if constexpr (NW == 32) tmem_ld_x32p(scol + c0, r);
         else if constexpr (NW == 16) tmem_ld_x16p(scol + c0, r);
         if (GLOBAL) {
           uint32_t rb;
@@ -461,7 +472,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const uint32_t tag = static_cast<uint32_t>(j);
       const uint32_t mine = (__float_as_uint(m_half) & 0xFFFFFF00u) | tag;
       const uint32_t xaddr = smem_u32(xm) + static_cast<uint32_t>(((pb * 128 + t) * 2) * 4);
-      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(xaddr + 4u * half), "r"(mine) : "memory");
+      if (SPLIT == 2) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(xaddr + 4u * half), "r"(mine) : "memory");
       uint32_t pk[NR / 2];
       float2 ta, tb;
       auto exps = [&](float c) {
@@ -478,10 +489,12 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       if (act && j > 0) exps(bh - m_used);
       ATTN_TRACE(warp, j, 3);
-      uint32_t theirs;
-      do {
-        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(theirs) : "r"(xaddr + 4u * (half ^ 1)) : "memory");
-      } while ((theirs & 0xFFu) != tag);
+      uint32_t theirs = mine;
+      if (SPLIT == 2) {
+        do {
+          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(theirs) : "r"(xaddr + 4u * (half ^ 1)) : "memory");
+        } while ((theirs & 0xFFu) != tag);
+      }
       ATTN_TRACE(warp, j, 4);
       const float m_cand = fmaxf(__uint_as_float(mine & 0xFFFFFF00u), __uint_as_float(theirs & 0xFFFFFF00u));
       // identical in both warps of the pair: they see the same 32 pairs of half-row maxima
@@ -518,7 +531,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         l2a = add2(l2a, ta); l2b = add2(l2b, tb);
         tc_fence_after();
         const uint32_t pcol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
-        if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
+        if constexpr (NW == 64) tmem_st_x32p(pcol, pk);
+        else if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
         else if constexpr (NW == 16) tmem_st_x8p(pcol, pk);
         tmem_st_wait();
         tc_fence_before();
@@ -528,19 +542,20 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       ATTN_TRACE(warp, j, 6);
     };
 
+    using ITW = std::integral_constant<int, TW>;
     using I32 = std::integral_constant<int, 32>;
     using I16 = std::integral_constant<int, 16>;
     using I4 = std::integral_constant<int, 4>;
     using I0 = std::integral_constant<int, 0>;
     if (GLOBAL) {
-      for (int j = 0; j < ntiles; ++j) do_tile(I32{}, I32{}, j, [&](int i) { return bias[i]; }, 32 * half);
+      for (int j = 0; j < ntiles; ++j) do_tile(ITW{}, ITW{}, j, [&](int i) { return bias[i]; }, TW * half);
     } else {
       // key k = 64 j + 32 half + i of the window: kh = k / 14, kw = k % 14 (compile-time after unrolling)
       auto window_tiles = [&](auto half_c) {
         constexpr int HF = decltype(half_c)::value;
         auto tile = [&](auto j_c) {
-          constexpr int K0 = 64 * decltype(j_c)::value + 32 * HF;
-          do_tile(I32{}, I32{}, decltype(j_c)::value, [&](int i) { return bias[(K0 + i) / 14] + bias[14 + (K0 + i) % 14]; }, 32 * HF);
+          constexpr int K0 = 64 * decltype(j_c)::value + TW * HF;
+          do_tile(ITW{}, ITW{}, decltype(j_c)::value, [&](int i) { return bias[(K0 + i) / 14] + bias[14 + (K0 + i) % 14]; }, TW * HF);
         };
         tile(std::integral_constant<int, 0>{}); tile(std::integral_constant<int, 1>{}); tile(std::integral_constant<int, 2>{});
         if (HF == 0)        // ragged last tile (keys 192..195 + 12 masked columns): the first half of the pair takes it
@@ -552,15 +567,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
     // row sum = both halves
     xl[t * 2 + half] = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+    if (SPLIT == 1) xl[t * 2 + 1] = 0.f;
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_fin + 8 * rq);
+    if (SPLIT == 2 && lane == 0) mbar_arrive(bar_fin + 8 * rq);
     mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
-    mbar_wait(bar_fin + 8 * rq, 0);
+    if (SPLIT == 2) mbar_wait(bar_fin + 8 * rq, 0);
     if (warp_active) {
       uint32_t o[OH];
-      tmem_ld_x32p(ocol, o);
-      if constexpr (OH > 32) tmem_ld_x8p(ocol + 32, o + 32);
+#pragma unroll
+      for (int c = 0; c < OH; c += 8) tmem_ld_x8p(ocol + c, o + c);
       tmem_ld_wait();
       const float inv = 1.0f / (xl[t * 2] + xl[t * 2 + 1]);
       long long orow = -1;
