@@ -109,7 +109,10 @@ struct Cfg {
   static constexpr int OFF_XL = OFF_XM + 2048;              // fp32 [128][2]: half-row sums at the end
   static constexpr int SMEM_BYTES = OFF_XL + 1024 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 256;                     // 2 S buffers (P_j overwrites the first 32 columns of S_j) + O
-  static constexpr int S_N = GLOBAL ? 80 : 64;              // columns of one S buffer
+  // windowed, one thread per row: the window's 196 keys are three tiles (64, 64, 68 of 80 columns) instead of four
+  // (64, 64, 64, 4 of 16): one pass through the per-tile fixed costs less
+  static constexpr bool W3 = !GLOBAL && SPLIT == 1;
+  static constexpr int S_N = (GLOBAL || W3) ? 80 : 64;      // columns of one S buffer
   static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
   static constexpr int COL_O = 2 * S_N;
   static constexpr int COL_TH = 0;                          // windowed setup only
@@ -173,7 +176,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int row0 = seq * p.T;                 // first row of this sequence in the qkv matrix
-  const int ntiles = GLOBAL ? p.T / BKV : 4;
+  const int ntiles = GLOBAL ? p.T / BKV : (C::W3 ? 3 : 4);
   const int cq = head * HD, ck = p.D + head * HD, cv = 2 * p.D + head * HD;
   constexpr int NSM = 32 * SM_WARPS;          // softmax threads
 #ifdef YSI_ATTN_TRACE
@@ -283,7 +286,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       // ---- rel-pos table MMA(s), then S_t = Q K_t^T into S buffer t & 1 as soon as P.V_{t-2} -- whose A operand P_{t-2}
       // sits in the first columns of that buffer -- has completed: about one softmax tile before S_t is needed
       constexpr uint32_t idesc_tab = umma_idesc_op16(128, C::TAB_ROWS, 0, 0);
-      constexpr uint32_t idesc_s = umma_idesc_op16(128, C::S_N, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_op16(128, GLOBAL ? 80 : 64, 0, 0);
+      constexpr uint32_t idesc_s80 = umma_idesc_op16(128, 80, 0, 0);
       constexpr uint32_t idesc_s16 = umma_idesc_op16(128, 16, 0, 0);
       uint64_t qdesc[NKS];
 #pragma unroll
@@ -307,11 +311,12 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         mbar_wait(bar_kfull + 8 * st, ph);
+        if (C::W3 && t == 2) mbar_wait(bar_kfull + 8 * 3, 0);      // the last window tile spans K tiles 2 and 3
         ATTN_TRACE(9, t, 0);
         if (t >= 2) mbar_wait(bar_p_free + 8 * buf, ((t >> 1) - 1) & 1);     // P.V_{t-2} done: S / P buffer t & 1 is free
         ATTN_TRACE(9, t, 1);
         tc_fence_after();
-        const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : idesc_s;
+        const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : ((C::W3 && t == 2) ? idesc_s80 : idesc_s);
         const uint32_t d = tmem_base + C::COL_S + buf * C::S_N;
         const uint32_t kbase = k_tile_addr(st), kbase1 = k1_tile_addr(st);
         if (lead) {
@@ -335,6 +340,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       uint32_t ph = 0;
       for (int j = 0; j < ntiles; ++j) {
         mbar_wait(bar_vfull + 8 * st, ph);
+        if (C::W3 && j == 2) mbar_wait(bar_vfull + 8 * 3, 0);
         ATTN_TRACE(10, j, 0);
         mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
         ATTN_TRACE(10, j, 1);
@@ -345,12 +351,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (GLOBAL || j < 3) {
 #pragma unroll
             for (int k = 0; k < BKV / 16; ++k) umma_op16_ts(otm, ptm + 8u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
+            if (C::W3 && j == 2) umma_op16_ts(otm, ptm + 8u * 4, vdesc + 128u * 4, idesc_pv64, 1u);     // keys 192..207 (196.. are zero in P)
           } else {
             umma_op16_ts(otm, ptm, vdesc, idesc_pv64, 1u);
           }
           if (HAS1) {                // head columns 64..79: a second, 16-wide MMA from the V chunk with 32-byte rows
             const uint64_t vdesc1 = umma_desc_sw32(v1_tile_addr(st), 256, 256);      // MN-major: 8 key rows per 256 B group
-            const int ksteps = (!GLOBAL && j == 3) ? 1 : BKV / 16;
+            const int ksteps = (!GLOBAL && j == 3) ? 1 : ((C::W3 && j == 2) ? 5 : BKV / 16);
             for (int k = 0; k < ksteps; ++k) umma_op16_ts(otm + 64, ptm + 8u * k, vdesc1 + 32u * k, idesc_pv16, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(bar_vempty + 8 * st);
@@ -442,7 +449,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const bool act = warp_active && NW > 0;
       if (act) {
         const uint32_t scol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N);
-        if constexpr (NW == 64) { tmem_ld_x32p(scol + c0, r); tmem_ld_x32p(scol + c0 + 32, r + 32); }
+        if constexpr (NW == 80) { tmem_ld_x32p(scol, r); tmem_ld_x32p(scol + 32, r + 32); tmem_ld_x16p(scol + 64, r + 64); }
+        else if constexpr (NW == 64) { tmem_ld_x32p(scol + c0, r); tmem_ld_x32p(scol + c0 + 32, r + 32); }
         else if constexpr (NW == 32) tmem_ld_x32p(scol + c0, r);
         else if constexpr (NW == 16) tmem_ld_x16p(scol + c0, r);
         if (GLOBAL) {
@@ -531,7 +539,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         l2a = add2(l2a, ta); l2b = add2(l2b, tb);
         tc_fence_after();
         const uint32_t pcol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
-        if constexpr (NW == 64) tmem_st_x32p(pcol, pk);
+        if constexpr (NW == 80) { tmem_st_x32p(pcol, pk); tmem_st_x8p(pcol + 32, pk + 32); }
+        else if constexpr (NW == 64) tmem_st_x32p(pcol, pk);
         else if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
         else if constexpr (NW == 16) tmem_st_x8p(pcol, pk);
         tmem_st_wait();
@@ -557,7 +566,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           constexpr int K0 = 64 * decltype(j_c)::value + TW * HF;
           do_tile(ITW{}, ITW{}, decltype(j_c)::value, [&](int i) { return bias[(K0 + i) / 14] + bias[14 + (K0 + i) % 14]; }, TW * HF);
         };
-        tile(std::integral_constant<int, 0>{}); tile(std::integral_constant<int, 1>{}); tile(std::integral_constant<int, 2>{});
+        tile(std::integral_constant<int, 0>{}); tile(std::integral_constant<int, 1>{});
+        if constexpr (C::W3) {   // keys 128..195 + 12 masked columns in one 80-column tile
+          do_tile(std::integral_constant<int, 80>{}, std::integral_constant<int, 68>{}, 2,
+                  [&](int i) { return i < 68 ? bias[(128 + i) / 14] + bias[14 + (128 + i) % 14] : 0.f; }, 0);
+          return;
+        }
+        tile(std::integral_constant<int, 2>{});
         if (HF == 0)        // ragged last tile (keys 192..195 + 12 masked columns): the first half of the pair takes it
           do_tile(I16{}, I4{}, 3, [&](int i) { return i < 4 ? bias[(192 + i) / 14] + bias[14 + (192 + i) % 14] : 0.f; }, 0);
         else
