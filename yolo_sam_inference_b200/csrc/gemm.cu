@@ -118,6 +118,12 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
   if (use_pair && N % 256 == 0 && M >= 2048) {
     // big GEMMs: CTA pairs (cta_group::2), each CTA loads half of the B tile
     const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 128);
+    // 192-column tiles where they need less time than 256-column ones: rounds over the CTA pairs x columns per tile
+    const int pairs = sm_count() / 2, m_tiles = ceil_div(M, 2 * GEMM_BM);
+    static const int allow192 = [] { const char* e = getenv("YSI_GEMM_BN192"); return e ? atoi(e) : 1; }();
+    const bool bn192 = allow192 && N % 192 == 0 &&
+                       ceil_div(m_tiles * (N / 192), pairs) * 192 < ceil_div(m_tiles * (N / 256), pairs) * 256;
+    const CUtensorMap tmB192 = bn192 ? make_tmap_op16_2d(W, N, K, ldw, 96) : tmB;
     static const int use_staged = [] { const char* e = getenv("YSI_GEMM_STAGED"); return e ? atoi(e) : 1; }();
     const bool plain = !ep.row_map && !ep.add_src && ep.act != ACT_RELU;
     if (use_staged && plain && ep.out_op16 && !ep.out_f32) {
@@ -133,14 +139,16 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
       es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
       es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
       es.f32_add = 1;
-      launch_gemm2(tmA, tmB, M, N, K, es, stream);
+      if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, es, stream);
+      else launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && !ep.accumulate && ep.act == ACT_NONE && ep.scale_c1 <= ep.scale_c0) {
       // plain fp32 output (decoder image-side projections): staged 128-byte rows, TMA store
       EpiStaged es;
       es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
       es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
       es.f32_add = 2;
-      launch_gemm2(tmA, tmB, M, N, K, es, stream);
+      if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, es, stream);
+      else launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else {
       launch_gemm2(tmA, tmB, M, N, K, epi, stream);
     }

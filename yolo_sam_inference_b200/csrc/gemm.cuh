@@ -422,10 +422,13 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //                        8 epilogue warps on their own 128 accumulator lanes, which release the accumulator
 //                        on the leader's barrier
 // ------------------------------------------------------------------------------------------------
+// BN_ = 256, or 192 where that fills the last wave better (N = 768 at 8 images: 384 tiles on 74 CTA pairs are 5.2 waves,
+// 512 tiles of 192 columns are 6.9); 192 only with the fp32 epilogues (their 32-column slabs divide the 96-column half).
+template <int BN_>
 struct Gemm2Cfg {
-  static constexpr int BN = 256;
+  static constexpr int BN = BN_;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB: this CTA's 128 rows
-  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the B tile
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // 16 / 12 KB: this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 5;
   static constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * 2 * 4096;   // two 32-row x 128-byte slabs per epilogue warp
@@ -433,11 +436,11 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
 };
 
-template <class Epi>
+template <int BN_, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                   const __grid_constant__ Epi epi) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<BN_>;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -561,10 +564,10 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <class Epi>
+template <int BN_ = 256, class Epi>
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg;
-  auto kern = gemm2_op16_kernel<Epi>;
+  using Cfg = Gemm2Cfg<BN_>;
+  auto kern = gemm2_op16_kernel<BN_, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
