@@ -111,3 +111,25 @@ def test_run_stream_equals_run_batch(tiny_stage):
     for r, g in zip(ref, got):
         for (rm, rmet, rc), (gm, gmet, gc) in zip(r, g):
             assert np.array_equal(rm, gm) and rmet == gmet and len(rc) == len(gc)
+
+
+@pytest.mark.parametrize("H,W", [(1024, 1024), (348, 701)])
+def test_packed_mask_wire_format(tiny_stage, H, W):
+    """f2 of SURVEY section 8f: masks as np.packbits rows (utils/mask_encoding.py:24), byte-identical to packing the
+    byte masks on the host, with the same metrics; 348 x 701 has a pixel count that is not a multiple of 8."""
+    import base64
+    import zlib
+    from yolo_sam_inference_b200.synth import gray_to_rgb_u8, synth_image
+    g, b = synth_image(90, max(H, W), 2)
+    img = np.ascontiguousarray(gray_to_rgb_u8(g)[:H, :W])
+    b = np.clip(b, 0, [W - 1, H - 1, W - 1, H - 1]).astype(np.float32)
+    tiny_stage.on_empty = "zeros"
+    masks, mets, _ = tiny_stage.run(img, b)
+    packed, mets2 = tiny_stage.run_packed(img, b)
+    assert mets2 == mets
+    for k in range(len(masks)):
+        assert np.array_equal(packed[k], np.packbits(masks[k]))
+        # the reference's encode / decode round trip on the packed row (mask_encoding.py:10-58)
+        data = base64.b64encode(zlib.compress(packed[k].tobytes())).decode("ascii")
+        back = np.unpackbits(np.frombuffer(zlib.decompress(base64.b64decode(data)), np.uint8))[:H * W].reshape(H, W)
+        assert np.array_equal(back.astype(bool), masks[k])
