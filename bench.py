@@ -311,10 +311,13 @@ def run_ours(args):
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "frac_of_burst": achieved / pk["bf16_tflops"],
                 "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
-                "traffic_note": "ncu --set full (profiles/r01b_ncu_top.txt): fc1-shaped launch 378 MB DRAM r+w for 256 MB algorithmic, "
-                                "fc2-shaped 329 MB, qkv-shaped 188 MB; a class-wide per-launch average is not captured",
+                "traffic_note": "bytes per launch, dram read+write from one ncu --set full capture of two consecutive layers "
+                                "(profiles/r01c_ncu_gemm_layers.txt): qkv 149 / 191 MB (windowed / global layer), proj 194, fc1 204, "
+                                "fc2 384 -> class average 238 MB against 286 MB algorithmic (operands + outputs once); below the "
+                                "algorithmic figure because producer -> consumer activations partly stay in the 126 MB L2",
                 "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1),
-                "share_of_step": g_ms / tot_ms if tot_ms else None, "traffic": None,
+                "share_of_step": g_ms / tot_ms if tot_ms else None,
+                "traffic": 238.0e6 if (MODEL == "vit_b" and BATCH == 8) else None,
                 "how": f"CUDA events around every launch, {psteps} profiled steps after the timed region"}
         breakdown = {k: {"ms_per_step": v["ms"] / psteps,
                          "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
