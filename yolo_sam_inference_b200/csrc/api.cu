@@ -408,7 +408,10 @@ void create_impl(ysi_ctx* c) {
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
     const char* e = getenv("YSI_L2_PERSIST_MB");
-    size_t want = e ? static_cast<size_t>(atoi(e)) << 20 : static_cast<size_t>(32) << 20;
+    const size_t xb = sizeof(float) * B * 4096 * D;
+    // default: only when x itself is about the size of the L2 (ViT-B at 8 images: 100 MB); for ViT-H (168 MB) the window
+    // costs more GEMM operand reuse than it saves (163 vs 166 images/s)
+    size_t want = e ? static_cast<size_t>(atoi(e)) << 20 : (xb <= (static_cast<size_t>(128) << 20) ? static_cast<size_t>(32) << 20 : 0);
     if (want > static_cast<size_t>(max_persist)) want = static_cast<size_t>(max_persist);
     const size_t xbytes = sizeof(float) * B * 4096 * D;
     if (want > 0 && max_window > 0) {
