@@ -44,13 +44,20 @@ def tiny_oracle(tiny_weights):
 
 
 @pytest.fixture(scope="session")
-def tiny_stage(tiny_weights):
+def _tiny_stage_session(tiny_weights):
     """vit_t context sized for every GPU parity test (up to 2048x2048 images, 40 masks)."""
     from yolo_sam_inference_b200.sam_stage import SamStage
     st = SamStage("vit_t", device="cuda:0", state_dict=tiny_weights, max_batch=2, max_boxes=40,
                   max_image_hw=(2048, 2048))
     yield st
     st.close()
+
+
+@pytest.fixture
+def tiny_stage(_tiny_stage_session):
+    """The shared context, handed to every test in its default state (tests may change ``on_empty``)."""
+    _tiny_stage_session.on_empty = "raise"
+    return _tiny_stage_session
 
 
 def op16_round(a, precision):
