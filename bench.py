@@ -69,9 +69,25 @@ def init_dist(world: int, backend: str):
     import torch.distributed as dist
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group(backend)
+        # NCCL prints its version banner to the process's stdout (fd 1) when the first communicator is created; rank 0
+        # must print ONE JSON line, so fd 1 points at /dev/null until the communicator exists.
+        import torch
+        sys.stdout.flush()
+        saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            dist.init_process_group(backend)
+            if backend == "nccl":
+                local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+                torch.cuda.set_device(local)
+                t = torch.zeros(1, device=f"cuda:{local}")
+                dist.all_reduce(t)                 # creates the communicator (and prints the banner into /dev/null)
+                torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
     return dist
 
 
