@@ -637,9 +637,11 @@ struct EpiConvT1 {
       for (int c = 0; c < 8; ++c) {
         float u[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; k += 2) {          // packed erf-GELU (|abs err| <= 1.5e-7), as in the fc1 epilogue
           const int i = 8 * c + k;
-          u[k] = gelu_erf((v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i));
+          const float2 gg = gelu_erf2(make_float2((v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i),
+                                                  (v[i + 1] - mean) * rstd * __ldg(g + i + 1) + __ldg(b + i + 1)));
+          u[k] = gg.x; u[k + 1] = gg.y;
         }
         uint4 o;
         o.x = pack_op16x2(u[0], u[1]); o.y = pack_op16x2(u[2], u[3]); o.z = pack_op16x2(u[4], u[5]); o.w = pack_op16x2(u[6], u[7]);
@@ -670,7 +672,11 @@ struct EpiConvT2 {
       if (!active) continue;
       float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc = fmaf(gelu_erf(__uint_as_float(r[i]) + __ldg(bias + i)), __ldg(hyper + box * 32 + i), acc);
+      for (int i = 0; i < 32; i += 2) {
+        const float2 gg = gelu_erf2(make_float2(__uint_as_float(r[i]) + __ldg(bias + i), __uint_as_float(r[i + 1]) + __ldg(bias + i + 1)));
+        acc = fmaf(gg.x, __ldg(hyper + box * 32 + i), acc);
+        acc = fmaf(gg.y, __ldg(hyper + box * 32 + i + 1), acc);
+      }
       low[static_cast<size_t>(box) * 65536 + (2 * Y + (sp >> 1)) * 256 + 2 * X + (sp & 1)] = acc;
     }
   }
