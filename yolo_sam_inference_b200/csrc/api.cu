@@ -358,8 +358,9 @@ void create_impl(ysi_ctx* c) {
   dw.keys = c->dalloc<float>(NB * 4096 * 256);
   dw.keys_bf = c->dalloc<op16>(NB * 4096 * 512);
   dw.keyspos_bf = c->dalloc<op16>(NB * 4096 * 256);
-  dw.kq = c->dalloc<float>(NB * 4096 * 256);
-  dw.v = c->dalloc<float>(NB * 4096 * 128);
+  dw.kq = c->dalloc<float>(NB * 4096 * 256);          // pre-LayerNorm key update (fp32)
+  dw.kq16 = c->dalloc<op16>(NB * 4096 * 256);
+  dw.v16 = c->dalloc<op16>(NB * 4096 * 128);
   dw.attn_i2t = c->dalloc<op16>(NB * 4096 * 128);
   dw.up1 = c->dalloc<op16>(NB * 16384 * 128);
   dw.tok0 = c->dalloc<float>(NB * 7 * 256);

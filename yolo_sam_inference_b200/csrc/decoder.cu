@@ -326,6 +326,25 @@ tok_self_attn_core_kernel(const float* __restrict__ q, const float* __restrict__
   }
 }
 
+// 16 consecutive values of an fp32 or op16 row (one head's slice of an image-side K / V / Q projection)
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(op16 v) { return op2f(v); }
+__device__ __forceinline__ void load16(const float* p, float (&o)[16]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float4 v = __ldg(q + i); o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w; }
+}
+__device__ __forceinline__ void load16(const op16* p, float (&o)[16]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 v = __ldg(q + i);
+    const float2 a = unpack_op16x2(v.x), b = unpack_op16x2(v.y), c = unpack_op16x2(v.z), d = unpack_op16x2(v.w);
+    o[8 * i] = a.x; o[8 * i + 1] = a.y; o[8 * i + 2] = b.x; o[8 * i + 3] = b.y;
+    o[8 * i + 4] = c.x; o[8 * i + 5] = c.y; o[8 * i + 6] = d.x; o[8 * i + 7] = d.y;
+  }
+}
+
 // token -> image attention core: 7 queries x 4096 keys, 8 heads x 16, scale 0.25   (:324-327, :398-401)
 // grid (8 heads, nb, T2I_SPLIT key ranges): every CTA produces the un-normalised partial (max, sum, P.V) of its
 // 1024 keys; t2i_merge_kernel combines the ranges. K: fp32 rows of pitch ldk (head h at columns h*16..),
@@ -334,8 +353,9 @@ constexpr int T2I_SPLIT = 4;
 constexpr int T2I_KEYS = 4096 / T2I_SPLIT;
 constexpr int T2I_PART = NT * 2 + NT * 16;     // per (box, head, split): m[7], l[7], o[7][16]
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ K, int ldk, const float* __restrict__ V,
+t2i_attention_kernel(const float* __restrict__ q_t2i, const T* __restrict__ K, int ldk, const T* __restrict__ V,
                      int ldv, const int* __restrict__ group, float* __restrict__ part) {
   __shared__ float s_sc[NT * T2I_KEYS];        // 28 KB
   __shared__ float s_qh[NT * 16];
@@ -344,8 +364,8 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
   __shared__ float s_part[2 * NT * 16];
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const size_t seq = group ? group[b] : b;
-  const float* Kb = K + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS) * ldk + h * 16;
-  const float* Vb = V + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS) * ldv + h * 16;
+  const T* Kb = K + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS) * ldk + h * 16;
+  const T* Vb = V + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS) * ldv + h * 16;
   float* pout = part + ((static_cast<size_t>(b) * 8 + h) * T2I_SPLIT + sp) * T2I_PART;
   if (t < NT * 16) s_qh[t] = q_t2i[(static_cast<size_t>(b) * NT + t / 16) * 128 + h * 16 + (t % 16)];
   __syncthreads();
@@ -355,15 +375,15 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
 #pragma unroll
   for (int it = 0; it < T2I_KEYS / 256; ++it) {
     const int key = t + it * 256;
-    const float4* kp = reinterpret_cast<const float4*>(Kb + static_cast<size_t>(key) * ldk);
-    const float4 k0 = __ldg(kp), k1 = __ldg(kp + 1), k2 = __ldg(kp + 2), k3 = __ldg(kp + 3);
+    float kk[16];
+    load16(Kb + static_cast<size_t>(key) * ldk, kk);
 #pragma unroll
     for (int r = 0; r < NT; ++r) {
       const float* q = s_qh + r * 16;
-      float a = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w;
-      a += q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
-      a += q[8] * k2.x + q[9] * k2.y + q[10] * k2.z + q[11] * k2.w;
-      a += q[12] * k3.x + q[13] * k3.y + q[14] * k3.z + q[15] * k3.w;
+      float a = q[0] * kk[0] + q[1] * kk[1] + q[2] * kk[2] + q[3] * kk[3];
+      a += q[4] * kk[4] + q[5] * kk[5] + q[6] * kk[6] + q[7] * kk[7];
+      a += q[8] * kk[8] + q[9] * kk[9] + q[10] * kk[10] + q[11] * kk[11];
+      a += q[12] * kk[12] + q[13] * kk[13] + q[14] * kk[14] + q[15] * kk[15];
       a *= 0.25f;
       s_sc[r * T2I_KEYS + key] = a;
       lmax[r] = fmaxf(lmax[r], a);
@@ -413,12 +433,13 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
     const int half = t / (NT * 16), idx = t % (NT * 16), r = idx / 16, d = idx % 16;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     const float* pr = s_sc + r * T2I_KEYS + half * (T2I_KEYS / 2);
-    const float* vp = Vb + static_cast<size_t>(half) * (T2I_KEYS / 2) * ldv + d;
+    const T* vp = Vb + static_cast<size_t>(half) * (T2I_KEYS / 2) * ldv + d;
+    auto vat = [&](int key) { return to_f32(__ldg(vp + static_cast<size_t>(key) * ldv)); };
     for (int key = 0; key < T2I_KEYS / 2; key += 4) {
-      acc0 = fmaf(pr[key], __ldg(vp + static_cast<size_t>(key) * ldv), acc0);
-      acc1 = fmaf(pr[key + 1], __ldg(vp + static_cast<size_t>(key + 1) * ldv), acc1);
-      acc2 = fmaf(pr[key + 2], __ldg(vp + static_cast<size_t>(key + 2) * ldv), acc2);
-      acc3 = fmaf(pr[key + 3], __ldg(vp + static_cast<size_t>(key + 3) * ldv), acc3);
+      acc0 = fmaf(pr[key], vat(key), acc0);
+      acc1 = fmaf(pr[key + 1], vat(key + 1), acc1);
+      acc2 = fmaf(pr[key + 2], vat(key + 2), acc2);
+      acc3 = fmaf(pr[key + 3], vat(key + 3), acc3);
     }
     s_part[t] = (acc0 + acc1) + (acc2 + acc3);
   }
@@ -432,8 +453,9 @@ t2i_attention_kernel(const float* __restrict__ q_t2i, const float* __restrict__ 
 // 7 x 1024 scores to shared memory, re-reading them twice and fetching V element-wise seven times.
 constexpr int T2O_TK = 256;
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-t2i_attention_online_kernel(const float* __restrict__ q_t2i, const float* __restrict__ K, int ldk, const float* __restrict__ V,
+t2i_attention_online_kernel(const float* __restrict__ q_t2i, const T* __restrict__ K, int ldk, const T* __restrict__ V,
                             int ldv, const int* __restrict__ group, float* __restrict__ attn_out) {
   __shared__ float4 s_k[T2O_TK][4];
   __shared__ float4 s_v[T2O_TK][4];
@@ -441,8 +463,8 @@ t2i_attention_online_kernel(const float* __restrict__ q_t2i, const float* __rest
   const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int r = lane & 7, kl = lane >> 3;
   const size_t seq = group ? group[b] : b;
-  const float* Kb = K + seq * 4096 * ldk + h * 16;
-  const float* Vb = V + seq * 4096 * ldv + h * 16;
+  const T* Kb = K + seq * 4096 * ldk + h * 16;
+  const T* Vb = V + seq * 4096 * ldv + h * 16;
   float q[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i)      // scale 16^-0.5 and log2(e): softmax in base 2 (ex2.approx is one MUFU)
@@ -453,10 +475,14 @@ t2i_attention_online_kernel(const float* __restrict__ q_t2i, const float* __rest
   for (int tile = 0; tile < 4096 / T2O_TK; ++tile) {
     {
       const size_t key = static_cast<size_t>(tile) * T2O_TK + t;
-      const float4* kp = reinterpret_cast<const float4*>(Kb + key * ldk);
-      const float4* vp = reinterpret_cast<const float4*>(Vb + key * ldv);
+      float kk[16], vv[16];
+      load16(Kb + key * ldk, kk);
+      load16(Vb + key * ldv, vv);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { s_k[t][i] = __ldg(kp + i); s_v[t][i] = __ldg(vp + i); }
+      for (int i = 0; i < 4; ++i) {
+        s_k[t][i] = make_float4(kk[4 * i], kk[4 * i + 1], kk[4 * i + 2], kk[4 * i + 3]);
+        s_v[t][i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+      }
     }
     __syncthreads();
 #pragma unroll 2
@@ -542,8 +568,9 @@ t2i_merge_kernel(const float* __restrict__ part, float* __restrict__ attn_out) {
 
 // image -> token attention (:337-341): every image token attends over the 7 tokens of its box.
 // Q: fp32 [*,ldq] (columns 128..255 of the fused k|q projection). One thread = (token, head).
+template <typename T>
 __global__ void __launch_bounds__(256)
-i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict__ group, const float* __restrict__ k_tok,
+i2t_attention_kernel(const T* __restrict__ Q, int ldq, const int* __restrict__ group, const float* __restrict__ k_tok,
                      const float* __restrict__ v_tok, op16* __restrict__ out) {
   // k / v of the box's 7 tokens, head h at floats [h*20, h*20+16) of a 160-float row: the 8 heads of a quarter-warp
   // then read their 16-byte pieces from 8 different bank groups (a 64-byte head stride would be a 4-way conflict)
@@ -557,10 +584,11 @@ i2t_attention_kernel(const float* __restrict__ Q, int ldq, const int* __restrict
   __syncthreads();
   const int tok = blockIdx.x * 32 + (t >> 3), h = t & 7;
   const size_t seq = group ? group[b] : b;
-  const float4* qp = reinterpret_cast<const float4*>(Q + (seq * 4096 + tok) * ldq + h * 16);
+  float qq[16];
+  load16(Q + (seq * 4096 + tok) * ldq + h * 16, qq);
   float4 q[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = __ldg(qp + i);
+  for (int i = 0; i < 4; ++i) q[i] = make_float4(qq[4 * i], qq[4 * i + 1], qq[4 * i + 2], qq[4 * i + 3]);
   float sc[NT], m = -INFINITY;
 #pragma unroll
   for (int r = 0; r < NT; ++r) {
@@ -709,13 +737,14 @@ static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s)
 
 // token -> image attention: few boxes -> key ranges split over CTAs + merge (parallelism); many -> one streaming CTA
 // per (head, box)
-static int launch_t2i(const float* q, const float* K, int ldk, const float* V, int ldv, const int* group, float* part,
+template <typename T>
+static int launch_t2i(const float* q, const T* K, int ldk, const T* V, int ldv, const int* group, float* part,
                       float* attn_out, int nb, cudaStream_t s) {
   if (nb >= 16) {
-    t2i_attention_online_kernel<<<dim3(8, nb), 256, 0, s>>>(q, K, ldk, V, ldv, group, attn_out);
+    t2i_attention_online_kernel<T><<<dim3(8, nb), 256, 0, s>>>(q, K, ldk, V, ldv, group, attn_out);
     return 1;
   }
-  t2i_attention_kernel<<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(q, K, ldk, V, ldv, group, part);
+  t2i_attention_kernel<T><<<dim3(8, nb, T2I_SPLIT), 256, 0, s>>>(q, K, ldk, V, ldv, group, part);
   t2i_merge_kernel<<<nb, 256, 0, s>>>(part, attn_out);
   return 2;
 }
@@ -753,8 +782,8 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     const int rows = per_img ? TI : TB;
     const op16* a_keys = per_img ? wk.keys0_bf : wk.keys_bf;
     const op16* a_keyspos = per_img ? wk.keyspos0_bf : wk.keyspos_bf;
-    float* kq = per_img ? wk.kq0 : wk.kq;
-    float* v = per_img ? wk.v0 : wk.v;
+    // block 0: k|q and v projections once per image, fp32; block 1 and the final attention: per box, stored as op16 --
+    // these [boxes x 4096 x 256] intermediates are what the decoder's time goes into at many boxes per image
     const int* group = per_img ? wk.box_img : nullptr;
     {
       // self attention (:316-321; block 0 has neither PE nor residual), LN1, token->image query projection
@@ -776,13 +805,17 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     {
       ProfScope ps(prof, KC_DEC_GEMM, 2.0 * rows * 384 * 256);
       GemmEpilogue ep;
-      ep.bias = lw.b_kq_img; ep.out_f32 = kq; ep.ld_out = 256;
+      ep.bias = lw.b_kq_img;
+      if (per_img) { ep.out_f32 = wk.kq0; ep.ld_out = 256; } else { ep.out_op16 = wk.kq16; ep.ld_out_op16 = 256; }
       gemm_op16(a_keyspos, C, lw.w_kq_img, C, rows, 256, C, ep, s); ++nl;
       GemmEpilogue ev;
-      ev.bias = lw.t2i.bv; ev.out_f32 = v; ev.ld_out = 128;
+      ev.bias = lw.t2i.bv;
+      if (per_img) { ev.out_f32 = wk.v0; ev.ld_out = 128; } else { ev.out_op16 = wk.v16; ev.ld_out_op16 = 128; }
       gemm_op16(a_keys, per_img ? C : KEYS_LD, lw.w_v_img, C, rows, 128, C, ev, s); ++nl;
     }
-    { ProfScope ps(prof, KC_DEC_ATTN); nl += launch_t2i(wk.q_t2i, kq, 256, v, 128, group, t_part, wk.attn_t2i, nb, s); }
+    { ProfScope ps(prof, KC_DEC_ATTN);
+      if (per_img) nl += launch_t2i(wk.q_t2i, wk.kq0, 256, wk.v0, 128, group, t_part, wk.attn_t2i, nb, s);
+      else nl += launch_t2i(wk.q_t2i, wk.kq16, 256, wk.v16, 128, group, t_part, wk.attn_t2i, nb, s); }
     {
       // queries += out_proj(attn); LN2; MLP; LN3; image->token key / value projections   (:328-341)
       ProfScope ps(prof, KC_DEC_TOKEN);
@@ -799,7 +832,10 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       launch_tok_linear(kv, 2, R, s); ++nl;
       YSI_CUDA(cudaGetLastError());
     }
-    { ProfScope ps(prof, KC_DEC_ATTN); i2t_attention_kernel<<<dim3(128, nb), 256, 0, s>>>(kq + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t); ++nl; }
+    { ProfScope ps(prof, KC_DEC_ATTN);
+      if (per_img) i2t_attention_kernel<float><<<dim3(128, nb), 256, 0, s>>>(wk.kq0 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
+      else i2t_attention_kernel<op16><<<dim3(128, nb), 256, 0, s>>>(wk.kq16 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
+      ++nl; }
     YSI_CUDA(cudaGetLastError());
     {
       // keys = keys_prev + out_proj(attn) ; then LN4
@@ -825,13 +861,13 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   {
     ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 256);
     GemmEpilogue ek;
-    ek.bias = w.final_attn.bk; ek.out_f32 = wk.kq; ek.ld_out = 256;    // K in columns 0..127 of kq
+    ek.bias = w.final_attn.bk; ek.out_op16 = wk.kq16; ek.ld_out_op16 = 256;    // K in columns 0..127 of kq16
     gemm_op16(wk.keyspos_bf, C, w.w_k_final, C, TB, 128, C, ek, s); ++nl;
     GemmEpilogue ev;
-    ev.bias = w.final_attn.bv; ev.out_f32 = wk.v; ev.ld_out = 128;
+    ev.bias = w.final_attn.bv; ev.out_op16 = wk.v16; ev.ld_out_op16 = 128;
     gemm_op16(wk.keys_bf, KEYS_LD, w.w_v_final, C, TB, 128, C, ev, s); ++nl;
   }
-  { ProfScope ps(prof, KC_DEC_ATTN); nl += launch_t2i(wk.q_t2i, wk.kq, 256, wk.v, 128, nullptr, t_part, wk.attn_t2i, nb, s); }
+  { ProfScope ps(prof, KC_DEC_ATTN); nl += launch_t2i(wk.q_t2i, wk.kq16, 256, wk.v16, 128, nullptr, t_part, wk.attn_t2i, nb, s); }
   {
     // queries += out_proj(attn); layer_norm_final_attn (eps 1e-5); hypernetwork MLP of mask token 0 (= token row 1)
     ProfScope ps(prof, KC_DEC_TOKEN);

@@ -156,9 +156,10 @@ struct DecoderW {
 struct DecoderWork {           // workspace for cap_img images and cap_box boxes
   int cap_img, cap_box;
   float* keys0;  op16* keys0_bf;  op16* keyspos0_bf;    // [cap_img*4096, 256]
+  op16* kq16;    op16* v16;                              // [cap_box*4096, 256] / [cap_box*4096,128] per-box k|q and v projections
   float* kq0;    float* v0;                              // [cap_img*4096, 256] / [cap_img*4096,128]
   float* keys;   op16* keys_bf;   op16* keyspos_bf;      // [cap_box*4096, 256] per-box keys
-  float* kq;     float* v;                               // [cap_box*4096, 256] / [.,128]
+  float* kq;                                             // [cap_box*4096, 256] pre-LayerNorm key update (fp32)
   op16* attn_i2t;                                        // [cap_box*4096, 128]
   op16* up1;                                             // [cap_box*16384, 128]  hi | lo
   float *tok0, *queries, *q_t2i, *attn_t2i, *k_tok, *v_tok, *hyper;   // token-side [cap_box, 7, *]

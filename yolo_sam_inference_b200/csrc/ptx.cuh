@@ -373,6 +373,14 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+// one packed pair of 16-bit operands -> two fp32
+__device__ __forceinline__ float2 unpack_op16x2(uint32_t u) {
+#ifdef YSI_OP_FP16
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+#else
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+#endif
+}
 // two fp32 -> one packed pair of 16-bit operands (round to nearest even), lo in the low half
 __device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi) {
 #ifdef YSI_OP_FP16
