@@ -222,10 +222,13 @@ __device__ __forceinline__ int window_row_to_token(int wrow) {   // row within o
 template <bool WINDOWED, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, op16* __restrict__ out_bf, float* __restrict__ out_f) {
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                 const float* __restrict__ beta, float eps, op16* __restrict__ out_bf, float* __restrict__ out_f, int reverse) {
+  // reverse: rows are processed last-to-first when the producing GEMM wrote (reduce-added) x in ascending tile order --
+  // the rows most likely still in the L2 are then the last ones -- and first-to-last after a GEMM that ran descending
+  const int warp_lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp_global >= rows_out) return;
+  if (warp_lin >= rows_out) return;
+  const int warp_global = reverse ? rows_out - 1 - warp_lin : warp_lin;
   int src_row = warp_global;
   if (WINDOWED) {
     const int img = warp_global / 4900;
@@ -296,15 +299,15 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
 }
 
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
-                      op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split) {
+                      op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split, bool reverse) {
   YSI_CHECK(D % 8 == 0 && D <= 1280, "LayerNorm width must be a multiple of 8 and <= 1280");
   const int blocks = ceil_div(rows_out, 8);
   if (split)
-    layernorm_kernel<false, true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
+    layernorm_kernel<false, true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f, reverse ? 1 : 0);
   else if (windowed)
-    layernorm_kernel<true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
+    layernorm_kernel<true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f, reverse ? 1 : 0);
   else
-    layernorm_kernel<false><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f);
+    layernorm_kernel<false><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f, reverse ? 1 : 0);
   YSI_CUDA(cudaGetLastError());
 }
 
@@ -378,7 +381,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     const bool glob = lw.is_global != 0;
     const int rows = glob ? T : TW;
     // algorithmic FLOPs (pad rows / pad keys excluded) are attached to every record for the roofline
-    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s); ++nl; }
+    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s, false, /*reverse=*/li == 0); ++nl; }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_qkv; ep.out_op16 = work.qkv; ep.ld_out_op16 = 3 * D;
@@ -398,7 +401,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
       ProfScope ps(prof, KC_GEMM_PROJ, 2.0 * T * D * D);
       gemm_op16(work.attn, D, lw.w_proj, D, T, D, D, ep, s); ++nl;
     }
-    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s); ++nl; }
+    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s, false, /*reverse=*/true); ++nl; }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_fc1; ep.act = ACT_GELU; ep.out_op16 = work.u; ep.ld_out_op16 = w.mlp;
@@ -408,6 +411,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     {
       GemmEpilogue ep;
       ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
+      ep.reverse_m = 1;      // u (201 MB at 8 images) was written first-to-last by fc1: read its L2-resident tail first
       ProfScope ps(prof, KC_GEMM_FC2, 2.0 * T * w.mlp * D);
       gemm_op16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
     }

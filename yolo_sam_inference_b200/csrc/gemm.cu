@@ -113,6 +113,7 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
   YSI_CHECK(N % 32 == 0, "GEMM N must be a multiple of 32");
   YSI_CHECK(K % 8 == 0, "GEMM K must be a multiple of 8");
   EpiGeneric epi{ep};
+  epi.reverse_m = ep.reverse_m;
   const CUtensorMap tmA = make_tmap_op16_2d(A, M, K, lda, GEMM_BM);
   static const int use_pair = [] { const char* e = getenv("YSI_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   if (use_pair && N % 256 == 0 && M >= 2048) {
@@ -131,14 +132,14 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
       EpiStaged es;
       es.tm_out = make_tmap_op16_2d(ep.out_op16, M, N, ep.ld_out_op16, 32);
       es.bias = ep.bias; es.act = ep.act; es.col_scale = ep.col_scale; es.scale_c0 = ep.scale_c0; es.scale_c1 = ep.scale_c1;
-      es.f32_add = 0;
+      es.f32_add = 0; es.reverse_m = ep.reverse_m;
       launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && ep.accumulate && ep.act == ACT_NONE) {
       // residual add: x += tile through cp.reduce.async.bulk (fp32 add in the L2, 128-byte rows)
       EpiStaged es;
       es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
       es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
-      es.f32_add = 1;
+      es.f32_add = 1; es.reverse_m = ep.reverse_m;
       if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, es, stream);
       else launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && !ep.accumulate && ep.act == ACT_NONE && ep.scale_c1 <= ep.scale_c0) {
@@ -146,7 +147,7 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
       EpiStaged es;
       es.tm_out = make_tmap_f32_2d(ep.out_f32, M, N, ep.ld_out, 32);
       es.bias = ep.bias; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
-      es.f32_add = 2;
+      es.f32_add = 2; es.reverse_m = ep.reverse_m;
       if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, es, stream);
       else launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else {

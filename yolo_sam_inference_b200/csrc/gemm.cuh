@@ -78,6 +78,7 @@ struct EpiCtx {
 // Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_op16.
 struct EpiGeneric {
   GemmEpilogue p;
+  int reverse_m = 0;   // CTA-pair kernel: walk the row tiles last-to-first (see GemmEpilogue::reverse_m)
   __device__ __forceinline__ void finish(EpiCtx&) const {}
   // columns [c_begin, c_end) of the BN-wide accumulator tile belong to the calling warp
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
@@ -181,6 +182,7 @@ struct alignas(64) EpiStaged {
   float col_scale;
   int scale_c0, scale_c1;
   int f32_add;     // 0: op16 store, 1: fp32 reduce-add, 2: fp32 store
+  int reverse_m = 0;   // walk the row tiles last-to-first (GemmEpilogue::reverse_m)
   // bulk async-groups belong to the issuing thread: elect.sync picks the same lane for the same (full) mask every time
   __device__ __forceinline__ void finish(EpiCtx& ctx) const {
     if (elect_one()) bulk_wait_read<0>();
@@ -269,6 +271,7 @@ struct alignas(64) EpiStaged {
 // is an (impossible) sentinel, so the mainloop can be timed without the epilogue's global-memory traffic
 struct EpiDrain {
   float* sink;
+  int reverse_m = 0;
   __device__ __forceinline__ void finish(EpiCtx&) const {}
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     float acc = 0.f;
@@ -490,7 +493,8 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile / num_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+        const int mt = epi.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;      // optional last-to-first row-tile order
+        const int m0 = mt * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
         const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -545,7 +549,8 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     EpiCtx ctx{epi_smem + static_cast<uint32_t>(warp - 2) * 8192u, 0u, 0, lane};
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m0 = (tile / num_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+      const int mt = epi.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
+      const int m0 = mt * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (tile % num_n) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();

@@ -117,7 +117,7 @@ void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_
 void launch_im2col_patch_f32(const float* pixel_values, int n, op16* a_patch, cudaStream_t s);
 void launch_build_win_row_map(int* map, int n_images, cudaStream_t s);
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
-                      op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split = false);
+                      op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split = false, bool reverse = false);
 // runs the whole encoder on work.a_patch (n images); result: image embeddings fp32 token-major [n*4096, 256].
 // hidden_dump (optional, device) fp32 [(L+1), n*4096, D]
 void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* emb_out, float* hidden_dump,
