@@ -4,6 +4,7 @@ import re
 import subprocess
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -18,11 +19,14 @@ def test_header_and_binding_agree():
     assert _header_symbols() == sorted(nat.EXPORTS.keys())
 
 
-def test_library_loads_and_exports_every_symbol():
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_library_loads_and_exports_every_symbol(precision):
+    """Both operand-encoding builds (libysi_fp16.so, libysi.so) load side by side and export the same C ABI."""
     from yolo_sam_inference_b200 import _native as nat
-    lib = nat.load()
+    lib = nat.load(precision=precision)
     assert lib.ysi_version() == 1
-    out = subprocess.run(["nm", "-D", "--defined-only", nat.lib_path()], capture_output=True, text=True, check=True).stdout
+    assert lib.ysi_operand_dtype().decode() == precision
+    out = subprocess.run(["nm", "-D", "--defined-only", nat.lib_path(precision)], capture_output=True, text=True, check=True).stdout
     exported = sorted(set(re.findall(r" T (ysi_\w+)", out)))
     assert exported == _header_symbols()
     # nothing but the C ABI leaks out of the library
@@ -41,11 +45,12 @@ def test_sass_contains_blackwell_tensor_and_tma_ops():
     """UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor (B200_PROFILING.md table)."""
     from yolo_sam_inference_b200 import _native as nat
     nat.load()
-    sass = subprocess.run(["cuobjdump", "-sass", nat.lib_path()], capture_output=True, text=True).stdout
+    sass = subprocess.run(["cuobjdump", "-sass", nat.lib_path(nat.default_precision())], capture_output=True, text=True).stdout
     if not sass:
         return
-    for op in ("UTCHMMA", "LDTM", "UTMALDG"):
-        assert op in sass
+    # + STTM = tcgen05.st (P written to tensor memory), USETMAXREG = setmaxnreg, UTMASTG / UTMAREDG = TMA store / reduce
+    for op in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "USETMAXREG"):
+        assert op in sass, op
     assert "HMMA." not in sass.replace("UTCHMMA", "")       # no legacy mma.sync path
 
 
