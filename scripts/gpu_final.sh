@@ -23,7 +23,7 @@ timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/b
 # ncu: launch list of the same command, then full-set captures (after the plain runs above exited)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 1300 -c 330 --csv --log-file gpurun_out/ncu_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "launch list exit $?" >> gpurun_out/final_summary.txt
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'gemm2_op16_kernel|encoder_attention_kernel' -s 60 -c 10 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm2_op16_kernel|encoder_attention_kernel" -s 12 -c 12 \
   -o gpurun_out/ncu_top -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_top.log 2>&1; echo "ncu top exit $?" >> gpurun_out/final_summary.txt
 YSI_BENCH_BOXES=32 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'upsample_stats_fast|contour_hull_disk|EpiConvT|tok_gemm|t2i_attention' -s 40 -c 8 \
   -o gpurun_out/ncu_post -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_post.log 2>&1; echo "ncu post exit $?" >> gpurun_out/final_summary.txt

@@ -115,11 +115,8 @@ struct Cfg {
   static constexpr int S_N = (GLOBAL || W3) ? 80 : 64;      // columns of one S buffer
   static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
   static constexpr int COL_O = 2 * S_N;
-  // setup tables (Q . R^T): global -> 128 columns over the S buffers (S_0 waits until they have been read); windowed
-  // -> 2 x 32 columns over O, which is first written by P.V_0, so S_0 / S_1 are issued while the bias is still being
-  // re-indexed
-  static constexpr int COL_TH = COL_O;                      // windowed setup only
-  static constexpr int COL_TW = GLOBAL ? 0 : COL_O + 32;
+  static constexpr int COL_TH = 0;                          // windowed setup only
+  static constexpr int COL_TW = GLOBAL ? 0 : 32;
   static constexpr int CTAS_PER_SM = 2;
   static_assert(HD == 64 || HD == 80, "head_dim 64 or 80");
   static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_CHUNK % 1024 == 0, "swizzle atoms need 1 KB alignment");
@@ -308,7 +305,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, sbase + C::OFF_TABW1, k), idesc_tab, k);
         umma_commit(bar_tab);
       }
-      if (GLOBAL) mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
+      mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
       int st = 0;
       uint32_t ph = 0;
       for (int t = 0; t < ntiles; ++t) {
