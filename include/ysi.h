@@ -42,9 +42,10 @@ typedef struct {
   int32_t num_global;   /* entries used in global_attn_indexes */
   int32_t global_attn_indexes[YSI_MAX_GLOBAL_LAYERS];
   int32_t max_batch;    /* images per ysi_run_batch call (activation workspace is sized for this) */
-  int32_t max_boxes;    /* box prompts per batch (summed over its images) */
-  int32_t max_image_h;  /* largest original image the context will be given */
-  int32_t max_image_w;
+  int32_t max_boxes;    /* box prompts decoded per launch; a batch with more is processed in chunks of max_boxes that
+                           share the batch's image embeddings (the reference loops over any number, pipeline.py:170) */
+  int32_t max_image_h;  /* INITIAL capacity for original images; larger images (up to 4096 x 4096) re-allocate the */
+  int32_t max_image_w;  /* image-sized buffers on first use (the reference has no size limit, pipeline.py:206-210) */
 } ysi_config;
 
 /* One tensor of SamModel.state_dict() (the object built at pipeline.py:76), fp32, C-contiguous. */
@@ -80,6 +81,27 @@ typedef struct {
   float h2d_ms, preprocess_ms, encoder_ms, decoder_ms, postprocess_ms, metrics_ms, d2h_ms, total_ms;
 } ysi_timing;
 
+/* pixel formats of host images handed to ysi_submit */
+#define YSI_PIX_RGB8 0   /* uint8 [H, W, 3] RGB: what _load_image returns (pipeline.py:206-210) */
+#define YSI_PIX_GRAY8 1  /* uint8 [H, W]: the raw samples of an 8-bit single-channel file; the device replicates them to RGB */
+#define YSI_PIX_GRAY16 2 /* uint16 [H, W] little endian: raw samples of a 16-bit file; the device takes v >> 8 (what
+                            cv2.imread's default flags produce) and replicates to RGB */
+
+/* One batch of same-sized images with their box prompts (ysi_submit). Host pointers; pinned memory makes the copies
+ * asynchronous. Buffers must stay valid until the matching ysi_wait_batch. */
+typedef struct {
+  int32_t n_images;
+  int32_t height, width;
+  int32_t row_stride;            /* bytes between image rows */
+  int32_t pixel_format;          /* YSI_PIX_* */
+  const void* const* images;     /* n_images pointers */
+  const float* boxes_xyxy;       /* float32 [sum(box_counts), 4], original-image pixels (pipeline.py:84-87) */
+  const int32_t* box_counts;     /* boxes per image */
+  uint8_t* masks_out;            /* uint8 [nb, H, W] of 0/1, or NULL */
+  uint8_t* packed_out;           /* uint8 [nb, ceil(H*W/8)] np.packbits rows (utils/mask_encoding.py:24), or NULL */
+  ysi_mask_metrics* metrics_out; /* [nb], or NULL */
+} ysi_batch;
+
 /* ---- lifecycle -------------------------------------------------------------------------------- */
 /* replaces SamModel.from_pretrained(...).to(device), pipeline.py:69-77 */
 YSI_API int ysi_create(int device, const ysi_config* cfg, ysi_ctx** out);
@@ -114,6 +136,16 @@ YSI_API int ysi_submit_batch(ysi_ctx* ctx, int slot, int n_images, const uint8_t
                      const float* boxes_xyxy, const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out,
                      ysi_mask_metrics* metrics_out);
 YSI_API int ysi_wait_batch(ysi_ctx* ctx, int slot, ysi_timing* timing);
+/* ysi_submit_batch for any pixel format (GPU-side ingest). With YSI_PIX_GRAY8 / GRAY16 the host
+ * hands over the raw samples of a baseline (uncompressed) TIFF strip -- 1 or 2 bytes per pixel over PCIe instead of 3 --
+ * and the 16 -> 8 bit reduction and grey -> RGB replication of _load_image (pipeline.py:206-210) run on the device. */
+YSI_API int ysi_submit(ysi_ctx* ctx, int slot, const ysi_batch* batch);
+
+/* Page-locked host memory for image staging / result buffers (cudaHostAlloc): copies from and to it are truly
+ * asynchronous, so a decode thread pool can fill the next batches while the GPU works (the host side of the folder
+ * entry point, pipeline.py:212-263). Independent of any context. */
+YSI_API int ysi_alloc_pinned(int device, size_t bytes, void** out);   /* portable: usable by every context of the process */
+YSI_API void ysi_free_pinned(void* p);
 
 /* ---- measurement support (bench.py) ------------------------------------------------------------- */
 /* resident input pool: images uploaded once, then processed straight from HBM (device-resident leg) */
@@ -128,7 +160,8 @@ YSI_API int ysi_timer_elapsed_ms(ysi_ctx* ctx, int slot_a, int slot_b, float* ms
 YSI_API int ysi_sync(ysi_ctx* ctx);
 /* per-kernel-class event timing: enable, run steps, read (returns the number of classes written) */
 YSI_API int ysi_profile(ysi_ctx* ctx, int enable);
-YSI_API int ysi_profile_read(ysi_ctx* ctx, int max_classes, const char** names, double* ms, int64_t* records, double* flops);
+YSI_API int ysi_profile_read(ysi_ctx* ctx, int max_classes, const char** names, double* ms, int64_t* records, double* flops,
+                     double* bytes /* algorithmic HBM bytes of the HBM-bound classes, may be NULL */);
 
 /* ---- stage-level entry points (parity tests; each is one row of SURVEY.md section 8a) --------------- */
 /* a1: sam_processor(image) -> pixel_values fp32 [n,3,1024,1024] (image_processing_sam.py:205-250) */

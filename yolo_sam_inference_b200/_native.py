@@ -40,6 +40,16 @@ class YsiTiming(C.Structure):
         return {n: float(getattr(self, n)) for n, _ in self._fields_}
 
 
+PIX_RGB8, PIX_GRAY8, PIX_GRAY16 = 0, 1, 2
+
+
+class YsiBatch(C.Structure):
+    _fields_ = [("n_images", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("row_stride", C.c_int32),
+                ("pixel_format", C.c_int32), ("images", C.POINTER(C.c_void_p)), ("boxes_xyxy", C.POINTER(C.c_float)),
+                ("box_counts", C.POINTER(C.c_int32)), ("masks_out", C.POINTER(C.c_uint8)),
+                ("packed_out", C.POINTER(C.c_uint8)), ("metrics_out", C.c_void_p)]
+
+
 # numpy mirror of ysi_mask_metrics (same field order / sizes; no padding needed: all naturally aligned)
 METRICS_DTYPE = np.dtype([
     ("area", "<i8"), ("sum_r", "<i8"), ("sum_c", "<i8"),
@@ -72,13 +82,16 @@ EXPORTS = {
     "ysi_submit_batch": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p, _i32p,
                                    _u8p, _u8p, C.c_void_p]),
     "ysi_wait_batch": (C.c_int, [_ctx, C.c_int, C.POINTER(YsiTiming)]),
+    "ysi_submit": (C.c_int, [_ctx, C.c_int, C.POINTER(YsiBatch)]),
+    "ysi_alloc_pinned": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "ysi_free_pinned": (None, [C.c_void_p]),
     "ysi_pool_upload": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]),
     "ysi_compute_pool": (C.c_int, [_ctx, C.c_int, C.c_int, _f32p, _i32p, C.c_int, C.POINTER(YsiTiming)]),
     "ysi_timer_record": (C.c_int, [_ctx, C.c_int]),
     "ysi_timer_elapsed_ms": (C.c_int, [_ctx, C.c_int, C.c_int, _f32p]),
     "ysi_sync": (C.c_int, [_ctx]),
     "ysi_profile": (C.c_int, [_ctx, C.c_int]),
-    "ysi_profile_read": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_char_p), _f64p, C.POINTER(C.c_int64), _f64p]),
+    "ysi_profile_read": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_char_p), _f64p, C.POINTER(C.c_int64), _f64p, _f64p]),
     "ysi_preprocess": (C.c_int, [_ctx, C.c_int, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, _f32p]),
     "ysi_encode": (C.c_int, [_ctx, C.c_int, _f32p, _f32p, _f32p]),
     "ysi_decode": (C.c_int, [_ctx, _f32p, _f64p, C.c_int, _f32p, _f32p]),
@@ -127,6 +140,32 @@ def load(build_if_missing: bool = True, precision: Optional[str] = None) -> C.CD
         raise RuntimeError(f"{path} was built for {lib.ysi_operand_dtype().decode()} operands, expected {precision}")
     _LIBS[precision] = lib
     return lib
+
+
+class PinnedBuffer:
+    """Page-locked host memory (ysi_alloc_pinned) exposed as a uint8 numpy array; freed with the object."""
+
+    def __init__(self, nbytes: int, precision: Optional[str] = None, device: int = 0):
+        self._lib = load(precision=precision)
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        rc = self._lib.ysi_alloc_pinned(int(device), self.nbytes, C.byref(p))
+        if rc != 0 or not p.value:
+            raise MemoryError(f"ysi_alloc_pinned({nbytes}) failed ({rc})")
+        self._ptr = p
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(self.nbytes, 1)).from_address(p.value))[:self.nbytes]
+
+    def close(self) -> None:
+        if getattr(self, "_ptr", None):
+            self.array = None
+            self._lib.ysi_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def as_u8p(a: Optional[np.ndarray]):

@@ -68,11 +68,18 @@ struct ysi_ctx {
   Profiler prof;
   cudaEvent_t timers[8]{};
   cudaEvent_t join_ev = nullptr;
-  // pinned ring for the small per-step box arrays (lets ysi_compute_pool enqueue steps without syncing)
+  // pinned ring for the small per-step box arrays (lets ysi_compute_pool enqueue steps without syncing); an entry is
+  // reused only after the copies that read it have completed (ring_ev)
   static constexpr int RING = 64;
   double* h_boxes = nullptr;   // [RING, max_boxes, 4]
   int* h_box_img = nullptr;    // [RING, max_boxes]
+  cudaEvent_t ring_ev[RING]{};
+  bool ring_used[RING]{};
   int ring_pos = 0;
+  // image-size dependent buffers grow on demand (the reference has no size limit, pipeline.py:206-210); cfg.max_image_h/w
+  // is only the initial capacity
+  size_t cap_hw = 0;           // pixels per image the slot buffers hold
+  int rs_tmp_rows = 0;         // rows per image d_rs_tmp holds
 
   // Two-slot software pipeline: H2D of batch i+1 (s_in) | preprocess + encoder of batch i (stream) |
   // decoder + upsample + metrics of batch i-1 (s_aux) | D2H of batch i-1 (s_out). A slot owns the buffers that
@@ -81,12 +88,13 @@ struct ysi_ctx {
     uint8_t* d_rgb = nullptr;       // [max_batch, H, W, 3]
     uint16_t* d_sum3 = nullptr;     // [max_batch, H, W]
     uint8_t* d_gray = nullptr;      // [max_batch, H, W]  floor((R+G+B)/3)
+    uint8_t* d_raw = nullptr;       // [max_batch, H, W] x 2 bytes: raw 8/16-bit grey pixels before the ingest kernel (f3)
     float* d_emb = nullptr;         // [max_batch*4096, 256]
-    uint8_t* d_masks = nullptr;     // [max_boxes, H, W]
-    uint8_t* d_packed = nullptr;    // [max_boxes, ceil(H*W/8)] (lazily allocated)
+    uint8_t* d_masks = nullptr;     // [max_boxes, H, W]  byte masks (on request; scratch for non-1024 geometries)
+    uint8_t* d_packed = nullptr;    // [max_boxes, ceil(H*W/8)]  np.packbits rows: contour kernel input + wire format
     ysi_mask_metrics* d_metrics = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_enc = nullptr, ev_dec = nullptr, ev_d2h = nullptr;
-    cudaEvent_t t[8]{};             // stage timing: in0, enc0, enc_pre, enc1, dec0, dec1, post1, out0
+    cudaEvent_t t[9]{};             // stage timing: in0, enc0, enc_pre, enc1, dec0, dec1, post1, out0, out1
     int n = 0, H = 0, W = 0, nb = 0;
     bool host_in = false, host_out = false;
   };
@@ -100,6 +108,12 @@ struct ysi_ctx {
     YSI_CUDA(cudaMalloc(&p, n * sizeof(T)));
     allocs.push_back(p);
     return static_cast<T*>(p);
+  }
+  void dfree(void* p) {
+    if (!p) return;
+    for (auto it = allocs.begin(); it != allocs.end(); ++it)
+      if (*it == p) { allocs.erase(it); break; }
+    cudaFree(p);
   }
   float* upload_f32(const float* h, size_t n) {
     float* d = dalloc<float>(n);
@@ -308,6 +322,34 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   c->weights_loaded = true;
 }
 
+// every stream of the context idle
+void sync_all(ysi_ctx* c) {
+  for (cudaStream_t st : {c->s_in, c->stream, c->s_aux, c->s_out})
+    if (st) YSI_CUDA(cudaStreamSynchronize(st));
+}
+
+// Image-size dependent buffers of both slots hold images of up to cap_hw pixels; a larger image drains the context and
+// re-allocates them (rare: once per new largest size in a folder).
+void ensure_image_capacity(ysi_ctx* c, int H, int W) {
+  const size_t HW = static_cast<size_t>(H) * W;
+  if (HW <= c->cap_hw) return;
+  sync_all(c);
+  const size_t B = c->cfg.max_batch, NB = c->cfg.max_boxes;
+  for (auto& sl : c->slots) {
+    c->dfree(sl.d_rgb); c->dfree(sl.d_sum3); c->dfree(sl.d_gray); c->dfree(sl.d_raw); c->dfree(sl.d_masks); c->dfree(sl.d_packed);
+    sl.d_rgb = sl.d_gray = sl.d_raw = sl.d_masks = sl.d_packed = nullptr; sl.d_sum3 = nullptr;
+    sl.d_rgb = c->dalloc<uint8_t>(B * HW * 3);
+    sl.d_sum3 = c->dalloc<uint16_t>(B * HW);
+    sl.d_gray = c->dalloc<uint8_t>(B * HW);
+    sl.d_raw = c->dalloc<uint8_t>(B * HW * 2);
+    sl.d_masks = c->dalloc<uint8_t>(NB * HW);
+    sl.d_packed = c->dalloc<uint8_t>(NB * ((HW + 7) / 8 + 4));
+  }
+  c->cap_hw = HW;
+  // the stage-level entry points (parity tests) work on slot 0's buffers
+  c->d_rgb = c->slots[0].d_rgb; c->d_sum3 = c->slots[0].d_sum3; c->d_masks = c->slots[0].d_masks; c->d_packed = c->slots[0].d_packed;
+}
+
 void create_impl(ysi_ctx* c) {
   const ysi_config& cfg = c->cfg;
   YSI_CHECK(cfg.num_heads > 0 && cfg.hidden_size % cfg.num_heads == 0 &&
@@ -332,7 +374,6 @@ void create_impl(ysi_ctx* c) {
   for (int i = 0; i < 3; ++i) { c->mean255[i] = mean[i] * inv_rescale; c->std255[i] = sd[i] * inv_rescale; }
 
   const size_t B = cfg.max_batch, NB = cfg.max_boxes, D = cfg.hidden_size;
-  const size_t HW = static_cast<size_t>(cfg.max_image_h) * cfg.max_image_w;
   EncoderWork& ew = c->ew;
   ew.cap = cfg.max_batch;
   ew.a_patch = c->dalloc<op16>(B * 4096 * PATCH_K);
@@ -374,24 +415,20 @@ void create_impl(ysi_ctx* c) {
   dw.boxes1024 = c->dalloc<double>(NB * 4);
   dw.box_img = c->dalloc<int>(NB);
   for (auto& sl : c->slots) {
-    sl.d_rgb = c->dalloc<uint8_t>(B * HW * 3);
-    sl.d_sum3 = c->dalloc<uint16_t>(B * HW);
-    sl.d_gray = c->dalloc<uint8_t>(B * HW);
     sl.d_emb = c->dalloc<float>(B * 4096 * 256);
-    sl.d_masks = c->dalloc<uint8_t>(NB * HW);
     sl.d_metrics = c->dalloc<ysi_mask_metrics>(NB);
     for (cudaEvent_t* e : {&sl.ev_h2d, &sl.ev_enc, &sl.ev_dec, &sl.ev_d2h}) YSI_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto& e : sl.t) YSI_CUDA(cudaEventCreate(&e));
   }
-  // the stage-level entry points (parity tests) work on slot 0's buffers
-  c->d_rgb = c->slots[0].d_rgb; c->d_sum3 = c->slots[0].d_sum3; c->d_emb = c->slots[0].d_emb;
-  c->d_masks = c->slots[0].d_masks; c->d_metrics = c->slots[0].d_metrics;
-  c->d_low = c->dalloc<float>(NB * 65536);
-  c->d_stats = c->dalloc<MaskStatsDev>(NB);
-  c->d_mask_img = c->dalloc<int>(NB);
+  for (auto& e : c->ring_ev) YSI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   YSI_CUDA(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
   YSI_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   YSI_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  ensure_image_capacity(c, cfg.max_image_h, cfg.max_image_w);
+  c->d_emb = c->slots[0].d_emb; c->d_metrics = c->slots[0].d_metrics;
+  c->d_low = c->dalloc<float>(NB * 65536);
+  c->d_stats = c->dalloc<MaskStatsDev>(NB);
+  c->d_mask_img = c->dalloc<int>(NB);
   {
     void* p = nullptr;
     YSI_CUDA(cudaHostAlloc(&p, sizeof(double) * 4 * NB * ysi_ctx::RING, cudaHostAllocDefault));
@@ -459,7 +496,13 @@ void preprocess_images(ysi_ctx* c, const uint8_t* rgb, int n, int H, int W, floa
   int sh = H, sw = W, pitch = W * 3;
   size_t istride = static_cast<size_t>(H) * W * 3;
   if (g.rw != W) {
-    if (!c->d_rs_tmp) c->d_rs_tmp = c->dalloc<uint8_t>(static_cast<size_t>(c->cfg.max_batch) * c->cfg.max_image_h * 1024 * 3);
+    if (!c->d_rs_tmp || c->rs_tmp_rows < H) {
+      // (the buffer is only touched by the main stream; an earlier batch still using it there is ordered before the free
+      // by the stream-ordered semantics of cudaFree)
+      c->dfree(c->d_rs_tmp);
+      c->d_rs_tmp = c->dalloc<uint8_t>(static_cast<size_t>(c->cfg.max_batch) * H * 1024 * 3);
+      c->rs_tmp_rows = H;
+    }
     launch_resize_h(src, n, H, pitch, istride, resize_tables(c, W, g.rw), c->d_rs_tmp, c->stream);
     c->launches += 1;
     src = c->d_rs_tmp; sw = g.rw; pitch = g.rw * 3; istride = static_cast<size_t>(H) * g.rw * 3;
@@ -475,9 +518,8 @@ void preprocess_images(ysi_ctx* c, const uint8_t* rgb, int n, int H, int W, floa
 }
 
 // processing_sam.py:215-234: boxes (float32, original pixels) -> float64 in the resized frame
-void rescale_boxes(const float* boxes, int nb, int H, int W, std::vector<double>& out) {
+void rescale_boxes(const float* boxes, int nb, int H, int W, double* out) {
   const PostGeom g = make_post_geom(H, W);
-  out.resize(static_cast<size_t>(nb) * 4);
   const double sx = static_cast<double>(g.rw) / W, sy = static_cast<double>(g.rh) / H;
   for (int i = 0; i < nb; ++i) {
     out[4 * i + 0] = static_cast<double>(boxes[4 * i + 0]) * sx;
@@ -490,48 +532,71 @@ void rescale_boxes(const float* boxes, int nb, int H, int W, std::vector<double>
 void check_batch(ysi_ctx* c, int n, int H, int W, int nb) {
   YSI_CHECK(c->weights_loaded, "ysi_load_weights has not been called");
   YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
-  YSI_CHECK(nb >= 0 && nb <= c->cfg.max_boxes, "box count exceeds max_boxes");
-  YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+  YSI_CHECK(nb >= 0, "negative box count");
+  YSI_CHECK(H >= 2 && W >= 2 && H <= 4096 && W <= 4096, "image size out of range (2..4096 per side)");
+  ensure_image_capacity(c, H, W);
 }
 
-// Enqueue one batch into `slot` (see ysi_ctx::Slot). Images come from host memory (rgb != null; pinned memory makes the
-// copy asynchronous) or are already resident on the device (dev_src). Results are copied to the host buffers when any
-// is given, else they stay on the device. Returns immediately; wait_impl() blocks until the slot's batch is done.
-void submit_impl(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, const uint8_t* dev_src, int H, int W, int row_stride,
-                 const float* boxes, const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out,
-                 ysi_mask_metrics* metrics_out) {
+// One batch as the entry points describe it. Images: host pointers (`host`, pixel format `fmt`) or a dense device-resident
+// RGB block (`dev_rgb`, the bench's resident pool).
+struct BatchIn {
+  int n = 0, H = 0, W = 0, row_stride = 0;
+  int fmt = YSI_PIX_RGB8;
+  const void* const* host = nullptr;
+  const uint8_t* dev_rgb = nullptr;
+  const float* boxes = nullptr;
+  const int32_t* counts = nullptr;
+  uint8_t* masks_out = nullptr;
+  uint8_t* packed_out = nullptr;
+  ysi_mask_metrics* metrics_out = nullptr;
+};
+
+// Enqueue one batch into `slot` (see ysi_ctx::Slot). Results are copied to the host buffers when any is given, else they
+// stay on the device. Returns immediately; wait_impl() blocks until the slot's batch is done.
+// More boxes than the context's max_boxes are processed in chunks of max_boxes that share the batch's image embeddings
+// (the reference loops over any number of boxes, pipeline.py:170).
+void submit_impl(ysi_ctx* c, int slot, const BatchIn& in) {
+  const int n = in.n, H = in.H, W = in.W;
   int nb = 0;
-  for (int i = 0; i < n; ++i) nb += box_counts[i];
-  check_batch(c, n, H, W, nb);
+  for (int i = 0; i < n; ++i) { YSI_CHECK(in.counts[i] >= 0, "negative box count"); nb += in.counts[i]; }
   YSI_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
-  YSI_CHECK(rgb || dev_src, "no input images");
-  YSI_CHECK(!rgb || row_stride >= 3 * W, "row_stride smaller than 3*W");
+  check_batch(c, n, H, W, nb);
+  YSI_CHECK(in.host || in.dev_rgb, "no input images");
+  YSI_CHECK(in.fmt == YSI_PIX_RGB8 || in.fmt == YSI_PIX_GRAY8 || in.fmt == YSI_PIX_GRAY16, "unknown pixel format");
+  const int bpp = in.fmt == YSI_PIX_RGB8 ? 3 : (in.fmt == YSI_PIX_GRAY8 ? 1 : 2);
+  YSI_CHECK(!in.host || in.row_stride >= bpp * W, "row_stride smaller than one row of pixels");
   ysi_ctx::Slot& sl = c->slots[slot];
   sl.n = n; sl.H = H; sl.W = W; sl.nb = nb;
-  sl.host_in = rgb != nullptr;
-  sl.host_out = masks_out || packed_out || metrics_out;
+  sl.host_in = in.host != nullptr;
+  sl.host_out = in.masks_out || in.packed_out || in.metrics_out;
   Profiler* prof = c->prof.active ? &c->prof : nullptr;
   cudaStream_t sm = c->stream;
   cudaStream_t sd = prof ? c->stream : c->s_aux;     // per-class profiling needs one timeline
-  const size_t img_bytes = static_cast<size_t>(H) * W * 3, HW = static_cast<size_t>(H) * W;
-  const uint8_t* src = dev_src;
-  // ---- stage 1: H2D (s_in). d_rgb of this slot was last read by the encoder stage of the previous batch in the slot.
-  if (rgb) {
+  const size_t HW = static_cast<size_t>(H) * W, PB = (HW + 7) / 8;
+  const uint8_t* src = in.dev_rgb;
+  // ---- stage 1: H2D (s_in). d_rgb / d_raw of this slot were last read by the encoder stage of the previous batch in the slot.
+  if (in.host) {
     YSI_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_enc, 0));
     YSI_CUDA(cudaEventRecord(sl.t[0], c->s_in));
-    for (int i = 0; i < n; ++i)
-      YSI_CUDA(cudaMemcpy2DAsync(sl.d_rgb + i * img_bytes, static_cast<size_t>(W) * 3, rgb[i], row_stride,
-                                 static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, c->s_in));
+    uint8_t* dst = in.fmt == YSI_PIX_RGB8 ? sl.d_rgb : sl.d_raw;
+    const size_t row_bytes = static_cast<size_t>(W) * bpp;
+    for (int i = 0; i < n; ++i) {
+      if (static_cast<size_t>(in.row_stride) == row_bytes)
+        YSI_CUDA(cudaMemcpyAsync(dst + i * HW * bpp, in.host[i], HW * bpp, cudaMemcpyHostToDevice, c->s_in));
+      else
+        YSI_CUDA(cudaMemcpy2DAsync(dst + i * HW * bpp, row_bytes, in.host[i], in.row_stride, row_bytes, H, cudaMemcpyHostToDevice, c->s_in));
+    }
     YSI_CUDA(cudaEventRecord(sl.ev_h2d, c->s_in));
     YSI_CUDA(cudaStreamWaitEvent(sm, sl.ev_h2d, 0));
     src = sl.d_rgb;
   }
-  // ---- stage 2: preprocess + encoder (main stream). d_sum3 / d_emb of this slot were last read by its decoder stage.
+  // ---- stage 2: ingest / preprocess + encoder (main stream). d_sum3 / d_emb of this slot were last read by its decoder stage.
   YSI_CUDA(cudaStreamWaitEvent(sm, sl.ev_dec, 0));
   YSI_CUDA(cudaEventRecord(sl.t[1], sm));
   if (nb > 0) {
     ProfScope ps(prof, KC_PREPROCESS);
-    launch_sum3(src, n, H, W, W * 3, sl.d_sum3, sl.d_gray, sm);
+    if (in.host && in.fmt != YSI_PIX_RGB8) launch_gray_ingest(sl.d_raw, bpp, n, H, W, sl.d_rgb, sl.d_sum3, sl.d_gray, sm);
+    else launch_sum3(src, n, H, W, W * 3, sl.d_sum3, sl.d_gray, sm);
     c->launches += 1;
     preprocess_images(c, src, n, H, W, nullptr, c->ew.a_patch);
   }
@@ -539,61 +604,68 @@ void submit_impl(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, const u
   if (nb > 0) encoder_forward(c->enc, c->ew, n, sl.d_emb, nullptr, sm, &c->launches, prof);
   YSI_CUDA(cudaEventRecord(sl.t[3], sm));
   YSI_CUDA(cudaEventRecord(sl.ev_enc, sm));
-  // ---- stage 3: prompt encoder + decoder + upsample + metrics (s_aux). d_masks / d_metrics were last read by the D2H.
+  // ---- stage 3: prompt encoder + decoder + upsample + metrics (s_aux), stage 4: D2H (s_out); per chunk of boxes.
   YSI_CUDA(cudaStreamWaitEvent(sd, sl.ev_enc, 0));
-  YSI_CUDA(cudaStreamWaitEvent(sd, sl.ev_d2h, 0));
   YSI_CUDA(cudaEventRecord(sl.t[4], sd));
-  if (nb > 0) {
-    const int rs = c->ring_pos;
-    c->ring_pos = (c->ring_pos + 1) % ysi_ctx::RING;
-    double* hb = c->h_boxes + static_cast<size_t>(rs) * 4 * c->cfg.max_boxes;
-    int* hi = c->h_box_img + static_cast<size_t>(rs) * c->cfg.max_boxes;
-    std::vector<double> b1024;
-    rescale_boxes(boxes, nb, H, W, b1024);
-    std::memcpy(hb, b1024.data(), sizeof(double) * 4 * nb);
+  const int maxb = c->cfg.max_boxes;
+  std::vector<int> img_of(nb);
+  {
     int k = 0;
     for (int i = 0; i < n; ++i)
-      for (int j = 0; j < box_counts[i]; ++j) hi[k++] = i;
-    YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, hb, sizeof(double) * 4 * nb, cudaMemcpyHostToDevice, sd));
-    YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, sd));
-    YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, hi, sizeof(int) * nb, cudaMemcpyHostToDevice, sd));
-    decoder_forward(c->dec, c->dw, sl.d_emb, n, nb, c->d_low, nullptr, sd, &c->launches, prof);
+      for (int j = 0; j < in.counts[i]; ++j) img_of[k++] = i;
   }
-  YSI_CUDA(cudaEventRecord(sl.t[5], sd));
-  if (nb > 0) {
-    {
-      ProfScope ps(prof, KC_POST_UPSAMPLE);
-      launch_init_stats(c->d_stats, nb, sd);
-      launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), sl.d_sum3, sl.d_gray, c->d_mask_img, sl.d_masks, nullptr, c->d_stats, sd);
-      c->launches += 2;
+  const bool want_bytes = in.masks_out != nullptr;
+  for (int k0 = 0; k0 < nb || k0 == 0; k0 += maxb) {
+    const int kc = nb - k0 < maxb ? nb - k0 : maxb;
+    YSI_CUDA(cudaStreamWaitEvent(sd, sl.ev_d2h, 0));      // d_masks / d_packed / d_metrics were last read by the previous D2H
+    if (kc > 0) {
+      const int rs = c->ring_pos;
+      c->ring_pos = (c->ring_pos + 1) % ysi_ctx::RING;
+      if (c->ring_used[rs]) YSI_CUDA(cudaEventSynchronize(c->ring_ev[rs]));   // the copies that last read this entry are done
+      double* hb = c->h_boxes + static_cast<size_t>(rs) * 4 * maxb;
+      int* hi = c->h_box_img + static_cast<size_t>(rs) * maxb;
+      rescale_boxes(in.boxes + 4 * static_cast<size_t>(k0), kc, H, W, hb);
+      std::memcpy(hi, img_of.data() + k0, sizeof(int) * kc);
+      YSI_CUDA(cudaMemcpyAsync(c->dw.boxes1024, hb, sizeof(double) * 4 * kc, cudaMemcpyHostToDevice, sd));
+      YSI_CUDA(cudaMemcpyAsync(c->dw.box_img, hi, sizeof(int) * kc, cudaMemcpyHostToDevice, sd));
+      YSI_CUDA(cudaMemcpyAsync(c->d_mask_img, hi, sizeof(int) * kc, cudaMemcpyHostToDevice, sd));
+      YSI_CUDA(cudaEventRecord(c->ring_ev[rs], sd));
+      c->ring_used[rs] = true;
+      decoder_forward(c->dec, c->dw, sl.d_emb, n, kc, c->d_low, nullptr, sd, &c->launches, prof);
     }
-    YSI_CUDA(cudaEventRecord(sl.t[6], sd));
-    {
-      ProfScope ps(prof, KC_POST_HULL);
-      launch_contour_hull_disk(sl.d_masks, nb, H, W, sl.d_sum3, c->d_mask_img, c->d_stats, sl.d_metrics, sd);
-      c->launches += 1;
+    YSI_CUDA(cudaEventRecord(sl.t[5], sd));
+    if (kc > 0) {
+      {
+        ProfScope ps(prof, KC_POST_UPSAMPLE, 0.0, static_cast<double>(kc) * (65536.0 * 4 + (want_bytes ? HW : 0) + PB));
+        launch_init_stats(c->d_stats, kc, sd);
+        launch_upsample_stats(c->d_low, kc, make_post_geom(H, W), sl.d_sum3, sl.d_gray, c->d_mask_img, sl.d_masks, sl.d_packed,
+                              want_bytes, nullptr, c->d_stats, sd);
+        c->launches += 2 + ((H == 1024 && W == 1024) ? 0 : 1);
+      }
+      YSI_CUDA(cudaEventRecord(sl.t[6], sd));
+      {
+        ProfScope ps(prof, KC_POST_HULL, 0.0, static_cast<double>(kc) * (PB + sizeof(ysi_mask_metrics)));
+        launch_contour_hull_disk(sl.d_packed, kc, H, W, sl.d_sum3, c->d_mask_img, c->d_stats, sl.d_metrics, sd);
+        c->launches += 1;
+      }
+    } else {
+      YSI_CUDA(cudaEventRecord(sl.t[6], sd));
     }
-    if (packed_out) {
-      if (!sl.d_packed)
-        sl.d_packed = c->dalloc<uint8_t>(static_cast<size_t>(c->cfg.max_boxes) * ((static_cast<size_t>(c->cfg.max_image_h) * c->cfg.max_image_w + 7) / 8));
-      launch_packbits(sl.d_masks, sl.d_packed, nb, static_cast<long long>(HW), sd);
-      c->launches += 1;
+    YSI_CUDA(cudaEventRecord(sl.ev_dec, sd));
+    YSI_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_dec, 0));
+    YSI_CUDA(cudaEventRecord(sl.t[7], c->s_out));
+    if (kc > 0) {
+      if (in.packed_out)
+        YSI_CUDA(cudaMemcpyAsync(in.packed_out + static_cast<size_t>(k0) * PB, sl.d_packed, static_cast<size_t>(kc) * PB, cudaMemcpyDeviceToHost, c->s_out));
+      if (in.masks_out)
+        YSI_CUDA(cudaMemcpyAsync(in.masks_out + static_cast<size_t>(k0) * HW, sl.d_masks, static_cast<size_t>(kc) * HW, cudaMemcpyDeviceToHost, c->s_out));
+      if (in.metrics_out)
+        YSI_CUDA(cudaMemcpyAsync(in.metrics_out + k0, sl.d_metrics, sizeof(ysi_mask_metrics) * kc, cudaMemcpyDeviceToHost, c->s_out));
     }
-  } else {
-    YSI_CUDA(cudaEventRecord(sl.t[6], sd));
+    YSI_CUDA(cudaEventRecord(sl.t[8], c->s_out));
+    YSI_CUDA(cudaEventRecord(sl.ev_d2h, c->s_out));
+    if (nb == 0) break;
   }
-  YSI_CUDA(cudaEventRecord(sl.ev_dec, sd));
-  // ---- stage 4: D2H (s_out)
-  YSI_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_dec, 0));
-  YSI_CUDA(cudaEventRecord(sl.t[7], c->s_out));
-  if (nb > 0) {
-    if (packed_out)
-      YSI_CUDA(cudaMemcpyAsync(packed_out, sl.d_packed, static_cast<size_t>(nb) * ((HW + 7) / 8), cudaMemcpyDeviceToHost, c->s_out));
-    if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, sl.d_masks, nb * HW, cudaMemcpyDeviceToHost, c->s_out));
-    if (metrics_out)
-      YSI_CUDA(cudaMemcpyAsync(metrics_out, sl.d_metrics, sizeof(ysi_mask_metrics) * nb, cudaMemcpyDeviceToHost, c->s_out));
-  }
-  YSI_CUDA(cudaEventRecord(sl.ev_d2h, c->s_out));
 }
 
 void wait_impl(ysi_ctx* c, int slot, ysi_timing* tm) {
@@ -603,25 +675,19 @@ void wait_impl(ysi_ctx* c, int slot, ysi_timing* tm) {
   if (tm) {
     std::memset(tm, 0, sizeof(*tm));
     if (sl.n > 0) {
-      // (stage times of this batch on their own streams; with batches in flight the stages of different batches overlap)
-      YSI_CUDA(cudaEventSynchronize(sl.t[7]));
+      // (stage times of this batch on their own streams; with batches in flight the stages of different batches overlap.
+      // With more boxes than max_boxes the decoder / post / copy figures are those of the LAST chunk.)
+      YSI_CUDA(cudaEventSynchronize(sl.t[8]));
       if (sl.host_in) { YSI_CUDA(cudaEventElapsedTime(&tm->h2d_ms, sl.t[0], sl.t[1])); }
       YSI_CUDA(cudaEventElapsedTime(&tm->preprocess_ms, sl.t[1], sl.t[2]));
       YSI_CUDA(cudaEventElapsedTime(&tm->encoder_ms, sl.t[2], sl.t[3]));
-      YSI_CUDA(cudaEventElapsedTime(&tm->decoder_ms, sl.t[4], sl.t[5]));
+      if (sl.nb <= c->cfg.max_boxes) { YSI_CUDA(cudaEventElapsedTime(&tm->decoder_ms, sl.t[4], sl.t[5])); }
       YSI_CUDA(cudaEventElapsedTime(&tm->postprocess_ms, sl.t[5], sl.t[6]));
       YSI_CUDA(cudaEventElapsedTime(&tm->metrics_ms, sl.t[6], sl.t[7]));
-      tm->total_ms = tm->h2d_ms + tm->preprocess_ms + tm->encoder_ms + tm->decoder_ms + tm->postprocess_ms + tm->metrics_ms;
+      if (sl.host_out) { YSI_CUDA(cudaEventElapsedTime(&tm->d2h_ms, sl.t[7], sl.t[8])); }
+      tm->total_ms = tm->h2d_ms + tm->preprocess_ms + tm->encoder_ms + tm->decoder_ms + tm->postprocess_ms + tm->metrics_ms + tm->d2h_ms;
     }
   }
-}
-
-// every stream of the context idle
-void sync_all(ysi_ctx* c) {
-  YSI_CUDA(cudaStreamSynchronize(c->s_in));
-  YSI_CUDA(cudaStreamSynchronize(c->stream));
-  YSI_CUDA(cudaStreamSynchronize(c->s_aux));
-  YSI_CUDA(cudaStreamSynchronize(c->s_out));
 }
 
 }  // namespace
@@ -664,6 +730,8 @@ void ysi_destroy(ysi_ctx* c) {
   }
   for (auto& e : c->timers)
     if (e) cudaEventDestroy(e);
+  for (auto& e : c->ring_ev)
+    if (e) cudaEventDestroy(e);
   if (c->join_ev) cudaEventDestroy(c->join_ev);
   for (cudaStream_t st : {c->s_aux, c->s_in, c->s_out, c->stream})
     if (st) cudaStreamDestroy(st);
@@ -678,9 +746,37 @@ int ysi_load_weights(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   return guarded(c, [&] { load_weights_impl(c, tensors, n); });
 }
 
+namespace {
+BatchIn batch_rgb(int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes, const int32_t* box_counts,
+                  uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
+  BatchIn in;
+  in.n = n; in.H = H; in.W = W; in.row_stride = row_stride; in.fmt = YSI_PIX_RGB8;
+  in.host = reinterpret_cast<const void* const*>(rgb);
+  in.boxes = boxes; in.counts = box_counts; in.masks_out = masks_out; in.packed_out = packed_out; in.metrics_out = metrics_out;
+  return in;
+}
+BatchIn batch_of(const ysi_batch* b) {
+  BatchIn in;
+  in.n = b->n_images; in.H = b->height; in.W = b->width; in.row_stride = b->row_stride; in.fmt = b->pixel_format;
+  in.host = b->images; in.boxes = b->boxes_xyxy; in.counts = b->box_counts;
+  in.masks_out = b->masks_out; in.packed_out = b->packed_out; in.metrics_out = b->metrics_out;
+  return in;
+}
+}  // namespace
+
 int ysi_submit_batch(ysi_ctx* c, int slot, int n, const uint8_t* const* rgb, int H, int W, int row_stride, const float* boxes,
                      const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out) {
-  return guarded(c, [&] { submit_impl(c, slot, n, rgb, nullptr, H, W, row_stride, boxes, box_counts, masks_out, packed_out, metrics_out); });
+  return guarded(c, [&] {
+    YSI_CHECK(rgb && box_counts, "null argument");
+    submit_impl(c, slot, batch_rgb(n, rgb, H, W, row_stride, boxes, box_counts, masks_out, packed_out, metrics_out));
+  });
+}
+
+int ysi_submit(ysi_ctx* c, int slot, const ysi_batch* batch) {
+  return guarded(c, [&] {
+    YSI_CHECK(batch && batch->images && batch->box_counts, "null argument");
+    submit_impl(c, slot, batch_of(batch));
+  });
 }
 
 int ysi_wait_batch(ysi_ctx* c, int slot, ysi_timing* tm) {
@@ -691,7 +787,8 @@ int ysi_run_batch(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, in
                   const int32_t* box_counts, uint8_t* masks_out, uint8_t* packed_out, ysi_mask_metrics* metrics_out,
                   ysi_timing* tm) {
   return guarded(c, [&] {
-    submit_impl(c, 0, n, rgb, nullptr, H, W, row_stride, boxes, box_counts, masks_out, packed_out, metrics_out);
+    YSI_CHECK(rgb && box_counts, "null argument");
+    submit_impl(c, 0, batch_rgb(n, rgb, H, W, row_stride, boxes, box_counts, masks_out, packed_out, metrics_out));
     wait_impl(c, 0, tm);
   });
 }
@@ -707,10 +804,23 @@ int ysi_run(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, const 
   return ysi_run_batch(c, 1, imgs, H, W, row_stride, boxes, counts, masks_out, packed_out, metrics_out, tm);
 }
 
+int ysi_alloc_pinned(int device, size_t bytes, void** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  void* p = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -2; }     // (per calling thread)
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return -2; }
+  *out = p;
+  return 0;
+}
+void ysi_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 // ------------------------------------------------------------------------------------------- bench support
 int ysi_pool_upload(ysi_ctx* c, int pool_size, int idx, const uint8_t* rgb, int H, int W, int row_stride) {
   return guarded(c, [&] {
-    YSI_CHECK(H <= c->cfg.max_image_h && W <= c->cfg.max_image_w && pool_size >= 1 && idx >= 0 && idx < pool_size, "bad pool arguments");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= 4096 && W <= 4096 && pool_size >= 1 && idx >= 0 && idx < pool_size, "bad pool arguments");
     const size_t img_bytes = static_cast<size_t>(H) * W * 3;
     if (!c->d_pool || c->pool_cap < pool_size || c->pool_H != H || c->pool_W != W) {
       c->d_pool = c->dalloc<uint8_t>(img_bytes * pool_size);
@@ -726,8 +836,11 @@ int ysi_compute_pool(ysi_ctx* c, int first_idx, int n, const float* boxes, const
     YSI_CHECK(c->d_pool && first_idx >= 0 && first_idx + n <= c->pool_cap, "pool range out of bounds");
     const int slot = c->next_slot;
     c->next_slot ^= 1;
-    submit_impl(c, slot, n, nullptr, c->d_pool + static_cast<size_t>(first_idx) * c->pool_H * c->pool_W * 3, c->pool_H, c->pool_W, 0,
-                boxes, box_counts, nullptr, nullptr, nullptr);
+    BatchIn in;
+    in.n = n; in.H = c->pool_H; in.W = c->pool_W;
+    in.dev_rgb = c->d_pool + static_cast<size_t>(first_idx) * c->pool_H * c->pool_W * 3;
+    in.boxes = boxes; in.counts = box_counts;
+    submit_impl(c, slot, in);
     if (sync) wait_impl(c, slot, tm);
   });
 }
@@ -763,15 +876,18 @@ int ysi_profile(ysi_ctx* c, int enable) {
   });
 }
 
-int ysi_profile_read(ysi_ctx* c, int max_classes, const char** names, double* ms, int64_t* records, double* flops) {
+int ysi_profile_read(ysi_ctx* c, int max_classes, const char** names, double* ms, int64_t* records, double* flops, double* bytes) {
   int n = -2;
   guarded(c, [&] {
     YSI_CUDA(cudaStreamSynchronize(c->stream));
-    double m[KC_COUNT], f[KC_COUNT];
+    double m[KC_COUNT], f[KC_COUNT], by[KC_COUNT];
     long long l[KC_COUNT];
-    c->prof.collect(m, l, f);
+    c->prof.collect(m, l, f, by);
     n = KC_COUNT < max_classes ? KC_COUNT : max_classes;
-    for (int i = 0; i < n; ++i) { names[i] = kernel_class_name(i); ms[i] = m[i]; records[i] = l[i]; flops[i] = f[i]; }
+    for (int i = 0; i < n; ++i) {
+      names[i] = kernel_class_name(i); ms[i] = m[i]; records[i] = l[i]; flops[i] = f[i];
+      if (bytes) bytes[i] = by[i];
+    }
   });
   return n;
 }
@@ -780,7 +896,8 @@ int ysi_profile_read(ysi_ctx* c, int max_classes, const char** names, double* ms
 int ysi_preprocess(ysi_ctx* c, int n, const uint8_t* const* rgb, int H, int W, int row_stride, float* pixel_values_out) {
   return guarded(c, [&] {
     YSI_CHECK(n >= 1 && n <= c->cfg.max_batch, "n_images exceeds max_batch");
-    YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= 4096 && W <= 4096, "image size out of range (2..4096 per side)");
+    ensure_image_capacity(c, H, W);
     if (!c->d_pix) c->d_pix = c->dalloc<float>(static_cast<size_t>(c->cfg.max_batch) * 3 * 1024 * 1024);
     const size_t img_bytes = static_cast<size_t>(H) * W * 3;
     for (int i = 0; i < n; ++i)
@@ -842,13 +959,15 @@ int ysi_decode(ysi_ctx* c, const float* emb_nchw, const double* boxes_1024, int 
 int ysi_postprocess(ysi_ctx* c, const float* low_res, int nb, int H, int W, uint8_t* masks_out, float* upsampled_out) {
   return guarded(c, [&] {
     YSI_CHECK(nb >= 1 && nb <= c->cfg.max_boxes, "box count exceeds max_boxes");
-    YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= 4096 && W <= 4096, "image size out of range (2..4096 per side)");
+    ensure_image_capacity(c, H, W);
     const size_t HW = static_cast<size_t>(H) * W;
     YSI_CUDA(cudaMemcpyAsync(c->d_low, low_res, sizeof(float) * 65536 * nb, cudaMemcpyHostToDevice, c->stream));
     float* d_up = nullptr;
     if (upsampled_out) { YSI_CUDA(cudaMalloc(&d_up, sizeof(float) * nb * HW)); }
     launch_init_stats(c->d_stats, nb, c->stream);
-    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), nullptr, nullptr, nullptr, c->d_masks, d_up, c->d_stats, c->stream);
+    launch_upsample_stats(c->d_low, nb, make_post_geom(H, W), nullptr, nullptr, nullptr, c->d_masks, c->d_packed, true, d_up,
+                          c->d_stats, c->stream);
     c->launches += 2;
     if (masks_out) YSI_CUDA(cudaMemcpyAsync(masks_out, c->d_masks, nb * HW, cudaMemcpyDeviceToHost, c->stream));
     if (upsampled_out) YSI_CUDA(cudaMemcpyAsync(upsampled_out, d_up, sizeof(float) * nb * HW, cudaMemcpyDeviceToHost, c->stream));
@@ -861,7 +980,8 @@ int ysi_metrics(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, co
                 ysi_mask_metrics* metrics_out) {
   return guarded(c, [&] {
     YSI_CHECK(nb >= 1 && nb <= c->cfg.max_boxes, "mask count exceeds max_boxes");
-    YSI_CHECK(H >= 2 && W >= 2 && H <= c->cfg.max_image_h && W <= c->cfg.max_image_w, "image larger than max_image_h/w");
+    YSI_CHECK(H >= 2 && W >= 2 && H <= 4096 && W <= 4096, "image size out of range (2..4096 per side)");
+    ensure_image_capacity(c, H, W);
     const size_t HW = static_cast<size_t>(H) * W;
     YSI_CUDA(cudaMemcpy2DAsync(c->d_rgb, static_cast<size_t>(W) * 3, rgb, row_stride, static_cast<size_t>(W) * 3, H,
                                cudaMemcpyHostToDevice, c->stream));
@@ -869,8 +989,9 @@ int ysi_metrics(ysi_ctx* c, const uint8_t* rgb, int H, int W, int row_stride, co
     launch_sum3(c->d_rgb, 1, H, W, W * 3, c->d_sum3, nullptr, c->stream);
     launch_init_stats(c->d_stats, nb, c->stream);
     launch_mask_stats(c->d_masks, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->stream);
-    launch_contour_hull_disk(c->d_masks, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->d_metrics, c->stream);
-    c->launches += 4;
+    launch_packbits(c->d_masks, c->d_packed, nb, static_cast<long long>(HW), c->stream);
+    launch_contour_hull_disk(c->d_packed, nb, H, W, c->d_sum3, nullptr, c->d_stats, c->d_metrics, c->stream);
+    c->launches += 5;
     YSI_CUDA(cudaMemcpyAsync(metrics_out, c->d_metrics, sizeof(ysi_mask_metrics) * nb, cudaMemcpyDeviceToHost, c->stream));
     YSI_CUDA(cudaStreamSynchronize(c->stream));
   });

@@ -642,11 +642,7 @@ static void launch_attn_t(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const
                           const CUtensorMap& tmRel8, const CUtensorMap& tmQ1, const CUtensorMap& tmKV1, const CUtensorMap& tmKVtail1,
                           const CUtensorMap& tmRel1, const CUtensorMap& tmRel8_1, const AttnParams& p, dim3 grid, cudaStream_t stream) {
   using C = attn::Cfg<GLOBAL, HD>;
-  static bool init = false;
-  if (!init) {
-    YSI_CUDA(cudaFuncSetAttribute(encoder_attention_kernel<GLOBAL, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    init = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(encoder_attention_kernel<GLOBAL, HD>), C::SMEM_BYTES);
   encoder_attention_kernel<GLOBAL, HD><<<grid, attn::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmKVtail, tmRel, tmRel8, tmQ1, tmKV1, tmKVtail1,
                                                                                       tmRel1, tmRel8_1, p);
 }

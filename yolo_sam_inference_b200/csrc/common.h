@@ -91,7 +91,11 @@ struct GemmEpilogue {
 void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                cudaStream_t stream);
 
+// SM count of the CURRENT device (cached per device; thread-safe).
 int sm_count();
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device. The attribute is per device and per
+// function, so the bookkeeping is too (a process may hold contexts on several GPUs); thread-safe.
+void ensure_dyn_smem(const void* func, int bytes);
 
 // Optional per-launch CUDA-event timing by kernel class (bench.py's roofline / breakdown pass).
 // Inactive (null) in the product path: zero overhead.
@@ -105,20 +109,22 @@ const char* kernel_class_name(int kc);
 struct Profiler {
   cudaStream_t stream = nullptr;
   std::vector<cudaEvent_t> pool;
-  struct Rec { int kc; int e0, e1; double flops; };
+  struct Rec { int kc; int e0, e1; double flops; double bytes; };
   std::vector<Rec> recs;
   int next = 0;
   bool active = false;
-  int begin(int kc, double flops = 0.0);
+  int begin(int kc, double flops = 0.0, double bytes = 0.0);     // algorithmic FLOPs / HBM bytes of the record
   void end(int rec);
-  void collect(double* ms, long long* launches, double* flops);   // arrays of KC_COUNT; call after a stream sync
+  void collect(double* ms, long long* launches, double* flops, double* bytes);   // arrays of KC_COUNT; call after a stream sync
   void reset();
   ~Profiler();
 };
 // scope helper: times everything launched between construction and destruction as one record
 struct ProfScope {
   Profiler* p; int r;
-  ProfScope(Profiler* prof, int kc, double flops = 0.0) : p(prof && prof->active ? prof : nullptr), r(-1) { if (p) r = p->begin(kc, flops); }
+  ProfScope(Profiler* prof, int kc, double flops = 0.0, double bytes = 0.0) : p(prof && prof->active ? prof : nullptr), r(-1) {
+    if (p) r = p->begin(kc, flops, bytes);
+  }
   ~ProfScope() { if (p) p->end(r); }
 };
 

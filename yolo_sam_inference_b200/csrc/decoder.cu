@@ -753,10 +753,6 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
                      float* sparse_out, cudaStream_t s, int64_t* launches, Profiler* prof) {
   YSI_CHECK(n_img >= 1 && n_img <= wk.cap_img && nb >= 1 && nb <= wk.cap_box, "decoder batch exceeds the workspace");
   int64_t nl = 0;
-  static bool attr = false;
-  if (!attr) {
-    attr = true;
-  }
   const int TI = n_img * 4096, TB = nb * 4096;
   const int R = NT * nb;                                  // token rows of the whole batch
   // token-side scratch (all [R,256] unless noted)

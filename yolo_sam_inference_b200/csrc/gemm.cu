@@ -73,38 +73,54 @@ const char* kernel_class_name(int kc) {
   return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "?";
 }
 
-int Profiler::begin(int kc, double flops) {
+int Profiler::begin(int kc, double flops, double bytes) {
   while (static_cast<int>(pool.size()) < next + 2) {
     cudaEvent_t e;
     YSI_CUDA(cudaEventCreate(&e));
     pool.push_back(e);
   }
-  Rec r{kc, next, next + 1, flops};
+  Rec r{kc, next, next + 1, flops, bytes};
   next += 2;
   YSI_CUDA(cudaEventRecord(pool[r.e0], stream));
   recs.push_back(r);
   return static_cast<int>(recs.size()) - 1;
 }
 void Profiler::end(int rec) { YSI_CUDA(cudaEventRecord(pool[recs[rec].e1], stream)); }
-void Profiler::collect(double* ms, long long* launches, double* flops) {
-  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flops[i] = 0; }
+void Profiler::collect(double* ms, long long* launches, double* flops, double* bytes) {
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flops[i] = 0; bytes[i] = 0; }
   for (const Rec& r : recs) {
     float t = 0.f;
     YSI_CUDA(cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]));
-    ms[r.kc] += t; launches[r.kc] += 1; flops[r.kc] += r.flops;
+    ms[r.kc] += t; launches[r.kc] += 1; flops[r.kc] += r.flops; bytes[r.kc] += r.bytes;
   }
 }
 void Profiler::reset() { recs.clear(); next = 0; }
 Profiler::~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
 
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    YSI_CUDA(cudaGetDevice(&dev));
-    YSI_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static std::mutex mu;
+  static std::map<int, int> per_dev;
+  int dev = 0;
+  YSI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  auto it = per_dev.find(dev);
+  if (it != per_dev.end()) return it->second;
+  int n = 0;
+  YSI_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  per_dev[dev] = n;
   return n;
+}
+
+void ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> granted;     // (device, kernel) -> bytes opted in
+  int dev = 0;
+  YSI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  int& have = granted[std::make_pair(dev, func)];
+  if (bytes <= have) return;
+  YSI_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have = bytes;
 }
 
 void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,

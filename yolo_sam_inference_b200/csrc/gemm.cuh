@@ -573,11 +573,7 @@ template <int BN_ = 256, class Epi>
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN_>;
   auto kern = gemm2_op16_kernel<BN_, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   const int tiles = ceil_div(M, 2 * GEMM_BM) * (N / Cfg::BN);
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
   kern<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
@@ -589,11 +585,7 @@ void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, i
                  cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_op16_kernel<BN, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    YSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);

@@ -28,19 +28,30 @@ void launch_init_stats(MaskStatsDev* stats, int nmask, cudaStream_t s);
 // sum3: per-image R+G+B planes uint16 [n_img,H,W] (may be null: no intensity histogram),
 // mask_image[m]: image index of mask m (null => all image 0). up_logits optional fp32 [nmask,H,W].
 // gray: floor((R+G+B)/3) uint8 planes [n_img,H,W] (histogram bins; required with sum3 for the 1024x1024 fast path).
+// packed [nmask, ceil(H*W/8)] (np.packbits rows, utils/mask_encoding.py:24) is always written: it is what the contour
+// kernel reads and the default wire format; `masks` [nmask,H,W] holds the byte masks when want_bytes (and is scratch for
+// the generic geometry, which derives the packed rows from it).
 void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const uint8_t* gray,
-                           const int* mask_image, uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s);
+                           const int* mask_image, uint8_t* masks, uint8_t* packed, bool want_bytes, float* up_logits,
+                           MaskStatsDev* stats, cudaStream_t s);
 // same statistics from given mask bytes (a7 alone)
 void launch_mask_stats(const uint8_t* masks_in, int nmask, int H, int W, const uint16_t* sum3, const int* mask_image,
                        MaskStatsDev* stats, cudaStream_t s);
 // second half of a7: contour 0 -> convex hull -> hull raster stats; centre-disk brightness sums; final rows.
-void launch_contour_hull_disk(const uint8_t* masks, int nmask, int H, int W, const uint16_t* sum3,
+// (reads the PACKED mask rows)
+void launch_contour_hull_disk(const uint8_t* packed, int nmask, int H, int W, const uint16_t* sum3,
                               const int* mask_image, const MaskStatsDev* stats, ysi_mask_metrics* out,
                               cudaStream_t s);
 // np.packbits(mask.reshape(-1)) per mask: [nmask, ceil(H*W/8)]
 void launch_packbits(const uint8_t* masks, uint8_t* packed, int nmask, long long npix, cudaStream_t s);
 // uint8 RGB [n,H,W,3] (pitch row_stride) -> R+G+B uint16 planes
 void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, uint8_t* gray, cudaStream_t s);
+// f3 of SURVEY section 8f (GPU-side ingest): raw single-channel pixels as they sit in a baseline TIFF strip -- uint8, or
+// uint16 reduced to 8 bits exactly like cv2.imread's default flags do (v >> 8, pipeline.py:206-210) -- are expanded on
+// the device to the uint8 RGB image the rest of the path reads (grey replicated to three channels) together with the
+// R+G+B and floor((R+G+B)/3) planes. src: dense [n,H,W] of bytes_per_px (1 or 2, little endian).
+void launch_gray_ingest(const void* src, int bytes_per_px, int n, int H, int W, uint8_t* rgb, uint16_t* sum3, uint8_t* gray,
+                        cudaStream_t s);
 
 // ------------------------------------------------------------------ encoder
 // fused flash-style attention with decomposed rel-pos bias (attn.cu)

@@ -284,7 +284,7 @@ __device__ __forceinline__ unsigned int shr_in(unsigned int w, unsigned int next
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __restrict__ gray_all,
                            const int* __restrict__ mask_image, uint8_t* __restrict__ masks_out,
-                           MaskStatsDev* __restrict__ stats, int groups_per_warp) {
+                           uint8_t* __restrict__ packed_out, MaskStatsDev* __restrict__ stats, int groups_per_warp) {
   constexpr int H = 1024, W = 1024;
   __shared__ unsigned int s_hist[FAST_WARPS][2][256];
   const int m = blockIdx.y;
@@ -292,7 +292,8 @@ upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __r
   const float* low = low_all + static_cast<size_t>(m) * 65536;
   const bool want_hist = gray_all != nullptr;
   const uint8_t* gray = want_hist ? gray_all + static_cast<size_t>(mask_image ? mask_image[m] : 0) * H * W : nullptr;
-  uint8_t* mout = masks_out + static_cast<size_t>(m) * H * W;
+  uint8_t* mout = masks_out ? masks_out + static_cast<size_t>(m) * H * W : nullptr;
+  uint32_t* pout = reinterpret_cast<uint32_t*>(packed_out + static_cast<size_t>(m) * (H * W / 8));
   if (want_hist)
     for (int i = threadIdx.x; i < FAST_WARPS * 2 * 256; i += FAST_WARPS * 32) (&s_hist[0][0][0])[i] = 0;
   __syncthreads();
@@ -357,7 +358,13 @@ upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __r
             Wn |= (x > 0.0f) ? (1u << k) : 0u;
           }
           if (rn >= R0 && rn < R1) {
-            // bytes of this row: lane L writes columns 16 L .. +15 and 512 + 16 L .. +15
+            // np.packbits order (utils/mask_encoding.py:24): pixel 8 i + k of the row-major mask is bit 7 - k of byte i.
+            // Bit k of Wn is column 32 lane + k: reverse the bits, then the bytes (little-endian store) -- 128 contiguous
+            // bytes per warp and row.
+            pout[rn * (W / 32) + lane] = __byte_perm(__brev(Wn), 0u, 0x0123u);
+          }
+          if (mout && rn >= R0 && rn < R1) {
+            // bytes of this row (on request only): lane L writes columns 16 L .. +15 and 512 + 16 L .. +15
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const unsigned int ws = __shfl_sync(0xFFFFFFFFu, Wn, (lane >> 1) + 16 * hh);
@@ -486,13 +493,16 @@ upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __r
 }
 
 void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16_t* sum3, const uint8_t* gray,
-                           const int* mask_image, uint8_t* masks, float* up_logits, MaskStatsDev* stats, cudaStream_t s) {
+                           const int* mask_image, uint8_t* masks, uint8_t* packed, bool want_bytes, float* up_logits,
+                           MaskStatsDev* stats, cudaStream_t s) {
   if (nmask <= 0) return;
-  if (g.H == 1024 && g.W == 1024 && g.rh == 1024 && g.rw == 1024 && masks && !up_logits && (sum3 == nullptr || gray != nullptr)) {
+  YSI_CHECK(masks && packed, "upsample: mask scratch and packed output are required");
+  if (g.H == 1024 && g.W == 1024 && g.rh == 1024 && g.rw == 1024 && !up_logits && (sum3 == nullptr || gray != nullptr)) {
     // enough warps to fill the GPU for few masks, long bands (little halo recomputation) for many
     const int gpw = nmask >= 64 ? 16 : (nmask >= 16 ? 8 : 4);       // row groups (4 rows each) per warp
     const int ctas = ceil_div(257, FAST_WARPS * gpw);
-    upsample_stats_fast_kernel<<<dim3(ctas, nmask), FAST_WARPS * 32, 0, s>>>(low, sum3 ? gray : nullptr, mask_image, masks, stats, gpw);
+    upsample_stats_fast_kernel<<<dim3(ctas, nmask), FAST_WARPS * 32, 0, s>>>(low, sum3 ? gray : nullptr, mask_image,
+                                                                             want_bytes ? masks : nullptr, packed, stats, gpw);
     YSI_CUDA(cudaGetLastError());
     return;
   }
@@ -503,6 +513,9 @@ void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16
   dim3 grid(ceil_div(g.W, TC), ceil_div(g.H, TR), nmask);
   upsample_stats_kernel<0><<<grid, 256, 0, s>>>(low, nullptr, p, sum3, mask_image, masks, up_logits, stats);
   YSI_CUDA(cudaGetLastError());
+  // generic geometry: the byte masks are scratch, the packed rows (what the contour kernel and the wire format read)
+  // are derived from them
+  launch_packbits(masks, packed, nmask, static_cast<long long>(g.H) * g.W, s);
 }
 
 void launch_mask_stats(const uint8_t* masks_in, int nmask, int H, int W, const uint16_t* sum3, const int* mask_image,
@@ -525,9 +538,12 @@ void launch_mask_stats(const uint8_t* masks_in, int nmask, int H, int W, const u
 enum { E_T = 0, E_B = 1, E_L = 2, E_R = 3, E_NONE = 4 };
 
 struct CellWalk {
-  const uint8_t* mk;
+  const uint8_t* mk;      // np.packbits rows of the mask: pixel i = r W + c is bit 7 - (i & 7) of byte i >> 3
   int H, W;
-  __device__ __forceinline__ int px(int r, int c) const { return mk[static_cast<size_t>(r) * W + c] ? 1 : 0; }
+  __device__ __forceinline__ int px(int r, int c) const {
+    const unsigned int i = static_cast<unsigned int>(r) * W + c;
+    return (__ldg(mk + (i >> 3)) >> (7u - (i & 7u))) & 1u;       // read-only path: the walk revisits the same few lines
+  }
   // marching-squares case of cell (r0,c0): 1*ul + 2*ur + 4*ll + 8*lr   (_find_contours_cy.pyx)
   __device__ __forceinline__ int cell_case(int r0, int c0) const {
     return px(r0, c0) + 2 * px(r0, c0 + 1) + 4 * px(r0 + 1, c0) + 8 * px(r0 + 1, c0 + 1);
@@ -617,7 +633,7 @@ __device__ bool walk_contour(const CellWalk& cw, int r0, int c0, int e, int stop
 constexpr int K2_THREADS = 256;
 
 __global__ void __launch_bounds__(K2_THREADS)
-contour_hull_disk_kernel(const uint8_t* __restrict__ masks, int nmask, int H, int W,
+contour_hull_disk_kernel(const uint8_t* __restrict__ packed, int nmask, int H, int W,
                          const uint16_t* __restrict__ sum3_all, const int* __restrict__ mask_image,
                          const MaskStatsDev* __restrict__ stats, ysi_mask_metrics* __restrict__ out) {
   const int m = blockIdx.x;
@@ -651,7 +667,7 @@ contour_hull_disk_kernel(const uint8_t* __restrict__ masks, int nmask, int H, in
     rs.span = span; rs.ymin = INT_MAX; rs.ymax = INT_MIN; rs.npts = 0;
     bool truncated = false;
     if (st.first_cell != 0xFFFFFFFFu) {
-      CellWalk cw; cw.mk = masks + m * plane; cw.H = H; cw.W = W;
+      CellWalk cw; cw.mk = packed + static_cast<size_t>(m) * ((plane + 7) / 8); cw.H = H; cw.W = W;
       const int r0 = st.first_cell / W, c0 = st.first_cell % W;
       const int cs = cw.cell_case(r0, c0);
       int ef, et;
@@ -851,20 +867,15 @@ contour_hull_disk_kernel(const uint8_t* __restrict__ masks, int nmask, int H, in
   o->mask_hist[tid] = stp->mask_hist[tid];
 }
 
-void launch_contour_hull_disk(const uint8_t* masks, int nmask, int H, int W, const uint16_t* sum3,
+void launch_contour_hull_disk(const uint8_t* packed, int nmask, int H, int W, const uint16_t* sum3,
                               const int* mask_image, const MaskStatsDev* stats, ysi_mask_metrics* out,
                               cudaStream_t s) {
   if (nmask <= 0) return;
   // dynamic smem: row spans + two chains of (2H+1) (y,x) pairs + lo/hi for (H+4) rows
   const size_t smem = sizeof(int) * (6 * static_cast<size_t>(2 * H + 1) + 2 * static_cast<size_t>(H + 4));
-  YSI_CHECK(smem <= 200 * 1024, "image too tall for the hull kernel's shared memory");
-  static size_t attr = 0;
-  if (smem > attr) {
-    YSI_CUDA(cudaFuncSetAttribute(contour_hull_disk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    attr = smem;
-  }
-  contour_hull_disk_kernel<<<nmask, K2_THREADS, smem, s>>>(masks, nmask, H, W, sum3, mask_image, stats, out);
+  YSI_CHECK(smem <= 226 * 1024, "image too tall for the hull kernel's shared memory (H <= 4096)");
+  ensure_dyn_smem(reinterpret_cast<const void*>(contour_hull_disk_kernel), static_cast<int>(smem));
+  contour_hull_disk_kernel<<<nmask, K2_THREADS, smem, s>>>(packed, nmask, H, W, sum3, mask_image, stats, out);
   YSI_CUDA(cudaGetLastError());
 }
 
@@ -915,6 +926,53 @@ __global__ void sum3_kernel(const uint8_t* __restrict__ rgb, int H, int W, int r
 void launch_sum3(const uint8_t* rgb, int n, int H, int W, int row_stride, uint16_t* sum3, uint8_t* gray, cudaStream_t s) {
   dim3 grid(ceil_div(W, 256), H, n);
   sum3_kernel<<<grid, 256, 0, s>>>(rgb, H, W, row_stride, sum3, gray);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// f3: raw grey pixels (uint8, or uint16 -> v >> 8 as cv2.imread's default flags reduce 16-bit files) -> uint8 RGB (grey
+// replicated) + R+G+B (uint16) + floor((R+G+B)/3) = grey (uint8). One thread = 4 consecutive pixels of the flat array.
+template <int BPP>
+__global__ void __launch_bounds__(256)
+gray_ingest_kernel(const uint8_t* __restrict__ src, long long npix, uint8_t* __restrict__ rgb, uint16_t* __restrict__ sum3,
+                   uint8_t* __restrict__ gray) {
+  const long long ngrp = (npix + 3) / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < ngrp;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p0 = i * 4;
+    unsigned int g[4];
+    if (p0 + 4 <= npix) {
+      if (BPP == 1) {
+        const unsigned int w = *reinterpret_cast<const unsigned int*>(src + p0);
+        g[0] = w & 0xFFu; g[1] = (w >> 8) & 0xFFu; g[2] = (w >> 16) & 0xFFu; g[3] = w >> 24;
+      } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(src + 2 * p0);      // little-endian uint16: high byte = v >> 8
+        g[0] = (w.x >> 8) & 0xFFu; g[1] = w.x >> 24; g[2] = (w.y >> 8) & 0xFFu; g[3] = w.y >> 24;
+      }
+      // 12 RGB bytes: g0 g0 g0 g1 | g1 g1 g2 g2 | g2 g3 g3 g3
+      unsigned int* o = reinterpret_cast<unsigned int*>(rgb + 3 * p0);
+      o[0] = g[0] * 0x010101u | (g[1] << 24);
+      o[1] = g[1] * 0x0101u | (g[2] << 16) | (g[2] << 24);
+      o[2] = g[2] | (g[3] << 8) | (g[3] << 16) | (g[3] << 24);
+      *reinterpret_cast<uint2*>(sum3 + p0) = make_uint2((3u * g[0]) | ((3u * g[1]) << 16), (3u * g[2]) | ((3u * g[3]) << 16));
+      *reinterpret_cast<unsigned int*>(gray + p0) = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
+    } else {
+      for (long long p = p0; p < npix; ++p) {
+        const unsigned int v = BPP == 1 ? src[p] : src[2 * p + 1];
+        rgb[3 * p] = rgb[3 * p + 1] = rgb[3 * p + 2] = static_cast<uint8_t>(v);
+        sum3[p] = static_cast<uint16_t>(3u * v);
+        gray[p] = static_cast<uint8_t>(v);
+      }
+    }
+  }
+}
+
+void launch_gray_ingest(const void* src, int bytes_per_px, int n, int H, int W, uint8_t* rgb, uint16_t* sum3, uint8_t* gray,
+                        cudaStream_t s) {
+  YSI_CHECK(bytes_per_px == 1 || bytes_per_px == 2, "grey ingest takes 8- or 16-bit pixels");
+  const long long npix = static_cast<long long>(n) * H * W;
+  const int grid = static_cast<int>(std::min<long long>((npix / 4 + 255) / 256, 148 * 16));
+  if (bytes_per_px == 1) gray_ingest_kernel<1><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src), npix, rgb, sum3, gray);
+  else gray_ingest_kernel<2><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src), npix, rgb, sum3, gray);
   YSI_CUDA(cudaGetLastError());
 }
 

@@ -2,20 +2,33 @@
 
 Mirrors /root/reference/src/yolo_sam_inference/pipeline.py: same class names, constructor arguments,
 ``process_single_image`` / ``process_directory`` signatures, ``ProcessingResult`` /
-``BatchProcessingResult`` dataclasses (:31-45), timing keys (:143-194, :271-283) and CSV row builders
-(:293-317).  What changes is only the body of ``if len(boxes) > 0:`` (:161-175), which becomes one
-``SamStage.run`` call.  The YOLO detector stays on the reference's torch path (ultralytics, :72-73,
-:84-87); because ultralytics is not installable offline, any callable ``image -> float32[N,4] xyxy``
-can be injected as ``detector`` instead.
+``BatchProcessingResult`` dataclasses (:31-45), timing keys (:143-194, :271-283), CSV row builders
+(:293-317) and visualisation file layout (:331-438).  What changes is the body of ``if len(boxes) > 0:``
+(:161-175), which becomes SAM-stage calls on the device, and HOW a folder is driven through it:
 
-Out of scope here: visualisation / TIFF writers (:331-438), MLflow, ROI web UI.
+* ``process_directory`` (:212-263) no longer handles one image at a time.  A thread pool reads files ahead
+  (baseline TIFFs straight into page-locked memory as raw samples, everything else through the
+  reference's own ``cv2.imread`` path -- ``ingest.py``), consecutive same-sized images are grouped into
+  batches of ``batch_size`` and the batches flow through the two-slot pipeline of ``SamStage.run_stream``
+  (copies, encoder and decoder/metrics of neighbouring batches overlap).  Per-image ``ProcessingResult``s,
+  their order and the CSV rows are unchanged.
+* ``ParallelCellSegmentationPipeline`` (:440-584) spreads its replicas over GPUs (one persistent worker
+  process per replica, worker k on ``cuda:k % n_gpus``) instead of stacking them on one device; the folder
+  is split by the reference's ``ceil(n / num_pipelines)`` rule (:540-541), no collective is involved.
+
+The YOLO detector stays on the reference's torch path (ultralytics, :72-73, :84-87); because
+ultralytics is not installable offline, any callable ``image -> float32[N,4] xyxy`` can be injected as
+``detector`` instead.
 """
 from __future__ import annotations
 
 import logging
-import math
+import os
+import threading
 import time
 import uuid
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from datetime import datetime
 from pathlib import Path
@@ -23,6 +36,8 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
+from . import _native as nat
+from .ingest import as_rgb_u8, decode_rgb, probe_tiff, read_raw_into
 from .sam_stage import SamStage
 from .sharding import partition_contiguous
 
@@ -53,6 +68,7 @@ Detector = Callable[[np.ndarray], np.ndarray]
 
 class BoxTable:
     """Detector stand-in: boxes looked up by image file name (synthetic 'YOLO boxes' of BASELINE configs)."""
+    needs_pixels = False          # the pipeline may hand it the raw samples instead of building an RGB image
 
     def __init__(self, boxes_by_name: Dict[str, np.ndarray]):
         self.boxes_by_name = boxes_by_name
@@ -82,18 +98,100 @@ def _load_sam_state_dict(sam_model_type: str):
     return SamModel.from_pretrained(sam_model_type, local_files_only=True).state_dict()
 
 
+class _Prefetcher:
+    """Reads the files of a folder ahead of the GPU, in order, on a thread pool (bounded window).
+
+    Baseline TIFFs land as raw samples in recycled page-locked buffers (``readinto``: disk -> pinned memory, no copy in
+    between, GIL released); every other file goes through ``decode_rgb`` (cv2.imread + BGR->RGB, pipeline.py:206-210).
+    Iterating yields (index, path, image, load_seconds, token); ``release(token)`` returns a pinned buffer to the pool
+    once the device has consumed it."""
+
+    def __init__(self, files: Sequence[Path], workers: int, depth: int, raw_ingest: bool, precision: str, device: int):
+        self.files = [str(f) for f in files]
+        self.depth = max(1, depth)
+        self.raw_ingest = raw_ingest
+        self.precision, self.device = precision, device
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="ysi-load")
+        self.free: Dict[int, List[nat.PinnedBuffer]] = {}
+        self.all: List[nat.PinnedBuffer] = []
+        self.lock = threading.Lock()
+
+    def _acquire(self, nbytes: int) -> nat.PinnedBuffer:
+        with self.lock:
+            lst = self.free.get(nbytes)
+            if lst:
+                return lst.pop()
+        buf = nat.PinnedBuffer(nbytes, self.precision, self.device)
+        with self.lock:
+            self.all.append(buf)
+        return buf
+
+    def release(self, token) -> None:
+        if token is not None:
+            with self.lock:
+                self.free.setdefault(token.nbytes, []).append(token)
+
+    def _load(self, path: str):
+        t0 = time.time()
+        info = probe_tiff(path) if self.raw_ingest and path.lower().endswith((".tif", ".tiff")) else None
+        if info is not None:
+            buf = self._acquire(info.nbytes)
+            read_raw_into(info, buf.array)
+            image = buf.array.view(info.dtype).reshape(info.shape)
+            return image, time.time() - t0, buf
+        return decode_rgb(path), time.time() - t0, None
+
+    def __iter__(self):
+        window: deque = deque()
+        nxt = 0
+        n = len(self.files)
+        try:
+            while nxt < n or window:
+                while nxt < n and len(window) < self.depth:
+                    window.append((nxt, self.pool.submit(self._load, self.files[nxt])))
+                    nxt += 1
+                idx, fut = window.popleft()
+                image, t_load, token = fut.result()
+                yield idx, self.files[idx], image, t_load, token
+        finally:
+            for _, fut in window:
+                fut.cancel()
+
+    def close(self) -> None:
+        self.pool.shutdown(wait=True, cancel_futures=True)
+        for b in self.all:
+            b.close()
+        self.all, self.free = [], {}
+
+
 class CellSegmentationPipeline:
     def __init__(self, yolo_model_path: Union[str, Path, None], sam_model_type: str = "facebook/sam-vit-huge",
                  device: str = "cuda", *, detector: Optional[Detector] = None,
                  sam_state_dict: Optional[Dict[str, Any]] = None, max_boxes: int = 64,
-                 max_image_hw: Tuple[int, int] = (1024, 1024), on_empty: str = "raise"):
+                 max_image_hw: Tuple[int, int] = (1024, 1024), on_empty: str = "raise", batch_size: int = 8,
+                 decode_workers: Optional[int] = None, raw_ingest: bool = True, mask_output: Optional[str] = None,
+                 precision: Optional[str] = None):
+        """Beyond the reference's three arguments (keyword-only, all optional):
+        ``batch_size`` images per device launch in ``process_directory``; ``max_boxes`` / ``max_image_hw`` are capacity
+        hints, not limits (more boxes are decoded in chunks, larger images re-size the buffers); ``decode_workers`` threads
+        read files ahead; ``raw_ingest`` hands baseline TIFFs to the device undecoded; ``mask_output`` ("packed" | "bool" |
+        None) additionally keeps every image's masks in ``last_masks`` (None: masks stay on the device unless
+        visualisations are written)."""
         self.device = device
         self.sam_model_type = sam_model_type
         self.detector: Detector = detector if detector is not None else _load_yolo(yolo_model_path)
         sd = sam_state_dict if sam_state_dict is not None else _load_sam_state_dict(sam_model_type)
-        self.sam_stage = SamStage(sam_model_type, device=device, state_dict=sd, max_batch=1, max_boxes=max_boxes,
-                                  max_image_hw=max_image_hw, on_empty=on_empty)
+        self.batch_size = max(1, int(batch_size))
+        self.sam_stage = SamStage(sam_model_type, device=device, state_dict=sd, max_batch=self.batch_size,
+                                  max_boxes=max_boxes, max_image_hw=max_image_hw, on_empty=on_empty, precision=precision)
+        self.decode_workers = decode_workers if decode_workers else min(16, max(2, (os.cpu_count() or 4) // 2))
+        self.raw_ingest = raw_ingest
+        self.mask_output = mask_output
+        self.last_masks: Dict[str, np.ndarray] = {}
         self.run_id = self._generate_run_id()
+
+    def close(self) -> None:
+        self.sam_stage.close()
 
     @staticmethod
     def _generate_run_id() -> str:
@@ -101,6 +199,13 @@ class CellSegmentationPipeline:
 
     def _detect_cells(self, image: np.ndarray) -> np.ndarray:
         return np.asarray(self.detector(image), np.float32).reshape(-1, 4)
+
+    def _detect(self, image: np.ndarray, image_path: str) -> np.ndarray:
+        if isinstance(self.detector, BoxTable):
+            self.detector.current_name = Path(image_path).name
+        if image.ndim == 2 and getattr(self.detector, "needs_pixels", True):
+            image = as_rgb_u8(image)        # a real detector sees exactly what _load_image would have produced
+        return self._detect_cells(image)
 
     def process_single_image(self, image_path: Union[str, Path], output_path: Union[str, Path],
                              save_visualizations: bool = True) -> ProcessingResult:
@@ -110,9 +215,7 @@ class CellSegmentationPipeline:
         timings["image_load"] = time.time() - start_time
 
         start_time = time.time()
-        if isinstance(self.detector, BoxTable):
-            self.detector.current_name = Path(image_path).name
-        boxes = self._detect_cells(image)
+        boxes = self._detect(image, str(image_path))
         timings["yolo_detection"] = time.time() - start_time
 
         masks: Sequence[np.ndarray] = []
@@ -121,7 +224,10 @@ class CellSegmentationPipeline:
         if len(boxes) > 0:
             # pipeline.py:161-175 -> one call; the stage reports honest per-phase device times
             start_time = time.time()
-            masks, cell_metrics, _crops = self.sam_stage.run(image, boxes)
+            mode = "bool" if save_visualizations else self.mask_output
+            masks, cell_metrics, _crops = self.sam_stage.run(image, boxes, masks=mode)
+            if self.mask_output:
+                self.last_masks[Path(image_path).name] = masks
             t = self.sam_stage.last_timing
             timings["sam_preprocess"] = (t["h2d_ms"] + t["preprocess_ms"]) / 1e3
             sam_times["inference"] = (t["encoder_ms"] + t["decoder_ms"]) / 1e3
@@ -140,13 +246,132 @@ class CellSegmentationPipeline:
 
     @staticmethod
     def _load_image(image_path: str) -> np.ndarray:
-        import cv2                                   # pipeline.py:206-210
-        image = cv2.imread(image_path)
-        return cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+        return decode_rgb(image_path)                # pipeline.py:206-210
+
+    # ------------------------------------------------------------------ visualisation / TIFF writers (pipeline.py:331-438)
+    @staticmethod
+    def _write_tiff(path: Path, array: np.ndarray) -> None:
+        """utils/image_utils.save_optimized_tiff / save_mask_as_tiff (:8-102): uint8 TIFF with deflate compression. The
+        reference writes through tifffile (absent here); OpenCV's libtiff writer produces the same pixels."""
+        import cv2
+        if array.dtype == np.bool_:
+            array = array.astype(np.uint8) * 255
+        if array.ndim == 3:
+            array = cv2.cvtColor(array, cv2.COLOR_RGB2BGR)
+        if not cv2.imwrite(str(path), array, [cv2.IMWRITE_TIFF_COMPRESSION, 8]):      # 8 = Adobe deflate (zlib)
+            raise IOError(f"Failed to save TIFF file: {path}")
 
     def _save_visualizations(self, image, masks, boxes, cell_metrics, output_path) -> None:
-        """Visualisation / TIFF output (pipeline.py:331-438) is outside the accelerated path; nothing is written."""
-        logger.debug("save_visualizations requested for %s: not part of the SAM stage", output_path)
+        """Same folders and file names as the reference (pipeline.py:352-432): 1_original_images/<stem>_original.tiff (the
+        file the CSV consumers crop from), 2_yolo_detections, 3_processed_masks/{masks,overlay_images,convex_hull_overlay},
+        4_combined_visualization.  Errors are reported and swallowed like the reference does (:436-438)."""
+        try:
+            import cv2
+            image = as_rgb_u8(image)
+            output_path = Path(output_path)
+            base_dir = output_path.parent
+            dirs = {"original": base_dir / "1_original_images", "yolo": base_dir / "2_yolo_detections",
+                    "processed_masks": base_dir / "3_processed_masks/masks",
+                    "processed_overlays": base_dir / "3_processed_masks/overlay_images",
+                    "convex_hull": base_dir / "3_processed_masks/convex_hull_overlay",
+                    "combined": base_dir / "4_combined_visualization"}
+            for d in dirs.values():
+                d.mkdir(parents=True, exist_ok=True)
+            stem = output_path.stem
+            self._write_tiff(dirs["original"] / f"{stem}_original.tiff", image)
+            yolo_vis = image.copy()
+            for box in boxes:
+                x1, y1, x2, y2 = np.asarray(box).astype(int)
+                cv2.rectangle(yolo_vis, (int(x1), int(y1)), (int(x2), int(y2)), (255, 0, 0), 2)
+            self._write_tiff(dirs["yolo"] / f"{stem}_yolo.tiff", yolo_vis)
+            red = np.array([255, 0, 0])
+            for i, (mask, metrics) in enumerate(zip(masks, cell_metrics)):
+                mask = np.asarray(mask, bool)
+                self._write_tiff(dirs["processed_masks"] / f"{stem}_mask_{i}.tiff", mask)
+                overlay = image.copy()
+                overlay[mask] = overlay[mask] * 0.7 + red * 0.3
+                self._write_tiff(dirs["processed_overlays"] / f"{stem}_mask_{i}_overlay.tiff", overlay)
+                # metrics.py:102-119 never returns 'convex_hull_coords', so the reference's hull overlay is the plain image
+                self._write_tiff(dirs["convex_hull"] / f"{stem}_mask_{i}_convex_hull.tiff", image)
+            combined = np.zeros((image.shape[0], image.shape[1] * 2, 3), dtype=np.uint8)
+            combined[:, :image.shape[1]] = yolo_vis
+            overlay_vis = image.copy()
+            for mask in masks:
+                mask = np.asarray(mask, bool)
+                overlay_vis[mask] = overlay_vis[mask] * 0.8 + red * 0.2
+            combined[:, image.shape[1]:] = overlay_vis
+            self._write_tiff(dirs["combined"] / f"{stem}_combined.tiff", combined)
+        except Exception as e:                         # noqa: BLE001 - pipeline.py:436-438
+            print(f"Warning: Error during visualization saving: {str(e)}")
+
+    # ------------------------------------------------------------------ folder entry point
+    def process_files(self, image_files: Sequence[Union[str, Path]], output_dir: Union[str, Path],
+                      save_visualizations: bool = True, pbar=None) -> List[ProcessingResult]:
+        """The batched, pipelined body of ``process_directory``: results come back in the order of ``image_files``."""
+        files = [Path(f) for f in image_files]
+        output_dir = Path(output_dir)
+        n = len(files)
+        results: List[Optional[ProcessingResult]] = [None] * n
+        if n == 0:
+            return []
+        stage = self.sam_stage
+        mode = "bool" if save_visualizations else self.mask_output
+        pre = _Prefetcher(files, self.decode_workers, depth=4 * self.batch_size, raw_ingest=self.raw_ingest,
+                          precision=stage.precision, device=stage.device_index)
+        metas: deque = deque()        # bookkeeping of the batches handed to run_stream, in submission order
+
+        def finish_image(idx, image, boxes, timing, masks, cell_metrics):
+            t_vis0 = time.time()
+            if save_visualizations:
+                self._save_visualizations(image, masks if masks is not None else [], boxes, cell_metrics,
+                                          output_dir / files[idx].name)
+                timing["visualization"] = time.time() - t_vis0
+            if self.mask_output and masks is not None and len(boxes) > 0:
+                self.last_masks[files[idx].name] = np.array(masks, copy=True)
+            timing["total_time"] = sum(v for k, v in timing.items() if k != "cells_processed")
+            timing["cells_processed"] = len(boxes)
+            results[idx] = ProcessingResult(image_path=str(files[idx]), cell_metrics=cell_metrics,
+                                            num_cells=len(cell_metrics), timing=timing)
+            self._update_progress(pbar, results[idx])
+
+        def batches():
+            cur: List[Any] = []
+            key = None
+            for idx, path, image, t_load, token in pre:
+                t0 = time.time()
+                boxes = self._detect(image, path)
+                timing = {"image_load": t_load, "yolo_detection": time.time() - t0, "sam_preprocess": 0.0,
+                          "inference": 0.0, "postprocess": 0.0}
+                if len(boxes) == 0:                     # pipeline.py:176-179: SAM is skipped
+                    finish_image(idx, image, boxes, timing, None, [])
+                    pre.release(token)
+                    continue
+                k = (image.shape, image.dtype)
+                if cur and (k != key or len(cur) == self.batch_size):
+                    metas.append(cur)
+                    yield [c[1] for c in cur], [c[2] for c in cur]
+                    cur = []
+                key = k
+                cur.append((idx, image, boxes, timing, token))
+            if cur:
+                metas.append(cur)
+                yield [c[1] for c in cur], [c[2] for c in cur]
+
+        try:
+            for out in stage.run_stream(batches(), masks=mode, copy_masks=False):
+                meta = metas.popleft()
+                t = stage.last_timing
+                share = 1.0 / len(meta)
+                for (idx, image, boxes, timing, token), (masks, cell_metrics, _crops) in zip(meta, out):
+                    timing["sam_preprocess"] = (t["h2d_ms"] + t["preprocess_ms"]) / 1e3 * share
+                    timing["inference"] = (t["encoder_ms"] + t["decoder_ms"]) / 1e3 * share
+                    timing["postprocess"] = (t["postprocess_ms"] + t["metrics_ms"] + t["d2h_ms"]) / 1e3 * share
+                    finish_image(idx, image, boxes, timing, masks, cell_metrics)
+                    pre.release(token)
+        finally:
+            stage.sync()
+            pre.close()
+        return [r for r in results if r is not None]
 
     def process_directory(self, input_dir: Union[str, Path], output_dir: Union[str, Path],
                           save_visualizations: bool = True, pbar=None) -> BatchProcessingResult:
@@ -154,15 +379,18 @@ class CellSegmentationPipeline:
         output_dir = Path(output_dir) / self.run_id
         output_dir.mkdir(parents=True, exist_ok=True)
         image_files = self._get_image_files(input_dir)
-        results, metrics_data, timing_data = [], [], []
-        total_timing = self._initialize_timing_dict()
-        for image_path in image_files:
-            result = self.process_single_image(image_path, output_dir / image_path.name, save_visualizations)
-            results.append(result)
-            self._update_progress(pbar, result)
-            self._collect_metrics_data(metrics_data, result)
-            self._collect_timing_data(timing_data, result)
-            self._update_total_timing(total_timing, result.timing)
+        results = self.process_files(image_files, output_dir, save_visualizations, pbar)
+        return self._assemble(results)
+
+    @classmethod
+    def _assemble(cls, results: List[ProcessingResult]) -> BatchProcessingResult:
+        metrics_data: List[Dict[str, Any]] = []
+        timing_data: List[Dict[str, Any]] = []
+        total_timing = cls._initialize_timing_dict()
+        for result in results:
+            cls._collect_metrics_data(metrics_data, result)
+            cls._collect_timing_data(timing_data, result)
+            cls._update_total_timing(total_timing, result.timing)
         return BatchProcessingResult(results=results, total_timing=total_timing, metrics_data=metrics_data,
                                      timing_data=timing_data)
 
@@ -202,22 +430,49 @@ class CellSegmentationPipeline:
                 total_timing[key] += timing[key]
 
 
-def _worker_process_directory(rank: int, device: str, files: List[str], output_dir: str, save_visualizations: bool,
-                              ctor_kwargs: Dict[str, Any], queue) -> None:
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU folder partition
+# ---------------------------------------------------------------------------------------------------------------------
+def _worker_main(rank: int, device: str, ctor_kwargs: Dict[str, Any], conn) -> None:
+    """One persistent replica: builds its pipeline (context + weights) once, then serves requests until told to stop."""
     try:
         pipe = CellSegmentationPipeline(**ctor_kwargs, device=device)
-        out = [pipe.process_single_image(f, Path(output_dir) / Path(f).name, save_visualizations) for f in files]
-        queue.put((rank, out, None))
+        conn.send(("ready", rank, None))
     except Exception as e:   # noqa: BLE001 - forwarded to the parent
-        queue.put((rank, None, repr(e)))
+        conn.send(("error", rank, repr(e)))
+        return
+    while True:
+        try:
+            msg = conn.recv()
+        except EOFError:
+            break
+        if msg[0] == "stop":
+            break
+        try:
+            if msg[0] == "files":
+                _, files, output_dir, save_visualizations = msg
+                conn.send(("ok", rank, pipe.process_files(files, output_dir, save_visualizations)))
+            elif msg[0] == "image":
+                image = msg[1]
+                boxes = pipe._detect_cells(image)
+                masks = pipe.sam_stage.run(image, boxes)[0] if len(boxes) else np.zeros((0,) + image.shape[:2], bool)
+                conn.send(("ok", rank, (boxes, masks)))
+            else:
+                conn.send(("error", rank, f"unknown request {msg[0]!r}"))
+        except Exception as e:   # noqa: BLE001
+            conn.send(("error", rank, repr(e)))
+    pipe.close()
 
 
 class ParallelCellSegmentationPipeline:
     """pipeline.py:440-584 with replicas spread over GPUs instead of stacked on one device.
 
-    ``num_pipelines`` workers, worker k on ``cuda:k % n_gpus`` (one process per GPU, no NCCL: the path
-    has no cross-image reduction).  Files are split into contiguous chunks of ceil(n / num_pipelines)
-    (:540-541) and results are concatenated in chunk order (:569-577)."""
+    ``num_pipelines`` persistent worker processes (spawned on first use, kept until ``close()``), worker k on
+    ``cuda:k % n_gpus`` (one process / one ysi_ctx per replica, no NCCL: the path has no cross-image reduction).  Files are
+    split into contiguous chunks of ceil(n / num_pipelines) (:540-541), every worker runs the batched, pipelined
+    ``CellSegmentationPipeline.process_files`` on its chunk, and results are concatenated in chunk order (:569-577)."""
+
+    POLL_S = 0.2
 
     def __init__(self, yolo_model_path, sam_model_type: str = "facebook/sam-vit-huge", device: str = "cuda",
                  num_pipelines: int = 2, **kwargs):
@@ -225,50 +480,88 @@ class ParallelCellSegmentationPipeline:
         self.sam_model_type = sam_model_type
         self.num_pipelines = num_pipelines
         self._ctor_kwargs = dict(yolo_model_path=yolo_model_path, sam_model_type=sam_model_type, **kwargs)
+        self._workers: List[Tuple[Any, Any]] = []      # (process, parent end of the pipe)
         self.run_id = CellSegmentationPipeline._generate_run_id()
 
     _get_image_files = staticmethod(CellSegmentationPipeline._get_image_files)
     _initialize_timing_dict = staticmethod(CellSegmentationPipeline._initialize_timing_dict)
+    _generate_run_id = staticmethod(CellSegmentationPipeline._generate_run_id)
+
+    # -- worker management
+    def _recv(self, k: int, what: str):
+        """Next message of worker k; raises if the worker died (e.g. a native crash) instead of waiting forever."""
+        proc, conn = self._workers[k]
+        while not conn.poll(self.POLL_S):
+            if not proc.is_alive():
+                code = proc.exitcode
+                self.close()
+                raise RuntimeError(f"worker {k} died (exit code {code}) while {what}")
+        kind, rank, payload = conn.recv()
+        if kind == "error":
+            self.close()
+            raise RuntimeError(f"worker {rank} failed while {what}: {payload}")
+        return payload
+
+    def _ensure_workers(self) -> None:
+        if self._workers:
+            return
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        n_gpus = _gpu_count()
+        base = self.device.split(":")[0]
+        for k in range(self.num_pipelines):
+            parent, child = ctx.Pipe()
+            dev = f"{base}:{k % max(n_gpus, 1)}"
+            p = ctx.Process(target=_worker_main, args=(k, dev, self._ctor_kwargs, child), daemon=True)
+            p.start()
+            child.close()
+            self._workers.append((p, parent))
+        for k in range(self.num_pipelines):
+            self._recv(k, "starting up")
+
+    def close(self) -> None:
+        for p, conn in self._workers:
+            try:
+                conn.send(("stop",))
+            except Exception:
+                pass
+        for p, conn in self._workers:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()
+            conn.close()
+        self._workers = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference's public methods
+    def process_image(self, image: np.ndarray) -> Tuple[np.ndarray, List[np.ndarray], List[float]]:
+        """pipeline.py:469-503: one RGB array through detector + SAM on the first replica -> (boxes, masks, scores)."""
+        self._ensure_workers()
+        self._workers[0][1].send(("image", np.ascontiguousarray(image)))
+        boxes, masks = self._recv(0, "processing an image")
+        return boxes, [m for m in masks], [1.0] * len(boxes)
 
     def process_directory(self, input_dir, output_dir, save_visualizations: bool = True, pbar=None) -> BatchProcessingResult:
-        import multiprocessing as mp
         input_dir = Path(input_dir)
         output_dir = Path(output_dir) / self.run_id
         output_dir.mkdir(parents=True, exist_ok=True)
         files = [str(p) for p in self._get_image_files(input_dir)]
         chunks = partition_contiguous(files, self.num_pipelines)
-        n_gpus = _gpu_count()
-        ctx = mp.get_context("spawn")
-        queue = ctx.Queue()
-        procs = []
+        self._ensure_workers()
         for k, chunk in enumerate(chunks):
-            p = ctx.Process(target=_worker_process_directory,
-                            args=(k, f"cuda:{k % max(n_gpus, 1)}", chunk, str(output_dir), save_visualizations,
-                                  self._ctor_kwargs, queue))
-            p.start()
-            procs.append(p)
-        got: Dict[int, List[ProcessingResult]] = {}
-        for _ in procs:
-            rank, out, err = queue.get()
-            if err is not None:
-                for p in procs:
-                    p.terminate()
-                raise RuntimeError(f"worker {rank} failed: {err}")
-            got[rank] = out
-        for p in procs:
-            p.join()
-        results, metrics_data, timing_data = [], [], []
-        total_timing = self._initialize_timing_dict()
-        for k in range(len(chunks)):
-            for result in got[k]:
-                results.append(result)
-                if pbar:
-                    pbar.update(1)
-                CellSegmentationPipeline._collect_metrics_data(metrics_data, result)
-                CellSegmentationPipeline._collect_timing_data(timing_data, result)
-                CellSegmentationPipeline._update_total_timing(total_timing, result.timing)
-        return BatchProcessingResult(results=results, total_timing=total_timing, metrics_data=metrics_data,
-                                     timing_data=timing_data)
+            self._workers[k][1].send(("files", chunk, str(output_dir), save_visualizations))
+        results: List[ProcessingResult] = []
+        for k in range(len(chunks)):                   # chunk order == input order (pipeline.py:569-577)
+            out = self._recv(k, "processing its chunk")
+            results.extend(out)
+            if pbar:
+                pbar.update(len(out))
+        return CellSegmentationPipeline._assemble(results)
 
 
 def _gpu_count() -> int:

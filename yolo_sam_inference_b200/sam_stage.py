@@ -21,6 +21,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native as nat
+from .ingest import as_rgb_u8, pixel_format_of
 from .weights import SamVariant, variant_of
 
 
@@ -94,6 +95,38 @@ def metrics_from_raw(raw: np.void, on_empty: str = "raise") -> Dict[str, Any]:
     }
 
 
+def box_crop(image: np.ndarray, box: np.ndarray) -> np.ndarray:
+    """image[y1:y2, x1:x2] with ``box.astype(int)`` -- the reference's box-to-pixel convention (pipeline.py:379) -- as uint8
+    RGB (a zero-copy view for RGB inputs; raw grey samples are converted like ``_load_image`` does)."""
+    x1, y1, x2, y2 = np.asarray(box, np.float32).astype(int)
+    return as_rgb_u8(image[max(y1, 0):max(y2, 0), max(x1, 0):max(x2, 0)])
+
+
+def expanded_crop_window(min_x: int, min_y: int, max_x: int, max_y: int, H: int, W: int) -> Tuple[int, int, int, int]:
+    """The 2x-expanded mask-bbox window the reference's CSV consumers recompute from the metric row
+    (examples/plot_scatter_example.py:107-147, deformability_training_data.py:97-153): the CSV calls rows "x" and columns
+    "y", so they are swapped first; the box is doubled about its integer centre and clipped to the image.
+    Returns (row0, row1, col0, col1) with image[row0:row1, col0:col1] the crop."""
+    c0, c1, r0, r1 = int(min_y), int(max_y), int(min_x), int(max_x)
+    cc, rc = (c0 + c1) // 2, (r0 + r1) // 2
+    nw, nh = int((c1 - c0) * 2.0), int((r1 - r0) * 2.0)
+    c0, c1 = cc - nw // 2, cc + nw // 2
+    r0, r1 = rc - nh // 2, rc + nh // 2
+    c0 = max(0, min(c0, W - 1))
+    c1 = max(c0 + 1, min(c1, W))
+    r0 = max(0, min(r0, H - 1))
+    r1 = max(r0 + 1, min(r1, H))
+    return r0, r1, c0, c1
+
+
+def expanded_crop(image: np.ndarray, raw: np.void) -> np.ndarray:
+    """the expanded mask-bbox crop, cut from the image the stage was given using the bounding box
+    the CUDA kernels measured (a zero-copy view for RGB inputs), so downstream tools need not re-read the TIFF."""
+    H, W = image.shape[:2]
+    r0, r1, c0, c1 = expanded_crop_window(int(raw["min_r"]), int(raw["min_c"]), int(raw["max_r"]), int(raw["max_c"]), H, W)
+    return as_rgb_u8(image[r0:r1, c0:c1])
+
+
 def parse_device(device: str) -> int:
     """'cuda' / 'cuda:3' -> CUDA device index. 'cpu' is refused: this path has no CPU fallback."""
     d = str(device)
@@ -162,8 +195,11 @@ class SamStage:
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):
-            self._lib.ysi_destroy(self._ctx)
+            self._lib.ysi_destroy(self._ctx)       # drains every stream before the pinned result buffers go away
             self._ctx = None
+        for m, r in getattr(self, "_pinned", {}).values():
+            m.close(); r.close()
+        self._pinned = {}
 
     def __del__(self):
         try:
@@ -176,141 +212,157 @@ class SamStage:
         return int(self._lib.ysi_launch_count(self._ctx))
 
     # ------------------------------------------------------------------ the hot path
-    def run(self, image: np.ndarray, boxes: np.ndarray, want_masks: bool = True
-            ) -> Tuple[np.ndarray, List[Dict[str, Any]], List[np.ndarray]]:
-        out = self.run_batch([image], [boxes], want_masks=want_masks)
+    def run(self, image: np.ndarray, boxes: np.ndarray, want_masks: bool = True, masks: Optional[str] = "auto",
+            expanded_crops: bool = False):
+        out = self.run_batch([image], [boxes], want_masks=want_masks, masks=masks, expanded_crops=expanded_crops)
         return out[0]
 
     def run_packed(self, image: np.ndarray, boxes: np.ndarray) -> Tuple[np.ndarray, List[Dict[str, Any]]]:
         """Masks in the reference's wire format instead of one byte per pixel: row k is ``np.packbits(mask_k)`` (MSB
         first over the row-major mask), i.e. exactly what ``utils/mask_encoding.encode_binary_mask`` feeds to zlib
         (mask_encoding.py:24) -- 8x less device-to-host traffic.  Returns (uint8 [N, ceil(H*W/8)], metrics)."""
-        img = np.ascontiguousarray(image, np.uint8)
-        H, W = img.shape[:2]
-        b = np.ascontiguousarray(np.asarray(boxes, np.float32).reshape(-1, 4))
-        nb = len(b)
-        packed = np.zeros((nb, (H * W + 7) // 8), np.uint8)
-        if nb == 0:
-            return packed, []
-        rows = np.zeros(nb, dtype=nat.METRICS_DTYPE)
-        tm = nat.YsiTiming()
-        self._check(self._lib.ysi_run(self._ctx, nat.as_u8p(img), H, W, img.strides[0], nat.as_f32p(b), nb, None,
-                                      nat.as_u8p(packed), rows.ctypes.data_as(C.c_void_p), C.byref(tm)), "ysi_run")
-        self.last_timing = tm.as_dict()
-        return packed, [metrics_from_raw(rows[j], self.on_empty) for j in range(nb)]
+        m, mets, _ = self.run(image, boxes, masks="packed")
+        return m, mets
 
-    def run_batch(self, images: Sequence[np.ndarray], boxes: Sequence[np.ndarray], want_masks: bool = True,
-                  raw: bool = False):
-        """Process several same-sized images in one call. Returns a list of (masks, metrics, crops)."""
+    @staticmethod
+    def _mask_mode(want_masks: bool, masks: Optional[str]) -> Optional[str]:
+        if masks == "auto":
+            return "bool" if want_masks else None
+        if masks not in (None, "bool", "packed"):
+            raise ValueError(f"masks must be 'bool', 'packed' or None, got {masks!r}")
+        return masks
+
+    def _submit(self, slot: int, images: Sequence[np.ndarray], boxes: Sequence[np.ndarray], mode: Optional[str], pinned: bool):
+        """Validate one batch, allocate its result buffers and enqueue it into ``slot`` (ysi_submit). Returns the
+        bookkeeping record ``_finish`` needs, or None for a batch without boxes (nothing is launched, pipeline.py:176-179)."""
         n = len(images)
         assert n == len(boxes) and n >= 1
+        fmt = pixel_format_of(images[0])
         H, W = images[0].shape[:2]
         imgs = []
         for im in images:
-            assert im.dtype == np.uint8 and im.ndim == 3 and im.shape == (H, W, 3), "images must be uint8 [H,W,3], same size"
-            imgs.append(im if im.strides[2] == 1 and im.strides[1] == 3 else np.ascontiguousarray(im))
-        counts = np.array([len(b) for b in boxes], dtype=np.int32)
-        nb = int(counts.sum())
-        if nb == 0:                                   # pipeline.py:176-179
-            return [(np.zeros((0, H, W), bool), [], []) for _ in range(n)]
-        allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
+            if pixel_format_of(im) != fmt or im.shape[:2] != (H, W):
+                raise ValueError("images of one batch must share size and pixel format")
+            inner_ok = (im.strides[-1] == im.itemsize) and (im.ndim == 2 or im.strides[1] == 3)
+            imgs.append(im if inner_ok else np.ascontiguousarray(im))
         row_stride = imgs[0].strides[0]
-        assert all(im.strides[0] == row_stride for im in imgs)
-        ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in imgs])
-        masks = np.empty((nb, H, W), np.uint8) if want_masks else None
-        rows = np.zeros(nb, dtype=nat.METRICS_DTYPE)
+        if any(im.strides[0] != row_stride for im in imgs):
+            imgs = [np.ascontiguousarray(im) for im in imgs]
+            row_stride = imgs[0].strides[0]
+        blist = [np.asarray(b, np.float32).reshape(-1, 4) for b in boxes]
+        counts = np.array([len(b) for b in blist], dtype=np.int32)
+        nb = int(counts.sum())
+        if nb == 0:
+            return None
+        allb = np.ascontiguousarray(np.concatenate(blist, 0))
+        PB = (H * W + 7) // 8
+        if pinned:
+            mbuf, rows = self._out_buffers(slot, nb, H, W, mode)
+        else:
+            mbuf = np.empty((nb, H, W), np.uint8) if mode == "bool" else (np.empty((nb, PB), np.uint8) if mode == "packed" else None)
+            rows = np.zeros(nb, dtype=nat.METRICS_DTYPE)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        bt = nat.YsiBatch()
+        bt.n_images, bt.height, bt.width, bt.row_stride, bt.pixel_format = n, H, W, row_stride, fmt
+        bt.images = ptrs
+        bt.boxes_xyxy = nat.as_f32p(allb)
+        bt.box_counts = nat.as_i32p(counts)
+        bt.masks_out = nat.as_u8p(mbuf) if mode == "bool" else None
+        bt.packed_out = nat.as_u8p(mbuf) if mode == "packed" else None
+        bt.metrics_out = rows.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.ysi_submit(self._ctx, slot, C.byref(bt)), "ysi_submit")
+        return dict(slot=slot, images=images, boxes=blist, counts=counts, masks=mbuf, rows=rows, mode=mode, hw=(H, W),
+                    keep=(imgs, allb, ptrs, bt))
+
+    def _finish(self, rec, raw: bool, copy: bool, expanded_crops: bool):
         tm = nat.YsiTiming()
-        self._check(self._lib.ysi_run_batch(self._ctx, n, ptrs, H, W, row_stride, nat.as_f32p(allb), nat.as_i32p(counts),
-                                            nat.as_u8p(masks), None, rows.ctypes.data_as(C.c_void_p), C.byref(tm)),
-                    "ysi_run_batch")
+        self._check(self._lib.ysi_wait_batch(self._ctx, rec["slot"], C.byref(tm)), "ysi_wait_batch")
         self.last_timing = tm.as_dict()
         out = []
         k = 0
-        for i in range(n):
-            c = int(counts[i])
-            m = masks[k:k + c].view(bool) if want_masks else None
-            r = rows[k:k + c]
+        mbuf, rows, mode = rec["masks"], rec["rows"], rec["mode"]
+        H, W = rec["hw"]
+        for i, image in enumerate(rec["images"]):
+            c = int(rec["counts"][i])
+            if mode is None:
+                m = None
+            else:
+                m = mbuf[k:k + c].view(bool) if mode == "bool" else mbuf[k:k + c]
+                if copy:
+                    m = m.copy()
+            r = rows[k:k + c].copy() if copy else rows[k:k + c]
             mets = r if raw else [metrics_from_raw(r[j], self.on_empty) for j in range(c)]
-            crops = []
-            for bx in np.asarray(boxes[i], np.float32).reshape(-1, 4):
-                x1, y1, x2, y2 = bx.astype(int)
-                crops.append(images[i][max(y1, 0):max(y2, 0), max(x1, 0):max(x2, 0)])
-            out.append((m, mets, crops))
+            crops = [box_crop(image, bx) for bx in rec["boxes"][i]]
+            if expanded_crops:
+                out.append((m, mets, crops, [expanded_crop(image, r[j]) for j in range(c)]))
+            else:
+                out.append((m, mets, crops))
             k += c
         return out
+
+    def _empty_result(self, images, mode, expanded_crops):
+        res = []
+        for im in images:
+            H, W = im.shape[:2]
+            m = None if mode is None else (np.zeros((0, H, W), bool) if mode == "bool" else np.zeros((0, (H * W + 7) // 8), np.uint8))
+            res.append((m, [], [], []) if expanded_crops else (m, [], []))
+        return res
+
+    def run_batch(self, images: Sequence[np.ndarray], boxes: Sequence[np.ndarray], want_masks: bool = True,
+                  raw: bool = False, masks: Optional[str] = "auto", expanded_crops: bool = False):
+        """Process several same-sized images in one call. Returns a list of (masks, metrics, crops[, expanded crops]).
+
+        Images are uint8 [H,W,3] RGB (what ``_load_image`` returns) or the raw single-channel samples of the file (uint8 /
+        uint16 [H,W]; the device then performs ``_load_image``'s 16 -> 8 bit reduction and grey -> RGB replication).
+        ``masks``: "bool" (bool [N,H,W]), "packed" (uint8 [N, ceil(H*W/8)], np.packbits rows) or None (metrics only).
+        Any number of boxes is accepted; more than ``max_boxes`` are decoded in chunks that share the image embeddings."""
+        mode = self._mask_mode(want_masks, masks)
+        rec = self._submit(0, images, boxes, mode, pinned=False)
+        if rec is None:
+            return self._empty_result(images, mode, expanded_crops)
+        return self._finish(rec, raw, copy=False, expanded_crops=expanded_crops)
 
     # ------------------------------------------------------------------ pipelined form
-    def run_stream(self, batches, want_masks: bool = True, raw: bool = False, copy_masks: bool = True):
+    def run_stream(self, batches, want_masks: bool = True, raw: bool = False, copy_masks: bool = True,
+                   masks: Optional[str] = "auto", expanded_crops: bool = False):
         """Generator over ``batches`` (an iterable of (images, boxes) with same-sized images per batch) that keeps two
         batches in flight: the H2D copy and the encoder of batch i+1 overlap the decoder, metrics and D2H copy of
-        batch i (ysi_submit_batch / ysi_wait_batch). Yields, per batch, what ``run_batch`` returns.
+        batch i (ysi_submit / ysi_wait_batch). Yields, per batch, what ``run_batch`` returns.
 
-        ``copy_masks=False`` yields the masks as views into the slot's pinned host buffer instead of copies (at 32
+        ``copy_masks=False`` yields masks and raw rows as views into the slot's pinned host buffer instead of copies (at 32
         boxes per image the copies are 268 MB of host memcpy per batch and dominate); such a view is valid only until
         the generator is advanced again (the slot's buffer is then handed to the next batch)."""
-        pending = []                      # [(slot, images, boxes, counts, masks, rows, keepalive)]
+        mode = self._mask_mode(want_masks, masks)
+        pending: List[Any] = []
         slot = 0
-
-        def finish(item):
-            sl, images, boxes, counts, masks, rows, _keep = item
-            tm = nat.YsiTiming()
-            self._check(self._lib.ysi_wait_batch(self._ctx, sl, C.byref(tm)), "ysi_wait_batch")
-            self.last_timing = tm.as_dict()
-            return self._unpack(images, boxes, counts, masks, rows, want_masks, raw, copy_masks)
-
         for images, boxes in batches:
-            n = len(images)
-            H, W = images[0].shape[:2]
-            imgs = [im if im.strides[2] == 1 and im.strides[1] == 3 else np.ascontiguousarray(im) for im in images]
-            counts = np.array([len(b) for b in boxes], dtype=np.int32)
-            nb = int(counts.sum())
-            if nb == 0:
-                while pending:
-                    yield finish(pending.pop(0))
-                yield [(np.zeros((0, H, W), bool), [], []) for _ in range(n)]
-                continue
             if len(pending) == 2:
-                yield finish(pending.pop(0))
-            allb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in boxes], 0))
-            ptrs = (nat._u8p * n)(*[nat.as_u8p(im) for im in imgs])
-            masks, rows = self._out_buffers(slot, nb, H, W, want_masks)
-            self._check(self._lib.ysi_submit_batch(self._ctx, slot, n, ptrs, H, W, imgs[0].strides[0], nat.as_f32p(allb),
-                                                   nat.as_i32p(counts), nat.as_u8p(masks), None,
-                                                   rows.ctypes.data_as(C.c_void_p)), "ysi_submit_batch")
-            pending.append((slot, images, boxes, counts, masks, rows, (imgs, allb, ptrs)))
+                yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops)
+            rec = self._submit(slot, images, boxes, mode, pinned=True)
+            if rec is None:
+                while pending:
+                    yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops)
+                yield self._empty_result(images, mode, expanded_crops)
+                continue
+            pending.append(rec)
             slot ^= 1
         while pending:
-            yield finish(pending.pop(0))
+            yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops)
 
-    def _out_buffers(self, slot: int, nb: int, H: int, W: int, want_masks: bool):
-        """Pinned host buffers for a slot's results (true copy/compute overlap needs page-locked memory)."""
-        import torch
-        key = (slot, H, W, want_masks)
-        buf = self._pinned.get(key)
-        if buf is None:
-            m = torch.empty((self.max_boxes, H, W), dtype=torch.uint8).pin_memory() if want_masks else None
-            r = torch.empty((self.max_boxes * nat.METRICS_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
-            buf = self._pinned[key] = (m, r)
-        m, r = buf
-        masks = m.numpy()[:nb] if want_masks else None
-        rows = r.numpy()[:nb * nat.METRICS_DTYPE.itemsize].view(nat.METRICS_DTYPE)
+    def _out_buffers(self, slot: int, nb: int, H: int, W: int, mode: Optional[str]):
+        """Pinned host buffers for a slot's results (true copy/compute overlap needs page-locked memory); they grow when a
+        batch brings more boxes or larger images than any before."""
+        per = H * W if mode == "bool" else ((H * W + 7) // 8 if mode == "packed" else 0)
+        need_m, need_r = nb * per, nb * nat.METRICS_DTYPE.itemsize
+        m, r = self._pinned.get(slot, (None, None))
+        if m is None or m.nbytes < need_m:
+            m = nat.PinnedBuffer(max(need_m, self.max_boxes * per), self.precision, self.device_index)
+        if r is None or r.nbytes < need_r:
+            r = nat.PinnedBuffer(max(need_r, self.max_boxes * nat.METRICS_DTYPE.itemsize), self.precision, self.device_index)
+        self._pinned[slot] = (m, r)
+        masks = m.array[:need_m].reshape(nb, H, W) if mode == "bool" else (m.array[:need_m].reshape(nb, per) if mode == "packed" else None)
+        rows = r.array[:need_r].view(nat.METRICS_DTYPE)
         return masks, rows
-
-    def _unpack(self, images, boxes, counts, masks, rows, want_masks, raw, copy_masks=True):
-        out = []
-        k = 0
-        for i in range(len(images)):
-            c = int(counts[i])
-            m = (masks[k:k + c].view(bool).copy() if copy_masks else masks[k:k + c].view(bool)) if want_masks else None
-            r = rows[k:k + c].copy()
-            mets = r if raw else [metrics_from_raw(r[j], self.on_empty) for j in range(c)]
-            crops = []
-            for bx in np.asarray(boxes[i], np.float32).reshape(-1, 4):
-                x1, y1, x2, y2 = bx.astype(int)
-                crops.append(images[i][max(y1, 0):max(y2, 0), max(x1, 0):max(x2, 0)])
-            out.append((m, mets, crops))
-            k += c
-        return out
 
     # ------------------------------------------------------------------ measurement support (bench.py)
     def pool_upload(self, images: Sequence[np.ndarray]) -> None:
@@ -351,10 +403,13 @@ class SamStage:
         ms = np.zeros(n, np.float64)
         rec = np.zeros(n, np.int64)
         fl = np.zeros(n, np.float64)
-        k = self._lib.ysi_profile_read(self._ctx, n, names, nat.as_f64p(ms), rec.ctypes.data_as(C.POINTER(C.c_int64)), nat.as_f64p(fl))
+        by = np.zeros(n, np.float64)
+        k = self._lib.ysi_profile_read(self._ctx, n, names, nat.as_f64p(ms), rec.ctypes.data_as(C.POINTER(C.c_int64)), nat.as_f64p(fl),
+                                       nat.as_f64p(by))
         if k < 0:
             self._check(k, "ysi_profile_read")
-        return {names[i].decode(): {"ms": float(ms[i]), "records": int(rec[i]), "flops": float(fl[i])} for i in range(k)}
+        return {names[i].decode(): {"ms": float(ms[i]), "records": int(rec[i]), "flops": float(fl[i]), "bytes": float(by[i])}
+                for i in range(k)}
 
     # ------------------------------------------------------------------ stage-level API (parity tests)
     def preprocess(self, images: Sequence[np.ndarray]) -> np.ndarray:
