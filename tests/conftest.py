@@ -43,12 +43,13 @@ def tiny_oracle(tiny_weights):
     return sam_oracle.build_model("vit_t", state_dict=tiny_weights)
 
 
-@pytest.fixture(scope="session")
-def _tiny_stage_session(tiny_weights):
-    """vit_t context sized for every GPU parity test (up to 2048x2048 images, 40 masks)."""
+@pytest.fixture(scope="session", params=["fp16", "bf16"])
+def _tiny_stage_session(tiny_weights, request):
+    """vit_t context sized for every GPU parity test (up to 2048x2048 images, 40 masks), once per operand encoding: every
+    test that takes ``tiny_stage`` runs against libysi_fp16.so (the default build) AND libysi.so (bf16 operands)."""
     from yolo_sam_inference_b200.sam_stage import SamStage
     st = SamStage("vit_t", device="cuda:0", state_dict=tiny_weights, max_batch=2, max_boxes=40,
-                  max_image_hw=(2048, 2048))
+                  max_image_hw=(2048, 2048), precision=request.param)
     yield st
     st.close()
 
@@ -67,11 +68,32 @@ def op16_round(a, precision):
     return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dt).to(torch.float32).numpy()
 
 
-def iou_gate(precision):
-    """End-to-end mask IoU gate vs the fp32 oracle on random-init noise-field logits: the north-star
-    bar of 0.999 for fp16 operands (observed 0.9994-0.9998); bf16 operands (2^-9 rounding) cannot reach it on noise
-    masks (observed 0.995-0.998), their gate is the measured floor."""
-    return 0.999 if precision == "fp16" else 0.99
+LOGIT_TOL = 2e-2        # BASELINE.json north_star: logits within 2e-2 relative of the fp32 reference
+IOU_GATE = 0.999        # BASELINE.json north_star: thresholded masks
+
+
+def iou(a, b):
+    return float(np.logical_and(a, b).sum() / max(np.logical_or(a, b).sum(), 1))
+
+
+def check_mask_parity(mask, ref_mask, ref_up_logits, precision, what=""):
+    """End-to-end mask parity vs the fp32 oracle for one mask; returns the IoU.
+
+    fp16 operands (the default build, the one whose throughput is the headline): the north-star gate, IoU >= 0.999.
+    bf16 operands: random-init logits are a zero-mean noise field (~47 % positive, every zero crossing is a
+    band of near-zero logits), where bf16's 2^-9 operand rounding cannot reach 0.999 -- measured 0.995-0.998, and this
+    build is NOT claimed to meet that gate.  What is asserted instead is the statement the 2e-2 logit tolerance makes
+    about masks: a pixel may differ from the reference only where the reference logit itself lies inside the tolerance
+    band (|logit| <= 2e-2 * max|logit| of that mask); everywhere else the masks must be identical."""
+    v = iou(mask, ref_mask)
+    if precision == "fp16":
+        assert v >= IOU_GATE, (what, v)
+    else:
+        band = LOGIT_TOL * float(np.abs(ref_up_logits).max())
+        wrong = mask != ref_mask
+        assert not wrong.any() or float(np.abs(ref_up_logits[wrong]).max()) <= band, \
+            (what, "mask differs outside the logit tolerance band", v)
+    return v
 
 
 def rel_l2(a, b):

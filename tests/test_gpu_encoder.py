@@ -68,22 +68,29 @@ def test_preprocess_resize_is_bit_exact(tiny_stage, H, W):
     assert np.array_equal(got[0], ref[0].numpy())
 
 
-@pytest.mark.parametrize("variant", ["vit_t", "vit_t80"])
-def test_encoder_is_bitwise_reproducible(variant, tiny_weights):
+@pytest.mark.parametrize("variant,batch,repeats", [("vit_t", 2, 4), ("vit_t80", 2, 4), ("vit_b", 8, 10), ("vit_h", 8, 10)])
+def test_encoder_is_bitwise_reproducible(variant, batch, repeats, tiny_weights):
     """Every output element of the encoder is written or reduce-added exactly once per kernel, so two runs on the same
     input must agree bit for bit; any difference is a race (one was caught this way in round 1: a TMEM aliasing change
-    in the windowed attention kernel made ViT-H hidden states vary from run to run)."""
+    in the windowed attention kernel made ViT-H hidden states vary from run to run).  compute-sanitizer is closed on this
+    GPU pool (profiles/r02_sanitizer_closed.txt), so this is the race detector: the benchmarked models at the benchmarked
+    batch size (ViT-B / ViT-H, 8 images), ten repeats, every layer's hidden state."""
+    import zlib
     from yolo_sam_inference_b200.sam_stage import SamStage
     from yolo_sam_inference_b200.weights import seeded_state_dict
     rng = np.random.RandomState(5)
-    pv = rng.standard_normal((2, 3, 1024, 1024)).astype(np.float32)
+    pv = rng.standard_normal((batch, 3, 1024, 1024)).astype(np.float32)
     sd = tiny_weights if variant == "vit_t" else seeded_state_dict(variant, 1234)
-    stage = SamStage(variant, device="cuda:0", state_dict=sd, max_batch=2, max_boxes=2)
+    stage = SamStage(variant, device="cuda:0", state_dict=sd, max_batch=batch, max_boxes=2)
     try:
-        ref_emb, ref_hid = stage.encode(pv, want_hidden=True)
-        for _ in range(4):
+        ref = None
+        for _ in range(1 + repeats):
             emb, hid = stage.encode(pv, want_hidden=True)
-            assert np.array_equal(hid, ref_hid)
-            assert np.array_equal(emb, ref_emb)
+            sig = [zlib.crc32(np.ascontiguousarray(hid[li]).view(np.uint8)) for li in range(hid.shape[0])] + \
+                  [zlib.crc32(emb.view(np.uint8))]
+            del emb, hid
+            if ref is None:
+                ref = sig
+            assert sig == ref, [i for i, (a, b) in enumerate(zip(sig, ref)) if a != b]
     finally:
         stage.close()

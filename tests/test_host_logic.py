@@ -113,3 +113,79 @@ def test_two_rank_sharding_on_gloo(tmp_path):
     line = json.load(open(tmp_path / "line.json"))
     assert line["n_gpus"] == 2 and line["images_total"] == 10 and line["shards"] == [5, 5]
     assert line["scaling"] == "weak" or line["scaling"] == "strong"
+
+
+def _reference_expanded_window(min_x, min_y, max_x, max_y, img_w, img_h):
+    """examples/plot_scatter_example.py:114-140 restated (PIL box = (left, upper, right, lower))."""
+    min_x_img, max_x_img, min_y_img, max_y_img = int(min_y), int(max_y), int(min_x), int(max_x)
+    center_x = (min_x_img + max_x_img) // 2
+    center_y = (min_y_img + max_y_img) // 2
+    width, height = max_x_img - min_x_img, max_y_img - min_y_img
+    new_width, new_height = int(width * 2.0), int(height * 2.0)
+    min_x_img, max_x_img = center_x - (new_width // 2), center_x + (new_width // 2)
+    min_y_img, max_y_img = center_y - (new_height // 2), center_y + (new_height // 2)
+    min_x_img = max(0, min(min_x_img, img_w - 1))
+    max_x_img = max(min_x_img + 1, min(max_x_img, img_w))
+    min_y_img = max(0, min(min_y_img, img_h - 1))
+    max_y_img = max(min_y_img + 1, min(max_y_img, img_h))
+    return min_x_img, min_y_img, max_x_img, max_y_img
+
+
+def test_expanded_crop_is_what_the_csv_consumers_cut():
+    """f1: the 2x-expanded mask-bbox crop equals PIL's img.crop of the consumer's window, incl. clipping at every border."""
+    from PIL import Image
+    from yolo_sam_inference_b200 import _native as nat
+    from yolo_sam_inference_b200.sam_stage import expanded_crop, expanded_crop_window
+    rng = np.random.RandomState(11)
+    H, W = 90, 140
+    img = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    pil = Image.fromarray(img)
+    for _ in range(200):
+        r0, c0 = rng.randint(0, H - 1), rng.randint(0, W - 1)
+        r1, c1 = rng.randint(r0 + 1, H + 1), rng.randint(c0 + 1, W + 1)
+        box = _reference_expanded_window(r0, c0, r1, c1, W, H)
+        ref = np.asarray(pil.crop(box))
+        raw = np.zeros(1, dtype=nat.METRICS_DTYPE)[0]
+        raw["min_r"], raw["min_c"], raw["max_r"], raw["max_c"] = r0, c0, r1, c1
+        got = expanded_crop(img, raw)
+        assert np.array_equal(got, ref)
+        a, b, c, d = expanded_crop_window(r0, c0, r1, c1, H, W)
+        assert (c, a, d, b) == box
+    # raw grey samples give the same crop as the RGB image _load_image would have produced
+    g16 = rng.randint(0, 65536, (H, W)).astype(np.uint16)
+    rgb = np.repeat((g16 >> 8).astype(np.uint8)[:, :, None], 3, 2)
+    raw = np.zeros(1, dtype=nat.METRICS_DTYPE)[0]
+    raw["min_r"], raw["min_c"], raw["max_r"], raw["max_c"] = 10, 20, 40, 70
+    assert np.array_equal(expanded_crop(g16, raw), expanded_crop(rgb, raw))
+
+
+def test_visualisation_writer_layout(tmp_path):
+    """f4: folders and file names of pipeline.py:352-432; the original image round-trips through the TIFF writer."""
+    import cv2
+    from yolo_sam_inference_b200.pipeline import CellSegmentationPipeline
+    rng = np.random.RandomState(2)
+    img = rng.randint(0, 256, (40, 50, 3)).astype(np.uint8)
+    masks = np.zeros((2, 40, 50), bool)
+    masks[0, 5:15, 5:20] = True
+    masks[1, 20:30, 25:45] = True
+    boxes = np.array([[4, 4, 21, 16], [24, 19, 46, 31]], np.float32)
+    pipe = CellSegmentationPipeline.__new__(CellSegmentationPipeline)          # the writer needs no device
+    pipe._save_visualizations(img, masks, boxes, [{}, {}], tmp_path / "run" / "cell_007.tiff")
+    base = tmp_path / "run"
+    expect = ["1_original_images/cell_007_original.tiff", "2_yolo_detections/cell_007_yolo.tiff",
+              "3_processed_masks/masks/cell_007_mask_0.tiff", "3_processed_masks/masks/cell_007_mask_1.tiff",
+              "3_processed_masks/overlay_images/cell_007_mask_0_overlay.tiff",
+              "3_processed_masks/convex_hull_overlay/cell_007_mask_1_convex_hull.tiff",
+              "4_combined_visualization/cell_007_combined.tiff"]
+    for rel in expect:
+        assert (base / rel).exists(), rel
+    back = cv2.cvtColor(cv2.imread(str(base / expect[0])), cv2.COLOR_BGR2RGB)
+    assert np.array_equal(back, img)
+    m0 = cv2.imread(str(base / expect[2]), cv2.IMREAD_UNCHANGED)
+    assert m0.dtype == np.uint8 and np.array_equal(m0 > 0, masks[0]) and set(np.unique(m0)) == {0, 255}
+    comb = cv2.imread(str(base / expect[6]))
+    assert comb.shape == (40, 100, 3)
+    ov = cv2.cvtColor(cv2.imread(str(base / expect[4])), cv2.COLOR_BGR2RGB)
+    exp = img.copy()
+    exp[masks[0]] = exp[masks[0]] * 0.7 + np.array([255, 0, 0]) * 0.3
+    assert np.array_equal(ov, exp)
