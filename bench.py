@@ -342,7 +342,8 @@ def folder_e2e(model: str, grays, boxes, local: int, steps: int, warmup: int, di
     try:
         pipe = CellSegmentationPipeline(None, model, device=f"cuda:{local}", detector=BoxTable(table),
                                         sam_state_dict=seeded_state_dict(model, 1234), max_boxes=BATCH * nb, max_image_hw=(H, W),
-                                        on_empty="zeros", batch_size=BATCH, mask_output="packed", precision=precision)
+                                        on_empty="zeros", batch_size=BATCH, mask_output="packed",
+                                        mask_sink=lambda name, packed: None, precision=precision)
         cells = 0
         for _ in range(max(warmup, 1)):
             pipe.process_directory(folder, out_dir, save_visualizations=False)

@@ -423,6 +423,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
       for (int i = 0; i < 28; ++i) bias[i] = my[i * 128 + t];
     }
+    // The scratch this thread just wrote and read back through the generic proxy is about to be overwritten by the TMA
+    // (async proxy) with V tiles, as soon as the last softmax warp has arrived on bar_rel. Accesses of the two proxies
+    // to the same shared memory are only ordered by a proxy fence: without it V bytes could land before this warp's
+    // reads had been performed (a warp's bias registers then held V data) or a scratch store could land after them
+    // (corrupt V for the whole CTA). Found in round 2 with the run-to-run bit-equality test at ViT-H, batch 8
+    // (profiles/r02_race_diag_before_fix.txt): windowed head_dim-80 attention differed in whole 32-row blocks.
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_rel);

@@ -103,11 +103,11 @@ class _Prefetcher:
 
     Baseline TIFFs land as raw samples in recycled page-locked buffers (``readinto``: disk -> pinned memory, no copy in
     between, GIL released); every other file goes through ``decode_rgb`` (cv2.imread + BGR->RGB, pipeline.py:206-210).
-    Iterating yields (index, path, image, load_seconds, token); ``release(token)`` returns a pinned buffer to the pool
-    once the device has consumed it."""
+    ``iterate(files)`` yields (index, path, image, load_seconds, token); ``release(token)`` returns a pinned buffer to the
+    pool once the device has consumed it.  Threads and pinned buffers live as long as the pipeline (page-locking memory
+    costs milliseconds per buffer: it must not be paid per folder)."""
 
-    def __init__(self, files: Sequence[Path], workers: int, depth: int, raw_ingest: bool, precision: str, device: int):
-        self.files = [str(f) for f in files]
+    def __init__(self, workers: int, depth: int, raw_ingest: bool, precision: str, device: int):
         self.depth = max(1, depth)
         self.raw_ingest = raw_ingest
         self.precision, self.device = precision, device
@@ -141,21 +141,25 @@ class _Prefetcher:
             return image, time.time() - t0, buf
         return decode_rgb(path), time.time() - t0, None
 
-    def __iter__(self):
+    def iterate(self, files: Sequence[Union[str, Path]]):
+        files = [str(f) for f in files]
         window: deque = deque()
         nxt = 0
-        n = len(self.files)
+        n = len(files)
         try:
             while nxt < n or window:
                 while nxt < n and len(window) < self.depth:
-                    window.append((nxt, self.pool.submit(self._load, self.files[nxt])))
+                    window.append((nxt, self.pool.submit(self._load, files[nxt])))
                     nxt += 1
                 idx, fut = window.popleft()
                 image, t_load, token = fut.result()
-                yield idx, self.files[idx], image, t_load, token
+                yield idx, files[idx], image, t_load, token
         finally:
-            for _, fut in window:
-                fut.cancel()
+            for _, fut in window:             # abandoned mid-folder: let the reads finish, hand their buffers back
+                try:
+                    self.release(fut.result()[2])
+                except Exception:
+                    pass
 
     def close(self) -> None:
         self.pool.shutdown(wait=True, cancel_futures=True)
@@ -170,13 +174,14 @@ class CellSegmentationPipeline:
                  sam_state_dict: Optional[Dict[str, Any]] = None, max_boxes: int = 64,
                  max_image_hw: Tuple[int, int] = (1024, 1024), on_empty: str = "raise", batch_size: int = 8,
                  decode_workers: Optional[int] = None, raw_ingest: bool = True, mask_output: Optional[str] = None,
-                 precision: Optional[str] = None):
+                 mask_sink: Optional[Callable[[str, np.ndarray], None]] = None, precision: Optional[str] = None):
         """Beyond the reference's three arguments (keyword-only, all optional):
         ``batch_size`` images per device launch in ``process_directory``; ``max_boxes`` / ``max_image_hw`` are capacity
         hints, not limits (more boxes are decoded in chunks, larger images re-size the buffers); ``decode_workers`` threads
         read files ahead; ``raw_ingest`` hands baseline TIFFs to the device undecoded; ``mask_output`` ("packed" | "bool" |
-        None) additionally keeps every image's masks in ``last_masks`` (None: masks stay on the device unless
-        visualisations are written)."""
+        None) brings every image's masks to the host (None: masks stay on the device unless visualisations are written) and
+        hands them to ``mask_sink(image_name, masks)`` -- a view valid during the call, e.g. for utils/mask_encoding -- or,
+        without a sink, keeps copies in ``last_masks``."""
         self.device = device
         self.sam_model_type = sam_model_type
         self.detector: Detector = detector if detector is not None else _load_yolo(yolo_model_path)
@@ -187,11 +192,16 @@ class CellSegmentationPipeline:
         self.decode_workers = decode_workers if decode_workers else min(16, max(2, (os.cpu_count() or 4) // 2))
         self.raw_ingest = raw_ingest
         self.mask_output = mask_output
+        self.mask_sink = mask_sink
         self.last_masks: Dict[str, np.ndarray] = {}
+        self._prefetch: Optional[_Prefetcher] = None
         self.run_id = self._generate_run_id()
 
     def close(self) -> None:
-        self.sam_stage.close()
+        self.sam_stage.close()                 # drains the device before the pinned staging buffers are released
+        if self._prefetch is not None:
+            self._prefetch.close()
+            self._prefetch = None
 
     @staticmethod
     def _generate_run_id() -> str:
@@ -227,7 +237,10 @@ class CellSegmentationPipeline:
             mode = "bool" if save_visualizations else self.mask_output
             masks, cell_metrics, _crops = self.sam_stage.run(image, boxes, masks=mode)
             if self.mask_output:
-                self.last_masks[Path(image_path).name] = masks
+                if self.mask_sink is not None:
+                    self.mask_sink(Path(image_path).name, masks)
+                else:
+                    self.last_masks[Path(image_path).name] = masks
             t = self.sam_stage.last_timing
             timings["sam_preprocess"] = (t["h2d_ms"] + t["preprocess_ms"]) / 1e3
             sam_times["inference"] = (t["encoder_ms"] + t["decoder_ms"]) / 1e3
@@ -316,8 +329,10 @@ class CellSegmentationPipeline:
             return []
         stage = self.sam_stage
         mode = "bool" if save_visualizations else self.mask_output
-        pre = _Prefetcher(files, self.decode_workers, depth=4 * self.batch_size, raw_ingest=self.raw_ingest,
-                          precision=stage.precision, device=stage.device_index)
+        if self._prefetch is None:
+            self._prefetch = _Prefetcher(self.decode_workers, depth=4 * self.batch_size, raw_ingest=self.raw_ingest,
+                                         precision=stage.precision, device=stage.device_index)
+        pre = self._prefetch
         metas: deque = deque()        # bookkeeping of the batches handed to run_stream, in submission order
 
         def finish_image(idx, image, boxes, timing, masks, cell_metrics):
@@ -327,7 +342,10 @@ class CellSegmentationPipeline:
                                           output_dir / files[idx].name)
                 timing["visualization"] = time.time() - t_vis0
             if self.mask_output and masks is not None and len(boxes) > 0:
-                self.last_masks[files[idx].name] = np.array(masks, copy=True)
+                if self.mask_sink is not None:
+                    self.mask_sink(files[idx].name, masks)
+                else:
+                    self.last_masks[files[idx].name] = np.array(masks, copy=True)
             timing["total_time"] = sum(v for k, v in timing.items() if k != "cells_processed")
             timing["cells_processed"] = len(boxes)
             results[idx] = ProcessingResult(image_path=str(files[idx]), cell_metrics=cell_metrics,
@@ -337,7 +355,7 @@ class CellSegmentationPipeline:
         def batches():
             cur: List[Any] = []
             key = None
-            for idx, path, image, t_load, token in pre:
+            for idx, path, image, t_load, token in pre.iterate(files):
                 t0 = time.time()
                 boxes = self._detect(image, path)
                 timing = {"image_load": t_load, "yolo_detection": time.time() - t0, "sam_preprocess": 0.0,
@@ -358,7 +376,7 @@ class CellSegmentationPipeline:
                 yield [c[1] for c in cur], [c[2] for c in cur]
 
         try:
-            for out in stage.run_stream(batches(), masks=mode, copy_masks=False):
+            for out in stage.run_stream(batches(), masks=mode, copy_masks=False, crops=False):
                 meta = metas.popleft()
                 t = stage.last_timing
                 share = 1.0 / len(meta)
@@ -370,7 +388,6 @@ class CellSegmentationPipeline:
                     pre.release(token)
         finally:
             stage.sync()
-            pre.close()
         return [r for r in results if r is not None]
 
     def process_directory(self, input_dir: Union[str, Path], output_dir: Union[str, Path],
@@ -491,16 +508,32 @@ class ParallelCellSegmentationPipeline:
     def _recv(self, k: int, what: str):
         """Next message of worker k; raises if the worker died (e.g. a native crash) instead of waiting forever."""
         proc, conn = self._workers[k]
-        while not conn.poll(self.POLL_S):
-            if not proc.is_alive():
-                code = proc.exitcode
-                self.close()
-                raise RuntimeError(f"worker {k} died (exit code {code}) while {what}")
-        kind, rank, payload = conn.recv()
+        try:
+            while not conn.poll(self.POLL_S):
+                if not proc.is_alive():
+                    raise EOFError
+            kind, rank, payload = conn.recv()
+        except (EOFError, OSError):
+            proc.join(timeout=1)
+            code = proc.exitcode
+            self.close()
+            raise RuntimeError(f"worker {k} died (exit code {code}) while {what}") from None
         if kind == "error":
             self.close()
             raise RuntimeError(f"worker {rank} failed while {what}: {payload}")
         return payload
+
+    def _send(self, k: int, msg) -> None:
+        proc, conn = self._workers[k]
+        try:
+            if not proc.is_alive():
+                raise OSError
+            conn.send(msg)
+        except OSError:
+            proc.join(timeout=1)
+            code = proc.exitcode
+            self.close()
+            raise RuntimeError(f"worker {k} died (exit code {code}) before it could be given work") from None
 
     def _ensure_workers(self) -> None:
         if self._workers:
@@ -542,7 +575,7 @@ class ParallelCellSegmentationPipeline:
     def process_image(self, image: np.ndarray) -> Tuple[np.ndarray, List[np.ndarray], List[float]]:
         """pipeline.py:469-503: one RGB array through detector + SAM on the first replica -> (boxes, masks, scores)."""
         self._ensure_workers()
-        self._workers[0][1].send(("image", np.ascontiguousarray(image)))
+        self._send(0, ("image", np.ascontiguousarray(image)))
         boxes, masks = self._recv(0, "processing an image")
         return boxes, [m for m in masks], [1.0] * len(boxes)
 
@@ -554,7 +587,7 @@ class ParallelCellSegmentationPipeline:
         chunks = partition_contiguous(files, self.num_pipelines)
         self._ensure_workers()
         for k, chunk in enumerate(chunks):
-            self._workers[k][1].send(("files", chunk, str(output_dir), save_visualizations))
+            self._send(k, ("files", chunk, str(output_dir), save_visualizations))
         results: List[ProcessingResult] = []
         for k in range(len(chunks)):                   # chunk order == input order (pipeline.py:569-577)
             out = self._recv(k, "processing its chunk")

@@ -14,7 +14,6 @@ There is no CPU or PyTorch fallback: construction fails if the CUDA library or a
 from __future__ import annotations
 
 import ctypes as C
-from fractions import Fraction
 from math import sqrt
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -43,56 +42,84 @@ def _perimeter_from_bins(bins: np.ndarray) -> float:
     return float(hist @ _PERIM_W)          # the very reduction skimage performs
 
 
-def metrics_from_raw(raw: np.void, on_empty: str = "raise") -> Dict[str, Any]:
-    """ysi_mask_metrics row -> the dict of utils/metrics.py:102-119 (same keys, order and python types).
+_PERIM_W10 = np.array([_PERIM_W[c] for c in nat.PERIM_CODES], dtype=np.float64)
+_ZERO_ROW = {"deformability": 1.0, "area": 0, "area_ratio": 0.0, "circularity": 0.0, "convex_hull_area": 0,
+             "mask_x_length": 0, "mask_y_length": 0, "min_x": 0, "min_y": 0, "max_x": 0, "max_y": 0,
+             "mean_brightness": 0.0, "brightness_std": 0.0, "perimeter": 0.0, "aspect_ratio": 0.0,
+             "convex_hull_perimeter": 0.0}
+_PI = float(np.pi)
 
-    Every integer comes straight from the CUDA kernels; the float64 scalars are formed here with the
-    reference's own formulas (:62-100).  An empty mask raises IndexError like metrics.py:28 does
-    (``on_empty="raise"``, parity) or yields an all-zero row (``on_empty="zeros"``).
+
+def metrics_from_rows(rows: np.ndarray, on_empty: str = "raise") -> List[Dict[str, Any]]:
+    """ysi_mask_metrics rows -> the dicts of utils/metrics.py:102-119 (same keys, order and python types).
+
+    Every integer comes straight from the CUDA kernels; the float64 scalars are formed here with the reference's own
+    formulas (:62-100).  An empty mask raises IndexError like metrics.py:28 does (``on_empty="raise"``, parity) or yields an
+    all-zero row (``on_empty="zeros"``).  Works column-wise on the whole batch (one numpy -> python conversion per field);
+    the arithmetic per row is exactly the scalar one:
+      * perimeters: the 50-bin dot product skimage forms (``hist @ weights``, zero bins included) -- same call, same order
+      * mean / std of the centre disk: exact integer sums from the device, one correctly rounded division each (python's
+        int / int), which is what numpy's float64 mean / std agree with to 1e-9 (they sum pairwise)
     """
-    area = int(raw["area"])
-    if area == 0:
-        if on_empty == "raise":
-            raise IndexError("list index out of range")     # regionprops(mask)[0] on an empty mask
-        return {"deformability": 1.0, "area": 0, "area_ratio": 0.0, "circularity": 0.0, "convex_hull_area": 0,
-                "mask_x_length": 0, "mask_y_length": 0, "min_x": 0, "min_y": 0, "max_x": 0, "max_y": 0,
-                "mean_brightness": 0.0, "brightness_std": 0.0, "perimeter": 0.0, "aspect_ratio": 0.0,
-                "convex_hull_perimeter": 0.0}
-    degenerate = bool(int(raw["flags"]) & nat.FLAG_HULL_DEGENERATE)
-    perimeter = _perimeter_from_bins(raw["perim_hist"])                                   # :65
-    convex_hull_area = 0 if degenerate else int(raw["hull_area"])                           # :68
-    convex_hull_perimeter = 0 if degenerate else _perimeter_from_bins(raw["hull_perim_hist"])   # :69
-    area_ratio = convex_hull_area / area if area > 0 else 0                                 # :72
-    circularity = (2 * np.sqrt(np.pi * convex_hull_area)) / convex_hull_perimeter \
-        if convex_hull_perimeter > 0 else 0                                                 # :75
-    deformability = 1 - circularity                                                         # :78
-    n, s1, s2 = int(raw["disk_n"]), int(raw["disk_sum"]), int(raw["disk_sumsq"])
-    if n > 0:                                                                               # :92-94
-        mean_brightness = float(Fraction(s1, 3 * n))
-        brightness_std = sqrt(float(Fraction(n * s2 - s1 * s1, 9 * n * n)))
-    else:
-        mean_brightness = 0
-        brightness_std = 0
-    min_x, min_y, max_x, max_y = (int(raw["min_r"]), int(raw["min_c"]), int(raw["max_r"]), int(raw["max_c"]))  # :97
-    aspect_ratio = (max_x - min_x) / (max_y - min_y) if (max_x - min_x) > 0 and (max_y - min_y) > 0 else 0
-    return {
-        "deformability": float(deformability),
-        "area": int(area),
-        "area_ratio": float(area_ratio),
-        "circularity": float(circularity),
-        "convex_hull_area": int(convex_hull_area),
-        "mask_x_length": int(max_x - min_x),
-        "mask_y_length": int(max_y - min_y),
-        "min_x": int(min_x),
-        "min_y": int(min_y),
-        "max_x": int(max_x),
-        "max_y": int(max_y),
-        "mean_brightness": float(mean_brightness),
-        "brightness_std": float(brightness_std),
-        "perimeter": float(perimeter),
-        "aspect_ratio": float(aspect_ratio),
-        "convex_hull_perimeter": float(convex_hull_perimeter),
-    }
+    n = len(rows)
+    if n == 0:
+        return []
+    hist = np.zeros((n, 50), dtype=np.float64)
+    hist[:, list(nat.PERIM_CODES)] = rows["perim_hist"]
+    hull_hist = np.zeros((n, 50), dtype=np.float64)
+    hull_hist[:, list(nat.PERIM_CODES)] = rows["hull_perim_hist"]
+    area = rows["area"].tolist()
+    flags = rows["flags"].tolist()
+    hull_area = rows["hull_area"].tolist()
+    disk_n, disk_s1, disk_s2 = rows["disk_n"].tolist(), rows["disk_sum"].tolist(), rows["disk_sumsq"].tolist()
+    min_r, min_c, max_r, max_c = rows["min_r"].tolist(), rows["min_c"].tolist(), rows["max_r"].tolist(), rows["max_c"].tolist()
+    out: List[Dict[str, Any]] = []
+    for i in range(n):
+        a = area[i]
+        if a == 0:
+            if on_empty == "raise":
+                raise IndexError("list index out of range")     # regionprops(mask)[0] on an empty mask
+            out.append(dict(_ZERO_ROW))
+            continue
+        degenerate = bool(flags[i] & nat.FLAG_HULL_DEGENERATE)
+        perimeter = float(hist[i] @ _PERIM_W)                                            # :65
+        convex_hull_area = 0 if degenerate else hull_area[i]                              # :68
+        convex_hull_perimeter = 0.0 if degenerate else float(hull_hist[i] @ _PERIM_W)     # :69
+        area_ratio = convex_hull_area / a                                                 # :72
+        circularity = (2 * sqrt(_PI * convex_hull_area)) / convex_hull_perimeter if convex_hull_perimeter > 0 else 0.0   # :75
+        nn, s1, s2 = disk_n[i], disk_s1[i], disk_s2[i]
+        if nn > 0:                                                                        # :92-94
+            mean_brightness = s1 / (3 * nn)
+            brightness_std = sqrt((nn * s2 - s1 * s1) / (9 * nn * nn))
+        else:
+            mean_brightness = brightness_std = 0.0
+        dx, dy = max_r[i] - min_r[i], max_c[i] - min_c[i]                                 # :97-100 (rows are "x")
+        out.append({
+            "deformability": float(1 - circularity),                                      # :78
+            "area": a,
+            "area_ratio": float(area_ratio),
+            "circularity": float(circularity),
+            "convex_hull_area": convex_hull_area,
+            "mask_x_length": dx,
+            "mask_y_length": dy,
+            "min_x": min_r[i],
+            "min_y": min_c[i],
+            "max_x": max_r[i],
+            "max_y": max_c[i],
+            "mean_brightness": float(mean_brightness),
+            "brightness_std": float(brightness_std),
+            "perimeter": perimeter,
+            "aspect_ratio": float(dx / dy) if dx > 0 and dy > 0 else 0.0,
+            "convex_hull_perimeter": float(convex_hull_perimeter),
+        })
+    return out
+
+
+def metrics_from_raw(raw: np.void, on_empty: str = "raise") -> Dict[str, Any]:
+    """One ysi_mask_metrics row -> the dict of utils/metrics.py:102-119 (see ``metrics_from_rows``)."""
+    rows = np.zeros(1, dtype=nat.METRICS_DTYPE)
+    rows[0] = raw
+    return metrics_from_rows(rows, on_empty)[0]
 
 
 def box_crop(image: np.ndarray, box: np.ndarray) -> np.ndarray:
@@ -274,7 +301,7 @@ class SamStage:
         return dict(slot=slot, images=images, boxes=blist, counts=counts, masks=mbuf, rows=rows, mode=mode, hw=(H, W),
                     keep=(imgs, allb, ptrs, bt))
 
-    def _finish(self, rec, raw: bool, copy: bool, expanded_crops: bool):
+    def _finish(self, rec, raw: bool, copy: bool, expanded_crops: bool, want_crops: bool = True):
         tm = nat.YsiTiming()
         self._check(self._lib.ysi_wait_batch(self._ctx, rec["slot"], C.byref(tm)), "ysi_wait_batch")
         self.last_timing = tm.as_dict()
@@ -291,8 +318,8 @@ class SamStage:
                 if copy:
                     m = m.copy()
             r = rows[k:k + c].copy() if copy else rows[k:k + c]
-            mets = r if raw else [metrics_from_raw(r[j], self.on_empty) for j in range(c)]
-            crops = [box_crop(image, bx) for bx in rec["boxes"][i]]
+            mets = r if raw else metrics_from_rows(r, self.on_empty)
+            crops = [box_crop(image, bx) for bx in rec["boxes"][i]] if want_crops else None
             if expanded_crops:
                 out.append((m, mets, crops, [expanded_crop(image, r[j]) for j in range(c)]))
             else:
@@ -324,30 +351,31 @@ class SamStage:
 
     # ------------------------------------------------------------------ pipelined form
     def run_stream(self, batches, want_masks: bool = True, raw: bool = False, copy_masks: bool = True,
-                   masks: Optional[str] = "auto", expanded_crops: bool = False):
+                   masks: Optional[str] = "auto", expanded_crops: bool = False, crops: bool = True):
         """Generator over ``batches`` (an iterable of (images, boxes) with same-sized images per batch) that keeps two
         batches in flight: the H2D copy and the encoder of batch i+1 overlap the decoder, metrics and D2H copy of
         batch i (ysi_submit / ysi_wait_batch). Yields, per batch, what ``run_batch`` returns.
 
         ``copy_masks=False`` yields masks and raw rows as views into the slot's pinned host buffer instead of copies (at 32
         boxes per image the copies are 268 MB of host memcpy per batch and dominate); such a view is valid only until
-        the generator is advanced again (the slot's buffer is then handed to the next batch)."""
+        the generator is advanced again (the slot's buffer is then handed to the next batch). ``crops=False`` skips cutting
+        the box crops (the third element of every result is then None)."""
         mode = self._mask_mode(want_masks, masks)
         pending: List[Any] = []
         slot = 0
         for images, boxes in batches:
             if len(pending) == 2:
-                yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops)
+                yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops, crops)
             rec = self._submit(slot, images, boxes, mode, pinned=True)
             if rec is None:
                 while pending:
-                    yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops)
+                    yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops, crops)
                 yield self._empty_result(images, mode, expanded_crops)
                 continue
             pending.append(rec)
             slot ^= 1
         while pending:
-            yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops)
+            yield self._finish(pending.pop(0), raw, copy_masks, expanded_crops, crops)
 
     def _out_buffers(self, slot: int, nb: int, H: int, W: int, mode: Optional[str]):
         """Pinned host buffers for a slot's results (true copy/compute overlap needs page-locked memory); they grow when a
@@ -453,7 +481,7 @@ class SamStage:
         rows = np.zeros(m.shape[0], dtype=nat.METRICS_DTYPE)
         self._check(self._lib.ysi_metrics(self._ctx, nat.as_u8p(img), H, W, img.strides[0], nat.as_u8p(m), m.shape[0],
                                           rows.ctypes.data_as(C.c_void_p)), "ysi_metrics")
-        return rows if raw else [metrics_from_raw(rows[j], self.on_empty) for j in range(len(rows))]
+        return rows if raw else metrics_from_rows(rows, self.on_empty)
 
     def gemm(self, A: np.ndarray, W: np.ndarray, bias: Optional[np.ndarray] = None, act: int = 0) -> np.ndarray:
         A = np.ascontiguousarray(A, np.float32)
