@@ -74,4 +74,8 @@ def build(force: bool = False, verbose: bool = False, precision: str = "all") ->
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    prec = "all"
+    for a in sys.argv[1:]:
+        if a.startswith("--precision="):
+            prec = a.split("=", 1)[1]
+    print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, precision=prec))

@@ -50,6 +50,15 @@ constexpr int BQ = 128, BKV = 64;
 // builds (scripts/gpu_ab_split.sh): global layers equal (2.92 ms per 8-image step), windowed 1.05 vs 1.19 ms,
 // head_dim 80 windowed 5.7 vs 6.9 ms -- the per-tile fixed costs are paid by half as many warps.
 constexpr int SPLIT = YSI_ATTN_SPLIT;
+static_assert(SPLIT == 1, "the two-threads-per-row variant (round 1, measured slower) was removed with the round-2 softmax pipeline");
+// every POLY_EVERY-th pair of exponentials is evaluated with ex2_poly2 on the FMA pipe instead of MUFU.EX2 (0: none)
+#ifndef YSI_ATTN_POLY_EVERY
+#define YSI_ATTN_POLY_EVERY 4
+#endif
+constexpr int POLY_EVERY = YSI_ATTN_POLY_EVERY;
+#ifndef YSI_ATTN_PSEP
+#define YSI_ATTN_PSEP 1
+#endif
 constexpr int TW = BKV / SPLIT;              // key columns of a tile owned by one thread
 constexpr int SM_WARPS = 4 * SPLIT;          // softmax warps
 constexpr int THREADS = 32 * (SM_WARPS + 4); // + one producer warpgroup: TMA warp, S-MMA warp, PV-MMA warp, and a register donor
@@ -115,6 +124,12 @@ struct Cfg {
   static constexpr int S_N = (GLOBAL || W3) ? 80 : 64;      // columns of one S buffer
   static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
   static constexpr int COL_O = 2 * S_N;
+  // Global layers at head_dim 64 have 32 tensor-memory columns to spare (2 x 80 + 64 = 224 of 256): P gets its own columns
+  // instead of overwriting the S buffer it came from. S_{j+2} then only has to wait until the softmax warps have READ S_j
+  // (bar_s_free, early in tile j) instead of until P.V_j has completed, which takes the tensor-pipe round trip
+  // (p_full -> P.V_j -> commit -> S_{j+2} -> commit) and the slowest warp of the CTA out of the per-tile critical path.
+  static constexpr bool PSEP = GLOBAL && HD == 64 && (YSI_ATTN_PSEP != 0);
+  static constexpr int COL_P = COL_O + HD;                  // PSEP only: one P buffer (32 columns = 64 keys)
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
   static constexpr int CTAS_PER_SM = 2;
@@ -125,7 +140,7 @@ struct Cfg {
   static_assert(!ALIAS_V || V_TOTAL + V1_TOTAL >= (GLOBAL ? SCRATCH : 2 * 28 * 128 * 4), "the bias scratch aliases the V area");
   static_assert(2 * (OFF_BAR + 512 + 2048 + 1024 + 1024 + 1024) <= 232448, "two CTAs per SM");
   static_assert(NSTK <= 8 && NSTV <= 8, "barrier arrays");
-  static_assert(COL_O + HD <= TMEM_COLS, "TMEM budget");
+  static_assert(COL_O + HD + (PSEP ? 32 : 0) <= TMEM_COLS, "TMEM budget");
 };
 }  // namespace attn
 
@@ -170,6 +185,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t bar_vempty = bar + 264;   // [8]
   const uint32_t bar_fin = bar + 328;      // [4 row quarters]: the two warps sharing 32 rows exchange their row sums
   const uint32_t tmem_ptr_smem = bar + 360;
+  const uint32_t bar_s_free = bar + 376;   // [2] PSEP: every softmax warp has S buffer j & 1 in registers
   float* xm = reinterpret_cast<float*>(sgen + C::OFF_XM);
   float* xl = reinterpret_cast<float*>(sgen + C::OFF_XL);
 
@@ -196,6 +212,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_init(bar_vfull + 8 * i, 1); mbar_init(bar_vempty + 8 * i, 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 2);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_s_free + 8 * i, SM_WARPS);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 512; i += THREADS) reinterpret_cast<uint32_t*>(xm)[i] = 0xFFFFFFFFu;   // tag 0xFF: nothing published yet
@@ -313,7 +330,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(bar_kfull + 8 * st, ph);
         if (C::W3 && t == 2) mbar_wait(bar_kfull + 8 * 3, 0);      // the last window tile spans K tiles 2 and 3
         ATTN_TRACE(9, t, 0);
-        if (t >= 2) mbar_wait(bar_p_free + 8 * buf, ((t >> 1) - 1) & 1);     // P.V_{t-2} done: S / P buffer t & 1 is free
+        if (t >= 2) {
+          if (C::PSEP) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);   // S_{t-2} has been read out of buffer t & 1
+          else mbar_wait(bar_p_free + 8 * buf, ((t >> 1) - 1) & 1);           // P.V_{t-2} done: S / P buffer t & 1 is free
+        }
         ATTN_TRACE(9, t, 1);
         tc_fence_after();
         const uint32_t idesc = (!GLOBAL && t == 3) ? idesc_s16 : ((C::W3 && t == 2) ? idesc_s80 : idesc_s);
@@ -345,7 +365,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
         ATTN_TRACE(10, j, 1);
         tc_fence_after();
-        const uint32_t ptm = tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
+        const uint32_t ptm = C::PSEP ? tmem_base + C::COL_P : tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
         if (lead) {
           const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st), 1024, 1024);
           if (GLOBAL || j < 3) {
@@ -435,10 +455,24 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (lane == 0) mbar_arrive(bar_rel);
 
     bool s_ready = false;                            // S of the next tile already seen complete (probed a tile early)
+    bool p_pending = false;                          // P of the previous tile is stored (tcgen05.st issued) but not yet handed to the PV warp
+    uint32_t p_pending_bar = 0;
     float m_used = -INFINITY;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
     constexpr int OH = HD / SPLIT;                   // O columns owned by this thread
     const uint32_t ocol = tlane + C::COL_O + static_cast<uint32_t>(half * OH);
+
+    // hand P of the previous tile to the P.V warp: its tcgen05.st was issued at the end of that tile and has had the whole
+    // S load / bias / max phase of the current tile to complete, so this wait is (almost) free
+    auto finalize_p = [&]() {
+      if (p_pending) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_pending_bar);
+        p_pending = false;
+      }
+    };
 
     // one KV tile: this thread owns NW columns of S starting at column c0 (NW = 0: nothing, only the barriers),
     // the first NV of them valid keys; bfn(i) = bias of column i (log2 units; i is a compile-time constant after unrolling)
@@ -469,9 +503,14 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           tmem_ld_wait();
         }
       }
+      if (C::PSEP) {               // S_j is in registers: the S warp may overwrite this buffer with S_{j+2}
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s_free + 8 * pb);
+      }
       ATTN_TRACE(warp, j, 2);
       float2 y[NR / 2];
-      float m_half = -INFINITY;
+      float m_tile = -INFINITY;
       if (act) {
 #pragma unroll
         for (int i = 0; i < NW / 2; ++i)
@@ -479,44 +518,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < NV / 2; ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
-        m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
+        m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
       }
-      // publish this half-row maximum; the partner's is read after the (speculative) exponentials. One 32-bit word
-      // carries value and flag: the low mantissa byte is replaced by the tile index (both threads then use the same
-      // truncated values, so they take identical decisions) -- no barrier round trip on the per-tile path.
-      const uint32_t tag = static_cast<uint32_t>(j);
-      const uint32_t mine = (__float_as_uint(m_half) & 0xFFFFFF00u) | tag;
-      const uint32_t xaddr = smem_u32(xm) + static_cast<uint32_t>(((pb * 128 + t) * 2) * 4);
-      if (SPLIT == 2) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(xaddr + 4u * half), "r"(mine) : "memory");
-      uint32_t pk[NR / 2];
-      float2 ta, tb;
-      auto exps = [&](float c) {
-        const float2 c2 = make_float2(c, c);
-        ta = make_float2(0.f, 0.f); tb = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < NW / 2; ++i) {
-          float2 e = add2(y[i], c2);
-          e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
-          e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
-          if (i & 1) tb = add2(tb, e); else ta = add2(ta, e);
-          pk[i] = pack_op16x2(e.x, e.y);
-        }
-      };
-      if (act && j > 0) exps(bh - m_used);
+      finalize_p();
       ATTN_TRACE(warp, j, 3);
-      uint32_t theirs = mine;
-      if (SPLIT == 2) {
-        do {
-          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(theirs) : "r"(xaddr + 4u * (half ^ 1)) : "memory");
-        } while ((theirs & 0xFFu) != tag);
-      }
-      ATTN_TRACE(warp, j, 4);
-      const float m_cand = fmaxf(__uint_as_float(mine & 0xFFFFFF00u), __uint_as_float(theirs & 0xFFFFFF00u));
-      // identical in both warps of the pair: they see the same 32 pairs of half-row maxima
-      if (__any_sync(0xFFFFFFFFu, m_cand > m_used + LAZY_LOG2)) {
-        const float m_new = fmaxf(m_used, m_cand);
+      // Lazy rescale: the reference maximum m_used only moves when a row's maximum has grown by more than 2^8 (P stays
+      // below 2^8 in the 16-bit operand). Decided BEFORE the exponentials, which are therefore computed exactly once.
+      if (__any_sync(0xFFFFFFFFu, m_tile > m_used + LAZY_LOG2)) {
+        const float m_new = fmaxf(m_used, m_tile);
         if (j > 0) {
-          // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed, PV_j has not been issued
+          // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed (its P was handed over just above by
+          // every warp before its own check), PV_j has not been issued
           const float f = ex2_approx(m_used - m_new);
           mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
@@ -533,28 +545,46 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
         }
         m_used = m_new;
-        if (act) exps(bh - m_used);
       }
-      // P_j goes into the first 32 columns of S buffer pb. They are free: S_j (this buffer) was only issued after
-      // P.V_{j-2} had completed, this thread has its own S columns in registers, and the partner (whose S columns the
-      // second half of the pair overwrites) published its maximum -- i.e. finished its TMEM load -- before the pair
-      // exchange above completed. No wait on the tensor pipe in steady state.
+      ATTN_TRACE(warp, j, 4);
+      uint32_t pk[NR / 2];
+      if (act) {
+        const float c = bh - m_used;
+        const float2 c2 = make_float2(c, c);
+        float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NW / 2; ++i) {
+          float2 e = add2(y[i], c2);
+          // a fixed share of the pairs takes the polynomial on the FMA pipe instead of the MUFU (the kernel's bound)
+          if (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1) && 2 * i + 1 < NV) e = ex2_poly2(e);
+          else {
+            e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
+            e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
+          }
+          if (i & 1) tb = add2(tb, e); else ta = add2(ta, e);
+          pk[i] = pack_op16x2(e.x, e.y);
+        }
+        l2a = add2(l2a, ta); l2b = add2(l2b, tb);
+      }
+      // P_j goes into the first columns of S buffer pb. They are free: S_j (this buffer) was only issued after P.V_{j-2}
+      // had completed and this thread has its own S columns in registers. No wait on the tensor pipe in steady state.
       ATTN_TRACE(warp, j, 5);
       // probe the next tile's S now: the barrier unit's round trip overlaps the P store below
       s_ready = mbar_test_wait(bar_s_full + 8 * (pb ^ 1), static_cast<uint32_t>(((j + 1) >> 1) & 1));
+      if (C::PSEP && j > 0) {      // the single P buffer is free once P.V_{j-1} has completed (normally long ago)
+        mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+      }
       if (act) {
-        l2a = add2(l2a, ta); l2b = add2(l2b, tb);
         tc_fence_after();
-        const uint32_t pcol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
+        const uint32_t pcol = C::PSEP ? tlane + C::COL_P : tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
         if constexpr (NW == 80) { tmem_st_x32p(pcol, pk); tmem_st_x8p(pcol + 32, pk + 32); }
         else if constexpr (NW == 64) tmem_st_x32p(pcol, pk);
         else if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
         else if constexpr (NW == 16) tmem_st_x8p(pcol, pk);
-        tmem_st_wait();
-        tc_fence_before();
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full + 8 * pb);
+      // the hand-over (tcgen05.wait::st, fence, arrive on p_full) is deferred to the next tile, after its S load
+      p_pending = true;
+      p_pending_bar = bar_p_full + 8 * pb;
       ATTN_TRACE(warp, j, 6);
     };
 
@@ -587,6 +617,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       if (half == 0) window_tiles(std::integral_constant<int, 0>{}); else window_tiles(std::integral_constant<int, 1>{});
     }
+    finalize_p();
     // row sum = both halves
     xl[t * 2 + half] = (l2a.x + l2a.y) + (l2b.x + l2b.y);
     if (SPLIT == 1) xl[t * 2 + 1] = 0.f;

@@ -373,6 +373,40 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+__device__ __forceinline__ float2 fma2_(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// 2^x for a pair of values on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-5 polynomial (max relative error 3e-7, fitted on Chebyshev nodes), 2^n by adding n to the exponent
+// field. x is clamped below at -125 (the result is then < 2^-124: zero for every purpose of the softmax); callers
+// guarantee x <= 2^7. Used for a fixed share of the softmax exponentials, whose MUFU.EX2 rate (16 / clk / SM on B200)
+// otherwise bounds the attention kernel.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);          // 1.5 * 2^23: the add rounds x to an integer
+  const float2 t = add2(x, magic);
+  const float2 n = add2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = add2(x, make_float2(-n.x, -n.y));
+  float2 p = fma2_(f, make_float2(0.0013390867f, 0.0013390867f), make_float2(0.0096663737f, 0.0096663737f));
+  p = fma2_(p, f, make_float2(0.055503571f, 0.055503571f));
+  p = fma2_(p, f, make_float2(0.24022349f, 0.24022349f));
+  p = fma2_(p, f, make_float2(0.69314719f, 0.69314719f));
+  p = fma2_(p, f, make_float2(1.0f, 1.0f));
+  float2 r;
+  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));    // low mantissa bits of t = n (two's complement)
+  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+  return r;
+}
 // one packed pair of 16-bit operands -> two fp32
 __device__ __forceinline__ float2 unpack_op16x2(uint32_t u) {
 #ifdef YSI_OP_FP16
