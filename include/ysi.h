@@ -202,6 +202,9 @@ YSI_API int ysi_gemm_ex(ysi_ctx* ctx, const float* A, const float* W, const floa
  * mode 0 bf16-output epilogue, 1 fp32 red-add epilogue, 2 drain-only (mainloop speed); pair != 0: CTA-pair kernel. */
 YSI_API int ysi_gemm_bench(ysi_ctx* ctx, int M, int N, int K, int pair, int mode, int iters, float* ms_per_iter);
 
+/* measurement support: ms per launch of one attention shape on device-resident random operands */
+YSI_API int ysi_attention_bench(ysi_ctx* ctx, int n_seq, int heads, int head_dim, int is_global, int iters, float* ms_per_iter);
+
 /* image-wide positional embedding fp32 [256,64,64] (modeling_sam.py:1128-1139), computed at weight load */
 YSI_API int ysi_get_image_pe(ysi_ctx* ctx, float* out);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */

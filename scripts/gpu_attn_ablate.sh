@@ -1,6 +1,7 @@
 #!/bin/bash
-for d in 0 1 2 4 8 3 7 15; do
-  YSI_ATTN_DBG=$d timeout 100 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/abl_$d.json 2>/dev/null
-  python -c "
-import json;d=json.load(open('gpurun_out/abl_$d.json'));b=d['breakdown'];print('dbg $d', round(b['attn_global']['ms_per_step'],3), round(b['attn_window']['ms_per_step'],3))"
+# timing-only ablations of the attention softmax loop (WRONG results by construction): which instruction group bounds it?
+mkdir -p gpurun_out
+for V in ${1:-0 1 2 4 8 16 3 27}; do
+  YSI_NVCC_DEFINES="-DYSI_ATTN_ABLATE=$V ${EXTRA_DEFINES}" python -m yolo_sam_inference_b200.build --force --quiet --precision=fp16 > gpurun_out/abl_build_$V.log 2>&1 || { echo "build $V failed"; tail -3 gpurun_out/abl_build_$V.log; continue; }
+  timeout 120 python scripts/attn_micro.py "ablate=$V ${EXTRA_DEFINES}" 2>&1 | tail -1
 done

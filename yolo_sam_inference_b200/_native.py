@@ -101,6 +101,7 @@ EXPORTS = {
     "ysi_attention": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "ysi_gemm_ex": (C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "ysi_gemm_bench": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "ysi_attention_bench": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ysi_get_image_pe": (C.c_int, [_ctx, _f32p]),
     "ysi_launch_count": (C.c_int64, [_ctx]),
 }

@@ -427,7 +427,14 @@ void create_impl(ysi_ctx* c) {
     for (auto& e : sl.t) YSI_CUDA(cudaEventCreate(&e));
   }
   for (auto& e : c->ring_ev) YSI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  YSI_CUDA(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+  {
+    // decoder / metrics stream: its many small kernels run beside the next batch's encoder. Tuning knob YSI_AUX_PRIORITY
+    // (1: highest stream priority, -1: lowest, 0: default).
+    int lo = 0, hi = 0, want = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (const char* e = getenv("YSI_AUX_PRIORITY")) want = atoi(e);
+    YSI_CUDA(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, want > 0 ? hi : (want < 0 ? lo : 0)));
+  }
   YSI_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   YSI_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   ensure_image_capacity(c, cfg.max_image_h, cfg.max_image_w);
@@ -665,8 +672,9 @@ void submit_impl(ysi_ctx* c, int slot, const BatchIn& in) {
       for (int j = 0; j < in.counts[i]; ++j) img_of[k++] = i;
   }
   const bool want_bytes = in.masks_out != nullptr;
+  static const bool skip_decoder = getenv("YSI_DEV_SKIP_DECODER") != nullptr;      // timing experiments only (no results)
   for (int k0 = 0; k0 < nb || k0 == 0; k0 += maxb) {
-    const int kc = nb - k0 < maxb ? nb - k0 : maxb;
+    const int kc = skip_decoder ? 0 : (nb - k0 < maxb ? nb - k0 : maxb);
     YSI_CUDA(cudaStreamWaitEvent(sd, sl.ev_d2h, 0));      // d_masks / d_packed / d_metrics were last read by the previous D2H
     if (kc > 0) {
       const int rs = c->ring_pos;
@@ -1161,6 +1169,34 @@ int ysi_attention(ysi_ctx* c, const float* qkv, const float* rel_h, const float*
     YSI_CUDA(cudaMemcpyAsync(o.data(), dout, o.size() * 2, cudaMemcpyDeviceToHost, c->stream));
     YSI_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < o.size(); ++i) out[i] = op2f(o[i]);
+    cudaFree(dq); cudaFree(dt); cudaFree(dout);
+  });
+}
+
+// measurement support: time `iters` launches of one attention shape on device-resident random operands
+int ysi_attention_bench(ysi_ctx* c, int n_seq, int heads, int head_dim, int is_global, int iters, float* ms_per_iter) {
+  return guarded(c, [&] {
+    YSI_CHECK(head_dim == 64 || head_dim == 80, "head_dim must be 64 or 80");
+    const int T = is_global ? 4096 : 196, D = heads * head_dim, hdp = attn_table_cols(head_dim);
+    const size_t rows = static_cast<size_t>(n_seq) * T;
+    std::vector<op16> q(rows * 3 * D), tab(256 * hdp);
+    uint32_t st = 12345u;
+    auto rnd = [&] { st = st * 1664525u + 1013904223u; return (static_cast<float>(st >> 8) / 8388608.0f - 1.0f); };
+    for (auto& v : q) v = f2op(1.7f * rnd());
+    for (auto& v : tab) v = f2op(0.15f * rnd());
+    op16 *dq = nullptr, *dt = nullptr, *dout = nullptr;
+    YSI_CUDA(cudaMalloc(&dq, q.size() * 2)); YSI_CUDA(cudaMalloc(&dt, tab.size() * 2)); YSI_CUDA(cudaMalloc(&dout, rows * D * 2));
+    YSI_CUDA(cudaMemcpy(dq, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
+    YSI_CUDA(cudaMemcpy(dt, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 3; ++i) launch_encoder_attention(dq, dt, dout, n_seq, T, heads, head_dim, is_global != 0, false, c->stream);
+    YSI_CUDA(cudaEventRecord(c->timers[6], c->stream));
+    for (int i = 0; i < iters; ++i) launch_encoder_attention(dq, dt, dout, n_seq, T, heads, head_dim, is_global != 0, false, c->stream);
+    YSI_CUDA(cudaEventRecord(c->timers[7], c->stream));
+    YSI_CUDA(cudaEventSynchronize(c->timers[7]));
+    float ms = 0.f;
+    YSI_CUDA(cudaEventElapsedTime(&ms, c->timers[6], c->timers[7]));
+    *ms_per_iter = ms / iters;
+    c->launches += iters + 3;
     cudaFree(dq); cudaFree(dt); cudaFree(dout);
   });
 }

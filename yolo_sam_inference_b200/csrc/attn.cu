@@ -59,6 +59,20 @@ constexpr int POLY_EVERY = YSI_ATTN_POLY_EVERY;
 #ifndef YSI_ATTN_PSEP
 #define YSI_ATTN_PSEP 1
 #endif
+// timing-only ablation builds (WRONG results; scripts/gpu_attn_ablate.sh): 1 no bias add, 2 no row sums, 4 no row max,
+// 8 no exponentials, 16 no 16-bit packing
+#ifndef YSI_ATTN_ABLATE
+#define YSI_ATTN_ABLATE 0
+#endif
+constexpr int ABL = YSI_ATTN_ABLATE;
+// fetch the next S tile from tensor memory under the exponentials of the current one (global layers with PSEP)
+// Measured (round 2, profiles/r02_attention_experiments.txt): 704 vs 657 us per ViT-B batch-8 global layer -- slower; the
+// skeleton of the tile loop (tensor-memory round trips between the softmax warps and the two MMA warps), not the
+// exponentials, bounds the kernel, and splitting the S load lengthens it. Kept as a build option, off by default.
+#ifndef YSI_ATTN_PREFETCH
+#define YSI_ATTN_PREFETCH 0
+#endif
+constexpr bool PREFETCH = YSI_ATTN_PREFETCH != 0;
 constexpr int TW = BKV / SPLIT;              // key columns of a tile owned by one thread
 constexpr int SM_WARPS = 4 * SPLIT;          // softmax warps
 constexpr int THREADS = 32 * (SM_WARPS + 4); // + one producer warpgroup: TMA warp, S-MMA warp, PV-MMA warp, and a register donor
@@ -514,10 +528,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (act) {
 #pragma unroll
         for (int i = 0; i < NW / 2; ++i)
-          y[i] = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bfn(2 * i), bfn(2 * i + 1)));
+          y[i] = (ABL & 1) ? make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]))
+                           : add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bfn(2 * i), bfn(2 * i + 1)));
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < NV / 2; ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
+        for (int i = 0; i < ((ABL & 4) ? 1 : NV / 2); ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
         m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
       }
       finalize_p();
@@ -556,13 +571,14 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int i = 0; i < NW / 2; ++i) {
           float2 e = add2(y[i], c2);
           // a fixed share of the pairs takes the polynomial on the FMA pipe instead of the MUFU (the kernel's bound)
-          if (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1) && 2 * i + 1 < NV) e = ex2_poly2(e);
+          if (ABL & 8) { }
+          else if (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1) && 2 * i + 1 < NV) e = ex2_poly2(e);
           else {
             e.x = (2 * i < NV) ? ex2_approx(e.x) : 0.f;
             e.y = (2 * i + 1 < NV) ? ex2_approx(e.y) : 0.f;
           }
-          if (i & 1) tb = add2(tb, e); else ta = add2(ta, e);
-          pk[i] = pack_op16x2(e.x, e.y);
+          if (!(ABL & 2)) { if (i & 1) tb = add2(tb, e); else ta = add2(ta, e); }
+          pk[i] = (ABL & 16) ? __float_as_uint(e.x) : pack_op16x2(e.x, e.y);
         }
         l2a = add2(l2a, ta); l2b = add2(l2b, tb);
       }
@@ -593,7 +609,90 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     using I16 = std::integral_constant<int, 16>;
     using I4 = std::integral_constant<int, 4>;
     using I0 = std::integral_constant<int, 0>;
-    if (GLOBAL) {
+    if constexpr (C::PSEP && PREFETCH) {
+      // Global layers, head_dim 64: the S tile of step j + 1 is fetched from tensor memory WHILE the exponentials of step j
+      // run. The kernel's skeleton is bound by the tensor-memory read port (128 x 65 fp32 per tile and CTA at 64 B / clk / SM
+      // -- as long as the MUFU work of the same tile), so the two must overlap instead of alternating. S_{j+1} is
+      // available that early because P has its own columns (PSEP): the S warp only waits for bar_s_free.
+      // One register set r[64]: its first half is dead as soon as the first 32 scores have been biased, and is refilled with
+      // the first half of S_{j+1} at the start of the exponentials; the second half of S_j is fetched at the start of tile j
+      // and lands under the bias / max work of the first half.
+      uint32_t r[64], bh_bits = 0;
+      auto fetch_lo = [&](int jj) {
+        mbar_wait(bar_s_full + 8 * (jj & 1), static_cast<uint32_t>((jj >> 1) & 1));
+        tc_fence_after();
+        tmem_ld_x32p(tlane + C::COL_S + static_cast<uint32_t>((jj & 1) * C::S_N), r);
+      };
+      fetch_lo(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int pb = j & 1;
+        const uint32_t scol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N);
+        tmem_ld_wait();                                   // first half of S_j (fetched during tile j - 1)
+        tmem_ld_x32p(scol + 32, r + 32);
+        tmem_ld_x1(scol + 64u + static_cast<uint32_t>(rq >> 1), bh_bits);      // q . rel_pos_h[qh - j + 63]
+        float2 y[32];
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          y[i] = (ABL & 1) ? make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]))
+                           : add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bias[2 * i], bias[2 * i + 1]));
+          if (!(ABL & 4) || i == 0) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
+        }
+        tmem_ld_wait();                                   // second half + the rel_pos_h term
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s_free + 8 * pb);  // S_j is in registers: the S warp may overwrite this buffer with S_{j+2}
+        const float bh = __uint_as_float(bh_bits);
+#pragma unroll
+        for (int i = 16; i < 32; ++i) {
+          y[i] = (ABL & 1) ? make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]))
+                           : add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bias[2 * i], bias[2 * i + 1]));
+          if (!(ABL & 4)) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
+        }
+        const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
+        finalize_p();
+        if (__any_sync(0xFFFFFFFFu, m_tile > m_used + LAZY_LOG2)) {          // lazy rescale, see do_tile
+          const float m_new = fmaxf(m_used, m_tile);
+          if (j > 0) {
+            const float f = ex2_approx(m_used - m_new);
+            mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int qr = 0; qr < OH / 8; ++qr) {
+              uint32_t o[8];
+              tmem_ld_x8p(ocol + 8 * qr, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_x8p(ocol + 8 * qr, o);
+            }
+            tmem_st_wait();
+            l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
+          }
+          m_used = m_new;
+        }
+        if (j + 1 < ntiles) fetch_lo(j + 1);              // lands under the exponentials below
+        const float c = bh - m_used;
+        const float2 c2 = make_float2(c, c);
+        float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float2 e = add2(y[i], c2);
+          if (ABL & 8) { }
+          else if (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1)) e = ex2_poly2(e);
+          else { e.x = ex2_approx(e.x); e.y = ex2_approx(e.y); }
+          if (!(ABL & 2)) { if (i & 1) tb = add2(tb, e); else ta = add2(ta, e); }
+          pk[i] = (ABL & 16) ? __float_as_uint(e.x) : pack_op16x2(e.x, e.y);
+        }
+        l2a = add2(l2a, ta); l2b = add2(l2b, tb);
+        if (j > 0) mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);    // the single P buffer is free again
+        tc_fence_after();
+        tmem_st_x32p(tlane + C::COL_P, pk);
+        p_pending = true;
+        p_pending_bar = bar_p_full + 8 * pb;
+      }
+    } else if (GLOBAL) {
       for (int j = 0; j < ntiles; ++j) do_tile(ITW{}, ITW{}, j, [&](int i) { return bias[i]; }, TW * half);
     } else {
       // key k = 64 j + 32 half + i of the window: kh = k / 14, kw = k % 14 (compile-time after unrolling)

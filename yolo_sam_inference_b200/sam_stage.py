@@ -522,6 +522,13 @@ class SamStage:
         self._check(self._lib.ysi_gemm_bench(self._ctx, M, N, K, int(pair), mode, iters, C.byref(ms)), "ysi_gemm_bench")
         return float(ms.value)
 
+    def attention_bench(self, n_seq: int, heads: int, head_dim: int, is_global: bool, iters: int = 20) -> float:
+        """ms per launch of one attention shape on device-resident operands (measurement support)."""
+        ms = C.c_float(0)
+        self._check(self._lib.ysi_attention_bench(self._ctx, n_seq, heads, head_dim, int(is_global), iters, C.byref(ms)),
+                    "ysi_attention_bench")
+        return float(ms.value)
+
     def image_pe(self) -> np.ndarray:
         out = np.empty((256, 64, 64), np.float32)
         self._check(self._lib.ysi_get_image_pe(self._ctx, nat.as_f32p(out)), "ysi_get_image_pe")
