@@ -60,7 +60,7 @@ constexpr int POLY_EVERY = YSI_ATTN_POLY_EVERY;
 #define YSI_ATTN_PSEP 1
 #endif
 // timing-only ablation builds (WRONG results; scripts/gpu_attn_ablate.sh): 1 no bias add, 2 no row sums, 4 no row max,
-// 8 no exponentials, 16 no 16-bit packing
+// 8 no exponentials, 16 no 16-bit packing, 32 no S load from tensor memory, 64 no P store, 128 no P.V MMAs, 256 no S MMAs
 #ifndef YSI_ATTN_ABLATE
 #define YSI_ATTN_ABLATE 0
 #endif
@@ -73,6 +73,16 @@ constexpr int ABL = YSI_ATTN_ABLATE;
 #define YSI_ATTN_PREFETCH 0
 #endif
 constexpr bool PREFETCH = YSI_ATTN_PREFETCH != 0;
+// Global layers, head_dim 64: softmax steps of 128 keys (two key rows of the 64 x 64 grid) on a single S buffer of 144
+// columns instead of 64-key tiles on two buffers of 80. The per-step latencies that bound the 64-key loop (tensor-pipe and
+// barrier round trips, tensor-memory load / store latencies: profiles/r02_attention_experiments.txt) are paid half as
+// often; the two CTAs of an SM alternate between their MMA and their softmax phases.
+// Measured (round 2, same file): correct (attention / ViT-B parity / reproducibility tests green) but SLOWER, 2.92 vs 2.45 ms
+// per ViT-B batch-8 step: with a single S buffer a CTA's softmax and its MMAs no longer overlap, so each SM sub-partition
+// has one runnable softmax warp at a time and nothing hides its tensor-memory and MUFU latencies. Build option, off by default.
+#ifndef YSI_ATTN_BIG
+#define YSI_ATTN_BIG 0
+#endif
 constexpr int TW = BKV / SPLIT;              // key columns of a tile owned by one thread
 constexpr int SM_WARPS = 4 * SPLIT;          // softmax warps
 constexpr int THREADS = 32 * (SM_WARPS + 4); // + one producer warpgroup: TMA warp, S-MMA warp, PV-MMA warp, and a register donor
@@ -94,15 +104,17 @@ struct Cfg {
   static constexpr int NKS = HD / 16;                               // k-steps of Q K^T and of the table MMAs
   // K / V ring depths (window: whole window resident). A K tile is requested well before the S MMA that consumes it
   // and a V tile NSTV - 1 tiles ahead: one tile of lead time (~1 us) does not cover the L2 round trip of the TMA.
-  static constexpr int NSTK = GLOBAL ? (HAS1 ? 3 : 5) : 4;
-  static constexpr int NSTV = 4;
+  static constexpr bool BIG = GLOBAL && HD == 64 && (YSI_ATTN_BIG != 0);
+  static constexpr int STEP = BIG ? 128 : BKV;                      // keys per softmax step
+  static constexpr int NSTK = BIG ? 3 : (GLOBAL ? (HAS1 ? 3 : 5) : 4);
+  static constexpr int NSTV = BIG ? 2 : 4;
   // chunk 0: columns 0..63 (128-byte rows, SWIZZLE_128B); chunk 1 (HAS1): columns 64..79 (32-byte rows, SWIZZLE_32B)
   static constexpr int Q1_BYTES = HAS1 ? BQ * 32 : 0;
-  static constexpr int K_CHUNK = GLOBAL ? 80 * 128 : 208 * 128;     // global: 64 keys + 16 rows for the rel_pos_h "keys"
+  static constexpr int K_CHUNK = BIG ? 144 * 128 : (GLOBAL ? 80 * 128 : 208 * 128);     // global: keys + 16 rows for the rel_pos_h "keys"
   static constexpr int K1_CHUNK = HAS1 ? K_CHUNK / 4 : 0;
   static constexpr int K_TOTAL = GLOBAL ? NSTK * K_CHUNK : K_CHUNK; // window: tiles 8 KB (chunk 1: 2 KB) apart
   static constexpr int K1_TOTAL = ((GLOBAL ? NSTK * K1_CHUNK : K1_CHUNK) + 1023) / 1024 * 1024;
-  static constexpr int V_CHUNK = GLOBAL ? KV_BYTES : 208 * 128;
+  static constexpr int V_CHUNK = BIG ? 2 * KV_BYTES : (GLOBAL ? KV_BYTES : 208 * 128);
   static constexpr int V1_CHUNK = HAS1 ? V_CHUNK / 4 : 0;
   static constexpr int V_TOTAL = GLOBAL ? NSTV * V_CHUNK : V_CHUNK;
   static constexpr int V1_TOTAL = ((GLOBAL ? NSTV * V1_CHUNK : V1_CHUNK) + 1023) / 1024 * 1024;
@@ -135,14 +147,14 @@ struct Cfg {
   // windowed, one thread per row: the window's 196 keys are three tiles (64, 64, 68 of 80 columns) instead of four
   // (64, 64, 64, 4 of 16): one pass through the per-tile fixed costs less
   static constexpr bool W3 = !GLOBAL && SPLIT == 1;
-  static constexpr int S_N = (GLOBAL || W3) ? 80 : 64;      // columns of one S buffer
-  static constexpr int COL_S = 0;                           // two S buffers (alias the setup tables)
-  static constexpr int COL_O = 2 * S_N;
+  static constexpr int S_N = BIG ? 144 : ((GLOBAL || W3) ? 80 : 64);      // columns of one S buffer
+  static constexpr int COL_S = 0;                           // two S buffers -- one with BIG -- (alias the setup tables)
+  static constexpr int COL_O = BIG ? S_N : 2 * S_N;
   // Global layers at head_dim 64 have 32 tensor-memory columns to spare (2 x 80 + 64 = 224 of 256): P gets its own columns
   // instead of overwriting the S buffer it came from. S_{j+2} then only has to wait until the softmax warps have READ S_j
   // (bar_s_free, early in tile j) instead of until P.V_j has completed, which takes the tensor-pipe round trip
   // (p_full -> P.V_j -> commit -> S_{j+2} -> commit) and the slowest warp of the CTA out of the per-tile critical path.
-  static constexpr bool PSEP = GLOBAL && HD == 64 && (YSI_ATTN_PSEP != 0);
+  static constexpr bool PSEP = GLOBAL && HD == 64 && (YSI_ATTN_PSEP != 0) && !BIG;
   static constexpr int COL_P = COL_O + HD;                  // PSEP only: one P buffer (32 columns = 64 keys)
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
@@ -206,7 +218,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int row0 = seq * p.T;                 // first row of this sequence in the qkv matrix
-  const int ntiles = GLOBAL ? p.T / BKV : (C::W3 ? 3 : 4);
+  const int ntiles = GLOBAL ? p.T / C::STEP : (C::W3 ? 3 : 4);      // softmax steps (BIG: 128 keys each)
   const int cq = head * HD, ck = p.D + head * HD, cv = 2 * p.D + head * HD;
   constexpr int NSM = 32 * SM_WARPS;          // softmax threads
 #ifdef YSI_ATTN_TRACE
@@ -274,6 +286,15 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       auto load_k = [&](int tile, int st) {
         if (!lead) return;
+        if constexpr (C::BIG) {
+          // step `tile` = key rows kh = 2 tile, 2 tile + 1: 128 keys, then 8 rel_pos_h rows starting at (qh0 - kh - 1 + 63) with
+          // qh0 = 2 qt, kh = 2 tile: the three rows the CTA's two query rows need for the two key rows are rows 0..2 of them
+          mbar_arrive_expect_tx(bar_kfull + 8 * st, 2 * KV_BYTES + 8 * 128);
+          tma_load_2d(k_tile_addr(st), &tmKV, bar_kfull + 8 * st, ck, row0 + tile * 128);
+          tma_load_2d(k_tile_addr(st) + KV_BYTES, &tmKV, bar_kfull + 8 * st, ck, row0 + tile * 128 + 64);
+          tma_load_2d(k_tile_addr(st) + 2 * KV_BYTES, &tmRel8, bar_kfull + 8 * st, 0, 2 * qt - 2 * tile + 62);
+          return;
+        }
         const bool tail = !GLOBAL && tile == 3;
         const int bytes0 = GLOBAL ? KV_BYTES + 8 * 128 : (tail ? 16 * 128 : KV_BYTES);
         mbar_arrive_expect_tx(bar_kfull + 8 * st, bytes0 + (HAS1 ? bytes0 / 4 : 0));
@@ -287,6 +308,12 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       auto load_v = [&](int tile, int st) {
         if (!lead) return;
+        if constexpr (C::BIG) {
+          mbar_arrive_expect_tx(bar_vfull + 8 * st, 2 * KV_BYTES);
+          tma_load_2d(v_tile_addr(st), &tmKV, bar_vfull + 8 * st, cv, row0 + tile * 128);
+          tma_load_2d(v_tile_addr(st) + KV_BYTES, &tmKV, bar_vfull + 8 * st, cv, row0 + tile * 128 + 64);
+          return;
+        }
         const bool tail = !GLOBAL && tile == 3;
         const int bytes0 = tail ? 16 * 128 : KV_BYTES;
         mbar_arrive_expect_tx(bar_vfull + 8 * st, bytes0 + (HAS1 ? bytes0 / 4 : 0));
@@ -337,9 +364,51 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         umma_commit(bar_tab);
       }
       mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
+      if constexpr (C::BIG) {
+        // One thread issues S and P.V of every step in program order: P_j overwrites the first 64 columns of the single S
+        // buffer, so S_{j+1} must follow P.V_j in the (in-order) tensor pipe -- no barrier round trip between the two.
+        constexpr uint32_t idesc_s144 = umma_idesc_op16(128, 144, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_op16(128, 64, 0, 1);   // B (= V) is MN-major
+        const uint32_t d = tmem_base + C::COL_S, otm = tmem_base + C::COL_O;
+        auto issue_s = [&](int stage) {
+          const uint32_t kbase = k_tile_addr(stage);
+#pragma unroll
+          for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], umma_desc_sw128(kbase, 16, 1024) + 2u * static_cast<uint32_t>(k), idesc_s144, k);
+          umma_commit(bar_kempty + 8 * stage);
+          umma_commit(bar_s_full);
+        };
+        int sk = 0, sv = 0;
+        uint32_t pkf = 0, pvf = 0;
+        mbar_wait(bar_kfull + 8 * sk, pkf);
+        tc_fence_after();
+        if (lead) issue_s(sk);
+        __syncwarp();
+        if (++sk == C::NSTK) { sk = 0; pkf ^= 1u; }
+        for (int j = 0; j < ntiles; ++j) {
+          mbar_wait(bar_vfull + 8 * sv, pvf);
+          mbar_wait(bar_p_full, static_cast<uint32_t>(j & 1));
+          tc_fence_after();
+          if (lead) {
+            const uint64_t vdesc = umma_desc_sw128(v_tile_addr(sv), 1024, 1024);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_op16_ts(otm, d + 8u * k, vdesc + 128u * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            umma_commit(bar_vempty + 8 * sv);
+            umma_commit(bar_p_free);
+          }
+          __syncwarp();
+          if (++sv == C::NSTV) { sv = 0; pvf ^= 1u; }
+          if (j + 1 < ntiles) {
+            mbar_wait(bar_kfull + 8 * sk, pkf);
+            tc_fence_after();
+            if (lead) issue_s(sk);
+            __syncwarp();
+            if (++sk == C::NSTK) { sk = 0; pkf ^= 1u; }
+          }
+        }
+      }
       int st = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; !C::BIG && t < ntiles; ++t) {
         const int buf = t & 1;
         mbar_wait(bar_kfull + 8 * st, ph);
         if (C::W3 && t == 2) mbar_wait(bar_kfull + 8 * 3, 0);      // the last window tile spans K tiles 2 and 3
@@ -355,7 +424,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t kbase = k_tile_addr(st), kbase1 = k1_tile_addr(st);
         if (lead) {
 #pragma unroll
-          for (int k = 0; k < NKS; ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, kbase1, k), idesc, k);
+          for (int k = 0; k < ((ABL & 256) ? 0 : NKS); ++k) umma_op16_ss(d, qdesc[k], kdesc_at(kbase, kbase1, k), idesc, k);
           umma_commit(bar_kempty + 8 * st);
           umma_commit(bar_s_full + 8 * buf);
         }
@@ -372,7 +441,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const uint32_t otm = tmem_base + C::COL_O;
       int st = 0;
       uint32_t ph = 0;
-      for (int j = 0; j < ntiles; ++j) {
+      for (int j = 0; !C::BIG && j < ntiles; ++j) {
         mbar_wait(bar_vfull + 8 * st, ph);
         if (C::W3 && j == 2) mbar_wait(bar_vfull + 8 * 3, 0);
         ATTN_TRACE(10, j, 0);
@@ -382,7 +451,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t ptm = C::PSEP ? tmem_base + C::COL_P : tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
         if (lead) {
           const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st), 1024, 1024);
-          if (GLOBAL || j < 3) {
+          if (ABL & 128) {
+          } else if (GLOBAL || j < 3) {
 #pragma unroll
             for (int k = 0; k < BKV / 16; ++k) umma_op16_ts(otm, ptm + 8u * k, vdesc + 128u * k, idesc_pv64, (j | k) != 0 ? 1u : 0u);
             if (C::W3 && j == 2) umma_op16_ts(otm, ptm + 8u * 4, vdesc + 128u * 4, idesc_pv64, 1u);     // keys 192..207 (196.. are zero in P)
@@ -505,7 +575,12 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (act) {
         const uint32_t scol = tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N);
         if constexpr (NW == 80) { tmem_ld_x32p(scol, r); tmem_ld_x32p(scol + 32, r + 32); tmem_ld_x16p(scol + 64, r + 64); }
-        else if constexpr (NW == 64) { tmem_ld_x32p(scol + c0, r); tmem_ld_x32p(scol + c0 + 32, r + 32); }
+        else if constexpr (NW == 64) {
+          if (ABL & 32) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) r[i] = 0x3c000000u + i;
+          } else { tmem_ld_x32p(scol + c0, r); tmem_ld_x32p(scol + c0 + 32, r + 32); }
+        }
         else if constexpr (NW == 32) tmem_ld_x32p(scol + c0, r);
         else if constexpr (NW == 16) tmem_ld_x16p(scol + c0, r);
         if (GLOBAL) {
@@ -594,7 +669,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tc_fence_after();
         const uint32_t pcol = C::PSEP ? tlane + C::COL_P : tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
         if constexpr (NW == 80) { tmem_st_x32p(pcol, pk); tmem_st_x8p(pcol + 32, pk + 32); }
-        else if constexpr (NW == 64) tmem_st_x32p(pcol, pk);
+        else if constexpr (NW == 64) { if (!(ABL & 64)) tmem_st_x32p(pcol, pk); }
         else if constexpr (NW == 32) tmem_st_x16p(pcol, pk);
         else if constexpr (NW == 16) tmem_st_x8p(pcol, pk);
       }
@@ -609,7 +684,79 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     using I16 = std::integral_constant<int, 16>;
     using I4 = std::integral_constant<int, 4>;
     using I0 = std::integral_constant<int, 0>;
-    if constexpr (C::PSEP && PREFETCH) {
+    if constexpr (C::BIG) {
+      // 128 keys (key rows kh = 2 j and 2 j + 1) per step. Two passes over the S buffer so that only 64 scores are live at a
+      // time: pass 1 = row maximum, pass 2 = exponentials + P. P half h (32 columns) overwrites S columns 32 h .. 32 h + 31,
+      // which this thread has consumed by then (it only ever touches its own lane).
+      const uint32_t scol = tlane + C::COL_S;
+      const uint32_t hcol = scol + 129u + static_cast<uint32_t>(rq >> 1);       // rel_pos_h term of key row half h: column hcol - h
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(bar_s_full, static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        float bh[2];
+        float m_tile = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[64], rb;
+          tmem_ld_x32p(scol + 64u * h, r);
+          tmem_ld_x32p(scol + 64u * h + 32u, r + 32);
+          tmem_ld_x1(hcol - static_cast<uint32_t>(h), rb);
+          tmem_ld_wait();
+          bh[h] = __uint_as_float(rb);
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float2 y = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bias[2 * i], bias[2 * i + 1]));
+            mx[i & 3] = max3(mx[i & 3], y.x, y.y);
+          }
+          m_tile = fmaxf(m_tile, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh[h]);
+        }
+        if (__any_sync(0xFFFFFFFFu, m_tile > m_used + LAZY_LOG2)) {          // lazy rescale, see do_tile
+          const float m_new = fmaxf(m_used, m_tile);
+          if (j > 0) {
+            const float f = ex2_approx(m_used - m_new);
+            mbar_wait(bar_p_free, static_cast<uint32_t>((j - 1) & 1));       // P.V_{j-1}: complete since S_j is (same pipe, in order)
+            tc_fence_after();
+#pragma unroll
+            for (int qr = 0; qr < OH / 8; ++qr) {
+              uint32_t o[8];
+              tmem_ld_x8p(ocol + 8 * qr, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_x8p(ocol + 8 * qr, o);
+            }
+            l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
+          }
+          m_used = m_new;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[64];
+          tmem_ld_x32p(scol + 64u * h, r);
+          tmem_ld_x32p(scol + 64u * h + 32u, r + 32);
+          tmem_ld_wait();
+          const float c = bh[h] - m_used;
+          const float2 c2 = make_float2(c, c);
+          float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float2 e = add2(add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bias[2 * i], bias[2 * i + 1])), c2);
+            if (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1)) e = ex2_poly2(e);
+            else { e.x = ex2_approx(e.x); e.y = ex2_approx(e.y); }
+            if (i & 1) tb = add2(tb, e); else ta = add2(ta, e);
+            pk[i] = pack_op16x2(e.x, e.y);
+          }
+          l2a = add2(l2a, ta); l2b = add2(l2b, tb);
+          tmem_st_x32p(scol + 32u * h, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_full);
+      }
+    } else if constexpr (C::PSEP && PREFETCH) {
       // Global layers, head_dim 64: the S tile of step j + 1 is fetched from tensor memory WHILE the exponentials of step j
       // run. The kernel's skeleton is bound by the tensor-memory read port (128 x 65 fp32 per tile and CTA at 64 B / clk / SM
       // -- as long as the MUFU work of the same tile), so the two must overlap instead of alternating. S_{j+1} is
@@ -722,7 +869,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (SPLIT == 1) xl[t * 2 + 1] = 0.f;
     __syncwarp();
     if (SPLIT == 2 && lane == 0) mbar_arrive(bar_fin + 8 * rq);
-    mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
+    if (C::BIG) mbar_wait(bar_p_free, static_cast<uint32_t>((ntiles - 1) & 1));
+    else mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     if (SPLIT == 2) mbar_wait(bar_fin + 8 * rq, 0);
     if (warp_active) {
