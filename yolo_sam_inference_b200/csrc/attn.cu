@@ -53,11 +53,11 @@ constexpr int SPLIT = YSI_ATTN_SPLIT;
 static_assert(SPLIT == 1, "the two-threads-per-row variant (round 1, measured slower) was removed with the round-2 softmax pipeline");
 // every POLY_EVERY-th pair of exponentials is evaluated with ex2_poly2 on the FMA pipe instead of MUFU.EX2 (0: none)
 #ifndef YSI_ATTN_POLY_EVERY
-#define YSI_ATTN_POLY_EVERY 4
+#define YSI_ATTN_POLY_EVERY 8
 #endif
 constexpr int POLY_EVERY = YSI_ATTN_POLY_EVERY;
 #ifndef YSI_ATTN_PSEP
-#define YSI_ATTN_PSEP 1
+#define YSI_ATTN_PSEP 0
 #endif
 // timing-only ablation builds (WRONG results; scripts/gpu_attn_ablate.sh): 1 no bias add, 2 no row sums, 4 no row max,
 // 8 no exponentials, 16 no 16-bit packing, 32 no S load from tensor memory, 64 no P store, 128 no P.V MMAs, 256 no S MMAs
@@ -65,6 +65,19 @@ constexpr int POLY_EVERY = YSI_ATTN_POLY_EVERY;
 #define YSI_ATTN_ABLATE 0
 #endif
 constexpr int ABL = YSI_ATTN_ABLATE;
+// Sum-checked exponentials (round 2): after the first tile the row maximum is NOT computed. The exponentials are taken against
+// the current reference maximum m_used right away and their tile sum (needed anyway) is the overflow detector: a sum below
+// NOMAX_LIMIT bounds every P value of the tile (16-bit operand range), anything else -- including inf / NaN -- sends the warp
+// through the exact path (row maximum, fold the new reference into O and l, exponentials again). Steady state saves the
+// FMNMX pass and its dependency chain between the S load and the first MUFU.
+#ifndef YSI_ATTN_NOMAX
+#define YSI_ATTN_NOMAX 1
+#endif
+// Measured (profiles/r02_attention_experiments.txt): global head_dim 64 657 -> 611 us, global 80 919 -> 880, windowed 64 124 -> 120;
+// windowed head_dim 80 is 3 % slower with it (169 -> 174 us: one 80-column tile of three cannot skip the maximum) and keeps the
+// max-first loop.
+template <bool GLOBAL, int HD> constexpr bool nomax_v = (YSI_ATTN_NOMAX != 0) && (GLOBAL || HD == 64);
+constexpr float NOMAX_LIMIT = 16384.0f;
 // fetch the next S tile from tensor memory under the exponentials of the current one (global layers with PSEP)
 // Measured (round 2, profiles/r02_attention_experiments.txt): 704 vs 657 us per ViT-B batch-8 global layer -- slower; the
 // skeleton of the tile loop (tensor-memory round trips between the softmax warps and the two MMA warps), not the
@@ -155,6 +168,10 @@ struct Cfg {
   // (bar_s_free, early in tile j) instead of until P.V_j has completed, which takes the tensor-pipe round trip
   // (p_full -> P.V_j -> commit -> S_{j+2} -> commit) and the slowest warp of the CTA out of the per-tile critical path.
   static constexpr bool PSEP = GLOBAL && HD == 64 && (YSI_ATTN_PSEP != 0) && !BIG;
+  // YSI_ATTN_PSEP=2: P alternates between the dedicated columns (even tiles) and the first columns of S buffer 1 (odd tiles),
+  // i.e. P is double buffered inside the same 256 columns: storing P_j then waits for P.V_{j-2} (even j) or for nothing
+  // (odd j) instead of for P.V_{j-1}; S_t waits for "S_{t-2} read" (even t) or for P.V_{t-2} (odd t).
+  static constexpr bool PALT = PSEP && (YSI_ATTN_PSEP == 2);
   static constexpr int COL_P = COL_O + HD;                  // PSEP only: one P buffer (32 columns = 64 keys)
   static constexpr int COL_TH = 0;                          // windowed setup only
   static constexpr int COL_TW = GLOBAL ? 0 : 32;
@@ -414,7 +431,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         if (C::W3 && t == 2) mbar_wait(bar_kfull + 8 * 3, 0);      // the last window tile spans K tiles 2 and 3
         ATTN_TRACE(9, t, 0);
         if (t >= 2) {
-          if (C::PSEP) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);   // S_{t-2} has been read out of buffer t & 1
+          if (C::PSEP && !(C::PALT && buf)) mbar_wait(bar_s_free + 8 * buf, ((t >> 1) - 1) & 1);   // S_{t-2} has been read out of buffer t & 1
           else mbar_wait(bar_p_free + 8 * buf, ((t >> 1) - 1) & 1);           // P.V_{t-2} done: S / P buffer t & 1 is free
         }
         ATTN_TRACE(9, t, 1);
@@ -448,7 +465,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
         ATTN_TRACE(10, j, 1);
         tc_fence_after();
-        const uint32_t ptm = C::PSEP ? tmem_base + C::COL_P : tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
+        const uint32_t ptm = (C::PSEP && !(C::PALT && (j & 1))) ? tmem_base + C::COL_P
+                                                                : tmem_base + C::COL_S + static_cast<uint32_t>((j & 1) * C::S_N);
         if (lead) {
           const uint64_t vdesc = umma_desc_sw128(v_tile_addr(st), 1024, 1024);
           if (ABL & 128) {
@@ -599,26 +617,24 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       ATTN_TRACE(warp, j, 2);
       float2 y[NR / 2];
-      float m_tile = -INFINITY;
       if (act) {
 #pragma unroll
         for (int i = 0; i < NW / 2; ++i)
           y[i] = (ABL & 1) ? make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]))
                            : add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(bfn(2 * i), bfn(2 * i + 1)));
+      }
+      // row maximum of this tile (log2 units, rel_pos_h term included)
+      auto row_max = [&]() -> float {
+        if (!act) return -INFINITY;
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < ((ABL & 4) ? 1 : NV / 2); ++i) mx[i & 3] = max3(mx[i & 3], y[i].x, y[i].y);
-        m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
-      }
-      finalize_p();
-      ATTN_TRACE(warp, j, 3);
-      // Lazy rescale: the reference maximum m_used only moves when a row's maximum has grown by more than 2^8 (P stays
-      // below 2^8 in the 16-bit operand). Decided BEFORE the exponentials, which are therefore computed exactly once.
-      if (__any_sync(0xFFFFFFFFu, m_tile > m_used + LAZY_LOG2)) {
-        const float m_new = fmaxf(m_used, m_tile);
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + bh;
+      };
+      // move the reference maximum: fold the factor into O (TMEM) and l. PV_{j-1} must have landed (its P was handed over by
+      // finalize_p above, by every warp before its own check), PV_j has not been issued.
+      auto move_reference = [&](float m_new) {
         if (j > 0) {
-          // fold the new maximum into O (TMEM) and l; PV_{j-1} must have landed (its P was handed over just above by
-          // every warp before its own check), PV_j has not been issued
           const float f = ex2_approx(m_used - m_new);
           mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
@@ -635,17 +651,18 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
         }
         m_used = m_new;
-      }
-      ATTN_TRACE(warp, j, 4);
+      };
       uint32_t pk[NR / 2];
-      if (act) {
+      float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+      // exponentials against the current reference maximum -> packed P values + their sums
+      auto exp_pass = [&]() {
         const float c = bh - m_used;
         const float2 c2 = make_float2(c, c);
-        float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+        ta = make_float2(0.f, 0.f); tb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < NW / 2; ++i) {
           float2 e = add2(y[i], c2);
-          // a fixed share of the pairs takes the polynomial on the FMA pipe instead of the MUFU (the kernel's bound)
+          // a fixed share of the pairs takes the polynomial on the FMA pipe instead of the MUFU
           if (ABL & 8) { }
           else if (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY - 1) && 2 * i + 1 < NV) e = ex2_poly2(e);
           else {
@@ -655,19 +672,44 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (!(ABL & 2)) { if (i & 1) tb = add2(tb, e); else ta = add2(ta, e); }
           pk[i] = (ABL & 16) ? __float_as_uint(e.x) : pack_op16x2(e.x, e.y);
         }
-        l2a = add2(l2a, ta); l2b = add2(l2b, tb);
+      };
+      finalize_p();
+      ATTN_TRACE(warp, j, 3);
+      if constexpr (nomax_v<GLOBAL, HD>) {
+        // Tile 0 fixes the reference maximum; later tiles go straight to the exponentials and use their sum as the overflow
+        // detector (see NOMAX above). The exact path is warp-uniform and rare after the first tiles of a row.
+        if (j == 0) m_used = row_max();
+        if (act) exp_pass();
+        ATTN_TRACE(warp, j, 4);
+        if (j > 0) {
+          const float ts = (ta.x + ta.y) + (tb.x + tb.y);
+          if (__any_sync(0xFFFFFFFFu, act && !(ts <= NOMAX_LIMIT))) {
+            move_reference(fmaxf(m_used, row_max()));
+            if (act) exp_pass();
+          }
+        }
+      } else {
+        // Lazy rescale: the reference maximum m_used only moves when a row's maximum has grown by more than 2^8 (P stays
+        // below 2^8 in the 16-bit operand). Decided BEFORE the exponentials, which are therefore computed exactly once.
+        const float m_tile = row_max();
+        if (__any_sync(0xFFFFFFFFu, m_tile > m_used + LAZY_LOG2)) move_reference(fmaxf(m_used, m_tile));
+        ATTN_TRACE(warp, j, 4);
+        if (act) exp_pass();
       }
+      if (act) { l2a = add2(l2a, ta); l2b = add2(l2b, tb); }
       // P_j goes into the first columns of S buffer pb. They are free: S_j (this buffer) was only issued after P.V_{j-2}
       // had completed and this thread has its own S columns in registers. No wait on the tensor pipe in steady state.
       ATTN_TRACE(warp, j, 5);
       // probe the next tile's S now: the barrier unit's round trip overlaps the P store below
       s_ready = mbar_test_wait(bar_s_full + 8 * (pb ^ 1), static_cast<uint32_t>(((j + 1) >> 1) & 1));
-      if (C::PSEP && j > 0) {      // the single P buffer is free once P.V_{j-1} has completed (normally long ago)
+      if (C::PALT) {               // P alternates: even tiles own the dedicated columns (free once P.V_{j-2} has completed),
+        if (!pb && j >= 2) mbar_wait(bar_p_free, ((j - 2) >> 1) & 1);     // odd tiles overwrite their own S buffer (no wait)
+      } else if (C::PSEP && j > 0) {      // the single P buffer is free once P.V_{j-1} has completed (normally long ago)
         mbar_wait(bar_p_free + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
       }
       if (act) {
         tc_fence_after();
-        const uint32_t pcol = C::PSEP ? tlane + C::COL_P : tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
+        const uint32_t pcol = (C::PSEP && !(C::PALT && pb)) ? tlane + C::COL_P : tlane + C::COL_S + static_cast<uint32_t>(pb * C::S_N + c0 / 2);
         if constexpr (NW == 80) { tmem_st_x32p(pcol, pk); tmem_st_x8p(pcol + 32, pk + 32); }
         else if constexpr (NW == 64) { if (!(ABL & 64)) tmem_st_x32p(pcol, pk); }
         else if constexpr (NW == 32) tmem_st_x16p(pcol, pk);

@@ -198,26 +198,33 @@ tok_linear_kernel(TokLin3 P, int R) {
 // Same contract as tok_linear_kernel for many rows (config 4: 32 boxes/image -> R = 7*256): classic shared-memory
 // tiled fp32 GEMM, 64 x 64 output tile per CTA, 4 x 4 outputs per thread, K in slabs of 32, so weights and
 // activations are each read from L2 once per tile row / column instead of once per 8 x 8 block.
-constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32;
+constexpr int TG_BN = 64, TG_BK = 32;
 
+// BM = 64 or 32 rows per CTA (32: twice the CTAs for the narrow layers, whose 64-row grids leave SMs idle). The next K slab
+// is fetched into registers while the current one is multiplied, so a CTA is not exposed to one L2 round trip per slab
+// (round-2 ncu of the unpipelined version: 12 % warps active, long_scoreboard the top stall, 179 us for the K = 2048 layer).
+template <int BM>
 __global__ void __launch_bounds__(256)
 tok_gemm_kernel(TokLin3 P, int R) {
   const TokLin& p = P.t[blockIdx.z];
-  __shared__ float Xs[TG_BM][TG_BK + 1];
+  __shared__ float Xs[BM][TG_BK + 1];
   __shared__ float Ws[TG_BN][TG_BK + 1];
-  const int n0 = blockIdx.x * TG_BN, r0 = blockIdx.y * TG_BM;
+  constexpr int RT = BM / 16;          // output rows per thread
+  constexpr int XL = BM / 32;          // float4 loads of X per thread and slab
+  const int n0 = blockIdx.x * TG_BN, r0 = blockIdx.y * BM;
   if (n0 >= p.N) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  float acc[RT][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // loader mapping: 256 threads x 2 float4 = 64 rows x 32 k
-  const int lrow = tid >> 3, lk4 = tid & 7;          // rows lrow, lrow+32; k = lk4*4..+3
-  for (int k0 = 0; k0 < p.K; k0 += TG_BK) {
+  // loader mapping: 256 threads x float4 = 32 rows x 32 k per pass
+  const int lrow = tid >> 3, lk4 = tid & 7;
+  float4 xr[XL], wr[2];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < XL; ++h) {
       const int rr = lrow + 32 * h;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + rr < R) {
@@ -227,29 +234,46 @@ tok_gemm_kernel(TokLin3 P, int R) {
           x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
         }
       }
-      Xs[rr][lk4 * 4] = x.x; Xs[rr][lk4 * 4 + 1] = x.y; Xs[rr][lk4 * 4 + 2] = x.z; Xs[rr][lk4 * 4 + 3] = x.w;
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + rr < p.N) w = __ldg(reinterpret_cast<const float4*>(p.W + static_cast<size_t>(n0 + rr) * p.K + k0) + lk4);
-      Ws[rr][lk4 * 4] = w.x; Ws[rr][lk4 * 4 + 1] = w.y; Ws[rr][lk4 * 4 + 2] = w.z; Ws[rr][lk4 * 4 + 3] = w.w;
+      xr[h] = x;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rr = lrow + 32 * h;
+      wr[h] = n0 + rr < p.N ? __ldg(reinterpret_cast<const float4*>(p.W + static_cast<size_t>(n0 + rr) * p.K + k0) + lk4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < p.K; k0 += TG_BK) {
+#pragma unroll
+    for (int h = 0; h < XL; ++h) {
+      const int rr = lrow + 32 * h;
+      Xs[rr][lk4 * 4] = xr[h].x; Xs[rr][lk4 * 4 + 1] = xr[h].y; Xs[rr][lk4 * 4 + 2] = xr[h].z; Xs[rr][lk4 * 4 + 3] = xr[h].w;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rr = lrow + 32 * h;
+      Ws[rr][lk4 * 4] = wr[h].x; Ws[rr][lk4 * 4 + 1] = wr[h].y; Ws[rr][lk4 * 4 + 2] = wr[h].z; Ws[rr][lk4 * 4 + 3] = wr[h].w;
     }
     __syncthreads();
+    if (k0 + TG_BK < p.K) fetch(k0 + TG_BK);
 #pragma unroll
     for (int k = 0; k < TG_BK; ++k) {
-      float a[4], b[4];
+      float a[RT], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Xs[ty * 4 + i][k];
+      for (int i = 0; i < RT; ++i) a[i] = Xs[ty * RT + i][k];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = Ws[tx + 16 * j][k];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty * 4 + i;
+  for (int i = 0; i < RT; ++i) {
+    const int r = r0 + ty * RT + i;
     if (r >= R) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -545,6 +569,147 @@ t2i_attention_online_kernel(const float* __restrict__ q_t2i, const T* __restrict
   }
 }
 
+// 16 consecutive values of a K / V row, fetched one iteration ahead in their storage type and converted when consumed
+template <typename T> struct Raw16;
+template <> struct Raw16<float> {
+  float4 v[4];
+  __device__ __forceinline__ void load(const float* p) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
+  }
+  __device__ __forceinline__ void get(float (&o)[16]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[4 * i] = v[i].x; o[4 * i + 1] = v[i].y; o[4 * i + 2] = v[i].z; o[4 * i + 3] = v[i].w; }
+  }
+};
+template <> struct Raw16<op16> {
+  uint4 v[2];
+  __device__ __forceinline__ void load(const op16* p) {
+    v[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    v[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(float (&o)[16]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 a = unpack_op16x2(v[i].x), b = unpack_op16x2(v[i].y), c = unpack_op16x2(v[i].z), d = unpack_op16x2(v[i].w);
+      o[8 * i] = a.x; o[8 * i + 1] = a.y; o[8 * i + 2] = b.x; o[8 * i + 3] = b.y;
+      o[8 * i + 4] = c.x; o[8 * i + 5] = c.y; o[8 * i + 6] = d.x; o[8 * i + 7] = d.y;
+    }
+  }
+};
+
+// Very many boxes (configs[3] at batch 8: 256 per launch): one CTA = (key range, box) for ALL 8 heads. lane = (key slot 0..3,
+// head 0..7), 4 warps -> 16 keys per iteration; a thread owns one key at a time for the 7 query rows of its head:
+//  * K / V come straight from global memory, one iteration ahead -- the 8 head-lanes of a key read one contiguous 256-byte
+//    (op16) row, so nothing is staged in shared memory and no barrier sits in the key loop;
+//  * q is read from shared memory (head stride 116 floats: the 8 heads of an instruction hit 8 different bank quads, the 4
+//    key slots broadcast); the running (reference, sum, P.V) of the 7 rows stay in registers: 224 FMAs per 28 LDS.128;
+//  * fp32 has the range to never rescale in steady state: the reference exponent only moves when a score exceeds it by 2^32.
+// The streaming kernel above spends its time in shared-memory reads (ncu: l1tex 90 %, issue 23-30 %).
+// Output: the (max, sum, P.V) partials of t2i_attention_kernel (max converted to natural-log units), merged by t2i_merge_kernel.
+constexpr int T2R_THREADS = 128;
+constexpr int T2R_QP = NT * 16 + 4;          // floats per head in shared memory
+
+template <typename T>
+__global__ void __launch_bounds__(T2R_THREADS)
+t2i_attention_rows_kernel(const float* __restrict__ q_t2i, const T* __restrict__ K, int ldk, const T* __restrict__ V,
+                          int ldv, const int* __restrict__ group, float* __restrict__ part) {
+  __shared__ __align__(16) float s_q[8 * T2R_QP];
+  __shared__ float s_red[4][8][T2I_PART];
+  const int sp = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int h = lane & 7, ks = warp * 4 + (lane >> 3);
+  for (int i = t; i < NT * 128; i += T2R_THREADS) {      // scale 16^-0.5 and log2(e): softmax in base 2
+    const int r = i >> 7, c = i & 127;
+    s_q[(c >> 4) * T2R_QP + r * 16 + (c & 15)] = (0.25f * 1.4426950408889634f) * q_t2i[(static_cast<size_t>(b) * NT + r) * 128 + c];
+  }
+  __syncthreads();
+  const size_t seq = group ? group[b] : b;
+  const T* Kb = K + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS + ks) * ldk + h * 16;
+  const T* Vb = V + (seq * 4096 + static_cast<size_t>(sp) * T2I_KEYS + ks) * ldv + h * 16;
+  float m[NT], l[NT], o[NT][16];
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    m[r] = -INFINITY; l[r] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[r][d] = 0.f;
+  }
+  Raw16<T> kn, vn;
+  kn.load(Kb);
+  vn.load(Vb);
+  constexpr int NIT = T2I_KEYS / 16;
+  const float4* qh = reinterpret_cast<const float4*>(s_q + h * T2R_QP);
+  for (int it = 0; it < NIT; ++it) {
+    float kk[16], vv[16];
+    kn.get(kk);
+    vn.get(vv);
+    if (it + 1 < NIT) {
+      kn.load(Kb + static_cast<size_t>(it + 1) * 16 * ldk);
+      vn.load(Vb + static_cast<size_t>(it + 1) * 16 * ldv);
+    }
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const float4 qa = qh[r * 4 + j], qb = qh[r * 4 + j + 1];
+        s0 = fmaf(qa.x, kk[4 * j], s0); s0 = fmaf(qa.y, kk[4 * j + 1], s0); s0 = fmaf(qa.z, kk[4 * j + 2], s0); s0 = fmaf(qa.w, kk[4 * j + 3], s0);
+        s1 = fmaf(qb.x, kk[4 * j + 4], s1); s1 = fmaf(qb.y, kk[4 * j + 5], s1); s1 = fmaf(qb.z, kk[4 * j + 6], s1); s1 = fmaf(qb.w, kk[4 * j + 7], s1);
+      }
+      const float sc = s0 + s1;
+      if (sc > m[r] + 32.0f) {               // first key of the row, then (practically) never again
+        const float f = ex2_approx(m[r] - sc);
+        l[r] *= f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[r][d] *= f;
+        m[r] = sc;
+      }
+      const float pv = ex2_approx(sc - m[r]);
+      l[r] += pv;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[r][d] = fmaf(pv, vv[d], o[r][d]);
+    }
+  }
+  // merge the 4 key slots of the warp (every slot has seen keys: m is finite), then the 4 warps through shared memory
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      const float m2 = __shfl_xor_sync(0xFFFFFFFFu, m[r], off), l2 = __shfl_xor_sync(0xFFFFFFFFu, l[r], off);
+      const float mn = fmaxf(m[r], m2), f1 = ex2_approx(m[r] - mn), f2 = ex2_approx(m2 - mn);
+      l[r] = l[r] * f1 + l2 * f2;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[r][d] = o[r][d] * f1 + __shfl_xor_sync(0xFFFFFFFFu, o[r][d], off) * f2;
+      m[r] = mn;
+    }
+  }
+  if (lane < 8) {
+    float* dst = &s_red[warp][h][0];
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      dst[r] = m[r]; dst[NT + r] = l[r];
+#pragma unroll
+      for (int d = 0; d < 16; ++d) dst[2 * NT + r * 16 + d] = o[r][d];
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < 8 * NT * 16; i += T2R_THREADS) {
+    const int hh = i / (NT * 16), r = (i / 16) % NT, d = i & 15;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, s_red[w][hh][r]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float f = ex2_approx(s_red[w][hh][r] - mm);
+      ll = fmaf(f, s_red[w][hh][NT + r], ll);
+      oo = fmaf(f, s_red[w][hh][2 * NT + r * 16 + d], oo);
+    }
+    float* pout = part + ((static_cast<size_t>(b) * 8 + hh) * T2I_SPLIT + sp) * T2I_PART;
+    pout[2 * NT + r * 16 + d] = oo;
+    if (d == 0) { pout[r] = mm * 0.6931471805599453f; pout[NT + r] = ll; }      // t2i_merge_kernel works in natural-log units
+  }
+}
+
 // combine the key ranges: out[b][r][h*16+d] = sum_s e^(m_s-m) o_s / sum_s e^(m_s-m) l_s
 __global__ void __launch_bounds__(256)
 t2i_merge_kernel(const float* __restrict__ part, float* __restrict__ attn_out) {
@@ -627,6 +792,80 @@ i2t_attention_kernel(const T* __restrict__ Q, int ldq, const int* __restrict__ g
   v1.x = pack_op16x2(o[8], o[9]); v1.y = pack_op16x2(o[10], o[11]); v1.z = pack_op16x2(o[12], o[13]); v1.w = pack_op16x2(o[14], o[15]);
   dst[0] = v0;
   dst[1] = v1;
+}
+
+// Same contract, four image tokens per thread (tokens tok0 + 32 i of the CTA's 128): the 7 token keys / values of the
+// thread's head are read from shared memory once per FOUR tokens -- the one-token kernel above is bound by those reads
+// (ncu at 256 boxes: l1tex 95 %, issue 34 %). grid (32, nb).
+template <typename T>
+__global__ void __launch_bounds__(256)
+i2t_attention4_kernel(const T* __restrict__ Q, int ldq, const int* __restrict__ group, const float* __restrict__ k_tok,
+                      const float* __restrict__ v_tok, op16* __restrict__ out) {
+  __shared__ __align__(16) float s_k[NT * 160], s_v[NT * 160];
+  const int b = blockIdx.y, t = threadIdx.x;
+  for (int i = t; i < NT * 128; i += 256) {
+    const int rr = i >> 7, c = i & 127, j = rr * 160 + (c >> 4) * 20 + (c & 15);
+    s_k[j] = k_tok[static_cast<size_t>(b) * NT * 128 + i];
+    s_v[j] = v_tok[static_cast<size_t>(b) * NT * 128 + i];
+  }
+  __syncthreads();
+  const int tok0 = blockIdx.x * 128 + (t >> 3), h = t & 7;
+  const size_t seq = group ? group[b] : b;
+  float q[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) load16(Q + (seq * 4096 + tok0 + 32 * i) * ldq + h * 16, q[i]);
+  float sc[4][NT];
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    const float4* kp = reinterpret_cast<const float4*>(s_k + r * 160 + h * 20);
+    const float4 k0 = kp[0], k1 = kp[1], k2 = kp[2], k3 = kp[3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = 0.f, c = 0.f;
+      a = fmaf(q[i][0], k0.x, a); a = fmaf(q[i][1], k0.y, a); a = fmaf(q[i][2], k0.z, a); a = fmaf(q[i][3], k0.w, a);
+      c = fmaf(q[i][4], k1.x, c); c = fmaf(q[i][5], k1.y, c); c = fmaf(q[i][6], k1.z, c); c = fmaf(q[i][7], k1.w, c);
+      a = fmaf(q[i][8], k2.x, a); a = fmaf(q[i][9], k2.y, a); a = fmaf(q[i][10], k2.z, a); a = fmaf(q[i][11], k2.w, a);
+      c = fmaf(q[i][12], k3.x, c); c = fmaf(q[i][13], k3.y, c); c = fmaf(q[i][14], k3.z, c); c = fmaf(q[i][15], k3.w, c);
+      sc[i][r] = (a + c) * (0.25f * 1.4426950408889634f);     // scale 16^-0.5, base-2 softmax
+    }
+  }
+  float o[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float m = sc[i][0];
+#pragma unroll
+    for (int r = 1; r < NT; ++r) m = fmaxf(m, sc[i][r]);
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < NT; ++r) { sc[i][r] = ex2_approx(sc[i][r] - m); sum += sc[i][r]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int r = 0; r < NT; ++r) sc[i][r] *= inv;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[i][d] = 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    const float4* vp = reinterpret_cast<const float4*>(s_v + r * 160 + h * 20);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v4 = vp[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        o[i][4 * j] = fmaf(sc[i][r], v4.x, o[i][4 * j]); o[i][4 * j + 1] = fmaf(sc[i][r], v4.y, o[i][4 * j + 1]);
+        o[i][4 * j + 2] = fmaf(sc[i][r], v4.z, o[i][4 * j + 2]); o[i][4 * j + 3] = fmaf(sc[i][r], v4.w, o[i][4 * j + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * 4096 + tok0 + 32 * i) * 128 + h * 16);
+    uint4 v0, v1;
+    v0.x = pack_op16x2(o[i][0], o[i][1]); v0.y = pack_op16x2(o[i][2], o[i][3]); v0.z = pack_op16x2(o[i][4], o[i][5]); v0.w = pack_op16x2(o[i][6], o[i][7]);
+    v1.x = pack_op16x2(o[i][8], o[i][9]); v1.y = pack_op16x2(o[i][10], o[i][11]); v1.z = pack_op16x2(o[i][12], o[i][13]); v1.w = pack_op16x2(o[i][14], o[i][15]);
+    dst[0] = v0;
+    dst[1] = v1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -729,17 +968,25 @@ static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s)
       nmax = t[i].N > nmax ? t[i].N : nmax;
     }
   }
-  if (R >= 256)
-    tok_gemm_kernel<<<dim3(ceil_div(nmax, TG_BN), ceil_div(R, TG_BM), count), 256, 0, s>>>(P, R);
+  if (R >= 256) {
+    const int nt = ceil_div(nmax, TG_BN);
+    if (nt * ceil_div(R, 64) * count >= 296) tok_gemm_kernel<64><<<dim3(nt, ceil_div(R, 64), count), 256, 0, s>>>(P, R);
+    else tok_gemm_kernel<32><<<dim3(nt, ceil_div(R, 32), count), 256, 0, s>>>(P, R);
+  }
   else
     tok_linear_kernel<<<dim3(nmax / 8, ceil_div(R, TOK_ROWS), count), 256, 0, s>>>(P, R);
 }
 
-// token -> image attention: few boxes -> key ranges split over CTAs + merge (parallelism); many -> one streaming CTA
-// per (head, box)
+// token -> image attention: few boxes -> key ranges split over CTAs + merge (parallelism); 16..63 -> one streaming CTA
+// per (head, box); from 64 boxes up the register-resident kernel (one CTA per key range and box, all heads)
 template <typename T>
 static int launch_t2i(const float* q, const T* K, int ldk, const T* V, int ldv, const int* group, float* part,
                       float* attn_out, int nb, cudaStream_t s) {
+  if (nb >= 64) {
+    t2i_attention_rows_kernel<T><<<dim3(T2I_SPLIT, nb), T2R_THREADS, 0, s>>>(q, K, ldk, V, ldv, group, part);
+    t2i_merge_kernel<<<nb, 256, 0, s>>>(part, attn_out);
+    return 2;
+  }
   if (nb >= 16) {
     t2i_attention_online_kernel<T><<<dim3(8, nb), 256, 0, s>>>(q, K, ldk, V, ldv, group, attn_out);
     return 1;
@@ -829,7 +1076,10 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       YSI_CUDA(cudaGetLastError());
     }
     { ProfScope ps(prof, KC_DEC_ATTN);
-      if (per_img) i2t_attention_kernel<float><<<dim3(128, nb), 256, 0, s>>>(wk.kq0 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
+      if (nb >= 32) {        // enough boxes to fill the GPU with a quarter of the CTAs: four tokens per thread
+        if (per_img) i2t_attention4_kernel<float><<<dim3(32, nb), 256, 0, s>>>(wk.kq0 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
+        else i2t_attention4_kernel<op16><<<dim3(32, nb), 256, 0, s>>>(wk.kq16 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
+      } else if (per_img) i2t_attention_kernel<float><<<dim3(128, nb), 256, 0, s>>>(wk.kq0 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
       else i2t_attention_kernel<op16><<<dim3(128, nb), 256, 0, s>>>(wk.kq16 + 128, 256, group, wk.k_tok, wk.v_tok, wk.attn_i2t);
       ++nl; }
     YSI_CUDA(cudaGetLastError());
