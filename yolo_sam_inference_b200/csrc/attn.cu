@@ -173,8 +173,12 @@ struct Cfg {
   // (odd j) instead of for P.V_{j-1}; S_t waits for "S_{t-2} read" (even t) or for P.V_{t-2} (odd t).
   static constexpr bool PALT = PSEP && (YSI_ATTN_PSEP == 2);
   static constexpr int COL_P = COL_O + HD;                  // PSEP only: one P buffer (32 columns = 64 keys)
-  static constexpr int COL_TH = 0;                          // windowed setup only
-  static constexpr int COL_TW = GLOBAL ? 0 : 32;
+  // setup tables (Q . R^T): global -> 128 columns over the S buffers (S_0 waits until they have been read); windowed -> 2 x 32
+  // columns over O, which is first written by P.V_0 -- long after every softmax thread has its bias values -- so S_0 / S_1
+  // are issued while the bias is still being re-indexed. (Round 1 reverted this layout when ViT-H became non-deterministic;
+  // the cause was the missing proxy fence on the bias scratch, fixed in round 2, not the layout.)
+  static constexpr int COL_TH = GLOBAL ? 0 : COL_O;         // windowed setup only
+  static constexpr int COL_TW = GLOBAL ? 0 : COL_O + 32;
   static constexpr int CTAS_PER_SM = 2;
   static_assert(HD == 64 || HD == 80, "head_dim 64 or 80");
   static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && K_CHUNK % 1024 == 0, "swizzle atoms need 1 KB alignment");
@@ -239,7 +243,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int cq = head * HD, ck = p.D + head * HD, cv = 2 * p.D + head * HD;
   constexpr int NSM = 32 * SM_WARPS;          // softmax threads
 #ifdef YSI_ATTN_TRACE
-  const bool trace = GLOBAL && blockIdx.x == 7 && blockIdx.y == 3 && blockIdx.z == 0;
+  const bool trace = GLOBAL ? (blockIdx.x == 7 && blockIdx.y == 3 && blockIdx.z == 0) : (blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 150);
+  const long long t_entry = clock64();
 #endif
 
   if (threadIdx.x == 0) {
@@ -257,6 +262,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int i = 0; i < 4; ++i) mbar_init(bar_fin + 8 * i, 2);
     for (int i = 0; i < 2; ++i) mbar_init(bar_s_free + 8 * i, SM_WARPS);
     fence_mbar_init();
+    // Q tile + rel-pos table(s) are requested right here, before the tensor-memory allocation and the CTA barrier: their
+    // round trip (~1800 cycles in the windowed kernel's clock trace) is the head of every CTA's latency chain
+    mbar_arrive_expect_tx(bar_q, CH_Q + C::Q1_BYTES + (GLOBAL ? 1 : 2) * (C::TAB_CHUNK + C::TAB1_CHUNK));
+    tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
+    if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);        // rel_pos_h rows (zero padded)
+    tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);                   // rel_pos_w rows
+    if (C::HAS1) {
+      tma_load_2d(sbase + C::OFF_Q1, &tmQ1, bar_q, cq + 64, row0 + qt * BQ);
+      if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH1, &tmRel1, bar_q, 64, 0);
+      tma_load_2d(sbase + C::OFF_TABW1, &tmRel1, bar_q, 64, 128);
+    }
   }
   for (int i = threadIdx.x; i < 512; i += THREADS) reinterpret_cast<uint32_t*>(xm)[i] = 0xFFFFFFFFu;   // tag 0xFF: nothing published yet
   if (warp == SM_WARPS) {
@@ -289,18 +305,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // Each role runs with the whole warp converged (all lanes poll the barriers) and one elected lane issuing.
     if (warp == SM_WARPS) {
       const bool lead = elect_one();
-      // ---- TMA: Q tile + rel-pos table(s), then the K / V rings
-      if (lead) {
-        mbar_arrive_expect_tx(bar_q, CH_Q + C::Q1_BYTES + (GLOBAL ? 1 : 2) * (C::TAB_CHUNK + C::TAB1_CHUNK));
-        tma_load_2d(sbase + C::OFF_Q, &tmQ, bar_q, cq, row0 + qt * BQ);
-        if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH, &tmRel, bar_q, 0, 0);        // rel_pos_h rows (zero padded)
-        tma_load_2d(sbase + C::OFF_TABW, &tmRel, bar_q, 0, 128);                   // rel_pos_w rows
-        if (HAS1) {
-          tma_load_2d(sbase + C::OFF_Q1, &tmQ1, bar_q, cq + 64, row0 + qt * BQ);
-          if (!GLOBAL) tma_load_2d(sbase + C::OFF_TABH1, &tmRel1, bar_q, 64, 0);
-          tma_load_2d(sbase + C::OFF_TABW1, &tmRel1, bar_q, 64, 128);
-        }
-      }
+      // ---- TMA: the K / V rings (Q tile + rel-pos tables were requested by thread 0 before the CTA barrier)
       auto load_k = [&](int tile, int st) {
         if (!lead) return;
         if constexpr (C::BIG) {
@@ -380,7 +385,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           umma_op16_ss(tmem_base + C::COL_TW, qdesc[k], kdesc_at(sbase + C::OFF_TABW, sbase + C::OFF_TABW1, k), idesc_tab, k);
         umma_commit(bar_tab);
       }
-      mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
+      if (GLOBAL) mbar_wait(bar_rel, 0);     // bias tables copied out of TMEM: the S columns are free
       if constexpr (C::BIG) {
         // One thread issues S and P.V of every step in program order: P_j overwrites the first 64 columns of the single S
         // buffer, so S_{j+1} must follow P.V_j in the (in-order) tensor pipe -- no barrier round trip between the two.
@@ -506,7 +511,9 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     constexpr int NB = GLOBAL ? TW : 28;             // bias registers: rel_w of this thread's TW keys | rel_h[14] + rel_w[14]
     float bias[NB];
 
+    ATTN_TRACE(warp, 60, 0);
     mbar_wait(bar_tab, 0);
+    ATTN_TRACE(warp, 60, 1);
     tc_fence_after();
     // Q.table^T sits in TMEM as [query][table row]; thread t needs column (q_pos - k_pos + S-1) for every key
     // position it owns: scatter through smem scratch [k][t] (the column is thread dependent), then keep it in registers.
@@ -551,6 +558,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // reads had been performed (a warp's bias registers then held V data) or a scratch store could land after them
     // (corrupt V for the whole CTA). Found in round 2 with the run-to-run bit-equality test at ViT-H, batch 8
     // (profiles/r02_race_diag_before_fix.txt): windowed head_dim-80 attention differed in whole 32-row blocks.
+    ATTN_TRACE(warp, 60, 2);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
@@ -679,6 +687,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         // Tile 0 fixes the reference maximum; later tiles go straight to the exponentials and use their sum as the overflow
         // detector (see NOMAX above). The exact path is warp-uniform and rare after the first tiles of a row.
         if (j == 0) m_used = row_max();
+        ATTN_TRACE(warp, j, 7);
         if (act) exp_pass();
         ATTN_TRACE(warp, j, 4);
         if (j > 0) {
@@ -905,6 +914,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       if (half == 0) window_tiles(std::integral_constant<int, 0>{}); else window_tiles(std::integral_constant<int, 1>{});
     }
+    ATTN_TRACE(warp, 60, 3);
     finalize_p();
     // row sum = both halves
     xl[t * 2 + half] = (l2a.x + l2a.y) + (l2b.x + l2b.y);
@@ -914,41 +924,74 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (C::BIG) mbar_wait(bar_p_free, static_cast<uint32_t>((ntiles - 1) & 1));
     else mbar_wait(bar_p_free + 8 * ((ntiles - 1) & 1), ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
+    ATTN_TRACE(warp, 60, 4);
     if (SPLIT == 2) mbar_wait(bar_fin + 8 * rq, 0);
     if (warp_active) {
       uint32_t o[OH];
 #pragma unroll
       for (int c = 0; c < OH; c += 8) tmem_ld_x8p(ocol + c, o + c);
       tmem_ld_wait();
+      ATTN_TRACE(warp, 60, 6);
       const float inv = 1.0f / (xl[t * 2] + xl[t * 2 + 1]);
-      long long orow = -1;
+      int orow = -1;
       if (q_valid) {
         if (!GLOBAL && p.unwindow) {
           const int img = seq / 25, win = seq - img * 25;
           const int y = (win / 5) * 14 + qh, x = (win % 5) * 14 + qw;
-          if (y < 64 && x < 64) orow = static_cast<long long>(img) * 4096 + y * 64 + x;
+          if (y < 64 && x < 64) orow = img * 4096 + y * 64 + x;
         } else {
-          orow = static_cast<long long>(row0) + lq;
+          orow = row0 + lq;
         }
       }
-      if (orow >= 0) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(orow) * p.D + head * HD + half * OH);
+      // One row per lane would make every 16-byte store instruction touch 32 different lines (the windowed kernel's clock
+      // trace showed 2400 cycles in this epilogue). The warp's 32 rows are staged through the idle Q tile instead (all S /
+      // table MMAs that read it have completed) and leave as whole rows: consecutive lanes write consecutive 16-byte chunks
+      // (1450 cycles; windowed head_dim 64: 115.6 -> 111.6 us per ViT-B layer). Chunk c of row r sits at slot (c + r) mod NCH
+      // of its row, which spreads a store instruction's 32 chunks over the banks. Tried and rejected: one 128-byte
+      // cp.async.bulk per lane out of padded rows -- the copy engine needs ~2200 cycles for a warp's 32 small copies (113 us).
+      constexpr int NCH = HD / 8, ROWB = HD * 2;
+      static_assert(SPLIT == 1 && 128 * ROWB <= CH_Q + C::Q1_BYTES, "the output stage aliases the Q tile");
+      uint8_t* stage = sgen + C::OFF_Q + rq * 32 * ROWB;
 #pragma unroll
-        for (int c = 0; c < OH / 8; ++c) {
-          uint4 v;
-          v.x = pack_op16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-          v.y = pack_op16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-          v.z = pack_op16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-          v.w = pack_op16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-          dst[c] = v;
-        }
+      for (int c = 0; c < NCH; ++c) {
+        uint4 v;
+        v.x = pack_op16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+        v.y = pack_op16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+        v.z = pack_op16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+        v.w = pack_op16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(stage + lane * ROWB + ((c + lane) % NCH) * 16) = v;
+      }
+      __syncwarp();
+      ATTN_TRACE(warp, 60, 7);
+#pragma unroll
+      for (int it = 0; it < NCH; ++it) {
+        const int f = it * 32 + lane, row = f / NCH, slot = f - row * NCH;
+        const int c = (slot + NCH - row % NCH) % NCH;
+        const int dst_row = __shfl_sync(0xFFFFFFFFu, orow, row);
+        if (dst_row >= 0)
+          *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(dst_row) * p.D + head * HD + c * 8) =
+              *reinterpret_cast<const uint4*>(stage + f * 16);
       }
     }
   }
+  ATTN_TRACE(warp, 60, 5);
   tc_fence_before();
   __syncthreads();
 #ifdef YSI_ATTN_TRACE
-  if (trace && threadIdx.x == 0) {
+  if (!GLOBAL && trace && threadIdx.x == 0) {
+    const long long t0 = t_entry;
+    for (int w = 0; w < 4; ++w) {
+      printf("TW warp %d: setup %lld tab %lld bias %lld | loop_end %lld pv_done %lld o_loaded %lld staged %lld stored %lld | end %lld\n", w, g_attn_trace[w][60][0] - t0, g_attn_trace[w][60][1] - t0,
+             g_attn_trace[w][60][2] - t0, g_attn_trace[w][60][3] - t0, g_attn_trace[w][60][4] - t0, g_attn_trace[w][60][6] - t0, g_attn_trace[w][60][7] - t0, g_attn_trace[w][60][5] - t0, clock64() - t0);
+      for (int j = 0; j < 3; ++j)
+        printf("TW   tile %d: start %lld s_full %lld ld %lld fin %lld max %lld exps %lld pre_st %lld done %lld\n", j, g_attn_trace[w][j][0] - t0, g_attn_trace[w][j][1] - t0,
+               g_attn_trace[w][j][2] - t0, g_attn_trace[w][j][3] - t0, g_attn_trace[w][j][7] - t0, g_attn_trace[w][j][4] - t0, g_attn_trace[w][j][5] - t0, g_attn_trace[w][j][6] - t0);
+    }
+    for (int j = 0; j < 3; ++j)
+      printf("TW tile %d S-issue: kfull %lld free %lld issued %lld | PV: vfull %lld p_full %lld issued %lld\n", j, g_attn_trace[9][j][0] - t0, g_attn_trace[9][j][1] - t0,
+             g_attn_trace[9][j][2] - t0, g_attn_trace[10][j][0] - t0, g_attn_trace[10][j][1] - t0, g_attn_trace[10][j][2] - t0);
+  }
+  if (GLOBAL && trace && threadIdx.x == 0) {
     const long long t0 = g_attn_trace[0][20][0];
     for (int j = 20; j < 23; ++j) {
       for (int w = 0; w < 8; ++w)

@@ -646,6 +646,9 @@ t2i_attention_rows_kernel(const float* __restrict__ q_t2i, const T* __restrict__
       kn.load(Kb + static_cast<size_t>(it + 1) * 16 * ldk);
       vn.load(Vb + static_cast<size_t>(it + 1) * 16 * ldv);
     }
+    // all 7 scores first, ONE (rarely taken) branch for the reference update, then the 7 exponentials and the P.V updates:
+    // a branch per row would fence the scheduler into one row's dependent FMA chain at a time
+    float sc[NT];
 #pragma unroll
     for (int r = 0; r < NT; ++r) {
       float s0 = 0.f, s1 = 0.f;
@@ -655,15 +658,26 @@ t2i_attention_rows_kernel(const float* __restrict__ q_t2i, const T* __restrict__
         s0 = fmaf(qa.x, kk[4 * j], s0); s0 = fmaf(qa.y, kk[4 * j + 1], s0); s0 = fmaf(qa.z, kk[4 * j + 2], s0); s0 = fmaf(qa.w, kk[4 * j + 3], s0);
         s1 = fmaf(qb.x, kk[4 * j + 4], s1); s1 = fmaf(qb.y, kk[4 * j + 5], s1); s1 = fmaf(qb.z, kk[4 * j + 6], s1); s1 = fmaf(qb.w, kk[4 * j + 7], s1);
       }
-      const float sc = s0 + s1;
-      if (sc > m[r] + 32.0f) {               // first key of the row, then (practically) never again
-        const float f = ex2_approx(m[r] - sc);
-        l[r] *= f;
+      sc[r] = s0 + s1;
+    }
+    bool moved = false;
 #pragma unroll
-        for (int d = 0; d < 16; ++d) o[r][d] *= f;
-        m[r] = sc;
+    for (int r = 0; r < NT; ++r) moved |= sc[r] > m[r] + 32.0f;
+    if (moved) {                               // first key of the thread, then (practically) never again
+#pragma unroll
+      for (int r = 0; r < NT; ++r) {
+        if (sc[r] > m[r] + 32.0f) {
+          const float f = ex2_approx(m[r] - sc[r]);
+          l[r] *= f;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) o[r][d] *= f;
+          m[r] = sc[r];
+        }
       }
-      const float pv = ex2_approx(sc - m[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      const float pv = ex2_approx(sc[r] - m[r]);
       l[r] += pv;
 #pragma unroll
       for (int d = 0; d < 16; ++d) o[r][d] = fmaf(pv, vv[d], o[r][d]);

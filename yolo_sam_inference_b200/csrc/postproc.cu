@@ -272,7 +272,9 @@ upsample_stats_kernel(const float* __restrict__ low_all, const uint8_t* __restri
 //  * a warp walks down a band of rows with a two-row delay line (codes of row r need the border of rows r-1 .. r+1,
 //    which needs the mask of rows r-2 .. r+2); one row group above and one below the band are recomputed as halo.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FAST_WARPS = 8;
+// 4 warps per CTA and <= 128 registers per thread: four CTAs = 16 warps per SM (round-2 ncu of the 8-warp, 135-register
+// version: ONE resident CTA per SM, 12 % warps active, issue 33 % -- a latency-bound kernel starved of warps)
+constexpr int FAST_WARPS = 4;
 
 __device__ __forceinline__ unsigned int shl_in(unsigned int w, unsigned int prev_lane_word) {   // columns c-1 -> bit c
   return (w << 1) | (prev_lane_word >> 31);
@@ -281,7 +283,7 @@ __device__ __forceinline__ unsigned int shr_in(unsigned int w, unsigned int next
   return (w >> 1) | (next_lane_word << 31);
 }
 
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+__global__ void __launch_bounds__(FAST_WARPS * 32, 4)
 upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __restrict__ gray_all,
                            const int* __restrict__ mask_image, uint8_t* __restrict__ masks_out,
                            uint8_t* __restrict__ packed_out, MaskStatsDev* __restrict__ stats, int groups_per_warp) {
@@ -485,10 +487,12 @@ upsample_stats_fast_kernel(const float* __restrict__ low_all, const uint8_t* __r
   }
   if (want_hist) {
     __syncthreads();
-    unsigned int hsum = 0;
+    for (int bin = threadIdx.x; bin < 256; bin += FAST_WARPS * 32) {
+      unsigned int hsum = 0;
 #pragma unroll
-    for (int w = 0; w < FAST_WARPS; ++w) hsum += s_hist[w][0][threadIdx.x] + s_hist[w][1][threadIdx.x];
-    if (hsum) atomicAdd(&st->mask_hist[threadIdx.x], hsum);
+      for (int w = 0; w < FAST_WARPS; ++w) hsum += s_hist[w][0][bin] + s_hist[w][1][bin];
+      if (hsum) atomicAdd(&st->mask_hist[bin], hsum);
+    }
   }
 }
 
@@ -499,7 +503,9 @@ void launch_upsample_stats(const float* low, int nmask, PostGeom g, const uint16
   YSI_CHECK(masks && packed, "upsample: mask scratch and packed output are required");
   if (g.H == 1024 && g.W == 1024 && g.rh == 1024 && g.rw == 1024 && !up_logits && (sum3 == nullptr || gray != nullptr)) {
     // enough warps to fill the GPU for few masks, long bands (little halo recomputation) for many
-    const int gpw = nmask >= 64 ? 16 : (nmask >= 16 ? 8 : 4);       // row groups (4 rows each) per warp
+    // 257 row groups per mask. Many masks: 33 groups per warp = 8 warps = 2 CTAs per mask, so 256 masks are one wave of 512 CTAs
+    // (592 slots) with 6 % halo recomputation; few masks: short bands, more warps
+    const int gpw = nmask >= 64 ? 33 : (nmask >= 16 ? 8 : 4);       // row groups (4 rows each) per warp
     const int ctas = ceil_div(257, FAST_WARPS * gpw);
     upsample_stats_fast_kernel<<<dim3(ctas, nmask), FAST_WARPS * 32, 0, s>>>(low, sum3 ? gray : nullptr, mask_image,
                                                                              want_bytes ? masks : nullptr, packed, stats, gpw);

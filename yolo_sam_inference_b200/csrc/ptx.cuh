@@ -113,6 +113,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
                "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
 }
+// shared -> global copy of `bytes` contiguous bytes (multiple of 16, both sides 16-byte aligned), bulk async-group completion;
+// every thread may issue its own
+__device__ __forceinline__ void bulk_store_1d(void* dst_global, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
