@@ -91,6 +91,10 @@ struct GemmEpilogue {
 void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                cudaStream_t stream);
 
+// 3x3 / pad-1 convolution over the 64 x 64 token grid as an implicit GEMM (no im2col buffer): in = op16 [n_images*4096, channels]
+// token-major, W = [N, 9*channels] tap-major ((ky*3+kx)*channels + c), out = fp32 [n_images*4096, N].
+void gemm_conv3x3_grid(const op16* in, int n_images, int channels, const op16* W, float* out_f32, int N, cudaStream_t stream);
+
 // SM count of the CURRENT device (cached per device; thread-safe).
 int sm_count();
 // Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device. The attribute is per device and per

@@ -8,6 +8,8 @@
 // Token-side work (7 tokens per box) runs in small fp32 CUDA-core kernels, one CTA per box.
 // Block-0 image-side projections are box independent (keys = image_emb + no_mask_embed for every box)
 // and are computed once per image.
+#include <cstdlib>
+
 #include "gemm.cuh"
 #include "kernels.h"
 
@@ -891,49 +893,163 @@ struct EpiConvT1 {
   const float *bias, *g, *b;
   op16* out;   // [nb*16384, 128]: 64 channels as a two-term split [hi | lo]
   __device__ __forceinline__ void finish(EpiCtx&) const {}
-  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
-    const bool active = row < M;
-    const int box = row >> 12, tok = row & 4095, y = tok >> 6, x = tok & 63;
+  // M is a multiple of 4096 (whole boxes), so every row of a tile exists; the 32 rows of a warp are 32 consecutive x of one
+  // (box, y): for a sub-position their [hi | lo] segments lie 512 bytes apart and are written as two coalesced slabs.
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx& ctx) const {
+    const int box = ctx.row0 >> 12, tok0 = ctx.row0 & 4095, y = tok0 >> 6, x0 = tok0 & 63;
     for (int sp = c_begin / 64; sp < c_end / 64; ++sp) {
-      uint32_t r0[32], r1[32];
-      tmem_ld_x32(taddr_row + sp * 64, r0);
-      tmem_ld_x32(taddr_row + sp * 64 + 32, r1);
-      tmem_ld_wait();
-      if (!active) continue;
-      float v[64];
-      float sum = 0.f;
+      float mean, rstd;
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_x32(taddr_row + sp * 64, r0);
+        tmem_ld_x32(taddr_row + sp * 64 + 32, r1);
+        tmem_ld_wait();
+        float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        v[i] = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) + __ldg(bias + i);
-        sum += v[i];
-      }
-      const float mean = sum * (1.0f / 64.0f);
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; sq += d * d; }
-      const float rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-6f);
-      const int dy = sp >> 1, dx = sp & 1;
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(box) * 16384 + (2 * y + dy) * 128 + (2 * x + dx)) * 128);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float u[8];
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {          // packed erf-GELU (|abs err| <= 1.5e-7), as in the fc1 epilogue
-          const int i = 8 * c + k;
-          const float2 gg = gelu_erf2(make_float2((v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i),
-                                                  (v[i + 1] - mean) * rstd * __ldg(g + i + 1) + __ldg(b + i + 1)));
-          u[k] = gg.x; u[k + 1] = gg.y;
+        for (int i = 0; i < 64; ++i) {
+          const float x = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) + __ldg(bias + i);
+          if (i < 32) r0[i] = __float_as_uint(x); else r1[i - 32] = __float_as_uint(x);
+          sum += x;
         }
-        uint4 o;
-        o.x = pack_op16x2(u[0], u[1]); o.y = pack_op16x2(u[2], u[3]); o.z = pack_op16x2(u[4], u[5]); o.w = pack_op16x2(u[6], u[7]);
-        dst[c] = o;
+        mean = sum * (1.0f / 64.0f);
+        float sq = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) u[k] -= op2f(f2op(u[k]));
-        o.x = pack_op16x2(u[0], u[1]); o.y = pack_op16x2(u[2], u[3]); o.z = pack_op16x2(u[4], u[5]); o.w = pack_op16x2(u[6], u[7]);
-        dst[8 + c] = o;
+        for (int i = 0; i < 64; ++i) { const float d = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) - mean; sq += d * d; }
+        rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-6f);
+      }
+      const int dy = sp >> 1, dx = sp & 1;
+      op16* dst0 = out + (static_cast<size_t>(box) * 16384 + (2 * y + dy) * 128 + (2 * x0 + dx)) * 128;     // row x0 of the slab
+      // 32 channels at a time (re-read from the accumulator: holding all 64 values across the GELU chains spills): hi and lo
+      // segments of 64 bytes per row, one 2 KB slab each
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a[32];
+        tmem_ld_x32(taddr_row + sp * 64 + 32 * h, a);
+        tmem_ld_wait();
+        const float *bh = bias + 32 * h, *gh = g + 32 * h, *bth = b + 32 * h;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {          // packed erf-GELU (|abs err| <= 1.5e-7), as in the fc1 epilogue
+            const int i = 8 * c + 2 * k;
+            const float x0v = __uint_as_float(a[i]) + __ldg(bh + i), x1v = __uint_as_float(a[i + 1]) + __ldg(bh + i + 1);
+            const float2 gg = gelu_erf2(make_float2((x0v - mean) * rstd * __ldg(gh + i) + __ldg(bth + i),
+                                                    (x1v - mean) * rstd * __ldg(gh + i + 1) + __ldg(bth + i + 1)));
+            hw[k] = pack_op16x2(gg.x, gg.y);
+            lw[k] = pack_op16x2(gg.x - op2f(f2op(gg.x)), gg.y - op2f(f2op(gg.y)));
+          }
+          slab64_put(ctx.smem, ctx.lane, c, hw[0], hw[1], hw[2], hw[3]);
+          slab64_put(ctx.smem + 2048u, ctx.lane, c, lw[0], lw[1], lw[2], lw[3]);
+        }
+        slab64_flush(ctx.smem, ctx.lane, dst0 + 32 * h, 2 * 128 * sizeof(op16));
+        slab64_flush(ctx.smem + 2048u, ctx.lane, dst0 + 64 + 32 * h, 2 * 128 * sizeof(op16));
       }
     }
   }
+};
+template <>
+struct EpiTraits<EpiConvT1> {
+  static constexpr bool FULL_ROW = false;
+  static constexpr int WARP_SMEM = 4096;
+};
+
+// image->token out-projection (+ bias, + residual keys) fused with LayerNorm4 and the three operand copies the next
+// stages read (:343-347, what keys_ln_kernel did from an fp32 intermediate): keys (fp32, optional), op16 keys as
+// [hi | lo] (lo optional) and op16(keys + pe).  N = BN = 256: a tile holds whole rows (EpiTraits::FULL_ROW); a thread
+// owns one row, keeps the pre-LayerNorm values in its accumulator columns (tcgen05.st) between the mean, variance and
+// output passes, and every global access goes through the warp's shared-memory slab (full 128-byte lines).
+struct EpiKeysLN {
+  const float* bias;       // [256] out_proj bias
+  const float* res;        // residual rows (fp32, pitch 256): the previous block's keys
+  const int* res_group;    // block 0: box -> image (the residual is the image's keys, shared by its boxes); null: one row per GEMM row
+  const float *g, *b;      // LayerNorm4
+  const float* pe;         // [4096,256] image positional encoding
+  float* keys;             // fp32 [M,256] or null
+  op16* keys_bf;           // [M,KEYS_LD]: hi at column 0, lo at column 256 (want_lo)
+  op16* keyspos_bf;        // [M,256]
+  int want_lo;
+  __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx& ctx) const {
+    const int lane = ctx.lane, row0 = ctx.row0;          // 32 consecutive tokens of one box (M is a multiple of 4096)
+    const size_t rrow0 = res_group ? static_cast<size_t>(res_group[row0 >> 12]) * 4096 + (row0 & 4095) : static_cast<size_t>(row0);
+    const float* rbase = res + rrow0 * C;
+    const float* pbase = pe + static_cast<size_t>(row0 & 4095) * C;
+    // pass 1: v = (acc + bias) + residual, kept in the accumulator columns; row sum
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int c = 0; c < C; c += 32) {
+      uint32_t a[32], r[32];
+      tmem_ld_x32(taddr_row + c, a);
+      slab_load(ctx.smem, lane, rbase + c, C * sizeof(float), r);
+      tmem_ld_wait();
+      const float4* b4 = reinterpret_cast<const float4*>(bias + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = __ldg(b4 + i);
+        const float v0 = (__uint_as_float(a[4 * i]) + bb.x) + __uint_as_float(r[4 * i]);
+        const float v1 = (__uint_as_float(a[4 * i + 1]) + bb.y) + __uint_as_float(r[4 * i + 1]);
+        const float v2 = (__uint_as_float(a[4 * i + 2]) + bb.z) + __uint_as_float(r[4 * i + 2]);
+        const float v3 = (__uint_as_float(a[4 * i + 3]) + bb.w) + __uint_as_float(r[4 * i + 3]);
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        a[4 * i] = __float_as_uint(v0); a[4 * i + 1] = __float_as_uint(v1);
+        a[4 * i + 2] = __float_as_uint(v2); a[4 * i + 3] = __float_as_uint(v3);
+      }
+      tmem_st_x32p(taddr_row + c, a);
+    }
+    tmem_st_wait();
+    const float mean = ((s0 + s1) + (s2 + s3)) / C;
+    // pass 2: centred second moment
+    s0 = s1 = s2 = s3 = 0.f;
+    for (int c = 0; c < C; c += 32) {
+      uint32_t a[32];
+      tmem_ld_x32(taddr_row + c, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float d0 = __uint_as_float(a[i]) - mean, d1 = __uint_as_float(a[i + 1]) - mean;
+        const float d2 = __uint_as_float(a[i + 2]) - mean, d3 = __uint_as_float(a[i + 3]) - mean;
+        s0 += d0 * d0; s1 += d1 * d1; s2 += d2 * d2; s3 += d3 * d3;
+      }
+    }
+    const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) / C + 1e-6f);
+    // pass 3: normalise 64 columns at a time (one 128-byte slab of op16 per output) and write
+    for (int c = 0; c < C; c += 64) {
+      uint32_t hi[32], lo[32], kp[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a[32], pp[32];
+        tmem_ld_x32(taddr_row + c + 32 * h, a);
+        slab_load(ctx.smem, lane, pbase + c + 32 * h, C * sizeof(float), pp);
+        tmem_ld_wait();
+        const float4* g4 = reinterpret_cast<const float4*>(g + c + 32 * h);
+        const float4* b4 = reinterpret_cast<const float4*>(b + c + 32 * h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
+          const float y0 = (__uint_as_float(a[4 * i]) - mean) * rstd * gg.x + bb.x;
+          const float y1 = (__uint_as_float(a[4 * i + 1]) - mean) * rstd * gg.y + bb.y;
+          const float y2 = (__uint_as_float(a[4 * i + 2]) - mean) * rstd * gg.z + bb.z;
+          const float y3 = (__uint_as_float(a[4 * i + 3]) - mean) * rstd * gg.w + bb.w;
+          a[4 * i] = __float_as_uint(y0); a[4 * i + 1] = __float_as_uint(y1);
+          a[4 * i + 2] = __float_as_uint(y2); a[4 * i + 3] = __float_as_uint(y3);
+          hi[16 * h + 2 * i] = pack_op16x2(y0, y1);
+          hi[16 * h + 2 * i + 1] = pack_op16x2(y2, y3);
+          lo[16 * h + 2 * i] = pack_op16x2(y0 - op2f(f2op(y0)), y1 - op2f(f2op(y1)));
+          lo[16 * h + 2 * i + 1] = pack_op16x2(y2 - op2f(f2op(y2)), y3 - op2f(f2op(y3)));
+          kp[16 * h + 2 * i] = pack_op16x2(y0 + __uint_as_float(pp[4 * i]), y1 + __uint_as_float(pp[4 * i + 1]));
+          kp[16 * h + 2 * i + 1] = pack_op16x2(y2 + __uint_as_float(pp[4 * i + 2]), y3 + __uint_as_float(pp[4 * i + 3]));
+        }
+        if (keys) slab_store(ctx.smem, lane, a, keys + static_cast<size_t>(row0) * C + c + 32 * h, C * sizeof(float));
+      }
+      slab_store(ctx.smem, lane, hi, keys_bf + static_cast<size_t>(row0) * KEYS_LD + c, KEYS_LD * sizeof(op16));
+      if (want_lo) slab_store(ctx.smem, lane, lo, keys_bf + static_cast<size_t>(row0) * KEYS_LD + C + c, KEYS_LD * sizeof(op16));
+      slab_store(ctx.smem, lane, kp, keyspos_bf + static_cast<size_t>(row0) * C + c, C * sizeof(op16));
+    }
+  }
+};
+template <>
+struct EpiTraits<EpiKeysLN> {
+  static constexpr bool FULL_ROW = true;
+  static constexpr int WARP_SMEM = 4096;
 };
 
 // ConvTranspose2d(64->32,k2,s2) as a GEMM with N = 4 x 32; per sub-position: + bias, GELU, dot with the
@@ -1100,15 +1216,25 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     {
       // keys = keys_prev + out_proj(attn) ; then LN4
       ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 128);
-      GemmEpilogue ep;
-      ep.bias = lw.i2t.bo; ep.out_f32 = wk.kq; ep.ld_out = 256;      // kq (per-box) is free now: reuse as pre-LN buffer
-      ep.add_src = per_img ? wk.keys0 : wk.keys; ep.ld_add = 256;
-      if (per_img) { ep.add_mod = 4096; ep.add_group = wk.box_img; } else { ep.add_mod = TB; }
-      // block 1 reads kq (q columns) in i2t above, which is complete before this GEMM starts (same stream)
-      gemm_op16(wk.attn_i2t, 128, lw.w_i2t_out, 128, TB, 256, 128, ep, s); ++nl;
       const bool last = li == 1;
-      keys_ln_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(wk.kq, TB, lw.ln4_g, lw.ln4_b, w.image_pe, last ? nullptr : wk.keys, wk.keys_bf,
-                                                     wk.keyspos_bf, last ? 1 : 0); ++nl;
+      static const bool fused_ln = [] { const char* e = getenv("YSI_DEC_FUSED_LN"); return e ? atoi(e) != 0 : true; }();
+      if (fused_ln) {
+        // one launch: the [boxes x 4096, 256] fp32 pre-LayerNorm intermediate never leaves the SM (EpiKeysLN)
+        const CUtensorMap tmA = make_tmap_op16_2d(wk.attn_i2t, TB, 128, 128, GEMM_BM);
+        const CUtensorMap tmB = make_tmap_op16_2d(lw.w_i2t_out, 256, 128, 128, 256);
+        EpiKeysLN e{lw.i2t.bo, per_img ? wk.keys0 : wk.keys, per_img ? wk.box_img : nullptr, lw.ln4_g, lw.ln4_b, w.image_pe,
+                    last ? nullptr : wk.keys, wk.keys_bf, wk.keyspos_bf, last ? 1 : 0};
+        launch_gemm<256>(tmA, tmB, TB, 256, 128, e, s); ++nl;
+      } else {
+        GemmEpilogue ep;
+        ep.bias = lw.i2t.bo; ep.out_f32 = wk.kq; ep.ld_out = 256;      // kq (per-box) is free now: reuse as pre-LN buffer
+        ep.add_src = per_img ? wk.keys0 : wk.keys; ep.ld_add = 256;
+        if (per_img) { ep.add_mod = 4096; ep.add_group = wk.box_img; } else { ep.add_mod = TB; }
+        // block 1 reads kq (q columns) in i2t above, which is complete before this GEMM starts (same stream)
+        gemm_op16(wk.attn_i2t, 128, lw.w_i2t_out, 128, TB, 256, 128, ep, s); ++nl;
+        keys_ln_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(wk.kq, TB, lw.ln4_g, lw.ln4_b, w.image_pe, last ? nullptr : wk.keys, wk.keys_bf,
+                                                       wk.keyspos_bf, last ? 1 : 0); ++nl;
+      }
       YSI_CUDA(cudaGetLastError());
     }
   }

@@ -1,7 +1,9 @@
 // SAM ViT image encoder assembly (modeling_sam.py:1058-1072): preprocessing, patch-embed im2col,
 // LayerNorm (+ window partition), neck; the contractions run on the tcgen05 GEMM / attention kernels.
 #include "kernels.h"
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "ptx.cuh"
 
@@ -225,9 +227,11 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
                  const float* __restrict__ beta, float eps, op16* __restrict__ out_bf, float* __restrict__ out_f, int reverse) {
   // reverse: rows are processed last-to-first when the producing GEMM wrote (reduce-added) x in ascending tile order --
   // the rows most likely still in the L2 are then the last ones -- and first-to-last after a GEMM that ran descending
-  const int warp_lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // grid-stride over the rows (the launch sizes the grid to what is resident at once): with one row per warp and
+  // rows / 8 CTAs the last of 3.5 waves left most SMs idle for an eighth of this bandwidth-bound kernel
   const int lane = threadIdx.x & 31;
-  if (warp_lin >= rows_out) return;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int warp_lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp_lin < rows_out; warp_lin += warps_total) {
   const int warp_global = reverse ? rows_out - 1 - warp_lin : warp_lin;
   int src_row = warp_global;
   if (WINDOWED) {
@@ -238,7 +242,7 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
         uint4* o = reinterpret_cast<uint4*>(out_bf + static_cast<size_t>(warp_global) * D);
         for (int i = lane; i < D / 8; i += 32) o[i] = make_uint4(0, 0, 0, 0);
       }
-      return;
+      continue;
     }
     src_row = img * 4096 + tok;
   }
@@ -296,12 +300,25 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
       }
     }
   }
+  }
 }
 
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
                       op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split, bool reverse) {
   YSI_CHECK(D % 8 == 0 && D <= 1280, "LayerNorm width must be a multiple of 8 and <= 1280");
-  const int blocks = ceil_div(rows_out, 8);
+  // resident CTAs per SM of the three variants (register limited: 3 at ~80 registers); YSI_LN_CTAS_PER_SM overrides, 0 = one row per warp
+  static const int ctas_per_sm = [] {
+    const char* e = getenv("YSI_LN_CTAS_PER_SM");
+    if (e) return atoi(e);
+    int a = 0, b = 0, c = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, layernorm_kernel<false, false>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, layernorm_kernel<true, false>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, layernorm_kernel<false, true>, 256, 0);
+    const int m = std::min(a, std::min(b, c));
+    return m > 0 ? m : 3;
+  }();
+  const int full = ceil_div(rows_out, 8);
+  const int blocks = ctas_per_sm > 0 ? std::min(full, sm_count() * ctas_per_sm) : full;
   if (split)
     layernorm_kernel<false, true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f, reverse ? 1 : 0);
   else if (windowed)
@@ -432,12 +449,18 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     ep.out_f32 = work.n1; ep.ld_out = 256;
     gemm_op16(work.u, 2 * D, w.w_neck1, 2 * D, T, 256, 2 * D, ep, s); ++nl;
     launch_layernorm(work.n1, T, 256, w.neck_ln1_g, w.neck_ln1_b, 1e-6f, work.n1b, nullptr, false, s, /*split=*/true); ++nl;
-    const long long tot = static_cast<long long>(T) * 9 * 64;
-    im2col_3x3_kernel<<<static_cast<int>(std::min<long long>((tot + 255) / 256, 148 * 16)), 256, 0, s>>>(work.n1b, n, work.a_neck);
-    YSI_CUDA(cudaGetLastError()); ++nl;
-    GemmEpilogue ep2;
-    ep2.out_f32 = work.n2; ep2.ld_out = 256;
-    gemm_op16(work.a_neck, NECK_K2, w.w_neck2, NECK_K2, T, 256, NECK_K2, ep2, s); ++nl;
+    static const bool implicit = [] { const char* e = getenv("YSI_NECK_IMPLICIT"); return e ? atoi(e) != 0 : true; }();
+    if (implicit) {
+      // 3x3 convolution as an implicit GEMM: the nine shifted views of n1b are fetched by 4-D TMA boxes (zero fill = padding)
+      gemm_conv3x3_grid(work.n1b, n, NECK_C2, w.w_neck2, work.n2, 256, s); ++nl;
+    } else {
+      const long long tot = static_cast<long long>(T) * 9 * 64;
+      im2col_3x3_kernel<<<static_cast<int>(std::min<long long>((tot + 255) / 256, 148 * 16)), 256, 0, s>>>(work.n1b, n, work.a_neck);
+      YSI_CUDA(cudaGetLastError()); ++nl;
+      GemmEpilogue ep2;
+      ep2.out_f32 = work.n2; ep2.ld_out = 256;
+      gemm_op16(work.a_neck, NECK_K2, w.w_neck2, NECK_K2, T, 256, NECK_K2, ep2, s); ++nl;
+    }
     launch_layernorm(work.n2, T, 256, w.neck_ln2_g, w.neck_ln2_b, 1e-6f, nullptr, emb_out, false, s); ++nl;
   }
   *launches += nl;

@@ -66,6 +66,45 @@ static CUtensorMap make_tmap_2d(const void* base, int esize, uint64_t rows, uint
   return m;
 }
 
+// [images, 64, 64, channels] op16 map (token-major activations of the 64 x 64 grid) as a 4-D tensor map with a
+// {64 channels, 64 x, 2 y, 1 image} box = the 128 x 64 A tile of the GEMM; out-of-range x / y read as zero (conv padding).
+static CUtensorMap make_tmap_op16_grid4d(const void* base, int n_images, int channels) {
+  typedef std::tuple<const void*, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(base, n_images, channels);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  YSI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && channels % 64 == 0, "grid map: alignment / channel count");
+  CUtensorMap m;
+  const cuuint64_t row = static_cast<cuuint64_t>(channels) * 2;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(channels), 64, 64, static_cast<cuuint64_t>(n_images)};
+  cuuint64_t gstride[3] = {row, 64 * row, 4096 * row};
+  cuuint32_t box[4] = {64, 64, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_fn()(&m, OP16_TMAP_TYPE, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YSI_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D) failed with code " + std::to_string(static_cast<int>(r)));
+  std::lock_guard<std::mutex> g(mu);
+  cache[key] = m;
+  return m;
+}
+
+void gemm_conv3x3_grid(const op16* in, int n_images, int channels, const op16* W, float* out_f32, int N, cudaStream_t stream) {
+  YSI_CHECK(channels == 512 && N == 256, "implicit 3x3 convolution GEMM: 512 input values per position (8 k-blocks per tap), 256 outputs");
+  const int M = n_images * 4096, K = 9 * channels;
+  const CUtensorMap tmA = make_tmap_op16_grid4d(in, n_images, channels);
+  const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, K, 128);
+  EpiStaged es;
+  es.tm_out = make_tmap_f32_2d(out_f32, M, N, N, 32);
+  es.bias = nullptr; es.act = ACT_NONE; es.col_scale = 1.f; es.scale_c0 = es.scale_c1 = 0;
+  es.f32_add = 2; es.reverse_m = 0;
+  launch_gemm2<256, 1>(tmA, tmB, M, N, K, es, stream);
+}
+
 const char* kernel_class_name(int kc) {
   static const char* names[KC_COUNT] = {"preprocess", "layernorm", "gemm_patch", "gemm_qkv", "attn_window", "attn_global",
                                         "gemm_proj", "gemm_fc1", "gemm_fc2", "neck", "dec_token", "dec_gemm", "dec_attn",

@@ -75,6 +75,92 @@ struct EpiCtx {
   int lane;
 };
 
+// Per-epilogue kernel options of gemm_op16_kernel (specialise for an epilogue type):
+//   WARP_SMEM : bytes of staging shared memory per epilogue warp, handed over in EpiCtx::smem
+//   FULL_ROW  : an accumulator tile is drained by FOUR warps that own whole rows (all BN columns) instead of eight that own
+//               half a row each: the warps of column half h take the tiles that land in accumulator buffer h, so both
+//               groups work at the same time on consecutive tiles and a row-wise reduction (LayerNorm over the tile's
+//               columns) needs no exchange between warps
+template <class Epi>
+struct EpiTraits {
+  static constexpr bool FULL_ROW = false;
+  static constexpr int WARP_SMEM = 0;
+};
+
+// Warp-collective transposition through a 4 KB shared-memory slab of 32 rows x 128 bytes (16-byte pieces XOR-swizzled by
+// the row, conflict free both ways).  An epilogue thread owns one accumulator ROW, so its own loads / stores touch 32
+// different 128-byte lines per instruction (16 useful bytes each); through the slab every global instruction moves four
+// whole lines instead.  g_row0 = address of the slab's first row (row r of the slab lives pitch_bytes * r further).
+__device__ __forceinline__ void slab_put(uint32_t sm, int lane, int j, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  // 16-byte piece j (0..7) of the calling lane's row
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sm + static_cast<uint32_t>(lane) * 128u +
+                                                                ((static_cast<uint32_t>(j) ^ static_cast<uint32_t>(lane & 7)) << 4)),
+               "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void slab_flush(uint32_t sm, int lane, void* g_row0, size_t pitch_bytes) {
+  __syncwarp();
+  uint8_t* g = static_cast<uint8_t*>(g_row0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t r = static_cast<uint32_t>(4 * j + (lane >> 3)), pc = static_cast<uint32_t>(lane & 7);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sm + r * 128u + ((pc ^ (r & 7u)) << 4)) : "memory");
+    *reinterpret_cast<uint4*>(g + pitch_bytes * r + pc * 16u) = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void slab_store(uint32_t sm, int lane, const uint32_t (&pk)[32], void* g_row0, size_t pitch_bytes) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) slab_put(sm, lane, j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  slab_flush(sm, lane, g_row0, pitch_bytes);
+}
+// Half-width variant: 32 rows x 64 bytes in 2 KB (four 16-byte pieces per row, swizzled by row >> 1), for outputs whose
+// rows are 64-byte segments; two of them fit the warp's 4 KB.
+__device__ __forceinline__ void slab64_put(uint32_t sm, int lane, int p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sm + static_cast<uint32_t>(lane) * 64u +
+                                                                ((static_cast<uint32_t>(p) ^ static_cast<uint32_t>((lane >> 1) & 3)) << 4)),
+               "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void slab64_flush(uint32_t sm, int lane, void* g_row0, size_t pitch_bytes) {
+  __syncwarp();
+  uint8_t* g = static_cast<uint8_t*>(g_row0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t r = static_cast<uint32_t>(8 * j + (lane >> 2)), pc = static_cast<uint32_t>(lane & 3);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sm + r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4)) : "memory");
+    *reinterpret_cast<uint4*>(g + pitch_bytes * r + pc * 16u) = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void slab_load(uint32_t sm, int lane, const void* g_row0, size_t pitch_bytes, uint32_t (&out)[32]) {
+  const uint8_t* g = static_cast<const uint8_t*>(g_row0);
+  uint4 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t r = static_cast<uint32_t>(4 * j + (lane >> 3)), pc = static_cast<uint32_t>(lane & 7);
+    v[j] = __ldg(reinterpret_cast<const uint4*>(g + pitch_bytes * r + pc * 16u));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t r = static_cast<uint32_t>(4 * j + (lane >> 3)), pc = static_cast<uint32_t>(lane & 7);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sm + r * 128u + ((pc ^ (r & 7u)) << 4)), "r"(v[j].x), "r"(v[j].y),
+                 "r"(v[j].z), "r"(v[j].w)
+                 : "memory");
+  }
+  __syncwarp();
+  const uint32_t rowp = sm + static_cast<uint32_t>(lane) * 128u, swz = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(out[4 * j]), "=r"(out[4 * j + 1]), "=r"(out[4 * j + 2]), "=r"(out[4 * j + 3])
+                 : "r"(rowp + ((static_cast<uint32_t>(j) ^ swz) << 4)) : "memory");
+  __syncwarp();
+}
+
 // Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_op16.
 struct EpiGeneric {
   GemmEpilogue p;
@@ -291,9 +377,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  Epi epi) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool FULL_ROW = EpiTraits<Epi>::FULL_ROW;
+  constexpr int WARP_SMEM = EpiTraits<Epi>::WARP_SMEM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_smem = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;       // GEMM_EPI_WARPS x WARP_SMEM of epilogue staging
+  const uint32_t bar_base = epi_smem + GEMM_EPI_WARPS * WARP_SMEM;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -317,7 +406,7 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
+      mbar_init(tempty_bar(a), FULL_ROW ? GEMM_EPI_WARPS / 2 : GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -392,20 +481,23 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
-    const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
+    const int c_begin = FULL_ROW ? 0 : half * (BN / 2), c_end = FULL_ROW ? BN : c_begin + BN / 2;
+    const uint32_t my_smem = WARP_SMEM ? epi_smem + static_cast<uint32_t>(warp - 2) * WARP_SMEM : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * GEMM_BM;
-      const int n0 = (tile % num_n) * BN;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-      EpiCtx ctx{0u, 0u, m0 + q * 32, lane};
-      epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end, ctx);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (!FULL_ROW || acc == half) {      // FULL_ROW: this warp group owns the tiles of accumulator buffer `half`
+        const int m0 = (tile / num_n) * GEMM_BM;
+        const int n0 = (tile % num_n) * BN;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
+        EpiCtx ctx{my_smem, 0u, m0 + q * 32, lane};
+        epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end, ctx);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -439,7 +531,11 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN_, class Epi>
+// AMODE 1: the A operand is the implicit im2col of a 3x3 / pad-1 convolution over a [images, 64, 64, 512] op16 map (tmA is
+// the 4-D tensor map of it, box = 64 channels x 64 x x 2 y): k-block kb = tap (kb / 8) x 64-channel slice (kb % 8), the 128
+// rows of a CTA are two rows of the 64 x 64 grid, and the tile of tap (ky, kx) is the box shifted by (ky - 1, kx - 1) with
+// the TMA's zero fill as the padding -- the [tokens, 9 x 512] im2col matrix is never written.
+template <int BN_, class Epi, int AMODE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                   const __grid_constant__ Epi epi) {
@@ -501,7 +597,12 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lead) {
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-            tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            if (AMODE == 1) {
+              const int tap = kb >> 3;
+              tma_load_4d_cg2(sa, &tmA, full_bar(stage), (kb & 7) * GEMM_BK, tap % 3 - 1, ((m0 & 4095) >> 6) + tap / 3 - 1, m0 >> 12);
+            } else {
+              tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            }
             tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
           }
           __syncwarp();
@@ -569,10 +670,10 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN_ = 256, class Epi>
+template <int BN_ = 256, int AMODE = 0, class Epi>
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN_>;
-  auto kern = gemm2_op16_kernel<BN_, Epi>;
+  auto kern = gemm2_op16_kernel<BN_, Epi, AMODE>;
   ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   const int tiles = ceil_div(M, 2 * GEMM_BM) * (N / Cfg::BN);
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
@@ -584,11 +685,14 @@ template <int BN, class Epi>
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi,
                  cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
+  constexpr int SMEM = Cfg::SMEM_BYTES + GEMM_EPI_WARPS * EpiTraits<Epi>::WARP_SMEM;
+  static_assert(SMEM <= 232448, "shared memory of the GEMM stages + epilogue staging exceeds one SM");
+  static_assert(EpiTraits<Epi>::WARP_SMEM % 1024 == 0, "epilogue staging slabs are 1 KB aligned");
   auto kern = gemm_op16_kernel<BN, Epi>;
-  ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
+  ensure_dyn_smem(reinterpret_cast<const void*>(kern), SMEM);
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  kern<<<grid, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, M, N, K, epi);
   YSI_CUDA(cudaGetLastError());
 }
 
