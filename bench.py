@@ -188,18 +188,28 @@ def write_folder(grays, boxes, prefix="img", repeat=1):
     many times under different names: a longer folder from the same synthetic frames, so that one process_directory call is
     many batches long and the two-slot pipeline's fill / drain does not dominate the measurement."""
     import cv2
-    need = repeat * sum(g.nbytes for g in grays) * 1.25
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) and \
-        shutil.disk_usage("/dev/shm").free > need else None
-    d = tempfile.mkdtemp(prefix="ysi_bench_", dir=base)
-    table = {}
-    for r in range(repeat):
-        for i, (g, b) in enumerate(zip(grays, boxes)):
-            name = f"{prefix}_{r * len(grays) + i:05d}.tiff"
-            if not cv2.imwrite(os.path.join(d, name), g, [cv2.IMWRITE_TIFF_COMPRESSION, 1]):
-                raise IOError(f"could not write {name} into {d}")
-            table[name] = b
-    return d, table
+    need = repeat * sum(g.nbytes for g in grays) * 1.5
+    bases = []
+    if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) and shutil.disk_usage("/dev/shm").free > need:
+        bases.append("/dev/shm")
+    bases.append(None)                   # the default temporary directory: always tried last
+    for base in bases:
+        d = tempfile.mkdtemp(prefix="ysi_bench_", dir=base)
+        table, ok = {}, True
+        for r in range(repeat):
+            for i, (g, b) in enumerate(zip(grays, boxes)):
+                name = f"{prefix}_{r * len(grays) + i:05d}.tiff"
+                path = os.path.join(d, name)
+                if not cv2.imwrite(path, g, [cv2.IMWRITE_TIFF_COMPRESSION, 1]) or os.path.getsize(path) < g.nbytes:
+                    ok = False           # e.g. another rank filled the shared-memory file system meanwhile
+                    break
+                table[name] = b
+            if not ok:
+                break
+        if ok:
+            return d, table
+        shutil.rmtree(d, ignore_errors=True)
+    raise IOError("could not write the benchmark folder (no space in /dev/shm nor in the temporary directory)")
 
 
 # --------------------------------------------------------------------------------------------------

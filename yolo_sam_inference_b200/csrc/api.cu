@@ -213,6 +213,27 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
     lw.w_proj = b16(p + "attn.proj.weight", {D, D}); lw.b_proj = f32(p + "attn.proj.bias", {D});
     lw.w_fc1 = b16(p + "mlp.lin1.weight", {mlp, D}); lw.b_fc1 = f32(p + "mlp.lin1.bias", {mlp});
     lw.w_fc2 = b16(p + "mlp.lin2.weight", {D, mlp}); lw.b_fc2 = f32(p + "mlp.lin2.bias", {D});
+    {
+      // folded LayerNorm (encoder.cu): column sums of the weights AS THE TENSOR CORE SEES THEM (op16) against gamma and beta
+      auto fold = [&](const std::string& wname, const std::string& bname, int N, const std::string& ln, const float** cs_out,
+                      const float** wb_out, const float** bw_out) {
+        const HostTensor& wt = wm.get(wname); const HostTensor& bs = wm.get(bname);
+        const HostTensor& g = wm.get(ln + ".weight"); const HostTensor& bt = wm.get(ln + ".bias");
+        std::vector<float> cs(N), wb(N), bw(N);
+        for (int n2 = 0; n2 < N; ++n2) {
+          double a = 0.0, b2 = 0.0;
+          for (int k = 0; k < D; ++k) {
+            const double w16 = static_cast<double>(op2f(f2op(wt.data[static_cast<size_t>(n2) * D + k])));
+            a += static_cast<double>(g.data[k]) * w16; b2 += static_cast<double>(bt.data[k]) * w16;
+          }
+          cs[n2] = static_cast<float>(a); wb[n2] = static_cast<float>(b2); bw[n2] = static_cast<float>(b2 + static_cast<double>(bs.data[n2]));
+        }
+        *cs_out = c->upload_f32(cs.data(), cs.size()); *wb_out = c->upload_f32(wb.data(), wb.size());
+        *bw_out = c->upload_f32(bw.data(), bw.size());
+      };
+      fold(p + "attn.qkv.weight", p + "attn.qkv.bias", 3 * D, p + "layer_norm1", &lw.cs_qkv, &lw.wb_qkv, &lw.bw_qkv);
+      fold(p + "mlp.lin1.weight", p + "mlp.lin1.bias", mlp, p + "layer_norm2", &lw.cs_fc1, &lw.wb_fc1, &lw.bw_fc1);
+    }
     const HostTensor& rh = wm.get(p + "attn.rel_pos_h", {2 * S - 1, hd});
     const HostTensor& rw = wm.get(p + "attn.rel_pos_w", {2 * S - 1, hd});
     std::vector<op16> tab(256 * hdp, f2op(0.f));
@@ -395,6 +416,14 @@ void create_impl(ysi_ctx* c) {
   int* map = c->dalloc<int>(B * 4900);
   launch_build_win_row_map(map, cfg.max_batch, c->stream);
   ew.win_row_map = map;
+  {
+    ew.h_win = c->dalloc<op16>(B * 4900 * D);
+    YSI_CUDA(cudaMemsetAsync(ew.h_win, 0, sizeof(op16) * B * 4900 * D, c->stream));     // the 64 -> 70 pad rows are never written
+    int* tw = c->dalloc<int>(B * 4096);
+    launch_build_tok_win_map(tw, cfg.max_batch, c->stream);
+    ew.tok_win_map = tw;
+    ew.ln_stats = c->dalloc<float2>(B * 4096 * LN_STAT_SLOTS);
+  }
   DecoderWork& dw = c->dw;
   dw.cap_img = cfg.max_batch; dw.cap_box = cfg.max_boxes;
   dw.keys0 = c->dalloc<float>(B * 4096 * 256);

@@ -85,7 +85,28 @@ struct GemmEpilogue {
   // rows its producer wrote last -- the ones still in the 126 MB L2 -- instead of the ones evicted first (used for fc2;
   // measured effect at 8 images: within run-to-run noise, LayerNorm's matching row order -2 %).
   int reverse_m = 0;
+  // LayerNorm folded into the GEMMs on either side of it (CTA-pair kernel; encoder.cu explains the algebra):
+  //  producer (a residual add, accumulate != 0): besides x += ..., write op16(x16_gamma[col] * x_new) to row
+  //    x16_rowmap[row] (null: row) of x16_out and the row's partial (sum, sum of squares) to stats_out[row][slot]
+  //  consumer (op16 output): A is such an x16; y = rstd * acc - rstd * mean * ln_cs[n] + ln_bw[n] (ln_bw = bias + wb) with mean /
+  //    rstd from ln_stats[ln_rowmap[row] or row][0..ln_np); a negative map entry is a zero (pad) row: its output is ln_bw - ln_wb
+  op16* x16_out = nullptr;
+  int ld_x16 = 0;
+  const float* x16_gamma = nullptr;
+  const int* x16_rowmap = nullptr;
+  float2* stats_out = nullptr;
+  const float2* ln_stats = nullptr;
+  int ln_np = 0;
+  const int* ln_rowmap = nullptr;
+  int ln_dim = 0;
+  float ln_eps = 1e-6f;
+  const float* ln_cs = nullptr;
+  const float* ln_bw = nullptr;   // bias + wb (the epilogue then ignores `bias`)
+  const float* ln_wb = nullptr;
 };
+
+// number of statistics slots per row the producer writes for an output width N (two column halves per N tile)
+int gemm_ln_stat_slots(int M, int N);
 
 // C[M,N] = A[M,K] * W[N,K]^T, op16 operands, fp32 accumulation in TMEM. A: row pitch lda, W: row pitch ldw.
 void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,

@@ -974,12 +974,22 @@ struct EpiKeysLN {
     const size_t rrow0 = res_group ? static_cast<size_t>(res_group[row0 >> 12]) * 4096 + (row0 & 4095) : static_cast<size_t>(row0);
     const float* rbase = res + rrow0 * C;
     const float* pbase = pe + static_cast<size_t>(row0 & 4095) * C;
-    // pass 1: v = (acc + bias) + residual, kept in the accumulator columns; row sum
+    // pass 1: v = (acc + bias) + residual, kept in the accumulator columns; row sum. The residual slab of the next 32 columns
+    // is in flight while the current one is transposed and added (a warp otherwise has 4 KB of loads outstanding at a time,
+    // and eight such warps per SM do not cover the memory latency: 3.1 TB/s measured without the prefetch).
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    uint4 nxt[8];
+    slab_load_issue(lane, rbase, C * sizeof(float), nxt);
+#pragma unroll
     for (int c = 0; c < C; c += 32) {
       uint32_t a[32], r[32];
+      uint4 cur[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (c + 32 < C) slab_load_issue(lane, rbase + c + 32, C * sizeof(float), nxt);
+      else slab_load_issue(lane, pbase, C * sizeof(float), nxt);            // first pe slab of pass 3
       tmem_ld_x32(taddr_row + c, a);
-      slab_load(ctx.smem, lane, rbase + c, C * sizeof(float), r);
+      slab_load_finish(ctx.smem, lane, cur, r);
       tmem_ld_wait();
       const float4* b4 = reinterpret_cast<const float4*>(bias + c);
 #pragma unroll
@@ -1011,38 +1021,51 @@ struct EpiKeysLN {
       }
     }
     const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) / C + 1e-6f);
-    // pass 3: normalise 64 columns at a time (one 128-byte slab of op16 per output) and write
-    for (int c = 0; c < C; c += 64) {
-      uint32_t hi[32], lo[32], kp[32];
+    // pass 3: normalise 32 columns at a time and write: fp32 rows as one 128-byte slab, the op16 outputs as 64-byte slabs
+    // (two fit the warp's 4 KB); the pe slab of the next 32 columns is in flight meanwhile
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t a[32], pp[32];
-        tmem_ld_x32(taddr_row + c + 32 * h, a);
-        slab_load(ctx.smem, lane, pbase + c + 32 * h, C * sizeof(float), pp);
-        tmem_ld_wait();
-        const float4* g4 = reinterpret_cast<const float4*>(g + c + 32 * h);
-        const float4* b4 = reinterpret_cast<const float4*>(b + c + 32 * h);
+    for (int c = 0; c < C; c += 32) {
+      uint32_t a[32], pp[32];
+      uint4 cur[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
-          const float y0 = (__uint_as_float(a[4 * i]) - mean) * rstd * gg.x + bb.x;
-          const float y1 = (__uint_as_float(a[4 * i + 1]) - mean) * rstd * gg.y + bb.y;
-          const float y2 = (__uint_as_float(a[4 * i + 2]) - mean) * rstd * gg.z + bb.z;
-          const float y3 = (__uint_as_float(a[4 * i + 3]) - mean) * rstd * gg.w + bb.w;
-          a[4 * i] = __float_as_uint(y0); a[4 * i + 1] = __float_as_uint(y1);
-          a[4 * i + 2] = __float_as_uint(y2); a[4 * i + 3] = __float_as_uint(y3);
-          hi[16 * h + 2 * i] = pack_op16x2(y0, y1);
-          hi[16 * h + 2 * i + 1] = pack_op16x2(y2, y3);
-          lo[16 * h + 2 * i] = pack_op16x2(y0 - op2f(f2op(y0)), y1 - op2f(f2op(y1)));
-          lo[16 * h + 2 * i + 1] = pack_op16x2(y2 - op2f(f2op(y2)), y3 - op2f(f2op(y3)));
-          kp[16 * h + 2 * i] = pack_op16x2(y0 + __uint_as_float(pp[4 * i]), y1 + __uint_as_float(pp[4 * i + 1]));
-          kp[16 * h + 2 * i + 1] = pack_op16x2(y2 + __uint_as_float(pp[4 * i + 2]), y3 + __uint_as_float(pp[4 * i + 3]));
-        }
-        if (keys) slab_store(ctx.smem, lane, a, keys + static_cast<size_t>(row0) * C + c + 32 * h, C * sizeof(float));
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (c + 32 < C) slab_load_issue(lane, pbase + c + 32, C * sizeof(float), nxt);
+      tmem_ld_x32(taddr_row + c, a);
+      slab_load_finish(ctx.smem, lane, cur, pp);
+      tmem_ld_wait();
+      const float4* g4 = reinterpret_cast<const float4*>(g + c);
+      const float4* b4 = reinterpret_cast<const float4*>(b + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
+        a[4 * i] = __float_as_uint((__uint_as_float(a[4 * i]) - mean) * rstd * gg.x + bb.x);
+        a[4 * i + 1] = __float_as_uint((__uint_as_float(a[4 * i + 1]) - mean) * rstd * gg.y + bb.y);
+        a[4 * i + 2] = __float_as_uint((__uint_as_float(a[4 * i + 2]) - mean) * rstd * gg.z + bb.z);
+        a[4 * i + 3] = __float_as_uint((__uint_as_float(a[4 * i + 3]) - mean) * rstd * gg.w + bb.w);
       }
-      slab_store(ctx.smem, lane, hi, keys_bf + static_cast<size_t>(row0) * KEYS_LD + c, KEYS_LD * sizeof(op16));
-      if (want_lo) slab_store(ctx.smem, lane, lo, keys_bf + static_cast<size_t>(row0) * KEYS_LD + C + c, KEYS_LD * sizeof(op16));
-      slab_store(ctx.smem, lane, kp, keyspos_bf + static_cast<size_t>(row0) * C + c, C * sizeof(op16));
+      if (keys) slab_store(ctx.smem, lane, a, keys + static_cast<size_t>(row0) * C + c, C * sizeof(float));
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4) {          // 8 columns = one 16-byte piece of the hi / lo slabs
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(a[8 * p4 + k]);
+        slab64_put(ctx.smem, lane, p4, pack_op16x2(y[0], y[1]), pack_op16x2(y[2], y[3]), pack_op16x2(y[4], y[5]), pack_op16x2(y[6], y[7]));
+        if (want_lo)
+          slab64_put(ctx.smem + 2048u, lane, p4, pack_op16x2(y[0] - op2f(f2op(y[0])), y[1] - op2f(f2op(y[1]))),
+                     pack_op16x2(y[2] - op2f(f2op(y[2])), y[3] - op2f(f2op(y[3]))),
+                     pack_op16x2(y[4] - op2f(f2op(y[4])), y[5] - op2f(f2op(y[5]))),
+                     pack_op16x2(y[6] - op2f(f2op(y[6])), y[7] - op2f(f2op(y[7]))));
+      }
+      slab64_flush(ctx.smem, lane, keys_bf + static_cast<size_t>(row0) * KEYS_LD + c, KEYS_LD * sizeof(op16));
+      if (want_lo) slab64_flush(ctx.smem + 2048u, lane, keys_bf + static_cast<size_t>(row0) * KEYS_LD + C + c, KEYS_LD * sizeof(op16));
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4) {
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = __uint_as_float(a[8 * p4 + k]) + __uint_as_float(pp[8 * p4 + k]);
+        slab64_put(ctx.smem, lane, p4, pack_op16x2(y[0], y[1]), pack_op16x2(y[2], y[3]), pack_op16x2(y[4], y[5]), pack_op16x2(y[6], y[7]));
+      }
+      slab64_flush(ctx.smem, lane, keyspos_bf + static_cast<size_t>(row0) * C + c, C * sizeof(op16));
     }
   }
 };

@@ -227,11 +227,11 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
                  const float* __restrict__ beta, float eps, op16* __restrict__ out_bf, float* __restrict__ out_f, int reverse) {
   // reverse: rows are processed last-to-first when the producing GEMM wrote (reduce-added) x in ascending tile order --
   // the rows most likely still in the L2 are then the last ones -- and first-to-last after a GEMM that ran descending
-  // grid-stride over the rows (the launch sizes the grid to what is resident at once): with one row per warp and
-  // rows / 8 CTAs the last of 3.5 waves left most SMs idle for an eighth of this bandwidth-bound kernel
+  // (one row per warp, rows / 8 CTAs. A grid-stride loop over 2 / 3 / 4 resident CTAs per SM was measured in round 2:
+  // 0.95 / 0.81 / 0.97 ms per batch against 0.78 -- the hardware's CTA dispatch balances this bandwidth-bound kernel better.)
+  const int warp_lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (int warp_lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp_lin < rows_out; warp_lin += warps_total) {
+  if (warp_lin >= rows_out) return;
   const int warp_global = reverse ? rows_out - 1 - warp_lin : warp_lin;
   int src_row = warp_global;
   if (WINDOWED) {
@@ -242,7 +242,7 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
         uint4* o = reinterpret_cast<uint4*>(out_bf + static_cast<size_t>(warp_global) * D);
         for (int i = lane; i < D / 8; i += 32) o[i] = make_uint4(0, 0, 0, 0);
       }
-      continue;
+      return;
     }
     src_row = img * 4096 + tok;
   }
@@ -300,25 +300,12 @@ layernorm_kernel(const float* __restrict__ x, int rows_out, int D, const float* 
       }
     }
   }
-  }
 }
 
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
                       op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split, bool reverse) {
   YSI_CHECK(D % 8 == 0 && D <= 1280, "LayerNorm width must be a multiple of 8 and <= 1280");
-  // resident CTAs per SM of the three variants (register limited: 3 at ~80 registers); YSI_LN_CTAS_PER_SM overrides, 0 = one row per warp
-  static const int ctas_per_sm = [] {
-    const char* e = getenv("YSI_LN_CTAS_PER_SM");
-    if (e) return atoi(e);
-    int a = 0, b = 0, c = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, layernorm_kernel<false, false>, 256, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, layernorm_kernel<true, false>, 256, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, layernorm_kernel<false, true>, 256, 0);
-    const int m = std::min(a, std::min(b, c));
-    return m > 0 ? m : 3;
-  }();
-  const int full = ceil_div(rows_out, 8);
-  const int blocks = ctas_per_sm > 0 ? std::min(full, sm_count() * ctas_per_sm) : full;
+  const int blocks = ceil_div(rows_out, 8);
   if (split)
     layernorm_kernel<false, true><<<blocks, 256, 0, s>>>(x, rows_out, D, gamma, beta, eps, out_bf, out_f, reverse ? 1 : 0);
   else if (windowed)
@@ -339,6 +326,60 @@ __global__ void build_win_row_map_kernel(int* map, int total) {
 void launch_build_win_row_map(int* map, int n_images, cudaStream_t s) {
   const int total = n_images * 4900;
   build_win_row_map_kernel<<<ceil_div(total, 256), 256, 0, s>>>(map, total);
+  YSI_CUDA(cudaGetLastError());
+}
+
+__global__ void build_tok_win_map_kernel(int* map, int total) {     // token row -> row in window-partition order
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = i >> 12, tok = i & 4095, y = tok >> 6, x = tok & 63;
+  map[i] = img * 4900 + ((y / 14) * 5 + x / 14) * 196 + (y % 14) * 14 + x % 14;
+}
+
+void launch_build_tok_win_map(int* map, int n_images, cudaStream_t s) {
+  const int total = n_images * 4096;
+  build_tok_win_map_kernel<<<ceil_div(total, 256), 256, 0, s>>>(map, total);
+  YSI_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm folded into the GEMMs around it (round 2).  LN(x) W^T + b, with LN(x) = (x - mean) * rstd * gamma + beta, is
+//     rstd * [ (gamma . x) W^T - mean * cs ] + wb + b,      cs[n] = sum_k gamma[k] W[n,k],  wb[n] = sum_k beta[k] W[n,k]
+// so the qkv / fc1 GEMM can run on  x16 = op16(gamma . x)  of the RAW residual stream and apply mean / rstd per row in its
+// epilogue (EpiStaged::prefetch / run).  x16 and the row statistics come out of the epilogue that produced x -- the proj / fc2
+// residual adds (EpiResidLN: x_new is in registers there anyway) -- so the 24 LayerNorm passes over the fp32 stream
+// (read 100 MB + write 50 MB each at 8 ViT-B images) disappear; what remains is this kernel for the first layer.
+// Rounding: the operand is rounded at gamma * x instead of at LN(x): the same relative step, on a value that still carries
+// the row mean, which for these residual streams is small against the row's standard deviation.
+// Row statistics are (sum, sum of squares) in fp32, summed over at most LN_STAT_SLOTS partials in a fixed order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_operand_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ gamma, op16* __restrict__ x16,
+                  const int* __restrict__ tok_win_map, float2* __restrict__ stats, int slots) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  op16* orow = x16 + static_cast<size_t>(tok_win_map ? tok_win_map[row] : row) * D;
+  float sm = 0.f, sq = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = xr[i], g = __ldg(g4 + i);
+    sm += (v.x + v.y) + (v.z + v.w);
+    sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+    uint2 o;
+    o.x = pack_op16x2(g.x * v.x, g.y * v.y);
+    o.y = pack_op16x2(g.z * v.z, g.w * v.w);
+    reinterpret_cast<uint2*>(orow)[i] = o;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o); sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); }
+  if (lane < slots) stats[static_cast<size_t>(row) * slots + lane] = lane == 0 ? make_float2(sm, sq) : make_float2(0.f, 0.f);
+}
+
+void launch_ln_operand(const float* x, int rows, int D, const float* gamma, op16* x16, const int* tok_win_map, float2* stats,
+                       int slots, cudaStream_t s) {
+  YSI_CHECK(D % 4 == 0 && slots >= 1 && slots <= 32, "LayerNorm operand kernel: width / slot count");
+  ln_operand_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, D, gamma, x16, tok_win_map, stats, slots);
   YSI_CUDA(cudaGetLastError());
 }
 
@@ -393,18 +434,35 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     gemm_op16(work.a_patch, PATCH_K, w.w_patch, PATCH_K, T, D, PATCH_K, ep, s); ++nl;
   }
   if (hidden_dump) YSI_CUDA(cudaMemcpyAsync(hidden_dump, work.x, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, s));
+  // LayerNorm folded into the neighbouring GEMMs (see ln_operand_kernel). YSI_LN_FUSED is a bit mask: 1 = LayerNorm1 (fc2 of the
+  // previous layer -> qkv), 2 = LayerNorm2 (proj -> fc1), 0 = the separate LayerNorm kernels.
+  static const int ln_fused_env = [] { const char* e = getenv("YSI_LN_FUSED"); return e ? atoi(e) : 1; }();
+  static const bool pair_env = [] { const char* a = getenv("YSI_GEMM_PAIR"); const char* b = getenv("YSI_GEMM_STAGED");
+                                    return (!a || atoi(a) != 0) && (!b || atoi(b) != 0); }();
+  const int slots = gemm_ln_stat_slots(T, D);
+  const bool ln_ok = pair_env && T >= 2048 && D % 256 == 0 && w.mlp % 256 == 0 && slots <= LN_STAT_SLOTS && w.residual_mode == 2;
+  const bool ln1_fused = ln_ok && (ln_fused_env & 1), ln2_fused = ln_ok && (ln_fused_env & 2);
   for (int li = 0; li < w.L; ++li) {
     const EncoderLayerW& lw = w.layers[li];
     const bool glob = lw.is_global != 0;
     const int rows = glob ? T : TW;
     // algorithmic FLOPs (pad rows / pad keys excluded) are attached to every record for the roofline
-    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s, false, /*reverse=*/li == 0); ++nl; }
+    if (!ln1_fused) {
+      ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s, false, /*reverse=*/li == 0); ++nl;
+    } else if (li == 0) {
+      ProfScope ps(prof, KC_LAYERNORM);
+      launch_ln_operand(work.x, T, D, lw.ln1_g, glob ? work.h : work.h_win, glob ? nullptr : work.tok_win_map, work.ln_stats, slots, s); ++nl;
+    }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_qkv; ep.out_op16 = work.qkv; ep.ld_out_op16 = 3 * D;
       ep.col_scale = attn_k_scale(w.head_dim); ep.scale_c0 = D; ep.scale_c1 = 2 * D;     // K in log2 units for the attention kernel
+      if (ln1_fused) {
+        ep.ln_stats = work.ln_stats; ep.ln_np = slots; ep.ln_dim = D; ep.ln_rowmap = glob ? nullptr : work.win_row_map;
+        ep.ln_cs = lw.cs_qkv; ep.ln_wb = lw.wb_qkv; ep.ln_bw = lw.bw_qkv;
+      }
       ProfScope ps(prof, KC_GEMM_QKV, 2.0 * T * 3 * D * D);
-      gemm_op16(work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
+      gemm_op16((ln1_fused && !glob) ? work.h_win : work.h, D, lw.w_qkv, D, rows, 3 * D, D, ep, s); ++nl;
     }
     {
       const double S = glob ? 64.0 : 14.0, tok = glob ? 4096.0 : 196.0, nseq = glob ? n : n * 25.0;
@@ -415,13 +473,17 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     {
       GemmEpilogue ep;   // x += attn * Wproj^T + b ; the attention kernel already un-partitioned the windows
       ep.bias = lw.b_proj; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
+      if (ln2_fused) {      // LayerNorm2's operand copy (token order) and statistics come out of this epilogue
+        ep.stats_out = work.ln_stats; ep.x16_out = work.h; ep.ld_x16 = D; ep.x16_gamma = lw.ln2_g;
+      }
       ProfScope ps(prof, KC_GEMM_PROJ, 2.0 * T * D * D);
       gemm_op16(work.attn, D, lw.w_proj, D, T, D, D, ep, s); ++nl;
     }
-    { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s, false, /*reverse=*/true); ++nl; }
+    if (!ln2_fused) { ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, T, D, lw.ln2_g, lw.ln2_b, 1e-6f, work.h, nullptr, false, s, false, /*reverse=*/true); ++nl; }
     {
       GemmEpilogue ep;
       ep.bias = lw.b_fc1; ep.act = ACT_GELU; ep.out_op16 = work.u; ep.ld_out_op16 = w.mlp;
+      if (ln2_fused) { ep.ln_stats = work.ln_stats; ep.ln_np = slots; ep.ln_dim = D; ep.ln_cs = lw.cs_fc1; ep.ln_wb = lw.wb_fc1; ep.ln_bw = lw.bw_fc1; }
       ProfScope ps(prof, KC_GEMM_FC1, 2.0 * T * w.mlp * D);
       gemm_op16(work.h, D, lw.w_fc1, D, T, w.mlp, D, ep, s); ++nl;
     }
@@ -429,6 +491,11 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
       GemmEpilogue ep;
       ep.bias = lw.b_fc2; ep.out_f32 = work.x; ep.ld_out = D; ep.accumulate = w.residual_mode;
       ep.reverse_m = 1;      // u (201 MB at 8 images) was written first-to-last by fc1: read its L2-resident tail first
+      if (ln1_fused && li + 1 < w.L) {      // the next layer's LayerNorm1: operand copy in that layer's row order
+        const EncoderLayerW& nw = w.layers[li + 1];
+        ep.stats_out = work.ln_stats; ep.ld_x16 = D; ep.x16_gamma = nw.ln1_g;
+        if (nw.is_global) { ep.x16_out = work.h; } else { ep.x16_out = work.h_win; ep.x16_rowmap = work.tok_win_map; }
+      }
       ProfScope ps(prof, KC_GEMM_FC2, 2.0 * T * w.mlp * D);
       gemm_op16(work.u, w.mlp, lw.w_fc2, w.mlp, T, D, w.mlp, ep, s); ++nl;
     }

@@ -162,6 +162,14 @@ void ensure_dyn_smem(const void* func, int bytes) {
   have = bytes;
 }
 
+// tile width the CTA-pair kernel uses for an fp32-output GEMM of this shape (192-column tiles where they need fewer rounds)
+static bool pair_uses_bn192(int M, int N) {
+  static const int allow192 = [] { const char* e = getenv("YSI_GEMM_BN192"); return e ? atoi(e) : 1; }();
+  const int pairs = sm_count() / 2, m_tiles = ceil_div(M, 2 * GEMM_BM);
+  return allow192 && N % 192 == 0 && ceil_div(m_tiles * (N / 192), pairs) * 192 < ceil_div(m_tiles * (N / 256), pairs) * 256;
+}
+int gemm_ln_stat_slots(int M, int N) { return 2 * (pair_uses_bn192(M, N) ? N / 192 : N / 256); }
+
 void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                cudaStream_t stream) {
   YSI_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
@@ -175,19 +183,29 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
     // big GEMMs: CTA pairs (cta_group::2), each CTA loads half of the B tile
     const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 128);
     // 192-column tiles where they need less time than 256-column ones: rounds over the CTA pairs x columns per tile
-    const int pairs = sm_count() / 2, m_tiles = ceil_div(M, 2 * GEMM_BM);
-    static const int allow192 = [] { const char* e = getenv("YSI_GEMM_BN192"); return e ? atoi(e) : 1; }();
-    const bool bn192 = allow192 && N % 192 == 0 &&
-                       ceil_div(m_tiles * (N / 192), pairs) * 192 < ceil_div(m_tiles * (N / 256), pairs) * 256;
+    const bool bn192 = pair_uses_bn192(M, N);
     const CUtensorMap tmB192 = bn192 ? make_tmap_op16_2d(W, N, K, ldw, 96) : tmB;
     static const int use_staged = [] { const char* e = getenv("YSI_GEMM_STAGED"); return e ? atoi(e) : 1; }();
     const bool plain = !ep.row_map && !ep.add_src && ep.act != ACT_RELU;
-    if (use_staged && plain && ep.out_op16 && !ep.out_f32) {
+    YSI_CHECK(!ep.ln_stats || (plain && ep.out_op16 && !ep.out_f32 && ep.ln_cs && ep.ln_wb && ep.ln_bw && ep.ln_np > 0 && ep.ln_dim > 0),
+              "folded LayerNorm needs the staged op16 epilogue");
+    if (ep.stats_out) {
+      // residual add with the next LayerNorm's operand copy and statistics (EpiResidLN)
+      YSI_CHECK(plain && ep.out_f32 && !ep.out_op16 && ep.accumulate && ep.act == ACT_NONE && M % 32 == 0 && ep.bias,
+                "LayerNorm-producing epilogue: residual add only");
+      EpiResidLN er;
+      er.x = ep.out_f32; er.ld = ep.ld_out; er.bias = ep.bias; er.gamma = ep.x16_gamma; er.x16 = ep.x16_out; er.ld16 = ep.ld_x16;
+      er.rowmap = ep.x16_rowmap; er.stats = ep.stats_out; er.np = gemm_ln_stat_slots(M, N); er.reverse_m = ep.reverse_m;
+      if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, er, stream);
+      else launch_gemm2(tmA, tmB, M, N, K, er, stream);
+    } else if (use_staged && plain && ep.out_op16 && !ep.out_f32) {
       // op16 activation output: tile staged in shared memory, written with TMA stores
       EpiStaged es;
       es.tm_out = make_tmap_op16_2d(ep.out_op16, M, N, ep.ld_out_op16, 32);
       es.bias = ep.bias; es.act = ep.act; es.col_scale = ep.col_scale; es.scale_c0 = ep.scale_c0; es.scale_c1 = ep.scale_c1;
       es.f32_add = 0; es.reverse_m = ep.reverse_m;
+      es.ln_stats = ep.ln_stats; es.ln_rowmap = ep.ln_rowmap; es.ln_np = ep.ln_np; es.ln_eps = ep.ln_eps;
+      es.ln_inv_d = ep.ln_dim > 0 ? 1.0f / static_cast<float>(ep.ln_dim) : 0.f; es.ln_cs = ep.ln_cs; es.ln_bw = ep.ln_bw; es.ln_wb = ep.ln_wb;
       launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && ep.accumulate && ep.act == ACT_NONE) {
       // residual add: x += tile through cp.reduce.async.bulk (fp32 add in the L2, 128-byte rows)
@@ -206,10 +224,12 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
       if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, es, stream);
       else launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else {
+      YSI_CHECK(!ep.ln_stats, "folded LayerNorm needs the staged op16 epilogue (YSI_GEMM_STAGED=1)");
       launch_gemm2(tmA, tmB, M, N, K, epi, stream);
     }
     return;
   }
+  YSI_CHECK(!ep.ln_stats && !ep.stats_out, "folded LayerNorm is implemented in the CTA-pair kernel only (M >= 2048, N % 256 == 0)");
   // widest tile that does not waste more than a quarter of its columns
   if (N % 256 == 0 || N > 512) {
     const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 256);

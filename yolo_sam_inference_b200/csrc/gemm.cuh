@@ -67,12 +67,18 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return fma2(make_float2(fabsf(hx.x), fabsf(hx.y)), erfv, hx);
 }
 
+// what an epilogue may fetch per tile BEFORE the accumulator is ready (CTA-pair kernel: Epi::prefetch), so that the loads'
+// latency hides under the wait: the row's LayerNorm scalars
+struct EpiPre {
+  float2 row;        // (rstd, -rstd * mean) of the thread's row; (0, 0): zero (pad) row
+};
 // per-warp epilogue context: staging shared memory (CTA-pair kernel only) and the warp's first output row
 struct EpiCtx {
   uint32_t smem;     // 2 x 4 KB staging buffers of this warp (0: none)
   uint32_t nbuf;     // running buffer counter
   int row0;          // first row of the warp's 32-row slab
   int lane;
+  EpiPre pre;        // CTA-pair kernel: what Epi::prefetch() returned, loaded before the wait for the accumulator
 };
 
 // Per-epilogue kernel options of gemm_op16_kernel (specialise for an epilogue type):
@@ -137,14 +143,41 @@ __device__ __forceinline__ void slab64_flush(uint32_t sm, int lane, void* g_row0
   }
   __syncwarp();
 }
-__device__ __forceinline__ void slab_load(uint32_t sm, int lane, const void* g_row0, size_t pitch_bytes, uint32_t (&out)[32]) {
+// Loads come in two halves so that a caller can have the next slab's global loads in flight while it works on the current one.
+__device__ __forceinline__ void slab_load_issue(int lane, const void* g_row0, size_t pitch_bytes, uint4 (&v)[8]) {
   const uint8_t* g = static_cast<const uint8_t*>(g_row0);
-  uint4 v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t r = static_cast<uint32_t>(4 * j + (lane >> 3)), pc = static_cast<uint32_t>(lane & 7);
     v[j] = __ldg(reinterpret_cast<const uint4*>(g + pitch_bytes * r + pc * 16u));
   }
+}
+// same, with coherent loads (for memory this kernel also writes -- the residual stream -- where ld.global.nc is not allowed)
+__device__ __forceinline__ void slab_load_issue_rw(int lane, const void* g_row0, size_t pitch_bytes, uint4 (&v)[8]) {
+  const uint8_t* g = static_cast<const uint8_t*>(g_row0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t r = static_cast<uint32_t>(4 * j + (lane >> 3)), pc = static_cast<uint32_t>(lane & 7);
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                 : "l"(g + pitch_bytes * r + pc * 16u) : "memory");
+  }
+}
+// 64-byte slab written to mapped rows: slab row r goes to row dst_rows[r] of the destination (null: row0_dst + r)
+__device__ __forceinline__ void slab64_flush_map(uint32_t sm, int lane, void* g_base, size_t pitch_bytes, const int* dst_rows, int row0_dst) {
+  __syncwarp();
+  uint8_t* g = static_cast<uint8_t*>(g_base);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t r = static_cast<uint32_t>(8 * j + (lane >> 2)), pc = static_cast<uint32_t>(lane & 3);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sm + r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4)) : "memory");
+    const size_t drow = dst_rows ? static_cast<size_t>(__ldg(dst_rows + r)) : static_cast<size_t>(row0_dst) + r;
+    *reinterpret_cast<uint4*>(g + pitch_bytes * drow + pc * 16u) = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void slab_load_finish(uint32_t sm, int lane, const uint4 (&v)[8], uint32_t (&out)[32]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t r = static_cast<uint32_t>(4 * j + (lane >> 3)), pc = static_cast<uint32_t>(lane & 7);
@@ -160,12 +193,18 @@ __device__ __forceinline__ void slab_load(uint32_t sm, int lane, const void* g_r
                  : "r"(rowp + ((static_cast<uint32_t>(j) ^ swz) << 4)) : "memory");
   __syncwarp();
 }
+__device__ __forceinline__ void slab_load(uint32_t sm, int lane, const void* g_row0, size_t pitch_bytes, uint32_t (&out)[32]) {
+  uint4 v[8];
+  slab_load_issue(lane, g_row0, pitch_bytes, v);
+  slab_load_finish(sm, lane, v, out);
+}
 
 // Generic epilogue: v = acc + bias[col]; act; + add_src[(row % add_mod), col]; -> out_f32 (= or +=) / out_op16.
 struct EpiGeneric {
   GemmEpilogue p;
   int reverse_m = 0;   // CTA-pair kernel: walk the row tiles last-to-first (see GemmEpilogue::reverse_m)
   __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ EpiPre prefetch(int, int, int, int) const { return EpiPre{}; }
   // columns [c_begin, c_end) of the BN-wide accumulator tile belong to the calling warp
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     // every lane must execute the warp-collective tcgen05.ld convergently: predicate only the stores
@@ -269,6 +308,28 @@ struct alignas(64) EpiStaged {
   int scale_c0, scale_c1;
   int f32_add;     // 0: op16 store, 1: fp32 reduce-add, 2: fp32 store
   int reverse_m = 0;   // walk the row tiles last-to-first (GemmEpilogue::reverse_m)
+  // LayerNorm folded into this GEMM (op16 store path; GemmEpilogue::ln_stats): the A operand is op16(gamma * x) of the raw
+  // residual stream and  y = rstd * acc - rstd * mean * cs[n] + wb[n] + bias[n]  with the row's mean / rstd from its partial
+  // sums; a zero (pad) row of a padded window gets the plain bias
+  const float2* ln_stats = nullptr;      // [token rows][ln_np] partial (sum, sum of squares) written by EpiResidLN / ln_operand_kernel
+  const int* ln_rowmap = nullptr;        // GEMM row -> token row (< 0: zero pad row); null: identity
+  int ln_np = 0;
+  float ln_inv_d = 0.f, ln_eps = 0.f;
+  const float *ln_cs = nullptr, *ln_bw = nullptr, *ln_wb = nullptr;      // cs, bias + wb (real rows), wb (subtracted again on pad rows)
+  __device__ __forceinline__ EpiPre prefetch(int row, int M, int col0, int lane) const {
+    EpiPre p{};
+    if (!ln_stats) return p;
+    const int tok = row < M ? (ln_rowmap ? __ldg(ln_rowmap + row) : row) : -1;
+    if (tok >= 0) {
+      const float2* sp = ln_stats + static_cast<size_t>(tok) * ln_np;
+      float sm = 0.f, sq = 0.f;
+      for (int i = 0; i < ln_np; ++i) { const float2 t = __ldg(sp + i); sm += t.x; sq += t.y; }      // fixed order: bitwise reproducible
+      const float mean = sm * ln_inv_d;
+      const float rstd = rsqrtf(fmaxf(sq * ln_inv_d - mean * mean, 0.f) + ln_eps);
+      p.row = make_float2(rstd, -rstd * mean);
+    }
+    return p;
+  }
   // bulk async-groups belong to the issuing thread: elect.sync picks the same lane for the same (full) mask every time
   __device__ __forceinline__ void finish(EpiCtx& ctx) const {
     if (elect_one()) bulk_wait_read<0>();
@@ -313,6 +374,10 @@ struct alignas(64) EpiStaged {
         slab_out(ctx, r, col0);
       }
     } else {
+      // folded LayerNorm: this thread's row scalars (fetched by prefetch() before the accumulator was ready)
+      const float rs = ctx.pre.row.x, nrm = ctx.pre.row.y;
+      const bool pad = ln_stats && rs == 0.f;
+      const bool any_pad = ln_stats && __any_sync(0xFFFFFFFFu, pad);
       for (int c = c_begin; c < c_end; c += 64) {
         const int col0 = n0 + c;
         uint32_t pk[32];
@@ -325,7 +390,29 @@ struct alignas(64) EpiStaged {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           const int colh = col0 + 32 * h;
-          if (bias) {
+          if (ln_stats) {
+            // y = rs * acc + (nrm * cs[n] + bw[n]), two packed FFMA2 per pair of columns (bw = bias + wb, folded on the host).
+            // (Broadcasting cs / bw from registers spread over the lanes -- 256 shuffles per tile and warp -- measured slower
+            // than these loads, although they miss the ~24 KB of L1 this kernel leaves: qkv 1.23 vs 1.17 ms per batch.)
+            const float4* c4 = reinterpret_cast<const float4*>(ln_cs + colh);
+            const float4* w4 = reinterpret_cast<const float4*>(ln_bw + colh);
+            const float2 rs2 = make_float2(rs, rs), nrm2 = make_float2(nrm, nrm);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 cc = __ldg(c4 + i), ww = __ldg(w4 + i);
+              const float2 a0 = fma2(rs2, make_float2(v[4 * i], v[4 * i + 1]), fma2(nrm2, make_float2(cc.x, cc.y), make_float2(ww.x, ww.y)));
+              const float2 a1 = fma2(rs2, make_float2(v[4 * i + 2], v[4 * i + 3]), fma2(nrm2, make_float2(cc.z, cc.w), make_float2(ww.z, ww.w)));
+              v[4 * i] = a0.x; v[4 * i + 1] = a0.y; v[4 * i + 2] = a1.x; v[4 * i + 3] = a1.y;
+            }
+            if (any_pad && pad) {          // zero row of a padded window: the plain bias
+              const float4* p4 = reinterpret_cast<const float4*>(ln_wb + colh);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 ww = __ldg(p4 + i);
+                v[4 * i] -= ww.x; v[4 * i + 1] -= ww.y; v[4 * i + 2] -= ww.z; v[4 * i + 3] -= ww.w;
+              }
+            }
+          } else if (bias) {
             const float4* b4 = reinterpret_cast<const float4*>(bias + colh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -353,12 +440,76 @@ struct alignas(64) EpiStaged {
   }
 };
 
+// Residual add with the NEXT LayerNorm folded in (CTA-pair kernel): x_new = (acc + bias) + x is formed on the SM (coalesced
+// slab loads / stores of the fp32 stream instead of the L2 reduce-add), and while the values are in registers the epilogue
+// also emits what the following qkv / fc1 GEMM needs in place of a LayerNorm pass over x:
+//   x16   = op16(gamma * x_new), written to row rowmap[row] (window-partition order for windowed layers) or row itself
+//   stats = per-row (sum, sum of squares) of x_new over this warp's columns, one slot per (N tile, column half)
+// The consumer GEMM (EpiStaged::prefetch) turns them into mean / rstd.  x_new is bit-identical to the reduce-add path.
+struct alignas(64) EpiResidLN {
+  float* x; int ld;
+  const float* bias;
+  const float* gamma;
+  op16* x16; int ld16;
+  const int* rowmap;
+  float2* stats; int np;
+  int reverse_m = 0;
+  __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ EpiPre prefetch(int, int, int, int) const { return EpiPre{}; }
+  __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx& ctx) const {
+    const int lane = ctx.lane, row0 = ctx.row0;        // M is a multiple of 32: the warp's 32 rows all exist
+    float* xb = x + static_cast<size_t>(row0) * ld + n0;
+    const uint32_t buf0 = ctx.smem, buf1 = ctx.smem + 4096u;
+    float s = 0.f, ss = 0.f;
+    uint4 nxt[8];
+    slab_load_issue_rw(lane, xb + c_begin, static_cast<size_t>(ld) * sizeof(float), nxt);
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t a[32], r[32];
+      uint4 cur[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (c + 32 < c_end) slab_load_issue_rw(lane, xb + c + 32, static_cast<size_t>(ld) * sizeof(float), nxt);
+      tmem_ld_x32(taddr_row + c, a);
+      slab_load_finish(buf0, lane, cur, r);
+      tmem_ld_wait();
+      const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = __ldg(b4 + i);
+        const float v0 = (__uint_as_float(a[4 * i]) + bb.x) + __uint_as_float(r[4 * i]);
+        const float v1 = (__uint_as_float(a[4 * i + 1]) + bb.y) + __uint_as_float(r[4 * i + 1]);
+        const float v2 = (__uint_as_float(a[4 * i + 2]) + bb.z) + __uint_as_float(r[4 * i + 2]);
+        const float v3 = (__uint_as_float(a[4 * i + 3]) + bb.w) + __uint_as_float(r[4 * i + 3]);
+        s += (v0 + v1) + (v2 + v3);
+        ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+        a[4 * i] = __float_as_uint(v0); a[4 * i + 1] = __float_as_uint(v1);
+        a[4 * i + 2] = __float_as_uint(v2); a[4 * i + 3] = __float_as_uint(v3);
+      }
+      slab_store(buf0, lane, a, xb + c, static_cast<size_t>(ld) * sizeof(float));
+      if (x16) {
+        const float4* g4 = reinterpret_cast<const float4*>(gamma + n0 + c);
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4) {
+          const float4 g0 = __ldg(g4 + 2 * p4), g1 = __ldg(g4 + 2 * p4 + 1);
+          slab64_put(buf1, lane, p4, pack_op16x2(g0.x * __uint_as_float(a[8 * p4]), g0.y * __uint_as_float(a[8 * p4 + 1])),
+                     pack_op16x2(g0.z * __uint_as_float(a[8 * p4 + 2]), g0.w * __uint_as_float(a[8 * p4 + 3])),
+                     pack_op16x2(g1.x * __uint_as_float(a[8 * p4 + 4]), g1.y * __uint_as_float(a[8 * p4 + 5])),
+                     pack_op16x2(g1.z * __uint_as_float(a[8 * p4 + 6]), g1.w * __uint_as_float(a[8 * p4 + 7])));
+        }
+        slab64_flush_map(buf1, lane, x16 + n0 + c, static_cast<size_t>(ld16) * sizeof(op16), rowmap ? rowmap + row0 : nullptr, row0);
+      }
+    }
+    if (stats) stats[static_cast<size_t>(row0 + lane) * np + (n0 + c_begin) / (c_end - c_begin)] = make_float2(s, ss);
+  }
+};
+
 // measurement-only epilogue (ysi_gemm_bench): drains the accumulator from TMEM and stores nothing unless the value
 // is an (impossible) sentinel, so the mainloop can be timed without the epilogue's global-memory traffic
 struct EpiDrain {
   float* sink;
   int reverse_m = 0;
   __device__ __forceinline__ void finish(EpiCtx&) const {}
+  __device__ __forceinline__ EpiPre prefetch(int, int, int, int) const { return EpiPre{}; }
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx&) const {
     float acc = 0.f;
     for (int c = c_begin; c < c_end; c += 32) {
@@ -492,7 +643,7 @@ gemm_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-        EpiCtx ctx{my_smem, 0u, m0 + q * 32, lane};
+        EpiCtx ctx{my_smem, 0u, m0 + q * 32, lane, EpiPre{}};
         epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end, ctx);
         tc_fence_before();
         __syncwarp();
@@ -648,15 +799,16 @@ gemm2_op16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    EpiCtx ctx{epi_smem + static_cast<uint32_t>(warp - 2) * 8192u, 0u, 0, lane};
+    EpiCtx ctx{epi_smem + static_cast<uint32_t>(warp - 2) * 8192u, 0u, 0, lane, EpiPre{}};
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int mt = epi.reverse_m ? num_m - 1 - tile / num_n : tile / num_n;
       const int m0 = mt * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (tile % num_n) * BN;
+      ctx.row0 = m0 + q * 32;
+      ctx.pre = epi.prefetch(m0 + q * 32 + lane, M, n0 + c_begin, lane);      // per-row / per-column scalars: latency hides under the wait
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
-      ctx.row0 = m0 + q * 32;
       epi.run(taddr, m0 + q * 32 + lane, M, n0, N, c_begin, c_end, ctx);
       tc_fence_before();
       __syncwarp();

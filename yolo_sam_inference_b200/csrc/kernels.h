@@ -73,6 +73,8 @@ struct EncoderLayerW {
   const float *b_qkv, *b_proj, *b_fc1, *b_fc2;
   const op16* rel_tab;   // [256,HDP] * log2(e): rows 0..127 rel_pos_h (zero padded), rows 128..255 rel_pos_w
   int is_global;
+  // LayerNorm folded into qkv / fc1 (encoder.cu): cs[n] = sum_k gamma[k] W[n,k], wb[n] = sum_k beta[k] W[n,k], bw = bias + wb
+  const float *cs_qkv, *wb_qkv, *bw_qkv, *cs_fc1, *wb_fc1, *bw_fc1;
 };
 
 struct EncoderW {
@@ -102,7 +104,12 @@ struct EncoderWork {      // activation workspace for `cap` images
   op16* a_neck;           // [cap*4096, NECK_K2]
   float* n2;              // [cap*4096, 256]
   const int* win_row_map; // [cap*4900] window row -> token row (or -1)
+  // folded LayerNorm: windowed operand copy (pad rows stay zero for ever), token -> window row map, per-row statistics slots
+  op16* h_win;            // [cap*4900, D]
+  const int* tok_win_map; // [cap*4096] token row -> window row
+  float2* ln_stats;       // [cap*4096, LN_STAT_SLOTS]
 };
+constexpr int LN_STAT_SLOTS = 16;   // >= 2 * (D / 192) for every supported width (ViT-H: 1280 / 256 * 2 = 10, ViT-L: 1024 / 256 * 2 = 8)
 
 // torchvision / Pillow fixed-point antialias resampling tables for one axis (see encoder.cu)
 struct ResizeTables {
@@ -127,6 +134,11 @@ void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_
                        const float* std255, float* pixel_values, op16* a_patch, cudaStream_t s);
 void launch_im2col_patch_f32(const float* pixel_values, int n, op16* a_patch, cudaStream_t s);
 void launch_build_win_row_map(int* map, int n_images, cudaStream_t s);
+void launch_build_tok_win_map(int* map, int n_images, cudaStream_t s);
+// folded-LayerNorm operands of the first layer (what the residual epilogues produce for every later one): op16(gamma * x)
+// rows in token order or, with tok_win_map, window-partition order, and the per-row (sum, sum of squares) in slot 0
+void launch_ln_operand(const float* x, int rows, int D, const float* gamma, op16* x16, const int* tok_win_map, float2* stats,
+                       int slots, cudaStream_t s);
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
                       op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split = false, bool reverse = false);
 // runs the whole encoder on work.a_patch (n images); result: image embeddings fp32 token-major [n*4096, 256].
