@@ -411,7 +411,10 @@ void create_impl(ysi_ctx* c) {
   ew.u = c->dalloc<op16>(B * 4096 * cfg.mlp_dim);
   ew.n1 = c->dalloc<float>(B * 4096 * 256);
   ew.n1b = c->dalloc<op16>(B * 4096 * NECK_C2);
-  ew.a_neck = c->dalloc<op16>(B * 4096 * NECK_K2);
+  {     // im2col buffer of the neck's 3x3 convolution: only the YSI_NECK_IMPLICIT=0 fallback reads it (302 MB at 8 images)
+    const char* e = getenv("YSI_NECK_IMPLICIT");
+    ew.a_neck = (e && atoi(e) == 0) ? c->dalloc<op16>(B * 4096 * NECK_K2) : nullptr;
+  }
   ew.n2 = c->dalloc<float>(B * 4096 * 256);
   int* map = c->dalloc<int>(B * 4900);
   launch_build_win_row_map(map, cfg.max_batch, c->stream);

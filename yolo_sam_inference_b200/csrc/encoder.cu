@@ -347,42 +347,12 @@ void launch_build_tok_win_map(int* map, int n_images, cudaStream_t s) {
 //     rstd * [ (gamma . x) W^T - mean * cs ] + wb + b,      cs[n] = sum_k gamma[k] W[n,k],  wb[n] = sum_k beta[k] W[n,k]
 // so the qkv / fc1 GEMM can run on  x16 = op16(gamma . x)  of the RAW residual stream and apply mean / rstd per row in its
 // epilogue (EpiStaged::prefetch / run).  x16 and the row statistics come out of the epilogue that produced x -- the proj / fc2
-// residual adds (EpiResidLN: x_new is in registers there anyway) -- so the 24 LayerNorm passes over the fp32 stream
-// (read 100 MB + write 50 MB each at 8 ViT-B images) disappear; what remains is this kernel for the first layer.
+// residual adds and, for the first layer, the patch-embed GEMM (EpiResidLN: x_new is in registers there anyway) -- so the
+// LayerNorm passes over the fp32 stream (read 100 MB + write 50 MB each at 8 ViT-B images) disappear.
 // Rounding: the operand is rounded at gamma * x instead of at LN(x): the same relative step, on a value that still carries
 // the row mean, which for these residual streams is small against the row's standard deviation.
 // Row statistics are (sum, sum of squares) in fp32, summed over at most LN_STAT_SLOTS partials in a fixed order.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ln_operand_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ gamma, op16* __restrict__ x16,
-                  const int* __restrict__ tok_win_map, float2* __restrict__ stats, int slots) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  op16* orow = x16 + static_cast<size_t>(tok_win_map ? tok_win_map[row] : row) * D;
-  float sm = 0.f, sq = 0.f;
-  for (int i = lane; i < D / 4; i += 32) {
-    const float4 v = xr[i], g = __ldg(g4 + i);
-    sm += (v.x + v.y) + (v.z + v.w);
-    sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
-    uint2 o;
-    o.x = pack_op16x2(g.x * v.x, g.y * v.y);
-    o.y = pack_op16x2(g.z * v.z, g.w * v.w);
-    reinterpret_cast<uint2*>(orow)[i] = o;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o); sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); }
-  if (lane < slots) stats[static_cast<size_t>(row) * slots + lane] = lane == 0 ? make_float2(sm, sq) : make_float2(0.f, 0.f);
-}
-
-void launch_ln_operand(const float* x, int rows, int D, const float* gamma, op16* x16, const int* tok_win_map, float2* stats,
-                       int slots, cudaStream_t s) {
-  YSI_CHECK(D % 4 == 0 && slots >= 1 && slots <= 32, "LayerNorm operand kernel: width / slot count");
-  ln_operand_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, D, gamma, x16, tok_win_map, stats, slots);
-  YSI_CUDA(cudaGetLastError());
-}
-
 // 3x3 / pad 1 im2col over the 64x64 token grid, tap-major columns; a row of `in` is the 256 channels as a two-term
 // split [hi(256) | lo(256)] (NECK_C2 = 512 values):
 //   A[t, (ky*3+kx)*512 + c] = in[(y+ky-1, x+kx-1), c]  (zero outside the grid)
@@ -425,16 +395,7 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
   YSI_CHECK(n >= 1 && n <= work.cap, "encoder batch exceeds the workspace");
   const int D = w.D, T = n * 4096, TW = n * 4900;
   int64_t nl = 0;
-  // patch embed: x = A * Wp^T + b + pos_embed   (modeling_sam.py:128, 1065-1066)
-  {
-    GemmEpilogue ep;
-    ep.bias = w.b_patch; ep.add_src = w.pos_embed; ep.add_mod = 4096; ep.ld_add = D;
-    ep.out_f32 = work.x; ep.ld_out = D;
-    ProfScope ps(prof, KC_GEMM_PATCH, 2.0 * T * D * 768);      // algorithmic FLOPs: the lo term is overhead
-    gemm_op16(work.a_patch, PATCH_K, w.w_patch, PATCH_K, T, D, PATCH_K, ep, s); ++nl;
-  }
-  if (hidden_dump) YSI_CUDA(cudaMemcpyAsync(hidden_dump, work.x, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, s));
-  // LayerNorm folded into the neighbouring GEMMs (see ln_operand_kernel). YSI_LN_FUSED is a bit mask: 1 = LayerNorm1 (fc2 of the
+  // LayerNorm folded into the neighbouring GEMMs (see the comment on the folded LayerNorm above). YSI_LN_FUSED is a bit mask: 1 = LayerNorm1 (fc2 of the
   // previous layer -> qkv), 2 = LayerNorm2 (proj -> fc1), 0 = the separate LayerNorm kernels.
   static const int ln_fused_env = [] { const char* e = getenv("YSI_LN_FUSED"); return e ? atoi(e) : 1; }();
   static const bool pair_env = [] { const char* a = getenv("YSI_GEMM_PAIR"); const char* b = getenv("YSI_GEMM_STAGED");
@@ -442,6 +403,20 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
   const int slots = gemm_ln_stat_slots(T, D);
   const bool ln_ok = pair_env && T >= 2048 && D % 256 == 0 && w.mlp % 256 == 0 && slots <= LN_STAT_SLOTS && w.residual_mode == 2;
   const bool ln1_fused = ln_ok && (ln_fused_env & 1), ln2_fused = ln_ok && (ln_fused_env & 2);
+  // patch embed: x = A * Wp^T + b + pos_embed   (modeling_sam.py:128, 1065-1066)
+  {
+    GemmEpilogue ep;
+    ep.bias = w.b_patch; ep.add_src = w.pos_embed; ep.add_mod = 4096; ep.ld_add = D;
+    ep.out_f32 = work.x; ep.ld_out = D;
+    if (ln1_fused) {      // the first layer's LayerNorm1 operand and statistics come out of this epilogue as well
+      const bool g0 = w.layers[0].is_global != 0;
+      ep.stats_out = work.ln_stats; ep.ld_x16 = D; ep.x16_gamma = w.layers[0].ln1_g;
+      if (g0) { ep.x16_out = work.h; } else { ep.x16_out = work.h_win; ep.x16_rowmap = work.tok_win_map; }
+    }
+    ProfScope ps(prof, KC_GEMM_PATCH, 2.0 * T * D * 768);      // algorithmic FLOPs: the lo term is overhead
+    gemm_op16(work.a_patch, PATCH_K, w.w_patch, PATCH_K, T, D, PATCH_K, ep, s); ++nl;
+  }
+  if (hidden_dump) YSI_CUDA(cudaMemcpyAsync(hidden_dump, work.x, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, s));
   for (int li = 0; li < w.L; ++li) {
     const EncoderLayerW& lw = w.layers[li];
     const bool glob = lw.is_global != 0;
@@ -449,9 +424,6 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
     // algorithmic FLOPs (pad rows / pad keys excluded) are attached to every record for the roofline
     if (!ln1_fused) {
       ProfScope ps(prof, KC_LAYERNORM); launch_layernorm(work.x, rows, D, lw.ln1_g, lw.ln1_b, 1e-6f, work.h, nullptr, !glob, s, false, /*reverse=*/li == 0); ++nl;
-    } else if (li == 0) {
-      ProfScope ps(prof, KC_LAYERNORM);
-      launch_ln_operand(work.x, T, D, lw.ln1_g, glob ? work.h : work.h_win, glob ? nullptr : work.tok_win_map, work.ln_stats, slots, s); ++nl;
     }
     {
       GemmEpilogue ep;

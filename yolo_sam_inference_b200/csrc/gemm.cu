@@ -191,10 +191,12 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
               "folded LayerNorm needs the staged op16 epilogue");
     if (ep.stats_out) {
       // residual add with the next LayerNorm's operand copy and statistics (EpiResidLN)
-      YSI_CHECK(plain && ep.out_f32 && !ep.out_op16 && ep.accumulate && ep.act == ACT_NONE && M % 32 == 0 && ep.bias,
-                "LayerNorm-producing epilogue: residual add only");
+      const bool addend = ep.add_src && !ep.add_group && !ep.accumulate && ep.add_mod % 32 == 0;      // x = acc + bias + add_src[row % add_mod]
+      YSI_CHECK(!ep.row_map && ep.act != ACT_RELU && (addend || (!ep.add_src && ep.accumulate)) && ep.out_f32 && !ep.out_op16 &&
+                ep.act == ACT_NONE && M % 32 == 0 && ep.bias, "LayerNorm-producing epilogue: residual add (or bias + row-periodic addend) only");
       EpiResidLN er;
-      er.x = ep.out_f32; er.ld = ep.ld_out; er.bias = ep.bias; er.gamma = ep.x16_gamma; er.x16 = ep.x16_out; er.ld16 = ep.ld_x16;
+      er.x = ep.out_f32; er.ld = ep.ld_out; er.bias = ep.bias;
+      if (addend) { er.res = ep.add_src; er.ld_res = ep.ld_add; er.res_mod = ep.add_mod; } er.gamma = ep.x16_gamma; er.x16 = ep.x16_out; er.ld16 = ep.ld_x16;
       er.rowmap = ep.x16_rowmap; er.stats = ep.stats_out; er.np = gemm_ln_stat_slots(M, N); er.reverse_m = ep.reverse_m;
       if (bn192) launch_gemm2<192>(tmA, tmB192, M, N, K, er, stream);
       else launch_gemm2(tmA, tmB, M, N, K, er, stream);

@@ -311,7 +311,7 @@ struct alignas(64) EpiStaged {
   // LayerNorm folded into this GEMM (op16 store path; GemmEpilogue::ln_stats): the A operand is op16(gamma * x) of the raw
   // residual stream and  y = rstd * acc - rstd * mean * cs[n] + wb[n] + bias[n]  with the row's mean / rstd from its partial
   // sums; a zero (pad) row of a padded window gets the plain bias
-  const float2* ln_stats = nullptr;      // [token rows][ln_np] partial (sum, sum of squares) written by EpiResidLN / ln_operand_kernel
+  const float2* ln_stats = nullptr;      // [token rows][ln_np] partial (sum, sum of squares) written by EpiResidLN
   const int* ln_rowmap = nullptr;        // GEMM row -> token row (< 0: zero pad row); null: identity
   int ln_np = 0;
   float ln_inv_d = 0.f, ln_eps = 0.f;
@@ -319,11 +319,17 @@ struct alignas(64) EpiStaged {
   __device__ __forceinline__ EpiPre prefetch(int row, int M, int col0, int lane) const {
     EpiPre p{};
     if (!ln_stats) return p;
+    // (streamed once per tile: loaded without allocating in the ~24 KB of L1 this kernel leaves, which the per-column cs / bw
+    // vectors of run() should keep)
     const int tok = row < M ? (ln_rowmap ? __ldg(ln_rowmap + row) : row) : -1;
     if (tok >= 0) {
       const float2* sp = ln_stats + static_cast<size_t>(tok) * ln_np;
       float sm = 0.f, sq = 0.f;
-      for (int i = 0; i < ln_np; ++i) { const float2 t = __ldg(sp + i); sm += t.x; sq += t.y; }      // fixed order: bitwise reproducible
+      for (int i = 0; i < ln_np; ++i) {                                                              // fixed order: bitwise reproducible
+        float2 t;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "l"(sp + i));
+        sm += t.x; sq += t.y;
+      }
       const float mean = sm * ln_inv_d;
       const float rstd = rsqrtf(fmaxf(sq * ln_inv_d - mean * mean, 0.f) + ln_eps);
       p.row = make_float2(rstd, -rstd * mean);
@@ -448,6 +454,7 @@ struct alignas(64) EpiStaged {
 // The consumer GEMM (EpiStaged::prefetch) turns them into mean / rstd.  x_new is bit-identical to the reduce-add path.
 struct alignas(64) EpiResidLN {
   float* x; int ld;
+  const float* res = nullptr; int ld_res = 0, res_mod = 1;   // optional: the addend comes from res[row % res_mod] instead of x (patch embed: + pos_embed)
   const float* bias;
   const float* gamma;
   op16* x16; int ld16;
@@ -459,16 +466,18 @@ struct alignas(64) EpiResidLN {
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx& ctx) const {
     const int lane = ctx.lane, row0 = ctx.row0;        // M is a multiple of 32: the warp's 32 rows all exist
     float* xb = x + static_cast<size_t>(row0) * ld + n0;
+    const float* lb = res ? res + static_cast<size_t>(row0 % res_mod) * ld_res + n0 : xb;      // res_mod is a multiple of 32
+    const size_t lpitch = static_cast<size_t>(res ? ld_res : ld) * sizeof(float);
     const uint32_t buf0 = ctx.smem, buf1 = ctx.smem + 4096u;
     float s = 0.f, ss = 0.f;
     uint4 nxt[8];
-    slab_load_issue_rw(lane, xb + c_begin, static_cast<size_t>(ld) * sizeof(float), nxt);
+    slab_load_issue_rw(lane, lb + c_begin, lpitch, nxt);
     for (int c = c_begin; c < c_end; c += 32) {
       uint32_t a[32], r[32];
       uint4 cur[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-      if (c + 32 < c_end) slab_load_issue_rw(lane, xb + c + 32, static_cast<size_t>(ld) * sizeof(float), nxt);
+      if (c + 32 < c_end) slab_load_issue_rw(lane, lb + c + 32, lpitch, nxt);
       tmem_ld_x32(taddr_row + c, a);
       slab_load_finish(buf0, lane, cur, r);
       tmem_ld_wait();

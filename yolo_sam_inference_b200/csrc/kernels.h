@@ -135,10 +135,6 @@ void launch_preprocess(const uint8_t* rgb, int n, int src_h, int src_w, int row_
 void launch_im2col_patch_f32(const float* pixel_values, int n, op16* a_patch, cudaStream_t s);
 void launch_build_win_row_map(int* map, int n_images, cudaStream_t s);
 void launch_build_tok_win_map(int* map, int n_images, cudaStream_t s);
-// folded-LayerNorm operands of the first layer (what the residual epilogues produce for every later one): op16(gamma * x)
-// rows in token order or, with tok_win_map, window-partition order, and the per-row (sum, sum of squares) in slot 0
-void launch_ln_operand(const float* x, int rows, int D, const float* gamma, op16* x16, const int* tok_win_map, float2* stats,
-                       int slots, cudaStream_t s);
 void launch_layernorm(const float* x, int rows_out, int D, const float* gamma, const float* beta, float eps,
                       op16* out_bf, float* out_f, bool windowed, cudaStream_t s, bool split = false, bool reverse = false);
 // runs the whole encoder on work.a_patch (n images); result: image embeddings fp32 token-major [n*4096, 256].
