@@ -447,7 +447,10 @@ def run_ours(args):
                 "share_of_step": g_ms / tot_ms if tot_ms else None,
                 "traffic": ncu_traffic(f"gemm_class_{model}_b{BATCH}"),
                 "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, class average)",
-                "how": f"CUDA events around every launch, {pb} profiled batches of {BATCH} images after the timed region"}
+                "how": f"CUDA events around every launch, {pb} profiled batches of {BATCH} images after the timed region",
+                "note": "since round 2 this class also carries LayerNorm1 (folded into the patch-embed / fc2 / qkv epilogues: operand "
+                        "copy, row statistics, mean / rstd): 0.4 ms of LayerNorm kernels per batch became 0.25 ms of extra GEMM "
+                        "time (the class averaged 0.88 of the sustained peak with separate LayerNorm kernels, YSI_LN_FUSED=0)"}
         breakdown = {k: {"ms_per_batch": v["ms"] / pb,
                          "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
                      for k, v in prof.items()}

@@ -70,7 +70,8 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 // what an epilogue may fetch per tile BEFORE the accumulator is ready (CTA-pair kernel: Epi::prefetch), so that the loads'
 // latency hides under the wait: the row's LayerNorm scalars
 struct EpiPre {
-  float2 row;        // (rstd, -rstd * mean) of the thread's row; (0, 0): zero (pad) row
+  float2 row;        // EpiStaged: (rstd, -rstd * mean) of the thread's row; (0, 0): zero (pad) row
+  uint4 slab[8];     // EpiResidLN: the warp's first 32-column slab of the addend (slab_load_issue layout)
 };
 // per-warp epilogue context: staging shared memory (CTA-pair kernel only) and the warp's first output row
 struct EpiCtx {
@@ -319,16 +320,16 @@ struct alignas(64) EpiStaged {
   __device__ __forceinline__ EpiPre prefetch(int row, int M, int col0, int lane) const {
     EpiPre p{};
     if (!ln_stats) return p;
-    // (streamed once per tile: loaded without allocating in the ~24 KB of L1 this kernel leaves, which the per-column cs / bw
-    // vectors of run() should keep)
     const int tok = row < M ? (ln_rowmap ? __ldg(ln_rowmap + row) : row) : -1;
     if (tok >= 0) {
-      const float2* sp = ln_stats + static_cast<size_t>(tok) * ln_np;
+      // ln_np is even and the row 16-byte aligned: two slots per load. (Loading them with L1::no_allocate, to keep the L1 for the
+      // per-column vectors of run(), was measured slower: qkv 1.17 -> 1.38 ms per batch -- the eight loads of a row then each
+      // go to the L2 instead of hitting the line the first one brought in.)
+      const float4* sp = reinterpret_cast<const float4*>(ln_stats + static_cast<size_t>(tok) * ln_np);
       float sm = 0.f, sq = 0.f;
-      for (int i = 0; i < ln_np; ++i) {                                                              // fixed order: bitwise reproducible
-        float2 t;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "l"(sp + i));
-        sm += t.x; sq += t.y;
+      for (int i = 0; i < ln_np / 2; ++i) {                                                          // fixed order: bitwise reproducible
+        const float4 t = __ldg(sp + i);
+        sm += t.x; sq += t.y; sm += t.z; sq += t.w;
       }
       const float mean = sm * ln_inv_d;
       const float rstd = rsqrtf(fmaxf(sq * ln_inv_d - mean * mean, 0.f) + ln_eps);
@@ -462,7 +463,16 @@ struct alignas(64) EpiResidLN {
   float2* stats; int np;
   int reverse_m = 0;
   __device__ __forceinline__ void finish(EpiCtx&) const {}
-  __device__ __forceinline__ EpiPre prefetch(int, int, int, int) const { return EpiPre{}; }
+  // the first slab of the addend is requested before the wait for the accumulator: its HBM round trip (which the L2
+  // reduce-add of the plain residual epilogue never sees) hides under the tile's mainloop
+  __device__ __forceinline__ EpiPre prefetch(int row, int, int col0, int lane) const {
+    EpiPre p;
+    p.row = make_float2(0.f, 0.f);
+    const int row0 = row - lane;
+    const float* lb = res ? res + static_cast<size_t>(row0 % res_mod) * ld_res : x + static_cast<size_t>(row0) * ld;
+    slab_load_issue_rw(lane, lb + col0, static_cast<size_t>(res ? ld_res : ld) * sizeof(float), p.slab);
+    return p;
+  }
   __device__ __forceinline__ void run(uint32_t taddr_row, int row, int M, int n0, int N, int c_begin, int c_end, EpiCtx& ctx) const {
     const int lane = ctx.lane, row0 = ctx.row0;        // M is a multiple of 32: the warp's 32 rows all exist
     float* xb = x + static_cast<size_t>(row0) * ld + n0;
@@ -471,7 +481,8 @@ struct alignas(64) EpiResidLN {
     const uint32_t buf0 = ctx.smem, buf1 = ctx.smem + 4096u;
     float s = 0.f, ss = 0.f;
     uint4 nxt[8];
-    slab_load_issue_rw(lane, lb + c_begin, lpitch, nxt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nxt[j] = ctx.pre.slab[j];
     for (int c = c_begin; c < c_end; c += 32) {
       uint32_t a[32], r[32];
       uint4 cur[8];
