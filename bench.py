@@ -490,7 +490,7 @@ def run_ours(args):
                         "avg_launch_ms": {"upsample": up["ms"] / max(up["records"], 1), "hull": hull["ms"] / max(hull["records"], 1)},
                         "traffic": ncu_traffic("post_b32"), "workload": "configs[3]: 32 boxes/image, batch 8 images"}
             extra["configs3_breakdown_ms_per_batch"] = {k: v["ms"] / 3 for k, v in p32.items() if v["ms"] > 0}
-        e32 = folder_e2e("vit_b", l32.grays, l32.boxes, local, 3, 1, dist, dev, repeat=3)       # 96 files = 12 batches per call
+        e32 = folder_e2e("vit_b", l32.grays, l32.boxes, local, 3, 1, dist, dev, repeat=8)       # 256 files = 32 batches per call
         extra["configs3_b32_e2e_images_per_s"] = world * e32["images_per_s"]
         l32.close()
         # configs[2]'s model

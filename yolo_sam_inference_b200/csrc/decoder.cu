@@ -1091,11 +1091,15 @@ struct EpiConvT2 {
       tmem_ld_wait();
       if (!active) continue;
       float acc = 0.f;
+      const float4* b4 = reinterpret_cast<const float4*>(bias);
+      const float4* h4 = reinterpret_cast<const float4*>(hyper + box * 32);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float2 gg = gelu_erf2(make_float2(__uint_as_float(r[i]) + __ldg(bias + i), __uint_as_float(r[i + 1]) + __ldg(bias + i + 1)));
-        acc = fmaf(gg.x, __ldg(hyper + box * 32 + i), acc);
-        acc = fmaf(gg.y, __ldg(hyper + box * 32 + i + 1), acc);
+      for (int i = 0; i < 8; ++i) {          // 128-bit loads of the bias / hypernetwork vectors (64 scalar loads per 32 values before)
+        const float4 bb = __ldg(b4 + i), hh = __ldg(h4 + i);
+        const float2 g0 = gelu_erf2(make_float2(__uint_as_float(r[4 * i]) + bb.x, __uint_as_float(r[4 * i + 1]) + bb.y));
+        const float2 g1 = gelu_erf2(make_float2(__uint_as_float(r[4 * i + 2]) + bb.z, __uint_as_float(r[4 * i + 3]) + bb.w));
+        acc = fmaf(g0.x, hh.x, acc); acc = fmaf(g0.y, hh.y, acc);
+        acc = fmaf(g1.x, hh.z, acc); acc = fmaf(g1.y, hh.w, acc);
       }
       low[static_cast<size_t>(box) * 65536 + (2 * Y + (sp >> 1)) * 256 + 2 * X + (sp & 1)] = acc;
     }
