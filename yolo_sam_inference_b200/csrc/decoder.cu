@@ -978,18 +978,16 @@ struct EpiKeysLN {
     // is in flight while the current one is transposed and added (a warp otherwise has 4 KB of loads outstanding at a time,
     // and eight such warps per SM do not cover the memory latency: 3.1 TB/s measured without the prefetch).
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    uint4 nxt[8], nx2[8];                     // two slabs ahead (one was not enough: long-scoreboard was the top stall at 3.1 TB/s)
+    uint4 nxt[8];
     slab_load_issue(lane, rbase, C * sizeof(float), nxt);
-    slab_load_issue(lane, rbase + 32, C * sizeof(float), nx2);
 #pragma unroll
     for (int c = 0; c < C; c += 32) {
       uint32_t a[32], r[32];
       uint4 cur[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; nxt[j] = nx2[j]; }
-      if (c + 64 < C) slab_load_issue(lane, rbase + c + 64, C * sizeof(float), nx2);
-      else if (c + 64 == C) slab_load_issue(lane, pbase, C * sizeof(float), nx2);            // first two pe slabs of pass 3
-      else slab_load_issue(lane, pbase + 32, C * sizeof(float), nx2);
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (c + 32 < C) slab_load_issue(lane, rbase + c + 32, C * sizeof(float), nxt);
+      else slab_load_issue(lane, pbase, C * sizeof(float), nxt);            // first pe slab of pass 3
       tmem_ld_x32(taddr_row + c, a);
       slab_load_finish(ctx.smem, lane, cur, r);
       tmem_ld_wait();
@@ -1030,8 +1028,8 @@ struct EpiKeysLN {
       uint32_t a[32], pp[32];
       uint4 cur[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; nxt[j] = nx2[j]; }
-      if (c + 64 < C) slab_load_issue(lane, pbase + c + 64, C * sizeof(float), nx2);
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (c + 32 < C) slab_load_issue(lane, pbase + c + 32, C * sizeof(float), nxt);
       tmem_ld_x32(taddr_row + c, a);
       slab_load_finish(ctx.smem, lane, cur, pp);
       tmem_ld_wait();
