@@ -279,8 +279,23 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
   d.no_mask_embed = f32("prompt_encoder.no_mask_embed.weight", {1, 256});
   d.iou_token = f32("mask_decoder.iou_token.weight", {1, 256});
   d.mask_tokens = f32("mask_decoder.mask_tokens.weight", {4, 256});
+  // three-term op16 split of a token-side weight [N, K] -> [N, 3K] = [W_hi | W_hi | W_lo] (decoder.cu: tok_linear_tc)
+  auto split3 = [&](const std::string& name, int N, int K) {
+    const HostTensor& t = wm.get(name);
+    std::vector<op16> wv(static_cast<size_t>(N) * 3 * K);
+    for (int n2 = 0; n2 < N; ++n2)
+      for (int k = 0; k < K; ++k) {
+        const float w = t.data[static_cast<size_t>(n2) * K + k];
+        const op16 hi = f2op(w);
+        op16* row = wv.data() + static_cast<size_t>(n2) * 3 * K;
+        row[k] = hi; row[K + k] = hi; row[2 * K + k] = f2op(w - op2f(hi));
+      }
+    return c->upload_op16(wv);
+  };
   auto attn = [&](const std::string& p, int internal) {
     DecAttnW a;
+    a.wq3 = split3(p + ".q_proj.weight", internal, 256); a.wk3 = split3(p + ".k_proj.weight", internal, 256);
+    a.wv3 = split3(p + ".v_proj.weight", internal, 256); a.wo3 = split3(p + ".out_proj.weight", 256, internal);
     a.wq = f32(p + ".q_proj.weight", {internal, 256}); a.bq = f32(p + ".q_proj.bias", {internal});
     a.wk = f32(p + ".k_proj.weight", {internal, 256}); a.bk = f32(p + ".k_proj.bias", {internal});
     a.wv = f32(p + ".v_proj.weight", {internal, 256}); a.bv = f32(p + ".v_proj.bias", {internal});
@@ -299,6 +314,10 @@ void load_weights_impl(ysi_ctx* c, const ysi_tensor_desc* tensors, size_t n) {
     lw.ln4_g = f32(p + ".layer_norm4.weight", {256}); lw.ln4_b = f32(p + ".layer_norm4.bias", {256});
     lw.w_fc1 = f32(p + ".mlp.lin1.weight", {2048, 256}); lw.b_fc1 = f32(p + ".mlp.lin1.bias", {2048});
     lw.w_fc2 = f32(p + ".mlp.lin2.weight", {256, 2048}); lw.b_fc2 = f32(p + ".mlp.lin2.bias", {256});
+    {
+      lw.w_fc1_s3 = split3(p + ".mlp.lin1.weight", 2048, 256);
+      lw.w_fc2_s3 = split3(p + ".mlp.lin2.weight", 256, 2048);
+    }
     const HostTensor& wk = wm.get(p + ".cross_attn_token_to_image.k_proj.weight", {128, 256});
     const HostTensor& wq = wm.get(p + ".cross_attn_image_to_token.q_proj.weight", {128, 256});
     std::vector<op16> kq(256 * 256);
@@ -450,6 +469,7 @@ void create_impl(ysi_ctx* c) {
   dw.v_tok = c->dalloc<float>(NB * 7 * 128);
   dw.hyper = c->dalloc<float>(NB * 32);
   dw.tok_ws = c->dalloc<float>(NB * (7 * (6 * 256 + 2048) + 2 * 256 + 8 * 4 * 126));
+  dw.tok_a3 = c->dalloc<op16>(NB * 7 * 3 * 2048);
   dw.boxes1024 = c->dalloc<double>(NB * 4);
   dw.box_img = c->dalloc<int>(NB);
   for (auto& sl : c->slots) {

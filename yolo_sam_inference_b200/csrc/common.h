@@ -85,6 +85,7 @@ struct GemmEpilogue {
   // rows its producer wrote last -- the ones still in the 126 MB L2 -- instead of the ones evicted first (used for fc2;
   // measured effect at 8 images: within run-to-run noise, LayerNorm's matching row order -2 %).
   int reverse_m = 0;
+  int narrow_tiles = 0;          // single-CTA kernel: 64-column tiles whatever N is (few-row GEMMs: more CTAs instead of wider ones)
   // LayerNorm folded into the GEMMs on either side of it (CTA-pair kernel; encoder.cu explains the algebra):
   //  producer (a residual add, accumulate != 0): besides x += ..., write op16(x16_gamma[col] * x_new) to row
   //    x16_rowmap[row] (null: row) of x16_out and the row's partial (sum, sum of squares) to stats_out[row][slot]

@@ -8,6 +8,7 @@
 // Token-side work (7 tokens per box) runs in small fp32 CUDA-core kernels, one CTA per box.
 // Block-0 image-side projections are box independent (keys = image_emb + no_mask_embed for every box)
 // and are computed once per image.
+#include <algorithm>
 #include <cstdlib>
 
 #include "gemm.cuh"
@@ -146,6 +147,7 @@ struct TokLin {
   const float* res;  int ldres;                      // optional residual added to the output
   float* Y;  int ldy;
   int K, N, relu;                                    // K multiple of 128, <= 2048
+  const op16* W3;                                    // optional [N, 3K] three-term split of W (tensor-core path at many boxes)
 };
 struct TokLin3 { TokLin t[3]; };
 
@@ -286,6 +288,28 @@ tok_gemm_kernel(TokLin3 P, int R) {
       if (p.res) v += p.res[static_cast<size_t>(r) * p.ldres + n];
       p.Y[static_cast<size_t>(r) * p.ldy + n] = v;
     }
+  }
+}
+
+// fp32 [R, K] (row pitch ldx; optionally X + Xadd) -> op16 [R, 3K] = [x_hi | x_lo | x_hi]: the activation side of the three-term
+// split GEMM
+__global__ void tok_split3_kernel(const float* __restrict__ X, const float* __restrict__ Xadd, int ldx, int R, int K, op16* __restrict__ A3) {
+  const long long n4 = static_cast<long long>(R) * (K / 4);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / (K / 4)), k4 = static_cast<int>(i - static_cast<long long>(r) * (K / 4));
+    float4 v = *reinterpret_cast<const float4*>(X + static_cast<size_t>(r) * ldx + 4 * k4);
+    if (Xadd) {
+      const float4 a = *reinterpret_cast<const float4*>(Xadd + static_cast<size_t>(r) * ldx + 4 * k4);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    uint2 hi, lo;
+    hi.x = pack_op16x2(v.x, v.y); hi.y = pack_op16x2(v.z, v.w);
+    lo.x = pack_op16x2(v.x - op2f(f2op(v.x)), v.y - op2f(f2op(v.y))); lo.y = pack_op16x2(v.z - op2f(f2op(v.z)), v.w - op2f(f2op(v.w)));
+    op16* row = A3 + static_cast<size_t>(r) * 3 * K + 4 * k4;
+    *reinterpret_cast<uint2*>(row) = hi;
+    *reinterpret_cast<uint2*>(row + K) = lo;
+    *reinterpret_cast<uint2*>(row + 2 * K) = hi;
   }
 }
 
@@ -1108,14 +1132,44 @@ struct EpiConvT2 {
 
 // ---------------------------------------------------------------------------------------------------
 static TokLin tok_lin(const float* X, const float* Xadd, int ldx, const float* W, const float* b, int K, int N, float* Y, int ldy,
-                      const float* res = nullptr, int ldres = 0, int relu = 0) {
+                      const float* res = nullptr, int ldres = 0, int relu = 0, const op16* W3 = nullptr) {
   TokLin t;
   t.X = X; t.Xadd = Xadd; t.ldx = ldx; t.W = W; t.b = b; t.res = res; t.ldres = ldres; t.Y = Y; t.ldy = ldy;
-  t.K = K; t.N = N; t.relu = relu;
+  t.K = K; t.N = N; t.relu = relu; t.W3 = W3;
   return t;
 }
 
-static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s) {
+// token-side linear layers on the tensor cores (many boxes): Y = act((X [+ Xadd]) W^T + b) (+ res) through three-term op16 splits
+// on both sides (x_hi W_hi + x_lo W_hi + x_hi W_lo: fp32-level accuracy, the dropped term is 2^-22 relative). Returns the launches.
+static int tok_linear_tc(const TokLin* t, int count, int R, op16* a3, cudaStream_t s) {
+  int nl = 0;
+  const float *lastX = nullptr, *lastA = nullptr;
+  int lastK = 0;
+  for (int i = 0; i < count; ++i) {
+    const TokLin& p = t[i];
+    if (p.X != lastX || p.Xadd != lastA || p.K != lastK) {        // consecutive layers on the same input share the split
+      const long long n4 = static_cast<long long>(R) * (p.K / 4);
+      tok_split3_kernel<<<static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, s>>>(p.X, p.Xadd, p.ldx, R, p.K, a3);
+      YSI_CUDA(cudaGetLastError());
+      lastX = p.X; lastA = p.Xadd; lastK = p.K; ++nl;
+    }
+    GemmEpilogue ep;
+    ep.bias = p.b; ep.act = p.relu ? ACT_RELU : ACT_NONE; ep.out_f32 = p.Y; ep.ld_out = p.ldy; ep.narrow_tiles = 1;
+    if (p.res) { ep.add_src = p.res; ep.ld_add = p.ldres; ep.add_mod = R; }
+    gemm_op16(a3, 3 * p.K, p.W3, 3 * p.K, R, p.N, 3 * p.K, ep, s); ++nl;
+  }
+  return nl;
+}
+
+constexpr int TOK_TC_MIN_ROWS = 448;      // from 64 boxes per launch
+
+static int launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s, op16* a3 = nullptr) {
+  static const bool tok_tc = [] { const char* e = getenv("YSI_DEC_MLP_TC"); return e ? atoi(e) != 0 : true; }();
+  if (tok_tc && a3 && R >= TOK_TC_MIN_ROWS) {
+    bool all = true;
+    for (int i = 0; i < count; ++i) all = all && t[i].W3 != nullptr && t[i].N % 64 == 0 && t[i].ldx % 4 == 0;
+    if (all) return tok_linear_tc(t, count, R, a3, s);
+  }
   TokLin3 P;
   int nmax = 0;
   for (int i = 0; i < 3; ++i) {
@@ -1132,6 +1186,7 @@ static void launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s)
   }
   else
     tok_linear_kernel<<<dim3(nmax / 8, ceil_div(R, TOK_ROWS), count), 256, 0, s>>>(P, R);
+  return 1;
 }
 
 // token -> image attention: few boxes -> key ranges split over CTAs + merge (parallelism); 16..63 -> one streaming CTA
@@ -1190,16 +1245,16 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
       ProfScope ps(prof, KC_DEC_TOKEN);
       const float* qin = first ? wk.tok0 : wk.queries;
       const float* qadd = first ? nullptr : wk.tok0;
-      const TokLin qkv[3] = {tok_lin(qin, qadd, C, lw.self_attn.wq, lw.self_attn.bq, C, C, t_q, C),
-                             tok_lin(qin, qadd, C, lw.self_attn.wk, lw.self_attn.bk, C, C, t_k, C),
-                             tok_lin(qin, nullptr, C, lw.self_attn.wv, lw.self_attn.bv, C, C, t_v, C)};
-      launch_tok_linear(qkv, 3, R, s); ++nl;
+      const TokLin qkv[3] = {tok_lin(qin, qadd, C, lw.self_attn.wq, lw.self_attn.bq, C, C, t_q, C, nullptr, 0, 0, lw.self_attn.wq3),
+                             tok_lin(qin, qadd, C, lw.self_attn.wk, lw.self_attn.bk, C, C, t_k, C, nullptr, 0, 0, lw.self_attn.wk3),
+                             tok_lin(qin, nullptr, C, lw.self_attn.wv, lw.self_attn.bv, C, C, t_v, C, nullptr, 0, 0, lw.self_attn.wv3)};
+      nl += launch_tok_linear(qkv, 3, R, s, wk.tok_a3);
       tok_self_attn_core_kernel<<<nb, 256, 0, s>>>(t_q, t_k, t_v, t_a); ++nl;
-      const TokLin o = tok_lin(t_a, nullptr, C, lw.self_attn.wo, lw.self_attn.bo, C, C, t_tmp, C, first ? nullptr : wk.queries, C);
-      launch_tok_linear(&o, 1, R, s); ++nl;
+      const TokLin o = tok_lin(t_a, nullptr, C, lw.self_attn.wo, lw.self_attn.bo, C, C, t_tmp, C, first ? nullptr : wk.queries, C, 0, lw.self_attn.wo3);
+      nl += launch_tok_linear(&o, 1, R, s, wk.tok_a3);
       tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, lw.ln1_g, lw.ln1_b, 1e-6f, wk.tok0, wk.queries, t_qpe); ++nl;
-      const TokLin tq = tok_lin(t_qpe, nullptr, C, lw.t2i.wq, lw.t2i.bq, C, 128, wk.q_t2i, 128);
-      launch_tok_linear(&tq, 1, R, s); ++nl;
+      const TokLin tq = tok_lin(t_qpe, nullptr, C, lw.t2i.wq, lw.t2i.bq, C, 128, wk.q_t2i, 128, nullptr, 0, 0, lw.t2i.wq3);
+      nl += launch_tok_linear(&tq, 1, R, s, wk.tok_a3);
       YSI_CUDA(cudaGetLastError());
     }
     {
@@ -1219,17 +1274,18 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
     {
       // queries += out_proj(attn); LN2; MLP; LN3; image->token key / value projections   (:328-341)
       ProfScope ps(prof, KC_DEC_TOKEN);
-      const TokLin o = tok_lin(wk.attn_t2i, nullptr, 128, lw.t2i.wo, lw.t2i.bo, 128, C, t_tmp, C, wk.queries, C);
-      launch_tok_linear(&o, 1, R, s); ++nl;
+      const TokLin o = tok_lin(wk.attn_t2i, nullptr, 128, lw.t2i.wo, lw.t2i.bo, 128, C, t_tmp, C, wk.queries, C, 0, lw.t2i.wo3);
+      nl += launch_tok_linear(&o, 1, R, s, wk.tok_a3);
       tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, lw.ln2_g, lw.ln2_b, 1e-6f, nullptr, wk.queries, nullptr); ++nl;
-      const TokLin f1 = tok_lin(wk.queries, nullptr, C, lw.w_fc1, lw.b_fc1, C, 2048, t_hid, 2048, nullptr, 0, 1);
-      launch_tok_linear(&f1, 1, R, s); ++nl;
-      const TokLin f2 = tok_lin(t_hid, nullptr, 2048, lw.w_fc2, lw.b_fc2, 2048, C, t_tmp, C, wk.queries, C);
-      launch_tok_linear(&f2, 1, R, s); ++nl;
+      // (from 64 boxes per launch these run on the tensor cores through three-term op16 splits: launch_tok_linear / tok_linear_tc)
+      const TokLin f1 = tok_lin(wk.queries, nullptr, C, lw.w_fc1, lw.b_fc1, C, 2048, t_hid, 2048, nullptr, 0, 1, lw.w_fc1_s3);
+      nl += launch_tok_linear(&f1, 1, R, s, wk.tok_a3);
+      const TokLin f2 = tok_lin(t_hid, nullptr, 2048, lw.w_fc2, lw.b_fc2, 2048, C, t_tmp, C, wk.queries, C, 0, lw.w_fc2_s3);
+      nl += launch_tok_linear(&f2, 1, R, s, wk.tok_a3);
       tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, lw.ln3_g, lw.ln3_b, 1e-6f, wk.tok0, wk.queries, t_qpe); ++nl;
-      const TokLin kv[2] = {tok_lin(t_qpe, nullptr, C, lw.i2t.wk, lw.i2t.bk, C, 128, wk.k_tok, 128),
-                            tok_lin(wk.queries, nullptr, C, lw.i2t.wv, lw.i2t.bv, C, 128, wk.v_tok, 128)};
-      launch_tok_linear(kv, 2, R, s); ++nl;
+      const TokLin kv[2] = {tok_lin(t_qpe, nullptr, C, lw.i2t.wk, lw.i2t.bk, C, 128, wk.k_tok, 128, nullptr, 0, 0, lw.i2t.wk3),
+                            tok_lin(wk.queries, nullptr, C, lw.i2t.wv, lw.i2t.bv, C, 128, wk.v_tok, 128, nullptr, 0, 0, lw.i2t.wv3)};
+      nl += launch_tok_linear(kv, 2, R, s, wk.tok_a3);
       YSI_CUDA(cudaGetLastError());
     }
     { ProfScope ps(prof, KC_DEC_ATTN);
@@ -1268,8 +1324,8 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   // final token -> image attention (:394-404); t_qpe = queries + pe from LN3 of block 1
   {
     ProfScope ps(prof, KC_DEC_TOKEN);
-    const TokLin fq = tok_lin(t_qpe, nullptr, C, w.final_attn.wq, w.final_attn.bq, C, 128, wk.q_t2i, 128);
-    launch_tok_linear(&fq, 1, R, s); ++nl;
+    const TokLin fq = tok_lin(t_qpe, nullptr, C, w.final_attn.wq, w.final_attn.bq, C, 128, wk.q_t2i, 128, nullptr, 0, 0, w.final_attn.wq3);
+    nl += launch_tok_linear(&fq, 1, R, s, wk.tok_a3);
   }
   {
     ProfScope ps(prof, KC_DEC_GEMM, 2.0 * TB * 256 * 256);
@@ -1284,8 +1340,8 @@ void decoder_forward(const DecoderW& w, const DecoderWork& wk, const float* emb,
   {
     // queries += out_proj(attn); layer_norm_final_attn (eps 1e-5); hypernetwork MLP of mask token 0 (= token row 1)
     ProfScope ps(prof, KC_DEC_TOKEN);
-    const TokLin o = tok_lin(wk.attn_t2i, nullptr, 128, w.final_attn.wo, w.final_attn.bo, 128, C, t_tmp, C, wk.queries, C);
-    launch_tok_linear(&o, 1, R, s); ++nl;
+    const TokLin o = tok_lin(wk.attn_t2i, nullptr, 128, w.final_attn.wo, w.final_attn.bo, 128, C, t_tmp, C, wk.queries, C, 0, w.final_attn.wo3);
+    nl += launch_tok_linear(&o, 1, R, s, wk.tok_a3);
     tok_layernorm_kernel<<<ln_blocks, 256, 0, s>>>(t_tmp, R, w.lnf_g, w.lnf_b, 1e-5f, nullptr, wk.queries, nullptr); ++nl;
     const TokLin h0 = tok_lin(wk.queries + C, nullptr, NT * C, w.hy_w0, w.hy_b0, C, C, t_h0, C, nullptr, 0, 1);
     launch_tok_linear(&h0, 1, nb, s); ++nl;

@@ -233,7 +233,10 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
   }
   YSI_CHECK(!ep.ln_stats && !ep.stats_out, "folded LayerNorm is implemented in the CTA-pair kernel only (M >= 2048, N % 256 == 0)");
   // widest tile that does not waste more than a quarter of its columns
-  if (N % 256 == 0 || N > 512) {
+  if (ep.narrow_tiles && N % 64 == 0) {
+    const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 64);
+    launch_gemm<64>(tmA, tmB, M, N, K, epi, stream);
+  } else if (N % 256 == 0 || N > 512) {
     const CUtensorMap tmB = make_tmap_op16_2d(W, N, K, ldw, 256);
     launch_gemm<256>(tmA, tmB, M, N, K, epi, stream);
   } else if (N % 128 == 0) {

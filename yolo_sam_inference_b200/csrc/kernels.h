@@ -145,11 +145,16 @@ void encoder_forward(const EncoderW& w, const EncoderWork& work, int n, float* e
 // ------------------------------------------------------------------ prompt encoder + mask decoder
 struct DecAttnW {          // SamAttention weights, fp32 (token-side use)
   const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+  const op16 *wq3, *wk3, *wv3, *wo3;      // the four weights as three-term splits [W_hi | W_hi | W_lo] (tensor-core token path)
 };
 struct DecLayerW {
   DecAttnW self_attn, t2i, i2t;
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b, *ln4_g, *ln4_b;
   const float *w_fc1, *b_fc1, *w_fc2, *b_fc2;       // 256 -> 2048 -> 256 (ReLU)
+  // the same two weights as three-term op16 splits [W_hi | W_hi | W_lo] ([2048, 768] / [256, 6144]) for the tensor-core path of
+  // the token MLP at many boxes: against activations [x_hi | x_lo | x_hi] the products x_hi W_hi + x_lo W_hi + x_hi W_lo keep
+  // fp32-level accuracy (the dropped x_lo W_lo term is 2^-22 relative)
+  const op16 *w_fc1_s3, *w_fc2_s3;
   const op16* w_kq_img;    // [256,256]: rows 0..127 t2i.k_proj, rows 128..255 i2t.q_proj  (input keys + pos)
   const float* b_kq_img;   // [256]
   const op16* w_v_img;     // [128,256] t2i.v_proj (input keys)
@@ -183,6 +188,7 @@ struct DecoderWork {           // workspace for cap_img images and cap_box boxes
   op16* up1;                                             // [cap_box*16384, 128]  hi | lo
   float *tok0, *queries, *q_t2i, *attn_t2i, *k_tok, *v_tok, *hyper;   // token-side [cap_box, 7, *]
   float* tok_ws;                                         // token-side scratch: cap_box * (7*(6*256 + 2048) + 2*256 + 8*4*126) floats
+  op16* tok_a3;                                          // [cap_box*7, 3*2048] three-term split of a token-side GEMM input
   double* boxes1024;  int* box_img;                      // [cap_box,4] / [cap_box]
 };
 void launch_image_pe(const float* gauss, float* image_pe, cudaStream_t s);
