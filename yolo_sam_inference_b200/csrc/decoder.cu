@@ -1161,11 +1161,18 @@ static int tok_linear_tc(const TokLin* t, int count, int R, op16* a3, cudaStream
   return nl;
 }
 
-constexpr int TOK_TC_MIN_ROWS = 448;      // from 64 boxes per launch
+// Row threshold of the tensor-core path (YSI_DEC_TC_MIN_ROWS; default: always). Introduced for many boxes (7 x 256 rows: 0.77 ->
+// 0.45 ms); at 1 box per image (56 rows per launch) the kernels are hardly shorter when timed alone (0.42 -> 0.38 ms) but the
+// step is 1.7 % faster: the decoder shares the GPU with the next batch's encoder, and a few short GEMM CTAs disturb it less
+// than the 19 wide CUDA-core launches they replace.
+static int tok_tc_min_rows() {
+  static const int v = [] { const char* e = getenv("YSI_DEC_TC_MIN_ROWS"); return e ? atoi(e) : 1; }();
+  return v;
+}
 
 static int launch_tok_linear(const TokLin* t, int count, int R, cudaStream_t s, op16* a3 = nullptr) {
   static const bool tok_tc = [] { const char* e = getenv("YSI_DEC_MLP_TC"); return e ? atoi(e) != 0 : true; }();
-  if (tok_tc && a3 && R >= TOK_TC_MIN_ROWS) {
+  if (tok_tc && a3 && R >= tok_tc_min_rows()) {
     bool all = true;
     for (int i = 0; i < count; ++i) all = all && t[i].W3 != nullptr && t[i].N % 64 == 0 && t[i].ldx % 4 == 0;
     if (all) return tok_linear_tc(t, count, R, a3, s);
