@@ -189,3 +189,40 @@ def test_visualisation_writer_layout(tmp_path):
     exp = img.copy()
     exp[masks[0]] = exp[masks[0]] * 0.7 + np.array([255, 0, 0]) * 0.3
     assert np.array_equal(ov, exp)
+
+
+def test_bench_folder_writer_repeats_and_names(tmp_path, monkeypatch):
+    """bench.write_folder: `repeat` copies of the frames under distinct *.tiff names (what process_directory globs), one box
+    table entry per file, every file a complete baseline TIFF that the raw-strip ingest accepts."""
+    import shutil
+
+    import bench
+    from yolo_sam_inference_b200.ingest import probe_tiff
+    frames = [np.full((32, 48), 10 * (i + 1), np.uint8) for i in range(3)]
+    boxes = [np.array([[1.0, 2.0, 3.0 + i, 4.0]], np.float32) for i in range(3)]
+    d, table = bench.write_folder(frames, boxes, repeat=2)
+    try:
+        names = sorted(os.listdir(d))
+        assert names == sorted(table) and len(names) == 6 and all(n.endswith(".tiff") for n in names)
+        for k, n in enumerate(names):
+            assert np.array_equal(table[n], boxes[k % 3])
+            info = probe_tiff(os.path.join(d, n))
+            assert info is not None and tuple(info.shape) == (32, 48)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_window_partition_maps_are_inverse():
+    """The token -> window-row map the folded LayerNorm writes through (csrc/encoder.cu: build_tok_win_map_kernel) and the
+    window-row -> token map of the windowed layers (window_row_to_token) restated in numpy: inverse on the 4096 real tokens,
+    -1 exactly on the 804 pad rows of the 5 x 5 windows of 14 x 14."""
+    tok = np.arange(4096)
+    y, x = tok >> 6, tok & 63
+    t2w = ((y // 14) * 5 + x // 14) * 196 + (y % 14) * 14 + x % 14
+    w = np.arange(4900)
+    win, l = w // 196, w % 196
+    yy, xx = (win // 5) * 14 + l // 14, (win % 5) * 14 + l % 14
+    w2t = np.where((yy < 64) & (xx < 64), yy * 64 + xx, -1)
+    assert len(np.unique(t2w)) == 4096 and t2w.max() < 4900
+    assert np.array_equal(w2t[t2w], tok)
+    assert int((w2t < 0).sum()) == 804
