@@ -88,7 +88,7 @@ struct GemmEpilogue {
   int narrow_tiles = 0;          // single-CTA kernel: 64-column tiles whatever N is (few-row GEMMs: more CTAs instead of wider ones)
   // LayerNorm folded into the GEMMs on either side of it (CTA-pair kernel; encoder.cu explains the algebra):
   //  producer (a residual add, accumulate != 0): besides x += ..., write op16(x16_gamma[col] * x_new) to row
-  //    x16_rowmap[row] (null: row) of x16_out and the row's partial (sum, sum of squares) to stats_out[row][slot]
+  //    x16_rowmap[row] (null: row) of x16_out and the row's partial (mean, sum of squared deviations) to stats_out[row][slot]
   //  consumer (op16 output): A is such an x16; y = rstd * acc - rstd * mean * ln_cs[n] + ln_bw[n] (ln_bw = bias + wb) with mean /
   //    rstd from ln_stats[ln_rowmap[row] or row][0..ln_np); a negative map entry is a zero (pad) row: its output is ln_bw - ln_wb
   op16* x16_out = nullptr;

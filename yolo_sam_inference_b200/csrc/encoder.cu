@@ -351,7 +351,8 @@ void launch_build_tok_win_map(int* map, int n_images, cudaStream_t s) {
 // LayerNorm passes over the fp32 stream (read 100 MB + write 50 MB each at 8 ViT-B images) disappear.
 // Rounding: the operand is rounded at gamma * x instead of at LN(x): the same relative step, on a value that still carries
 // the row mean, which for these residual streams is small against the row's standard deviation.
-// Row statistics are (sum, sum of squares) in fp32, summed over at most LN_STAT_SLOTS partials in a fixed order.
+// Row statistics: every producer warp writes (mean, sum of squared deviations) of its 96 / 128 columns of the row; the consumer
+// merges the at most LN_STAT_SLOTS partials pairwise-stably (Chan et al.) in a fixed order -- no E[x^2] - mean^2 cancellation.
 // ------------------------------------------------------------------------------------------------
 // 3x3 / pad 1 im2col over the 64x64 token grid, tap-major columns; a row of `in` is the 256 channels as a two-term
 // split [hi(256) | lo(256)] (NECK_C2 = 512 values):

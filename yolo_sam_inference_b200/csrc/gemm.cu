@@ -208,6 +208,7 @@ void gemm_op16(const op16* A, int lda, const op16* W, int ldw, int M, int N, int
       es.f32_add = 0; es.reverse_m = ep.reverse_m;
       es.ln_stats = ep.ln_stats; es.ln_rowmap = ep.ln_rowmap; es.ln_np = ep.ln_np; es.ln_eps = ep.ln_eps;
       es.ln_inv_d = ep.ln_dim > 0 ? 1.0f / static_cast<float>(ep.ln_dim) : 0.f; es.ln_cs = ep.ln_cs; es.ln_bw = ep.ln_bw; es.ln_wb = ep.ln_wb;
+      es.ln_cols_per_slot = ep.ln_np > 0 ? static_cast<float>(ep.ln_dim) / static_cast<float>(ep.ln_np) : 0.f;
       launch_gemm2(tmA, tmB, M, N, K, es, stream);
     } else if (use_staged && plain && ep.out_f32 && !ep.out_op16 && ep.accumulate && ep.act == ACT_NONE) {
       // residual add: x += tile through cp.reduce.async.bulk (fp32 add in the L2, 128-byte rows)

@@ -312,10 +312,10 @@ struct alignas(64) EpiStaged {
   // LayerNorm folded into this GEMM (op16 store path; GemmEpilogue::ln_stats): the A operand is op16(gamma * x) of the raw
   // residual stream and  y = rstd * acc - rstd * mean * cs[n] + wb[n] + bias[n]  with the row's mean / rstd from its partial
   // sums; a zero (pad) row of a padded window gets the plain bias
-  const float2* ln_stats = nullptr;      // [token rows][ln_np] partial (sum, sum of squares) written by EpiResidLN
+  const float2* ln_stats = nullptr;      // [token rows][ln_np] partial (mean, sum of squared deviations) written by EpiResidLN
   const int* ln_rowmap = nullptr;        // GEMM row -> token row (< 0: zero pad row); null: identity
   int ln_np = 0;
-  float ln_inv_d = 0.f, ln_eps = 0.f;
+  float ln_inv_d = 0.f, ln_eps = 0.f, ln_cols_per_slot = 0.f;
   const float *ln_cs = nullptr, *ln_bw = nullptr, *ln_wb = nullptr;      // cs, bias + wb (real rows), wb (subtracted again on pad rows)
   __device__ __forceinline__ EpiPre prefetch(int row, int M, int col0, int lane) const {
     EpiPre p{};
@@ -325,14 +325,20 @@ struct alignas(64) EpiStaged {
       // ln_np is even and the row 16-byte aligned: two slots per load. (Loading them with L1::no_allocate, to keep the L1 for the
       // per-column vectors of run(), was measured slower: qkv 1.17 -> 1.38 ms per batch -- the eight loads of a row then each
       // go to the L2 instead of hitting the line the first one brought in.)
+      // slot i = (mean, sum of squared deviations) of the row over its i-th group of D / ln_np columns; merged pairwise-stably
+      // (Chan et al.), always in slot order: bitwise reproducible, and no E[x^2] - mean^2 cancellation for rows whose mean is
+      // large against their spread
       const float4* sp = reinterpret_cast<const float4*>(ln_stats + static_cast<size_t>(tok) * ln_np);
-      float sm = 0.f, sq = 0.f;
-      for (int i = 0; i < ln_np / 2; ++i) {                                                          // fixed order: bitwise reproducible
+      const float m = ln_cols_per_slot;
+      float mean = 0.f, m2 = 0.f, k = 0.f;
+      for (int i = 0; i < ln_np / 2; ++i) {
         const float4 t = __ldg(sp + i);
-        sm += t.x; sq += t.y; sm += t.z; sq += t.w;
+        float d = t.x - mean, r = __fdividef(1.f, k + 1.f);
+        mean += d * r; m2 += t.y + d * d * (m * k * r); k += 1.f;
+        d = t.z - mean; r = __fdividef(1.f, k + 1.f);
+        mean += d * r; m2 += t.w + d * d * (m * k * r); k += 1.f;
       }
-      const float mean = sm * ln_inv_d;
-      const float rstd = rsqrtf(fmaxf(sq * ln_inv_d - mean * mean, 0.f) + ln_eps);
+      const float rstd = rsqrtf(m2 * ln_inv_d + ln_eps);
       p.row = make_float2(rstd, -rstd * mean);
     }
     return p;
@@ -451,7 +457,7 @@ struct alignas(64) EpiStaged {
 // slab loads / stores of the fp32 stream instead of the L2 reduce-add), and while the values are in registers the epilogue
 // also emits what the following qkv / fc1 GEMM needs in place of a LayerNorm pass over x:
 //   x16   = op16(gamma * x_new), written to row rowmap[row] (window-partition order for windowed layers) or row itself
-//   stats = per-row (sum, sum of squares) of x_new over this warp's columns, one slot per (N tile, column half)
+//   stats = per-row (mean, sum of squared deviations) of x_new over this warp's columns, one slot per (N tile, column half)
 // The consumer GEMM (EpiStaged::prefetch) turns them into mean / rstd.  x_new is bit-identical to the reduce-add path.
 struct alignas(64) EpiResidLN {
   float* x; int ld;
@@ -479,7 +485,7 @@ struct alignas(64) EpiResidLN {
     const float* lb = res ? res + static_cast<size_t>(row0 % res_mod) * ld_res + n0 : xb;      // res_mod is a multiple of 32
     const size_t lpitch = static_cast<size_t>(res ? ld_res : ld) * sizeof(float);
     const uint32_t buf0 = ctx.smem, buf1 = ctx.smem + 4096u;
-    float s = 0.f, ss = 0.f;
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;      // running (count, mean, sum of squared deviations) of this row over the warp's columns
     uint4 nxt[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) nxt[j] = ctx.pre.slab[j];
@@ -500,10 +506,29 @@ struct alignas(64) EpiResidLN {
         const float v1 = (__uint_as_float(a[4 * i + 1]) + bb.y) + __uint_as_float(r[4 * i + 1]);
         const float v2 = (__uint_as_float(a[4 * i + 2]) + bb.z) + __uint_as_float(r[4 * i + 2]);
         const float v3 = (__uint_as_float(a[4 * i + 3]) + bb.w) + __uint_as_float(r[4 * i + 3]);
-        s += (v0 + v1) + (v2 + v3);
-        ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
         a[4 * i] = __float_as_uint(v0); a[4 * i + 1] = __float_as_uint(v1);
         a[4 * i + 2] = __float_as_uint(v2); a[4 * i + 3] = __float_as_uint(v3);
+      }
+      {
+        // statistics of these 32 values about their own mean, merged into the running ones (Chan et al.): stable whatever the
+        // row's mean is
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          s0 += __uint_as_float(a[i]); s1 += __uint_as_float(a[i + 1]); s2 += __uint_as_float(a[i + 2]); s3 += __uint_as_float(a[i + 3]);
+        }
+        const float cm = ((s0 + s1) + (s2 + s3)) * (1.0f / 32.0f);
+        s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float d0 = __uint_as_float(a[i]) - cm, d1 = __uint_as_float(a[i + 1]) - cm;
+          const float d2 = __uint_as_float(a[i + 2]) - cm, d3 = __uint_as_float(a[i + 3]) - cm;
+          s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+        }
+        const float d = cm - mean, tot = cnt + 32.f;
+        mean += d * (32.f / tot);
+        m2 += ((s0 + s1) + (s2 + s3)) + d * d * (cnt * 32.f / tot);
+        cnt = tot;
       }
       slab_store(buf0, lane, a, xb + c, static_cast<size_t>(ld) * sizeof(float));
       if (x16) {
@@ -519,7 +544,7 @@ struct alignas(64) EpiResidLN {
         slab64_flush_map(buf1, lane, x16 + n0 + c, static_cast<size_t>(ld16) * sizeof(op16), rowmap ? rowmap + row0 : nullptr, row0);
       }
     }
-    if (stats) stats[static_cast<size_t>(row0 + lane) * np + (n0 + c_begin) / (c_end - c_begin)] = make_float2(s, ss);
+    if (stats) stats[static_cast<size_t>(row0 + lane) * np + (n0 + c_begin) / (c_end - c_begin)] = make_float2(mean, m2);
   }
 };
 
