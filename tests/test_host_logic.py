@@ -226,3 +226,73 @@ def test_window_partition_maps_are_inverse():
     assert len(np.unique(t2w)) == 4096 and t2w.max() < 4900
     assert np.array_equal(w2t[t2w], tok)
     assert int((w2t < 0).sum()) == 804
+
+
+def test_epilogue_slab_index_maps():
+    """Index arithmetic of the GEMM epilogues' shared-memory slabs (csrc/gemm.cuh: slab_put / slab_flush / slab_load_*, slab64_*),
+    restated: a lane's row written piece by piece comes back as whole rows in the flush order and vice versa, and every
+    16-byte access of a quarter warp (8 lanes) goes to 8 different bank groups (128 B apart modulo 128 B)."""
+    # 128-byte rows: put = lane L, piece j -> L*128 + ((j ^ (L & 7)) << 4); flush / load step j: lane -> row 4j + L//8, piece L%8
+    put = {(L, j): L * 128 + ((j ^ (L & 7)) << 4) for L in range(32) for j in range(8)}
+    assert sorted(put.values()) == list(range(0, 4096, 16))                         # a bijection onto the 4 KB slab
+    for j in range(8):
+        addrs = []
+        for L in range(32):
+            r, pc = 4 * j + L // 8, L % 8
+            a = r * 128 + ((pc ^ (r & 7)) << 4)
+            assert a == put[(r, pc)]                                                 # reads what row r put as its piece pc
+            addrs.append(a)
+        for q in range(4):                                                           # quarter warps: conflict-free wavefronts
+            assert len({(a >> 4) & 7 for a in addrs[8 * q:8 * q + 8]}) == 8
+        for q in range(4):                                                           # the per-row writes as well
+            assert len({(put[(L, j)] >> 4) & 7 for L in range(8 * q, 8 * q + 8)}) == 8
+    # 64-byte rows: put = L*64 + ((p ^ ((L >> 1) & 3)) << 4); flush step j: lane -> row 8j + L//4, piece L%4
+    put64 = {(L, p): L * 64 + ((p ^ ((L >> 1) & 3)) << 4) for L in range(32) for p in range(4)}
+    assert sorted(put64.values()) == list(range(0, 2048, 16))
+    for j in range(4):
+        addrs = []
+        for L in range(32):
+            r, pc = 8 * j + L // 4, L % 4
+            a = r * 64 + ((pc ^ ((r >> 1) & 3)) << 4)
+            assert a == put64[(r, pc)]
+            addrs.append(a)
+        for q in range(4):
+            assert len({(a >> 4) & 7 for a in addrs[8 * q:8 * q + 8]}) == 8
+    for p in range(4):
+        for q in range(4):
+            assert len({(put64[(L, p)] >> 4) & 7 for L in range(8 * q, 8 * q + 8)}) == 8
+
+
+def test_folded_layernorm_statistics_merge():
+    """The folded LayerNorm's row statistics (csrc/gemm.cuh: EpiResidLN writes (mean, sum of squared deviations) per group of
+    columns, EpiStaged::prefetch merges them in slot order with Chan's update), restated in float32: equal to the two-pass
+    mean / variance also for rows whose mean dwarfs their spread, where sum / sum-of-squares statistics lose every digit."""
+    rng = np.random.RandomState(3)
+    D, slots = 768, 8
+    m = D // slots
+    for offset in (0.0, 50.0, 3000.0):
+        x = (rng.standard_normal(D) * 0.7 + offset).astype(np.float32)
+        parts = []
+        for s in range(slots):                       # producer: 32 columns at a time inside a slot
+            cnt = np.float32(0); mean = np.float32(0); m2 = np.float32(0)
+            for c in range(0, m, 32):
+                v = x[s * m + c:s * m + c + 32]
+                cm = np.float32(v.sum(dtype=np.float32) / np.float32(32))
+                cM2 = np.float32(((v - cm) ** 2).sum(dtype=np.float32))
+                d = cm - mean; tot = cnt + np.float32(32)
+                mean = np.float32(mean + d * (np.float32(32) / tot))
+                m2 = np.float32(m2 + cM2 + d * d * (cnt * np.float32(32) / tot))
+                cnt = tot
+            parts.append((mean, m2))
+        mean = np.float32(0); m2 = np.float32(0); k = np.float32(0)
+        for pm, pM2 in parts:                        # consumer
+            d = pm - mean; r = np.float32(1) / (k + np.float32(1))
+            mean = np.float32(mean + d * r)
+            m2 = np.float32(m2 + pM2 + d * d * (np.float32(m) * k * r))
+            k += np.float32(1)
+        ref_mean, ref_var = float(x.astype(np.float64).mean()), float(x.astype(np.float64).var())
+        assert abs(float(mean) - ref_mean) <= 1e-6 * max(1.0, abs(ref_mean))
+        assert abs(float(m2) / D - ref_var) <= 1e-4 * ref_var
+        naive = float(np.float32((x * x).sum(dtype=np.float32) / np.float32(D)) - np.float32(x.sum(dtype=np.float32) / np.float32(D)) ** 2)
+        if offset >= 3000.0:
+            assert abs(naive - ref_var) > 1e-2 * ref_var      # what the merge avoids
