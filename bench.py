@@ -501,7 +501,8 @@ def run_ours(args):
         lh.close()
         # configs[4]-style folder: 2048x2048 16-bit TIFFs from files
         g5, b5 = make_inputs(7000 + rank * 32, 32, 2048, 1, bit_depth=16)
-        e5 = folder_e2e("vit_b", g5, b5, local, 3, 1, dist, dev, repeat=4)                      # 128 files = 16 batches per call
+        # 128 files = 16 batches per call on one GPU; 64 per rank on several (1 GB of files per rank would crowd /dev/shm at 8 ranks)
+        e5 = folder_e2e("vit_b", g5, b5, local, 3, 1, dist, dev, repeat=4 if world == 1 else 2)
         extra["configs4_folder_2048_16bit_e2e_images_per_s"] = world * e5["images_per_s"]
         del g5, b5
         # the bf16-operand build on configs[1] (not the default, does not meet the IoU gate)
